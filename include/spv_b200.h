@@ -1,0 +1,123 @@
+/*
+ * spv_b200.h -- C ABI of the B200-native (sm_100a) differentiable Gaussian rasterizer.
+ *
+ * This is the drop-in boundary ("B1"): one extern "C" entry point per
+ * native function the reference binds through pybind11 in
+ *   /root/reference/src/submodules/dptr/dptr/gs/src/ext.cpp:14-32
+ * (18 m.def's taking torch::Tensor), restated with plain device pointers, sizes and a CUDA stream.
+ * No torch types cross this boundary.  The Python package splatter_a_video_b200.gs (a mirror of
+ * the reference's `dptr.gs` module) allocates every tensor with torch and passes data_ptr()s and
+ * torch.cuda.current_stream().cuda_stream.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers (fp32 / int32 / uint8 as typed), dense row-major.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *  - Functions never allocate and never synchronise the host; they return 0 on success or a
+ *    cudaError_t value (launch/config errors are checked after every launch, unlike the reference,
+ *    which checks none -- include/utils.h:9-10).  spv_last_error() gives a readable message.
+ *  - Outputs are fully written by the callee (the reference relies on torch::zeros; here the
+ *    callee clears what it must, so callers may pass torch.empty buffers).
+ *  - Tiles are 16x16 pixels, tile id = ty * ceil(W/16) + tx (include/config.h:7-10).
+ */
+#ifndef SPV_B200_H
+#define SPV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPV_ABI_VERSION 1
+#define SPV_TILE 16
+
+/* the library is built with -fvisibility=hidden; only these entry points are exported */
+#if defined(__GNUC__)
+#define SPV_API __attribute__((visibility("default")))
+#else
+#define SPV_API
+#endif
+
+SPV_API int spv_abi_version(void);
+SPV_API const char *spv_last_error(void);
+
+/* ---- K1/K2: project_point_forward/backward (ext.cpp:15-16; src/project_point.cu:13-145) ---------- */
+/* intr = [fx,fy,cx,cy]; extr = 12 floats, row-major 3x4 [R|t] (a 4x4 matrix's first 12 floats work). */
+SPV_API int spv_project_point_forward(int P, const float *xyz, const float *intr, const float *extr,
+                              int W, int H, float nearest, float extent,
+                              float *uv /*[P,2]*/, float *depth /*[P,1]*/, void *stream);
+/* dL_dintr[4] / dL_dextr[12] may be NULL (the reference passes nullptr unless requires_grad). */
+SPV_API int spv_project_point_backward(int P, const float *xyz, const float *intr, const float *extr,
+                               const float *depth, const float *dL_duv, const float *dL_ddepth,
+                               float *dL_dxyz /*[P,3]*/, float *dL_dintr, float *dL_dextr, void *stream);
+
+/* Orthographic projection of the video trainer (pointrix/renderer/dptr_ortho_enhanced.py:145-202;
+ * torch ops in the reference, one kernel here).  backward: d(uv,depth)/d(xyz) through the 3x4 extr. */
+SPV_API int spv_project_point_ortho_forward(int P, const float *xyz, const float *extr, int W, int H,
+                                    float nearest, float extent, float *uv, float *depth, void *stream);
+SPV_API int spv_project_point_ortho_backward(int P, const float *extr, int W, int H, const float *depth,
+                                     const float *dL_duv, const float *dL_ddepth, float *dL_dxyz, void *stream);
+
+/* ---- K3/K4: compute_cov3d_forward/backward (ext.cpp:17-18; src/compute_cov3d.cu:14-147) ----------- */
+SPV_API int spv_compute_cov3d_forward(int P, const float *scales, const float *uquats, const uint8_t *visible,
+                              float *cov3d /*[P,6]*/, void *stream);
+SPV_API int spv_compute_cov3d_backward(int P, const float *scales, const float *uquats, const uint8_t *visible,
+                               const float *dL_dcov3d, float *dL_dscales, float *dL_duquats, void *stream);
+
+/* ---- K5/K6: ewa_project_forward/backward (ext.cpp:19-20; src/ewa_project.cu:16-252) --------------- */
+SPV_API int spv_ewa_project_forward(int P, const float *xyz, const float *cov3d, const float *intr, const float *extr,
+                            const float *uv, int W, int H, const uint8_t *visible,
+                            float *conic /*[P,3]*/, int *radius /*[P]*/, int *tiles /*[P]*/, void *stream);
+SPV_API int spv_ewa_project_backward(int P, const float *xyz, const float *cov3d, const float *intr, const float *extr,
+                             const int *radius, const float *dL_dconic,
+                             float *dL_dxyz, float *dL_dcov3d, float *dL_dintr /*nullable*/,
+                             float *dL_dextr /*nullable*/, void *stream);
+/* Orthographic EWA of the video trainer (dptr_ortho_enhanced.py:18-111), J = diag(W/2,H/2) rows. */
+SPV_API int spv_ewa_project_ortho_forward(int P, const float *cov3d, const float *extr, const float *uv, int W, int H,
+                                  const uint8_t *visible, float *conic, int *radius, int *tiles, void *stream);
+SPV_API int spv_ewa_project_ortho_backward(int P, const float *cov3d, const float *extr, int W, int H, const int *radius,
+                                   const float *dL_dconic, float *dL_dcov3d, void *stream);
+
+/* ---- K7-K10: compute_sh(_free)_forward/backward (ext.cpp:23-24,29-30; src/compute_sh*.cu) --------- */
+/* shs is read with a per-point stride of (deg+1)^2 * 3 floats exactly like the reference
+ * (compute_sh.cu:45); S_alloc = shs.size(1) only sizes the zero-filled dL_dshs[P,S_alloc,3].          */
+SPV_API int spv_compute_sh_forward(int P, const float *shs, int deg, const float *dirs, const uint8_t *visible,
+                           int free_variant, float *colors /*[P,3]*/, uint8_t *clamped /*[P,3], NULL if free*/,
+                           void *stream);
+SPV_API int spv_compute_sh_backward(int P, const float *shs, int deg, const float *dirs, const uint8_t *visible,
+                            const uint8_t *clamped /*NULL if free*/, const float *dL_dcolors, int S_alloc,
+                            float *dL_dshs, float *dL_ddirs, void *stream);
+
+/* ---- K11-K14: sort_gaussian (ext.cpp:21-22; gs/sort_gaussian.py:41-54; src/sort_gaussian.cu) ------ */
+/* Step 1: inclusive scan of tiles-touched (torch.cumsum in the reference).  offsets[P-1] = I.        */
+SPV_API size_t spv_sort_scan_workspace_bytes(int P);
+SPV_API int spv_sort_scan(int P, const int *tiles, int *offsets /*[P]*/, void *workspace, size_t ws_bytes, void *stream);
+/* Step 2: emit (tile|depth) keys, radix-sort the significant bits, gather ids, tile ranges.          */
+SPV_API size_t spv_sort_workspace_bytes(int P, int64_t I);
+SPV_API int spv_sort_gaussian(int P, int64_t I, const float *uv, const float *depth, const int *radius,
+                      const int *offsets, int W, int H, int *idx_sorted /*[I]*/,
+                      int *tile_range /*[ceil(W/16)*ceil(H/16),2]*/, void *workspace, size_t ws_bytes, void *stream);
+
+/* ---- K15-K20: alpha_blending{,_enhanced,_with_bias}_forward/backward (ext.cpp:25-28,31-32) -------- */
+/* feature is [P,C] row-major (the reference transposes to [C,P] internally, alpha_blending.cu:282).
+ * gs_idx ([H,W,K], -1 padded; K=0/NULL for the plain variant), opacity_bias (NULL unless with_bias). */
+SPV_API int spv_alpha_blend_forward(int P, int C, int W, int H, int K, int enable_truncation,
+                            const float *uv, const float *conic, const float *opacity, const float *feature,
+                            const float *opacity_bias, const int *idx_sorted, const int *tile_range, float bg,
+                            float *rendered /*[C,H,W]*/, float *final_T /*[H,W]*/, int *ncontrib /*[H,W]*/,
+                            int *gs_idx, void *stream);
+SPV_API size_t spv_alpha_blend_backward_workspace_bytes(int P, int C);
+SPV_API int spv_alpha_blend_backward(int P, int C, int W, int H,
+                             const float *uv, const float *conic, const float *opacity, const float *feature,
+                             const float *opacity_bias, const int *idx_sorted, const int *tile_range, float bg,
+                             const float *final_T, const int *ncontrib, const float *dL_drendered /*[C,H,W]*/,
+                             float *dL_duv /*[P,2]*/, float *dL_dabs_uv /*[P,2]*/, float *dL_dconic /*[P,3]*/,
+                             float *dL_dopacity /*[P,1]*/, float *dL_dfeature /*[P,C]*/,
+                             float *dL_dopacity_bias /*[P,1] or NULL*/,
+                             void *workspace, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPV_B200_H */

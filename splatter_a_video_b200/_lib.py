@@ -1,0 +1,101 @@
+"""ctypes binding of libspv_b200.so (the C ABI declared in include/spv_b200.h).
+
+The product has NO CPU fallback: if the library is missing or a CUDA call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspv_b200.so")
+_lib = None
+
+P_ = c_void_p
+_SIGS = {
+    # name: (restype, [argtypes])
+    "spv_abi_version": (c_int, []),
+    "spv_last_error": (ctypes.c_char_p, []),
+    "spv_project_point_forward": (c_int, [c_int, P_, P_, P_, c_int, c_int, c_float, c_float, P_, P_, P_]),
+    "spv_project_point_backward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_project_point_ortho_forward": (c_int, [c_int, P_, P_, c_int, c_int, c_float, c_float, P_, P_, P_]),
+    "spv_project_point_ortho_backward": (c_int, [c_int, P_, c_int, c_int, P_, P_, P_, P_, P_]),
+    "spv_compute_cov3d_forward": (c_int, [c_int, P_, P_, P_, P_, P_]),
+    "spv_compute_cov3d_backward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_ewa_project_forward": (c_int, [c_int, P_, P_, P_, P_, P_, c_int, c_int, P_, P_, P_, P_, P_]),
+    "spv_ewa_project_backward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_ewa_project_ortho_forward": (c_int, [c_int, P_, P_, P_, c_int, c_int, P_, P_, P_, P_, P_]),
+    "spv_ewa_project_ortho_backward": (c_int, [c_int, P_, P_, c_int, c_int, P_, P_, P_, P_]),
+    "spv_compute_sh_forward": (c_int, [c_int, P_, c_int, P_, P_, c_int, P_, P_, P_]),
+    "spv_compute_sh_backward": (c_int, [c_int, P_, c_int, P_, P_, P_, P_, c_int, P_, P_, P_]),
+    "spv_sort_scan_workspace_bytes": (c_size_t, [c_int]),
+    "spv_sort_scan": (c_int, [c_int, P_, P_, P_, c_size_t, P_]),
+    "spv_sort_workspace_bytes": (c_size_t, [c_int, c_int64]),
+    "spv_sort_gaussian": (c_int, [c_int, c_int64, P_, P_, P_, P_, c_int, c_int, P_, P_, P_, c_size_t, P_]),
+    "spv_alpha_blend_forward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, P_, c_float,
+                                        P_, P_, P_, P_, P_]),
+    "spv_alpha_blend_backward_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "spv_alpha_blend_backward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, P_, c_float, P_, P_, P_,
+                                         P_, P_, P_, P_, P_, P_, P_, c_size_t, P_]),
+}
+
+EXPORTED = sorted(_SIGS)
+
+
+def load():
+    """dlopen the library (building is __graft_entry__.build()'s / build.py's job) and type every symbol."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m splatter_a_video_b200.build` "
+                "(there is no CPU fallback for the rasterizer).")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        if lib.spv_abi_version() != 1:
+            raise RuntimeError("libspv_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point; raise with the library's message on a CUDA error."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed: {lib.spv_last_error().decode()}")
+
+
+def query(name: str, *args) -> int:
+    return int(getattr(load(), name)(*args))
+
+
+def need_cuda(*tensors):
+    """Same contract as the reference's CHECK_INPUT (include/utils.h:9-10): inputs must be CUDA tensors."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("splatter_a_video_b200: all tensors must be CUDA tensors (no CPU path)")
+
+
+def f32c(t):
+    """fp32 + contiguous view/copy, like the `.contiguous().data_ptr<float>()` the reference does per call."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

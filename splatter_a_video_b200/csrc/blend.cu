@@ -1,0 +1,502 @@
+// Per-tile front-to-back alpha compositing ("renderCUDA") forward and backward for sm_100a.
+//
+// Semantics restate the reference kernels
+//   /root/reference/src/submodules/dptr/dptr/gs/src/alpha_blending.cu:16-249          (plain)
+//   /root/reference/src/submodules/dptr/dptr/gs/src/alpha_blending_enhanced.cu:16-273 (first-K ids, truncation)
+//   /root/reference/src/submodules/dptr/dptr/gs/src/alpha_blending_with_bias.cu       (per-Gaussian alpha bias)
+// (thresholds 1/255, 0.99, 1e-4; `ncontrib` = 1-based list position of the last applied Gaussian; bg added as
+// T*bg to every channel; fast exp like the reference's --use_fast_math build) but the machine mapping is new:
+//
+//  forward   one CTA per 16x16 tile, each warp owns a compact 8x4 pixel footprint (fewer warps touched per
+//            splat than the reference's 16x2 rows); every 256-entry chunk of the tile's list is staged in shared
+//            memory INCLUDING the features (the reference re-reads features from global per pixel x Gaussian,
+//            alpha_blending.cu:96-97), features come straight from the caller's [P,C] layout (no [C,P] transpose
+//            pass), feature rows are read back as broadcast LDS.128.
+//  backward  the reference issues C+8 global float atomics per (pixel, Gaussian) hit (alpha_blending.cu:219-246).
+//            Here each warp reduces its C+8 partial sums with a recursive-halving shuffle network (NV-1 shuffles
+//            for NV values instead of 5*NV), parks the per-warp totals in shared memory, the CTA folds the 8
+//            warps and issues ONE coalesced atomic row (NV consecutive floats) per (tile, Gaussian) into a packed
+//            [P,NV] gradient buffer; a streaming pass then unpacks it into the reference's output tensors.
+//            The per-channel `accum_rec/last_feature` recurrences of the reference collapse into one scalar
+//            recurrence on S = <colour behind, dL_dpixel> (same sum, C fewer registers x2).
+#include "common.cuh"
+#include "../../include/spv_b200.h"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kAlphaMax = 0.99f;
+constexpr float kTmin = 0.0001f;
+
+// warp w, lane l -> pixel inside the 16x16 tile: 8x4 footprint per warp, 2x4 warps per tile.
+__device__ __forceinline__ void thread_pixel(int tile_x, int tile_y, int &px, int &py) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    px = tile_x * SPV_TILE + ((warp & 1) << 3) + (lane & 7);
+    py = tile_y * SPV_TILE + ((warp >> 1) << 2) + (lane >> 3);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int CH, bool HAS_IDX, bool HAS_BIAS>
+__global__ void __launch_bounds__(kBlock)
+blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int trunc,
+                 const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
+                 const float *__restrict__ feature, const float *__restrict__ bias,
+                 const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg,
+                 float *__restrict__ rendered, float *__restrict__ final_T, int *__restrict__ ncontrib,
+                 int *__restrict__ gs_idx) {
+    __shared__ float2 s_xy[kBlock];
+    __shared__ float4 s_co[kBlock];  // conic a,b,c + opacity
+    __shared__ int s_id[kBlock];
+    __shared__ float s_bias[HAS_BIAS ? kBlock : 1];
+    __shared__ __align__(16) float s_feat[kBlock * CH];
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    int px, py;
+    thread_pixel(tile_x, tile_y, px, py);
+    const bool inside = px < W && py < H;
+    const size_t pix = (size_t)W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const int2 range = tile_range[tile];
+    const int n = range.y - range.x;
+
+    float T = 1.0f;
+    float F[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) F[c] = 0.f;
+    int last = 0, layer = 0;
+    bool done = !inside;
+
+    for (int base = 0; base < n; base += kBlock) {
+        if (__syncthreads_count(done) == kBlock) break;  // also fences reuse of the staging buffers
+        const int m = min(kBlock, n - base);
+        if ((int)threadIdx.x < m) {
+            const int id = idx_sorted[range.x + base + threadIdx.x];
+            s_id[threadIdx.x] = id;
+            s_xy[threadIdx.x] = uv[id];
+            s_co[threadIdx.x] = make_float4(conic[3 * id], conic[3 * id + 1], conic[3 * id + 2], opacity[id]);
+            if (HAS_BIAS) s_bias[threadIdx.x] = bias[id];
+        }
+        __syncthreads();
+        // feature rows: one coalesced row read per Gaussian, 32 Gaussians per warp
+        if (lane < C) {
+#pragma unroll 8
+            for (int jj = 0; jj < 32; ++jj) {
+                const int j = warp * 32 + jj;
+                if (j < m) s_feat[j * CH + lane] = feature[(size_t)s_id[j] * Cstride + c0 + lane];
+            }
+        }
+        __syncthreads();
+
+        for (int j = 0; !done && j < m; ++j) {
+            const float2 xy = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = xy.x - pxf, dy = xy.y - pyf;
+            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+            if (power > 0.f) continue;
+            float a = co.w * __expf(power);
+            if (HAS_BIAS) a += s_bias[j];
+            const float alpha = fminf(kAlphaMax, a);
+            if (alpha < kAlphaMin) continue;
+            const float next_T = T * (1.f - alpha);
+            if (next_T < kTmin) { done = true; continue; }
+            const float w = alpha * T;
+            const float *fr = s_feat + j * CH;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) F[c] = fmaf(fr[c], w, F[c]);
+            T = next_T;
+            last = base + j + 1;
+            if (HAS_IDX) {
+                if (trunc) {
+                    gs_idx[pix * K + layer] = s_id[j];
+                    if (++layer >= K) { done = true; continue; }
+                } else if (layer < K) {
+                    gs_idx[pix * K + layer] = s_id[j];
+                    ++layer;
+                }
+            }
+        }
+    }
+
+    if (inside) {
+        final_T[pix] = T;
+        ncontrib[pix] = last;
+        const size_t HW = (size_t)H * W;
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            if (c < C) rendered[c * HW + pix] = F[c] + T * bg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// Recursive-halving multi-value warp reduction: on return lane l holds, in v[0], the warp-wide sum of the
+// value with index (l % N).  N-1 shuffles (+1 for N=16) instead of 5*N.
+template <int N>
+__device__ __forceinline__ void halving_reduce(float (&v)[N], int lane) {
+#pragma unroll
+    for (int h = N / 2; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// Packed gradient row layout (NV floats per Gaussian):
+//   0,1 dL_duv   2,3 dL_dabs_uv   4,5,6 dL_dconic   7 dL_dopacity   8..8+CH-1 dL_dfeature   NV-1 dL_dbias (HAS_BIAS)
+constexpr int kG = 32;  // Gaussians per backward chunk
+
+template <int NV, int CH, bool HAS_BIAS>
+__global__ void __launch_bounds__(kBlock, 2)
+blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
+                 const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
+                 const float *__restrict__ feature, const float *__restrict__ bias,
+                 const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg,
+                 const float *__restrict__ final_T, const int *__restrict__ ncontrib,
+                 const float *__restrict__ dL_drendered, float *__restrict__ packed) {
+    static_assert(8 + CH + (HAS_BIAS ? 1 : 0) <= NV, "packed row too small");
+    __shared__ float2 s_xy[kG];
+    __shared__ float4 s_co[kG];
+    __shared__ int s_id[kG];
+    __shared__ float s_bias[HAS_BIAS ? kG : 1];
+    __shared__ __align__(16) float s_feat[kG * CH];
+    __shared__ float s_part[8][kG][NV];
+    __shared__ int s_max;
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    int px, py;
+    thread_pixel(tile_x, tile_y, px, py);
+    const bool inside = px < W && py < H;
+    const size_t pix = (size_t)W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const int2 range = tile_range[tile];
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    const int last_contrib = inside ? ncontrib[pix] : 0;
+
+    float d[CH];
+    float dsum = 0.f;
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        d[c] = (inside && c < C) ? dL_drendered[c * HW + pix] : 0.f;
+        dsum += d[c];
+    }
+    const float bg_dot = bg * dsum;
+
+    // positions >= max(last_contrib) are skipped by every pixel of the tile: do not even stage them
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, last_contrib);
+    if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int n_eff = min(range.y - range.x, s_max);
+
+    float last_alpha = 0.f, last_fd = 0.f, S = 0.f;
+
+    for (int p_hi = n_eff; p_hi > 0; p_hi -= kG) {
+        const int m = min(kG, p_hi);
+        __syncthreads();  // previous chunk's epilogue is done with s_id / s_part
+        if ((int)threadIdx.x < m) {
+            const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];  // j = 0 is the back-most entry
+            s_id[threadIdx.x] = id;
+            s_xy[threadIdx.x] = uv[id];
+            s_co[threadIdx.x] = make_float4(conic[3 * id], conic[3 * id + 1], conic[3 * id + 2], opacity[id]);
+            if (HAS_BIAS) s_bias[threadIdx.x] = bias[id];
+        }
+        __syncthreads();
+        // features: warp w stages Gaussians 4w..4w+3 of the chunk (row reads, lanes = channels)
+        if (lane < C) {
+#pragma unroll
+            for (int jj = 0; jj < kG / 8; ++jj) {
+                const int j = warp * (kG / 8) + jj;
+                if (j < m) s_feat[j * CH + lane] = feature[(size_t)s_id[j] * Cstride + c0 + lane];
+            }
+        }
+        __syncthreads();
+
+        for (int j = 0; j < m; ++j) {
+            const int p = p_hi - 1 - j;
+            bool contrib = false;
+            float dx = 0.f, dy = 0.f, Gv = 0.f, alpha = 0.f;
+            const float4 co = s_co[j];
+            if (p < last_contrib) {
+                const float2 xy = s_xy[j];
+                dx = xy.x - pxf; dy = xy.y - pyf;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                if (power <= 0.f) {
+                    Gv = __expf(power);
+                    float a = co.w * Gv;
+                    if (HAS_BIAS) a += s_bias[j];
+                    alpha = fminf(kAlphaMax, a);
+                    contrib = alpha >= kAlphaMin;
+                }
+            }
+            if (!__any_sync(0xffffffffu, contrib)) {
+                if (lane < NV) s_part[warp][j][lane] = 0.f;
+                continue;
+            }
+            float v[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] = 0.f;
+            if (contrib) {
+                const float rinv = __fdividef(1.f, 1.f - alpha);
+                T = T * rinv;  // transmittance in front of this Gaussian
+                const float w = alpha * T;
+                const float *fr = s_feat + j * CH;
+                float fd = 0.f;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    fd = fmaf(fr[c], d[c], fd);
+                    v[8 + c] = w * d[c];
+                }
+                S = last_alpha * last_fd + (1.f - last_alpha) * S;
+                float dL_dalpha = (fd - S) * T;
+                last_alpha = alpha;
+                last_fd = fd;
+                dL_dalpha += (-T_final * rinv) * bg_dot;
+                const float dL_dG = co.w * dL_dalpha;
+                const float dGx = -Gv * dx * co.x - Gv * dy * co.y;
+                const float dGy = -Gv * dy * co.z - Gv * dx * co.y;
+                const float g0 = dL_dG * dGx, g1 = dL_dG * dGy;
+                v[0] = g0; v[1] = g1; v[2] = fabsf(g0); v[3] = fabsf(g1);
+                v[4] = -0.5f * Gv * dx * dx * dL_dG;
+                v[5] = -Gv * dx * dy * dL_dG;
+                v[6] = -0.5f * Gv * dy * dy * dL_dG;
+                v[7] = Gv * dL_dalpha;
+                if (HAS_BIAS) v[NV - 1] = dL_dalpha;
+            }
+            halving_reduce<NV>(v, lane);
+            if (lane < NV) s_part[warp][j][lane] = v[0];
+        }
+        __syncthreads();
+        // fold the 8 warps and push one packed row per (tile, Gaussian)
+        if (NV == 32) {
+#pragma unroll
+            for (int jj = 0; jj < kG / 8; ++jj) {
+                const int j = warp * (kG / 8) + jj;
+                if (j < m) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][lane];
+                    if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * NV + lane, s);
+                }
+            }
+        } else {  // NV == 16: two Gaussians per warp pass
+            const int half = lane >> 4, l16 = lane & 15;
+#pragma unroll
+            for (int jj = 0; jj < kG / 16; ++jj) {
+                const int j = warp * (kG / 8) + jj * 2 + half;
+                if (j < m) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][l16];
+                    if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * NV + l16, s);
+                }
+            }
+        }
+    }
+}
+
+// packed [P,NV] -> the reference's separate gradient tensors.  accumulate: later channel chunks add their share
+// of the channel-summed gradients (uv, conic, opacity), exactly like the reference's per-chunk launches do.
+template <int NV>
+__global__ void __launch_bounds__(kBlock)
+unpack_kernel(int P, int C, int Cstride, int c0, int has_bias, int accumulate, const float *__restrict__ packed,
+              float2 *__restrict__ dL_duv, float2 *__restrict__ dL_dabs_uv, float *__restrict__ dL_dconic,
+              float *__restrict__ dL_dopacity, float *__restrict__ dL_dfeature, float *__restrict__ dL_dbias) {
+    const int g = blockIdx.x * kBlock + threadIdx.x;
+    if (g >= P) return;
+    float r[NV];
+    const float4 *row = reinterpret_cast<const float4 *>(packed + (size_t)g * NV);
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) {
+        const float4 q = row[k];
+        r[4 * k] = q.x; r[4 * k + 1] = q.y; r[4 * k + 2] = q.z; r[4 * k + 3] = q.w;
+    }
+    if (accumulate) {
+        const float2 a = dL_duv[g], b = dL_dabs_uv[g];
+        dL_duv[g] = make_float2(a.x + r[0], a.y + r[1]);
+        dL_dabs_uv[g] = make_float2(b.x + r[2], b.y + r[3]);
+        dL_dconic[3 * g] += r[4]; dL_dconic[3 * g + 1] += r[5]; dL_dconic[3 * g + 2] += r[6];
+        dL_dopacity[g] += r[7];
+        if (has_bias) dL_dbias[g] += r[NV - 1];
+    } else {
+        dL_duv[g] = make_float2(r[0], r[1]);
+        dL_dabs_uv[g] = make_float2(r[2], r[3]);
+        dL_dconic[3 * g] = r[4]; dL_dconic[3 * g + 1] = r[5]; dL_dconic[3 * g + 2] = r[6];
+        dL_dopacity[g] = r[7];
+        if (has_bias) dL_dbias[g] = r[NV - 1];
+    }
+#pragma unroll
+    for (int c = 0; c < NV - 8; ++c)
+        if (c < C) dL_dfeature[(size_t)g * Cstride + c0 + c] = r[8 + c];
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+struct FwdArgs {
+    int C, Cstride, c0, W, H, gx, K, trunc;
+    const float2 *uv; const float *conic, *opacity, *feature, *bias;
+    const int *idx_sorted; const int2 *tile_range; float bg;
+    float *rendered, *final_T; int *ncontrib, *gs_idx;
+};
+
+template <int CH, bool IDX, bool BIAS>
+void launch_fwd(const FwdArgs &a, int ntiles, cudaStream_t s) {
+    blend_fwd_kernel<CH, IDX, BIAS><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.K, a.trunc, a.uv,
+                                                             a.conic, a.opacity, a.feature, a.bias, a.idx_sorted,
+                                                             a.tile_range, a.bg, a.rendered, a.final_T, a.ncontrib,
+                                                             a.gs_idx);
+}
+
+template <bool IDX, bool BIAS>
+void dispatch_fwd(const FwdArgs &a, int ntiles, cudaStream_t s) {
+    const int C = a.C;
+    if (C <= 1) launch_fwd<1, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 2) launch_fwd<2, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 3) launch_fwd<3, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 4) launch_fwd<4, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 8) launch_fwd<8, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 12) launch_fwd<12, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 16) launch_fwd<16, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 20) launch_fwd<20, IDX, BIAS>(a, ntiles, s);
+    else if (C <= 24) launch_fwd<24, IDX, BIAS>(a, ntiles, s);
+    else launch_fwd<32, IDX, BIAS>(a, ntiles, s);
+}
+
+struct BwdArgs {
+    int C, Cstride, c0, W, H, gx;
+    const float2 *uv; const float *conic, *opacity, *feature, *bias;
+    const int *idx_sorted; const int2 *tile_range; float bg;
+    const float *final_T; const int *ncontrib; const float *dL_drendered; float *packed;
+};
+
+template <int NV, int CH, bool BIAS>
+void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
+    blend_bwd_kernel<NV, CH, BIAS><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
+                                                            a.opacity, a.feature, a.bias, a.idx_sorted, a.tile_range,
+                                                            a.bg, a.final_T, a.ncontrib, a.dL_drendered, a.packed);
+}
+
+// returns NV used
+template <bool BIAS>
+int dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
+    const int C = a.C;
+    constexpr int cap16 = BIAS ? 7 : 8, cap32 = BIAS ? 23 : 24;
+    if (C <= cap16) {
+        if (C <= 1) launch_bwd<16, 1, BIAS>(a, ntiles, s);
+        else if (C <= 3) launch_bwd<16, 3, BIAS>(a, ntiles, s);
+        else if (C <= 4) launch_bwd<16, 4, BIAS>(a, ntiles, s);
+        else launch_bwd<16, cap16, BIAS>(a, ntiles, s);
+        return 16;
+    }
+    if (C <= 12) launch_bwd<32, 12, BIAS>(a, ntiles, s);
+    else if (C <= 16) launch_bwd<32, 16, BIAS>(a, ntiles, s);
+    else if (C <= 20) launch_bwd<32, 20, BIAS>(a, ntiles, s);
+    else launch_bwd<32, cap32, BIAS>(a, ntiles, s);
+    return 32;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spv_alpha_blend_forward(int P, int C, int W, int H, int K, int enable_truncation, const float *uv,
+                            const float *conic, const float *opacity, const float *feature, const float *opacity_bias,
+                            const int *idx_sorted, const int *tile_range, float bg, float *rendered, float *final_T,
+                            int *ncontrib, int *gs_idx, void *stream) {
+    (void)P;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
+    if (W <= 0 || H <= 0) return 0;
+    const bool has_idx = gs_idx != nullptr && K > 0;
+    if (has_idx && opacity_bias) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_forward: gs_idx and opacity_bias are exclusive"); return (int)cudaErrorInvalidValue; }
+    if (has_idx) SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, s), "spv_alpha_blend_forward");
+    if (C <= 0) {  // still produce final_T / ncontrib? the reference launches nothing for C == 0
+        SPV_CUDA_TRY(cudaMemsetAsync(final_T, 0, sizeof(float) * (size_t)H * W, s), "spv_alpha_blend_forward");
+        SPV_CUDA_TRY(cudaMemsetAsync(ncontrib, 0, sizeof(int) * (size_t)H * W, s), "spv_alpha_blend_forward");
+        return 0;
+    }
+    // channels beyond 32 are processed in chunks; every chunk rewrites final_T / ncontrib with identical values
+    // (alpha_blending.cu:287-393).
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        FwdArgs a;
+        a.C = (C - c0 < 32) ? (C - c0) : 32; a.Cstride = C; a.c0 = c0; a.W = W; a.H = H; a.gx = gx; a.K = K;
+        a.trunc = enable_truncation;
+        a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = opacity_bias;
+        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg;
+        a.rendered = rendered + (size_t)c0 * H * W; a.final_T = final_T; a.ncontrib = ncontrib; a.gs_idx = gs_idx;
+        if (has_idx) dispatch_fwd<true, false>(a, ntiles, s);
+        else if (opacity_bias) dispatch_fwd<false, true>(a, ntiles, s);
+        else dispatch_fwd<false, false>(a, ntiles, s);
+        int rc = spv::check_launch("spv_alpha_blend_forward");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+size_t spv_alpha_blend_backward_workspace_bytes(int P, int C) {
+    (void)C;
+    return (size_t)(P > 0 ? P : 1) * 32 * sizeof(float);
+}
+
+int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const float *conic, const float *opacity,
+                             const float *feature, const float *opacity_bias, const int *idx_sorted,
+                             const int *tile_range, float bg, const float *final_T, const int *ncontrib,
+                             const float *dL_drendered, float *dL_duv, float *dL_dabs_uv, float *dL_dconic,
+                             float *dL_dopacity, float *dL_dfeature, float *dL_dopacity_bias, void *workspace,
+                             size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0) return 0;
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
+    if (ws_bytes < spv_alpha_blend_backward_workspace_bytes(P, C)) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_backward: workspace too small"); return (int)cudaErrorInvalidValue; }
+    const bool has_bias = opacity_bias != nullptr;
+    if (has_bias && !dL_dopacity_bias) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_backward: dL_dopacity_bias is NULL"); return (int)cudaErrorInvalidValue; }
+    float *packed = (float *)workspace;
+    const int cap = has_bias ? 23 : 24;
+    if (C <= 0 || W <= 0 || H <= 0) {
+        SPV_CUDA_TRY(cudaMemsetAsync(dL_duv, 0, sizeof(float) * 2 * (size_t)P, s), "spv_alpha_blend_backward");
+        SPV_CUDA_TRY(cudaMemsetAsync(dL_dabs_uv, 0, sizeof(float) * 2 * (size_t)P, s), "spv_alpha_blend_backward");
+        SPV_CUDA_TRY(cudaMemsetAsync(dL_dconic, 0, sizeof(float) * 3 * (size_t)P, s), "spv_alpha_blend_backward");
+        SPV_CUDA_TRY(cudaMemsetAsync(dL_dopacity, 0, sizeof(float) * (size_t)P, s), "spv_alpha_blend_backward");
+        if (has_bias) SPV_CUDA_TRY(cudaMemsetAsync(dL_dopacity_bias, 0, sizeof(float) * (size_t)P, s), "spv_alpha_blend_backward");
+        return 0;
+    }
+    for (int c0 = 0; c0 < C; c0 += cap) {
+        BwdArgs a;
+        a.C = (C - c0 < cap) ? (C - c0) : cap; a.Cstride = C; a.c0 = c0; a.W = W; a.H = H; a.gx = gx;
+        a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = opacity_bias;
+        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg;
+        a.final_T = final_T; a.ncontrib = ncontrib; a.dL_drendered = dL_drendered + (size_t)c0 * H * W;
+        a.packed = packed;
+        const int nv = (a.C <= (has_bias ? 7 : 8)) ? 16 : 32;
+        SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)nv * P, s), "spv_alpha_blend_backward");
+        if (has_bias) dispatch_bwd<true>(a, ntiles, s); else dispatch_bwd<false>(a, ntiles, s);
+        int rc = spv::check_launch("spv_alpha_blend_backward/blend");
+        if (rc) return rc;
+        const unsigned g = spv::cdiv(P, kBlock);
+        if (nv == 16)
+            unpack_kernel<16><<<g, kBlock, 0, s>>>(P, a.C, C, c0, has_bias, c0 > 0, packed, (float2 *)dL_duv,
+                                                   (float2 *)dL_dabs_uv, dL_dconic, dL_dopacity, dL_dfeature,
+                                                   dL_dopacity_bias);
+        else
+            unpack_kernel<32><<<g, kBlock, 0, s>>>(P, a.C, C, c0, has_bias, c0 > 0, packed, (float2 *)dL_duv,
+                                                   (float2 *)dL_dabs_uv, dL_dconic, dL_dopacity, dL_dfeature,
+                                                   dL_dopacity_bias);
+        rc = spv::check_launch("spv_alpha_blend_backward/unpack");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

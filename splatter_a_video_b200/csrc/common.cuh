@@ -1,0 +1,47 @@
+// Shared helpers for the sm_100a rasterizer kernels (no torch, no third-party headers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define SPV_TILE 16
+#define SPV_TILE_PIX 256
+
+namespace spv {
+
+// Error plumbing: every extern "C" entry returns this after its launches.
+void set_error(cudaError_t e, const char *where);
+inline int check_launch(const char *where) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        set_error(e, where);
+        (void)cudaGetLastError();  // clear the sticky-less error so later calls can proceed
+        return (int)e;
+    }
+    return 0;
+}
+#define SPV_CUDA_TRY(expr, where)                 \
+    do {                                          \
+        cudaError_t _e = (expr);                  \
+        if (_e != cudaSuccess) {                  \
+            spv::set_error(_e, where);            \
+            return (int)_e;                       \
+        }                                         \
+    } while (0)
+
+inline int tiles_x(int W) { return (W + SPV_TILE - 1) / SPV_TILE; }
+inline int tiles_y(int H) { return (H + SPV_TILE - 1) / SPV_TILE; }
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// Tile rectangle of a splat (semantics of the reference's get_rect, include/utils.h:17-37):
+// truncating float->int, clamped to [0, grid].
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx, int gy,
+                                          int &x0, int &y0, int &x1, int &y1) {
+    const float r = (float)radius;
+    x0 = min(gx, max(0, (int)((px - r) / 16.0f)));
+    y0 = min(gy, max(0, (int)((py - r) / 16.0f)));
+    x1 = min(gx, max(0, (int)((px + r + 16.0f - 1.0f) / 16.0f)));
+    y1 = min(gy, max(0, (int)((py + r + 16.0f - 1.0f) / 16.0f)));
+}
+
+}  // namespace spv

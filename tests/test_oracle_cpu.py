@@ -1,0 +1,186 @@
+"""CPU-only: the C oracle against (a) the independent pure-PyTorch restatement, (b) torch autograd for every
+hand-derived backward, (c) the golden outputs of the REAL reference captured on the B200 box
+(tests/golden/golden_ref_*.npz, produced by tests/test_ref_pin_gpu.py with SPV_WRITE_GOLDEN=1)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as Hh
+from helpers import O
+from oracle import torch_ref as TR
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    s = Hh.scene_np(1000, 64, 64, seed=1234)
+    return s, Hh.oracle_ortho(s), Hh.oracle_persp(s, nearest=0.01)
+
+
+def test_oracle_builds_and_versions():
+    assert O.lib().orc_version() == 1
+
+
+def test_ortho_chain_matches_torch_restatement(tiny):
+    s, oo, _ = tiny
+    W, H = s["W"], s["H"]
+    r = TR.render_ortho_frame(torch.from_numpy(s["xyz"]), torch.from_numpy(s["scaling"]), torch.from_numpy(s["rotation"]),
+                              torch.from_numpy(s["opacity"]), torch.from_numpy(s["shs"]), None, torch.from_numpy(s["extr"]), W, H)
+    assert np.array_equal(r["radius"].numpy(), oo["radius"]) and np.array_equal(r["tiles"].numpy(), oo["tiles"])
+    assert np.array_equal(r["idx_sorted"].numpy(), oo["idx_sorted"]) and np.array_equal(r["tile_range"].numpy(), oo["tile_range"])
+    np.testing.assert_allclose(r["uv"].numpy(), oo["uv"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(r["conic"].numpy(), oo["conic"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(r["colors"].numpy(), oo["rgb"], rtol=1e-5, atol=1e-6)
+    f = oo["blend_rgb"]
+    np.testing.assert_allclose(r["rgb"].numpy(), f["rendered"], rtol=0, atol=2e-6)
+    ok = ~f["fragile"]
+    assert np.array_equal(r["ncontrib"].numpy()[ok], f["ncontrib"][ok])
+    assert np.array_equal(r["gs_idx"].numpy()[ok], f["gs_idx"][ok])
+
+
+def test_perspective_chain_matches_torch_restatement(tiny):
+    s, _, op = tiny
+    W, H = s["W"], s["H"]
+    xyz, intr, extr = (torch.from_numpy(s[k]) for k in ("xyz", "intr", "extr"))
+    uv, depth = TR.project_point(xyz, intr, extr, W, H, nearest=0.01)
+    np.testing.assert_allclose(uv.numpy(), op["uv"], rtol=0, atol=2e-5)
+    vis = depth != 0
+    cov3d = TR.compute_cov3d(torch.from_numpy(s["scaling"]), torch.from_numpy(s["rotation"]), vis)
+    np.testing.assert_allclose(cov3d.numpy(), op["cov3d"], rtol=1e-5, atol=1e-12)
+    conic, radius, tiles = TR.ewa_project(xyz, torch.from_numpy(op["cov3d"]), intr, extr, torch.from_numpy(op["uv"]), W, H,
+                                          torch.from_numpy(op["vis"]))
+    assert (radius.numpy() != op["radius"]).mean() < 2e-3 and (tiles.numpy() != op["tiles"]).mean() < 2e-3
+    same = radius.numpy() == op["radius"]
+    np.testing.assert_allclose(conic.numpy()[same], op["conic"][same], rtol=2e-4, atol=1e-7)
+
+
+def test_blend_backward_matches_autograd(tiny):
+    s, oo, _ = tiny
+    W, H = s["W"], s["H"]
+    C = 5
+    rng = np.random.default_rng(0)
+    feat = rng.random((s["P"], C), dtype=np.float32)
+    op = np.minimum(s["opacity"], 0.985).astype(np.float32)   # keep alpha below the 0.99 clamp
+    g = rng.standard_normal((C, H, W)).astype(np.float32)
+    for bg in (0.0, 1.0):
+        leaves = [torch.from_numpy(a).clone().requires_grad_(True) for a in (oo["uv"], oo["conic"], op, feat)]
+        img, _, _, _ = TR.alpha_blending(*leaves, torch.from_numpy(oo["idx_sorted"]), torch.from_numpy(oo["tile_range"]), bg, W, H)
+        grads = torch.autograd.grad((img * torch.from_numpy(g)).sum(), leaves)
+        f = O.alpha_blending_forward(oo["uv"], oo["conic"], op, feat, oo["idx_sorted"], oo["tile_range"], bg, W, H)
+        b = O.alpha_blending_backward(oo["uv"], oo["conic"], op, feat, oo["idx_sorted"], oo["tile_range"], bg, W, H,
+                                      f["final_T"], f["ncontrib"], g)
+        for name, gt in zip(("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature"), grads):
+            Hh.assert_grad_close(b[name], gt.numpy(), f"oracle {name} (bg={bg})", norm_tol=1e-5)
+
+
+def test_bias_blend_backward_matches_autograd(tiny):
+    s, oo, _ = tiny
+    W, H, C = s["W"], s["H"], 2
+    rng = np.random.default_rng(1)
+    feat = rng.random((s["P"], C), dtype=np.float32)
+    op = np.minimum(s["opacity"], 0.9).astype(np.float32)
+    bias = (0.05 * rng.random((s["P"], 1))).astype(np.float32)
+    g = rng.standard_normal((C, H, W)).astype(np.float32)
+    leaves = [torch.from_numpy(a).clone().requires_grad_(True) for a in (oo["uv"], oo["conic"], op, feat, bias)]
+    img, _, _, _ = TR.alpha_blending(*leaves[:4], torch.from_numpy(oo["idx_sorted"]), torch.from_numpy(oo["tile_range"]), 0.5, W, H,
+                                     opacity_bias=leaves[4])
+    grads = torch.autograd.grad((img * torch.from_numpy(g)).sum(), leaves)
+    f = O.alpha_blending_forward(oo["uv"], oo["conic"], op, feat, oo["idx_sorted"], oo["tile_range"], 0.5, W, H, opacity_bias=bias)
+    b = O.alpha_blending_backward(oo["uv"], oo["conic"], op, feat, oo["idx_sorted"], oo["tile_range"], 0.5, W, H, f["final_T"],
+                                  f["ncontrib"], g, opacity_bias=bias)
+    for name, gt in zip(("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature", "dL_dopacity_bias"), grads):
+        Hh.assert_grad_close(b[name], gt.numpy(), f"oracle {name}", norm_tol=1e-5)
+
+
+def test_geometry_backwards_match_autograd(tiny):
+    s, oo, op = tiny
+    W, H, P = s["W"], s["H"], s["P"]
+    rng = np.random.default_rng(2)
+    # cov3d
+    sc = torch.from_numpy(s["scaling"]).requires_grad_(True); q = torch.from_numpy(s["rotation"]).requires_grad_(True)
+    g = rng.standard_normal((P, 6)).astype(np.float32)
+    TR.compute_cov3d(sc, q).backward(torch.from_numpy(g))
+    gs_, gq_ = O.compute_cov3d_backward(s["scaling"], s["rotation"], None, g)
+    Hh.assert_grad_close(gs_, sc.grad.numpy(), "cov3d dL_dscales", norm_tol=1e-5)
+    Hh.assert_grad_close(gq_, q.grad.numpy(), "cov3d dL_duquats", norm_tol=1e-5)
+    # perspective projection
+    xyz = torch.from_numpy(s["xyz"]).requires_grad_(True)
+    intr = torch.from_numpy(s["intr"]).requires_grad_(True); extr = torch.from_numpy(s["extr"][:3]).clone().requires_grad_(True)
+    uv, depth = TR.project_point(xyz, intr, extr, W, H, nearest=0.01)
+    guv = rng.standard_normal((P, 2)).astype(np.float32); gd = rng.standard_normal((P, 1)).astype(np.float32)
+    torch.autograd.backward([uv, depth], [torch.from_numpy(guv), torch.from_numpy(gd)])
+    ox, oi, oe = O.project_point_backward(s["xyz"], s["intr"], s["extr"], op["depth"], guv, gd, True, True)
+    Hh.assert_grad_close(ox, xyz.grad.numpy(), "project dL_dxyz", norm_tol=1e-5)
+    Hh.assert_grad_close(oi, intr.grad.numpy(), "project dL_dintr", norm_tol=1e-4)
+    # the reference's dL_dextr rows 0-1 carry an extra factor from its own derivation ("may be bugs?" project_point.cu:119):
+    # only the rows it gets right by construction (translation column of rows 0,1) are cross-checked here.
+    np.testing.assert_allclose(oe[:2, 3], extr.grad.numpy()[:2, 3], rtol=1e-3, atol=1e-3)
+    # perspective EWA
+    xyz2 = torch.from_numpy(s["xyz"]).requires_grad_(True); c3 = torch.from_numpy(op["cov3d"]).requires_grad_(True)
+    conic, radius, _ = TR.ewa_project(xyz2, c3, torch.from_numpy(s["intr"]), torch.from_numpy(s["extr"]), torch.from_numpy(op["uv"]),
+                                      W, H, torch.from_numpy(op["vis"]))
+    gc = rng.standard_normal((P, 3)).astype(np.float32)
+    same = radius.numpy() == op["radius"]
+    gc[~same] = 0
+    conic.backward(torch.from_numpy(gc))
+    gx, gcov, _, _ = O.ewa_project_backward(s["xyz"], op["cov3d"], s["intr"], s["extr"], op["radius"], gc)
+    Hh.assert_grad_close(gcov, c3.grad.numpy(), "ewa dL_dcov3d", norm_tol=1e-4)
+    Hh.assert_grad_close(gx, xyz2.grad.numpy(), "ewa dL_dxyz", norm_tol=1e-4)
+    # SH
+    shs = torch.from_numpy(s["shs"]).requires_grad_(True)
+    dirs_np = rng.standard_normal((P, 3)).astype(np.float32); dirs_np /= np.linalg.norm(dirs_np, axis=1, keepdims=True)
+    dirs = torch.from_numpy(dirs_np).requires_grad_(True)
+    col = TR.compute_sh(shs, 3, dirs)
+    gcol = rng.standard_normal((P, 3)).astype(np.float32)
+    col.backward(torch.from_numpy(gcol))
+    _, clamped = O.compute_sh(s["shs"], 3, dirs_np)
+    gsh, gdir = O.compute_sh_backward(s["shs"], 3, dirs_np, None, clamped, gcol)
+    Hh.assert_grad_close(gsh, shs.grad.numpy(), "sh dL_dshs", norm_tol=1e-5)
+    Hh.assert_grad_close(gdir, dirs.grad.numpy(), "sh dL_ddirs", norm_tol=1e-4)
+
+
+def test_sort_edge_cases():
+    # empty
+    idx, tr = O.sort_gaussian(np.zeros((4, 2), np.float32), np.zeros((4, 1), np.float32), 40, 24, np.zeros(4, np.int32),
+                              np.zeros(4, np.int32))
+    assert idx.size == 0 and tr.shape == (6, 2) and not tr.any()
+    # one splat covering everything, ragged image
+    uv = np.array([[20.0, 12.0]], np.float32)
+    idx, tr = O.sort_gaussian(uv, np.ones((1, 1), np.float32), 40, 24, np.array([100], np.int32), np.array([6], np.int32))
+    assert np.array_equal(idx, np.zeros(6, np.int32)) and np.array_equal(tr, np.stack([np.arange(6), np.arange(1, 7)], 1))
+
+
+GOLD = [f for f in ("golden_ref_chain.npz", "golden_ref_blend_C3.npz", "golden_ref_blend_C1.npz", "golden_ref_blend_C19.npz")
+        if os.path.exists(os.path.join(Hh.GOLDEN, f))]
+
+
+@pytest.mark.skipif(not GOLD, reason="reference goldens not captured yet (tests/golden/README.md)")
+def test_oracle_matches_real_reference_goldens(tiny):
+    """Golden vectors produced by the UNMODIFIED reference kernels on a B200 (fast-math build)."""
+    s, oo, op = tiny
+    W, H = s["W"], s["H"]
+    if "golden_ref_chain.npz" in GOLD:
+        g = np.load(os.path.join(Hh.GOLDEN, "golden_ref_chain.npz"))
+        np.testing.assert_allclose(op["uv"], g["uv"], rtol=1e-5, atol=2e-3)
+        np.testing.assert_allclose(op["cov3d"], g["cov3d"], rtol=1e-5, atol=1e-12)
+        assert np.array_equal(op["radius"], g["radius"]) and np.array_equal(op["tiles"], g["tiles"])
+        np.testing.assert_allclose(op["conic"], g["conic"], rtol=2e-4, atol=1e-7)
+        assert np.array_equal(op["tile_range"], g["tile_range"]) and np.array_equal(op["idx_sorted"], g["idx_sorted"])
+        np.testing.assert_allclose(oo["rgb"], g["rgb"], rtol=1e-5, atol=1e-6)
+    for C, bg, K, feat in ((3, 0.0, 20, oo["rgb"]), (1, 1.0, 0, oo["depth"]), (19, 0.0, 0, s["attrs"])):
+        name = f"golden_ref_blend_C{C}.npz"
+        if name not in GOLD:
+            continue
+        g = np.load(os.path.join(Hh.GOLDEN, name))
+        f = O.alpha_blending_forward(oo["uv"], oo["conic"], s["opacity"], feat, oo["idx_sorted"], oo["tile_range"], bg, W, H, K=K,
+                                     frag_eps=Hh.FRAG_EPS)
+        Hh.assert_pixels_close(f["rendered"], g["rendered"], f["fragile"], f"oracle vs reference golden C={C}")
+        ok = ~f["fragile"]
+        assert np.array_equal(f["ncontrib"][ok], g["ncontrib"][ok])
+        if K:
+            assert np.array_equal(f["gs_idx"][ok], g["gs_idx"][ok])
+        b = O.alpha_blending_backward(oo["uv"], oo["conic"], s["opacity"], feat, oo["idx_sorted"], oo["tile_range"], bg, W, H,
+                                      g["final_T"], g["ncontrib"], g["g"])
+        for k in ("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature", "dL_dabs_uv"):
+            Hh.assert_grad_close(b[k], g[k], f"oracle {k} vs reference golden C={C}", norm_tol=2e-4)
