@@ -674,12 +674,10 @@ void orc_alpha_blend_bwd(int P, int C, int W, int H,
                 unsigned contributor = (unsigned)(r1 - r0);
                 const int last_contributor = ncontrib[pix];
                 float last_alpha = 0;
-                float bg_dot_dpixel = 0;
                 for (int c = 0; c < C; ++c) {
                     accum_rec[c] = 0; last_feature[c] = 0;
                     dpix[c] = dL_drendered[(size_t)c * H * W + pix];
                 }
-                for (int c = 0; c < C; ++c) bg_dot_dpixel += bg * dpix[c];
                 for (int k = r1 - 1; k >= r0; --k) { /* back to front (:198 idx_sorted[range.y - progress - 1]) */
                     int g = idx_sorted[k];
                     contributor--;
@@ -696,23 +694,34 @@ void orc_alpha_blend_bwd(int P, int C, int W, int H,
                     if (alpha < 1.0f / 255.0f) continue;
                     T = T / (1.f - alpha);
                     const float dchannel_dcolor = alpha * T;
-                    float dL_dalpha = 0.0f;
                     double *A = acc + (size_t)g * S;
-                    for (int c = 0; c < C; ++c) {
-                        const float cf = feature[(size_t)g * C + c];
-                        accum_rec[c] = last_alpha * last_feature[c] + (1.f - last_alpha) * accum_rec[c];
-                        last_feature[c] = cf;
-                        dL_dalpha += (cf - accum_rec[c]) * dpix[c];
-                        float v = dchannel_dcolor * dpix[c];
-#pragma omp atomic
-                        A[9 + c] += (double)v;
-                    }
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                    const float dL_dG = opac * dL_dalpha;
                     const float dGx = -G * vx * ca - G * vy * cb;
                     const float dGy = -G * vy * cc - G * vx * cb;
+                    /* The reference launches one kernel per chunk of <=32 channels (alpha_blending.cu:440-576):
+                     * dL_dalpha, and therefore the |.| that feeds dL_dabs_uv, is formed per chunk and the chunk
+                     * results are summed by the atomics.  Same here. */
+                    float dL_dalpha = 0.0f, abs0 = 0.0f, abs1 = 0.0f;
+                    for (int cb0 = 0; cb0 < C; cb0 += 32) {
+                        const int cb1 = cb0 + 32 < C ? cb0 + 32 : C;
+                        float da = 0.0f, bgd = 0.0f;
+                        for (int c = cb0; c < cb1; ++c) {
+                            const float cf = feature[(size_t)g * C + c];
+                            accum_rec[c] = last_alpha * last_feature[c] + (1.f - last_alpha) * accum_rec[c];
+                            last_feature[c] = cf;
+                            da += (cf - accum_rec[c]) * dpix[c];
+                            float v = dchannel_dcolor * dpix[c];
+#pragma omp atomic
+                            A[9 + c] += (double)v;
+                        }
+                        da *= T;
+                        for (int c = cb0; c < cb1; ++c) bgd += bg * dpix[c];
+                        da += (-T_final / (1.f - alpha)) * bgd;
+                        abs0 += fabsf(opac * da * dGx);
+                        abs1 += fabsf(opac * da * dGy);
+                        dL_dalpha += da;
+                    }
+                    last_alpha = alpha;
+                    const float dL_dG = opac * dL_dalpha;
                     float g0 = dL_dG * dGx, g1 = dL_dG * dGy;
                     float g2 = -0.5f * G * vx * vx * dL_dG, g3 = -G * vx * vy * dL_dG, g4 = -0.5f * G * vy * vy * dL_dG;
                     float g5 = G * dL_dalpha;
@@ -721,9 +730,9 @@ void orc_alpha_blend_bwd(int P, int C, int W, int H,
 #pragma omp atomic
                     A[1] += (double)g1;
 #pragma omp atomic
-                    A[2] += (double)fabsf(g0);
+                    A[2] += (double)abs0;
 #pragma omp atomic
-                    A[3] += (double)fabsf(g1);
+                    A[3] += (double)abs1;
 #pragma omp atomic
                     A[4] += (double)g2;
 #pragma omp atomic
