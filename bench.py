@@ -1,0 +1,522 @@
+#!/usr/bin/env python
+"""Headline benchmark of the B200-native video-Gaussian rasterizer (contract: see the task statement / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference arm (see below)
+
+Metric (BASELINE.json): train iterations per second on the DAVIS-shaped workload (configs[1]: 854x480, 50 frames,
+200k Gaussians).  One "step" = one training-style pass of the hot path over one frame through the renderer plugin
+(`DPTROrthoEnhancedRender.render_batch`): SH -> ortho projection -> cov3d -> EWA -> tile sort -> RGB(K=20 ids) /
+depth / 19 attribute channels blended -> full backward to every per-Gaussian render_dict tensor.
+  value : inputs resident in HBM, upstream image gradients resident in HBM.
+  e2e   : the same step driven from HOST buffers: the step's ground-truth frame + upstream weights are copied H2D from
+          pinned memory, dL/dimage is formed on the device from them, and the scalar loss is read back D2H.
+Rendered FPS (forward only, the reference's render_video path) is reported beside it.
+
+Reference arm: the reference has NO CPU implementation (every native entry TORCH_CHECKs is_cuda,
+/root/reference/src/submodules/dptr/dptr/gs/include/utils.h:9-10), so `--impl reference` times the oracle port
+(oracle/spv_oracle.c, OpenMP on all host cores) on a bounded sample of the same workload (one frame per step), and --
+when oracle/_ref/_C.so (the unmodified reference .cu compiled for sm_100a) is present -- adds the reference's own CUDA
+path on the same GPU as `reference_gpu` for context.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from splatter_a_video_b200 import synth  # noqa: E402
+
+K_IDX = 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2_davis480p", choices=list(synth.CONFIGS))
+    ap.add_argument("--staged", action="store_true", help="reference op sequence (3 blend passes) instead of the fused renderer")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def blend_bwd_algorithmic_bytes(I, C, H, W, P):
+    """reads I*(28+4C) + H*W*(4C+8); writes P*4*(2+2+3+1+C)."""
+    return I * (28 + 4 * C) + H * W * (4 * C + 8) + P * 4 * (8 + C)
+
+
+def blend_fwd_algorithmic_bytes(I, C, H, W, K):
+    return I * (28 + 4 * C) + H * W * (4 * C + 8 + 4 * K)
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+class Workload:
+    """Device-resident leaves (the reference's render_dict tensors) + renderer plugin + camera dict."""
+
+    def __init__(self, cfg_name, device, fused):
+        from splatter_a_video_b200.parallel import FlatParams
+        from splatter_a_video_b200.renderer import parse_renderer
+        self.sc_cpu = synth.make_config(cfg_name)
+        sc = self.sc_cpu
+        self.P, self.W, self.H, self.frames = sc.P, sc.W, sc.H, sc.frames
+        self.device = device
+        dev = lambda x: x.to(device)
+        # trainable per-Gaussian tensors as views of one flat buffer (one all-reduce per step at N>1)
+        self.flat = FlatParams({"position": dev(sc.position), "scaling": dev(sc.scaling), "rotation": dev(sc.rotation),
+                                "opacity": dev(sc.opacity), "shs": dev(sc.shs),
+                                "mask_attribute": dev(sc.attrs["mask_attribute"]), "dino_attribute": dev(sc.attrs["dino_attribute"]),
+                                "pos_poly_feat": dev(sc.attrs["pos_poly_feat"])})
+        self.nodes = dev(sc.nodes)
+        self.extr = dev(sc.extr)
+        self.intr = dev(sc.intr)
+        name = "DPTROrthoEnhancedRenderB200" if fused else "DPTROrthoEnhancedRender"
+        self.renderer = parse_renderer({"name": name}, white_bg=False, device=device)
+        self.batch = {"FovX": 0.0, "FovY": 0.0, "height": self.H, "width": self.W, "extrinsic_matrix": self.extr,
+                      "intrinsic_matrix": self.intr, "camera_center": torch.zeros(3, device=device),
+                      "render_attributes_list": ["track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"], "num_idx": K_IDX}
+        g = torch.Generator().manual_seed(99)
+        # upstream image gradients, resident in HBM (N(0,1)) and pinned host copies for the e2e path
+        self.g_img = {"rgb": torch.randn(3, self.H, self.W, generator=g), "depth": torch.randn(1, self.H, self.W, generator=g),
+                      "track_gs": torch.randn(3, self.H, self.W, generator=g), "mask_attribute": torch.randn(1, self.H, self.W, generator=g),
+                      "pos_poly_feat": torch.randn(12, self.H, self.W, generator=g), "dino_attribute": torch.randn(3, self.H, self.W, generator=g)}
+        self.g_dev = {k: v.to(device) for k, v in self.g_img.items()}
+        self.gt_host = torch.rand(3, self.H, self.W, generator=g).pin_memory()
+        self.w_host = torch.cat([v for v in self.g_img.values()], 0).contiguous().pin_memory()   # [23,H,W]
+        self.gt_dev = torch.empty(3, self.H, self.W, device=device)
+        self.w_dev = torch.empty(23, self.H, self.W, device=device)
+        self.loss_host = torch.empty(1).pin_memory()
+
+    def render_dict(self, frame):
+        p = self.flat.params
+        with torch.no_grad():
+            disp = synth.eval_spline(self.nodes, frame / 5.0)
+            disp2 = synth.eval_spline(self.nodes, min(frame + 1, self.frames - 1) / 5.0)
+        pos = p["position"] + disp
+        track = (p["position"] + disp2).detach()
+        return {"position": pos, "opacity": p["opacity"], "scaling": p["scaling"], "rotation": p["rotation"], "shs": p["shs"],
+                "track_gs": track, "mask_attribute": p["mask_attribute"], "pos_poly_feat": p["pos_poly_feat"],
+                "dino_attribute": p["dino_attribute"]}
+
+    def forward(self, frame):
+        return self.renderer.render_batch(self.render_dict(frame), [dict(self.batch)])
+
+    def step_resident(self, frame):
+        out = self.forward(frame)
+        keys = ["rgb", "depth", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
+        torch.autograd.backward([out[k][0] for k in keys], [self.g_dev[k] for k in keys])
+        return out
+
+    def step_e2e(self, frame):
+        """Host-driven step: H2D of the frame's ground truth + per-pixel weights, loss gradient on device, D2H loss."""
+        self.gt_dev.copy_(self.gt_host, non_blocking=True)
+        self.w_dev.copy_(self.w_host, non_blocking=True)
+        out = self.forward(frame)
+        keys = ["rgb", "depth", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
+        imgs = torch.cat([out[k][0] for k in keys], 0)                       # [23,H,W]
+        diff = imgs.detach().clone()
+        diff[:3] -= self.gt_dev
+        loss = (diff * self.w_dev).sum() / diff.numel()
+        imgs.backward(self.w_dev / diff.numel())
+        self.loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                            # the D2H read of the step's result
+        return float(self.loss_host[0])
+
+    def render_only(self, frame, to_host=False):
+        with torch.no_grad():
+            b = dict(self.batch)
+            b["render_attributes_list"] = ["dino_attribute", "mask_attribute"]   # trainer_fragGS.py:1264-1306
+            b["num_idx"] = 10
+            out = self.renderer.render_batch(self.render_dict(frame), [b])
+            if to_host:
+                return out["rgb"].cpu()
+        return out
+
+
+def time_steps(fn, steps, warmup, flush_buf, world, rank, frames_of):
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(frames_of(i))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        if flush_buf is not None:
+            flush_buf.zero_()          # > L2 write between timed iterations (outside the per-step event bracket)
+        ev[i][0].record()
+        fn(frames_of(warmup + i))
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total = torch.tensor([sum(ms)], device="cuda")
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    return float(total.item()), ms
+
+
+def stage_breakdown(wl: Workload, frame):
+    """CUDA-event time of each C-ABI stage on one frame (L2 flushed before each), for the roofline block."""
+    from splatter_a_video_b200 import gs
+    from splatter_a_video_b200 import _lib as L
+    dev = wl.device
+    rd = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in wl.render_dict(frame).items()}
+    W, H, P = wl.W, wl.H, wl.P
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    res = {}
+
+    def timed(name, f, reps=5):
+        out = None
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); out = f(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        res[name] = float(np.median(ts))
+        return out
+
+    dirs = torch.zeros_like(rd["position"]); dirs[:, 2] = 1
+    rgb = timed("compute_sh", lambda: gs.compute_sh(rd["shs"], 3, dirs))
+    uv, depth = timed("project_point_ortho", lambda: gs.project_point_ortho(rd["position"], wl.extr, W, H, 0.01))
+    vis = depth != 0
+    cov3d = timed("compute_cov3d", lambda: gs.compute_cov3d(rd["scaling"], rd["rotation"], vis))
+    conic, radius, tiles = timed("ewa_project_ortho", lambda: gs.ewa_project_ortho(cov3d, wl.extr, uv, W, H, vis.squeeze(-1)))
+    idx, tr = timed("sort_gaussian", lambda: gs.sort_gaussian(uv, depth, W, H, radius, tiles))
+    I = int(idx.numel())
+    attrs = torch.cat([rd["track_gs"], rd["mask_attribute"], rd["pos_poly_feat"], rd["dino_attribute"]], 1).contiguous()
+    passes = {"rgb": (rgb, 0.0, K_IDX), "depth": (depth, 1.0, 0), "attrs": (attrs, 0.0, 0)}
+    info = {}
+    for name, (feat, bg, K) in passes.items():
+        C = feat.shape[1]
+        leaves = [t.detach().clone().requires_grad_(True) for t in (uv, conic, rd["opacity"], feat)]
+        if K:
+            img = timed(f"blend_fwd_{name}", lambda: gs.alpha_blending_enhanced(*leaves, idx, tr, bg, W, H, None, None, K=K)[0])
+        else:
+            img = timed(f"blend_fwd_{name}", lambda: gs.alpha_blending(*leaves, idx, tr, bg, W, H))
+        g = torch.randn_like(img)
+        timed(f"blend_bwd_{name}", lambda: torch.autograd.grad(img, leaves, g, retain_graph=True))
+        info[name] = dict(C=C, K=K, fwd_bytes=blend_fwd_algorithmic_bytes(I, C, H, W, K), bwd_bytes=blend_bwd_algorithmic_bytes(I, C, H, W, P))
+    res["sort_keys_per_s"] = I / (res["sort_gaussian"] * 1e-3)
+    return res, info, I
+
+
+def cpu_baseline_port(cfg_name, frame=0, max_seconds=30.0):
+    """The oracle port (oracle/spv_oracle.c, OpenMP) on ONE frame of the same workload: SH, projection, cov3d, EWA, sort,
+    three blend passes forward + backward (+ SH / cov3d backward).  Reported, not optimised."""
+    from oracle import oracle as O
+    sc = synth.make_config(cfg_name)
+    P, W, H = sc.P, sc.W, sc.H
+    s = dict(xyz=sc.frame_position(frame).numpy(), scaling=sc.scaling.numpy(), rotation=sc.rotation.numpy(),
+             opacity=sc.opacity.numpy(), shs=sc.shs.numpy(), attrs=sc.attr_features(frame + 1).numpy(), extr=sc.extr.numpy())
+    rng = np.random.default_rng(0)
+    grads = {3: rng.standard_normal((3, H, W)).astype(np.float32), 1: rng.standard_normal((1, H, W)).astype(np.float32),
+             19: rng.standard_normal((19, H, W)).astype(np.float32)}
+    O.lib()
+
+    def one():
+        dirs = np.zeros((P, 3), np.float32); dirs[:, 2] = 1
+        rgb, clamped = O.compute_sh(s["shs"], 3, dirs)
+        uv, depth = O.project_point_ortho(s["xyz"], s["extr"], W, H, nearest=0.01)
+        vis = depth.reshape(-1) != 0
+        cov3d = O.compute_cov3d(s["scaling"], s["rotation"], vis)
+        conic, radius, tiles = O.ewa_project_ortho(cov3d, s["extr"], uv, W, H, vis)
+        idx, tr = O.sort_gaussian(uv, depth, W, H, radius, tiles)
+        gcol = None
+        for feat, bg, K in ((rgb, 0.0, K_IDX), (depth, 1.0, 0), (s["attrs"], 0.0, 0)):
+            f = O.alpha_blending_forward(uv, conic, s["opacity"], feat, idx, tr, bg, W, H, K=K)
+            b = O.alpha_blending_backward(uv, conic, s["opacity"], feat, idx, tr, bg, W, H, f["final_T"], f["ncontrib"],
+                                          grads[feat.shape[1]])
+            if feat.shape[1] == 3:
+                gcol = b["dL_dfeature"]
+        O.compute_sh_backward(s["shs"], 3, dirs, vis, clamped, gcol)
+        O.compute_cov3d_backward(s["scaling"], s["rotation"], vis, np.zeros((P, 6), np.float32))
+        return len(idx)
+
+    one()  # warm-up (also builds the library)
+    ts = []
+    t_start = time.time()
+    while len(ts) < 5 and (time.time() - t_start) < max_seconds:
+        t0 = time.time(); I = one(); ts.append(time.time() - t0)
+    sec = float(np.median(ts))
+    return {"value": 1.0 / sec, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"1 frame of {cfg_name} per iteration (P={P}, {W}x{H}, I={I}): oracle/spv_oracle.c forward+backward of the "
+                      f"ortho chain, OpenMP on all host threads, median of {len(ts)} runs after 1 warm-up"}
+
+
+def cpu_torch_cfg1():
+    """BASELINE.json configs[0]: pure-PyTorch projection + alpha-blend of the tiny scene on the host cores."""
+    from oracle import torch_ref as TR
+    torch.set_num_threads(os.cpu_count())
+    sc = synth.make_config("cfg1_tiny")
+    ts = []
+    for rep in range(4):
+        t0 = time.time()
+        for f in range(sc.frames):
+            TR.render_ortho_frame(sc.frame_position(f), sc.scaling, sc.rotation, sc.opacity, sc.shs, sc.attr_features(f), sc.extr,
+                                  sc.W, sc.H, K=K_IDX)
+        if rep:
+            ts.append(time.time() - t0)
+    return {"seconds_per_2_frames": float(np.median(ts)), "fps": sc.frames / float(np.median(ts)), "cores": os.cpu_count(),
+            "what": "oracle/torch_ref.py forward (SH, ortho projection, cov3d, EWA, sort, 3 blends), 1k Gaussians, 2x64x64"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the rasterizer)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from splatter_a_video_b200 import _lib as L
+    from splatter_a_video_b200.parallel import frame_for_step
+    L.load()
+
+    fused = not args.staged
+    try:
+        from splatter_a_video_b200.gs import fused as _f  # noqa: F401
+    except ImportError:
+        fused = False
+    wl = Workload(args.config, device, fused=fused)
+    flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    frames_of = lambda i: frame_for_step(i, rank, world, wl.frames)
+
+    def train_step(frame):
+        wl.flat.zero_grad()
+        wl.step_resident(frame)
+        wl.flat.allreduce_grads()
+
+    def train_step_e2e(frame):
+        wl.flat.zero_grad()
+        wl.step_e2e(frame)
+        wl.flat.allreduce_grads()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = L.query("spv_launch_count")
+    total_ms, per_step = time_steps(train_step, args.steps, args.warmup, flush, world, rank, frames_of)
+    launches = (L.query("spv_launch_count") - n0) / (args.steps + args.warmup)
+    e2e_ms, _ = time_steps(train_step_e2e, args.steps, args.warmup, flush, world, rank, frames_of)
+    fps_ms, _ = time_steps(lambda f: wl.render_only(f), args.steps, args.warmup, flush, world, rank, frames_of)
+    fps_e2e_ms, _ = time_steps(lambda f: wl.render_only(f, to_host=True), args.steps, args.warmup, flush, world, rank, frames_of)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    its = world * args.steps / (total_ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    stages, info, I = stage_breakdown(wl, 0)
+    dom = max((k for k in stages if k.startswith("blend_")), key=lambda k: stages[k])
+    pname = dom.split("_", 2)[2]
+    abytes = info[pname]["bwd_bytes" if "bwd" in dom else "fwd_bytes"]
+    ach = abytes / (stages[dom] * 1e-3) / 1e9
+    line = {
+        "metric": "train_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: P={wl.P}, {wl.W}x{wl.H}, {wl.frames} frames, I={I} tile intersections/frame; one step = "
+                               "render one frame (RGB K=20 + depth + 19 attribute channels) forward+backward through "
+                               f"{type(wl.renderer).__name__}.render_batch; frames sharded {world}-way, one flat-gradient all-reduce/step",
+                   "renderer": type(wl.renderer).__name__, "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
+                   "grad_floats_per_gaussian": wl.flat.floats_per_gaussian(wl.P)},
+        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "it/s", "h2d_bytes_per_step": int(wl.gt_host.numel() * 4 + wl.w_host.numel() * 4),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "render_fps": world * args.steps / (fps_ms * 1e-3),
+        "render_fps_e2e": {"value": world * args.steps / (fps_e2e_ms * 1e-3), "d2h_bytes_per_frame": 3 * wl.H * wl.W * 4},
+        "roofline": {"bound": "hbm", "kernel": f"spv_alpha_blend_{'backward' if 'bwd' in dom else 'forward'} ({pname} pass, C={info[pname]['C']})",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": abytes, "ms": stages[dom]},
+        "stages_ms": stages,
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_port(args.config)
+        line["cpu_torch_cfg1"] = cpu_torch_cfg1()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------- reference arm
+def reference_gpu_arm(cfg_name, steps, warmup):
+    """The UNMODIFIED reference kernels (oracle/_ref/_C.so) driven in the trainer's op order on this GPU, forward +
+    backward of one frame per step; ortho projection / EWA are the reference's torch-op path (restated in torch_ref)."""
+    import importlib.util
+    path = os.path.join(ROOT, "oracle", "_ref", "_C.so")
+    if not (os.path.exists(path) and torch.cuda.is_available()):
+        return None
+    spec = importlib.util.spec_from_file_location("_C", path)
+    C_ = importlib.util.module_from_spec(spec); spec.loader.exec_module(C_)
+    from oracle import torch_ref as TR
+    dev = torch.device("cuda:0")
+    sc = synth.make_config(cfg_name).to(dev)
+    W, H, P = sc.W, sc.H, sc.P
+    g = torch.Generator().manual_seed(99)
+    grads = {3: torch.randn(3, H, W, generator=g).to(dev), 1: torch.randn(1, H, W, generator=g).to(dev), 19: torch.randn(19, H, W, generator=g).to(dev)}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def ortho_geometry(pos, cov3d, vis):
+        # torch-op path of the reference (dptr_ortho_enhanced.py:18-111,145-202), on the GPU
+        J = torch.tensor([[W / 2, 0, 0], [0, H / 2, 0]], dtype=torch.float32, device=dev)
+        T = J @ sc.extr[:3, :3]
+        c2 = T @ TR._sym3(cov3d) @ T.t()
+        return TR._finish_ewa(c2[:, 0, 0] + 0.3, c2[:, 0, 1], c2[:, 1, 1] + 0.3, uv_holder[0], W, H, vis, True)
+
+    uv_holder = [None]
+
+    def step(frame, backward=True):
+        pos = sc.frame_position(frame)
+        dirs = torch.zeros_like(pos); dirs[:, 2] = 1
+        vis_all = torch.ones(P, dtype=torch.bool, device=dev)
+        rgb, clamped = C_.compute_sh_forward(sc.shs, 3, dirs, vis_all)
+        uv, depth = TR.project_point_ortho(pos, sc.extr, W, H, nearest=0.01)
+        uv_holder[0] = uv
+        vis = depth != 0
+        cov3d = C_.compute_cov3d_forward(sc.scaling, sc.rotation, vis)
+        cov3d.requires_grad_(backward)
+        conic, radius, tiles = ortho_geometry(pos, cov3d, vis.reshape(-1))
+        cum = torch.cumsum(tiles, dim=0, dtype=torch.int32)
+        key, gidx = C_.compute_gaussian_key(uv, depth, W, H, radius, cum)
+        ks, indices = torch.sort(key)
+        idx = torch.gather(gidx, 0, indices)
+        tr = C_.compute_tile_gaussian_range(W, H, cum, ks)
+        attrs = sc.attr_features(min(frame + 1, sc.frames - 1))
+        cd = conic.detach()
+        outs = []
+        img, fT, nc, gs_idx = C_.alpha_blending_forward_enhanced(uv, cd, sc.opacity, rgb, idx, tr, 0.0, W, H, K_IDX, False)
+        outs.append((rgb, 0.0, fT, nc))
+        dimg, fT2, nc2 = C_.alpha_blending_forward(uv, cd, sc.opacity, depth, idx, tr, 1.0, W, H)
+        outs.append((depth, 1.0, fT2, nc2))
+        aimg, fT3, nc3 = C_.alpha_blending_forward(uv, cd, sc.opacity, attrs, idx, tr, 0.0, W, H)
+        outs.append((attrs, 0.0, fT3, nc3))
+        if not backward:
+            return
+        gconic = torch.zeros_like(cd)
+        gcol = None
+        for feat, bg, fT_, nc_ in outs:
+            fn = C_.alpha_blending_backward_enhanced if feat.shape[1] == 3 else C_.alpha_blending_backward
+            d_uv, d_conic, d_op, d_feat, d_abs = fn(uv, cd, sc.opacity, feat, idx, tr, bg, W, H, fT_, nc_, grads[feat.shape[1]])
+            gconic += d_conic
+            if feat.shape[1] == 3:
+                gcol = d_feat
+        conic.backward(gconic)
+        C_.compute_cov3d_backward(sc.scaling, sc.rotation, vis, cov3d.grad)
+        C_.compute_sh_backward(sc.shs, 3, dirs, vis_all, clamped, gcol)
+
+    def run(backward):
+        for i in range(warmup):
+            step(i % sc.frames, backward)
+        torch.cuda.synchronize()
+        tot = 0.0
+        for i in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step((warmup + i) % sc.frames, backward); b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return steps / (tot * 1e-3)
+
+    return {"train_iters_per_sec": run(True), "render_fps": run(False),
+            "what": "unmodified reference .cu (sm_100a build, -O3 --use_fast_math) + the reference's torch ortho path, same step "
+                    "definition, device-resident inputs, legacy default stream"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline_port(args.config, max_seconds=60.0)
+    line = {"impl": "reference", "metric": "train_iters_per_sec", "value": base["value"], "unit": "it/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: bounded sample = 1 frame per step, CPU oracle port of the reference algorithm "
+                                   "(the reference has no CPU implementation)"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:
+        rg = reference_gpu_arm(args.config, min(args.steps, 10), min(args.warmup, 3))
+        if rg:
+            line["reference_gpu"] = rg
+    except Exception as e:  # the reference build is optional context
+        line["reference_gpu"] = {"unavailable": repr(e)[:200]}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -41,6 +41,8 @@ extern "C" {
 
 SPV_API int spv_abi_version(void);
 SPV_API const char *spv_last_error(void);
+/* number of CUDA kernels this library has launched since load (bench.py reports it as `gpu_launches`) */
+SPV_API long long spv_launch_count(void);
 
 /* ---- K1/K2: project_point_forward/backward (ext.cpp:15-16; src/project_point.cu:13-145) ---------- */
 /* intr = [fx,fy,cx,cy]; extr = 12 floats, row-major 3x4 [R|t] (a 4x4 matrix's first 12 floats work). */

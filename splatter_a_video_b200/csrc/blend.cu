@@ -134,27 +134,29 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
 // ------------------------------------------------------------------------------------------------ backward
 // Recursive-halving multi-value warp reduction: on return lane l holds, in v[0], the warp-wide sum of the
 // value with index (l % N).  N-1 shuffles (+1 for N=16) instead of 5*N.
-template <int N>
-__device__ __forceinline__ void halving_reduce(float (&v)[N], int lane) {
+template <int N, int OFF, int TOT>
+__device__ __forceinline__ void halving_reduce(float (&v)[TOT], int lane) {
 #pragma unroll
     for (int h = N / 2; h >= 1; h >>= 1) {
         const bool up = (lane & h) != 0;
 #pragma unroll
         for (int i = 0; i < h; ++i) {
-            const float send = up ? v[i] : v[i + h];
-            const float keep = up ? v[i + h] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            const float send = up ? v[OFF + i] : v[OFF + i + h];
+            const float keep = up ? v[OFF + i + h] : v[OFF + i];
+            v[OFF + i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
         }
     }
-    if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+    if (N == 16) v[OFF] += __shfl_xor_sync(0xffffffffu, v[OFF], 16);
 }
 
 // Packed gradient row layout (NV floats per Gaussian):
 //   0,1 dL_duv   2,3 dL_dabs_uv   4,5,6 dL_dconic   7 dL_dopacity   8..8+CH-1 dL_dfeature   NV-1 dL_dbias (HAS_BIAS)
-constexpr int kG = 32;  // Gaussians per backward chunk
+// NV = 16 (C <= 8), 32 (C <= 24) or 64 (C <= 32: two 32-value networks, lane l ends up with values l and 32+l).
+// One launch covers up to 32 channels -- the same channel chunking as the reference (alpha_blending.cu:440-576), which
+// matters for dL_dabs_uv: |.| is taken of the per-chunk uv gradient.
 
 template <int NV, int CH, bool HAS_BIAS>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, NV == 64 ? 1 : 2)
 blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                  const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
                  const float *__restrict__ feature, const float *__restrict__ bias,
@@ -162,6 +164,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                  const float *__restrict__ final_T, const int *__restrict__ ncontrib,
                  const float *__restrict__ dL_drendered, float *__restrict__ packed) {
     static_assert(8 + CH + (HAS_BIAS ? 1 : 0) <= NV, "packed row too small");
+    constexpr int kG = (NV == 64) ? 16 : 32;  // Gaussians per backward chunk (keeps s_part at 32 KB)
     __shared__ float2 s_xy[kG];
     __shared__ float4 s_co[kG];
     __shared__ int s_id[kG];
@@ -244,6 +247,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
             }
             if (!__any_sync(0xffffffffu, contrib)) {
                 if (lane < NV) s_part[warp][j][lane] = 0.f;
+                if constexpr (NV == 64) s_part[warp][j][32 + lane] = 0.f;
                 continue;
             }
             float v[NV];
@@ -276,20 +280,30 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                 v[7] = Gv * dL_dalpha;
                 if (HAS_BIAS) v[NV - 1] = dL_dalpha;
             }
-            halving_reduce<NV>(v, lane);
-            if (lane < NV) s_part[warp][j][lane] = v[0];
+            if constexpr (NV == 64) {
+                halving_reduce<32, 0, NV>(v, lane);
+                halving_reduce<32, 32, NV>(v, lane);
+                s_part[warp][j][lane] = v[0];
+                s_part[warp][j][32 + lane] = v[32];
+            } else {
+                halving_reduce<NV, 0, NV>(v, lane);
+                if (lane < NV) s_part[warp][j][lane] = v[0];
+            }
         }
         __syncthreads();
         // fold the 8 warps and push one packed row per (tile, Gaussian)
-        if (NV == 32) {
+        if constexpr (NV >= 32) {
 #pragma unroll
             for (int jj = 0; jj < kG / 8; ++jj) {
                 const int j = warp * (kG / 8) + jj;
                 if (j < m) {
-                    float s = 0.f;
 #pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][lane];
-                    if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * NV + lane, s);
+                    for (int half = 0; half < NV / 32; ++half) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][half * 32 + lane];
+                        if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * NV + half * 32 + lane, s);
+                    }
                 }
             }
         } else {  // NV == 16: two Gaussians per warp pass
@@ -339,7 +353,7 @@ unpack_kernel(int P, int C, int Cstride, int c0, int has_bias, int accumulate, c
         if (has_bias) dL_dbias[g] = r[NV - 1];
     }
 #pragma unroll
-    for (int c = 0; c < NV - 8; ++c)
+    for (int c = 0; c < (NV == 64 ? 32 : NV - 8); ++c)
         if (c < C) dL_dfeature[(size_t)g * Cstride + c0 + c] = r[8 + c];
 }
 
@@ -388,9 +402,10 @@ void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
                                                             a.bg, a.final_T, a.ncontrib, a.dL_drendered, a.packed);
 }
 
-// returns NV used
+inline int bwd_nv(int C, bool bias) { return C <= (bias ? 7 : 8) ? 16 : (C <= (bias ? 23 : 24) ? 32 : 64); }
+
 template <bool BIAS>
-int dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
+void dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
     const int C = a.C;
     constexpr int cap16 = BIAS ? 7 : 8, cap32 = BIAS ? 23 : 24;
     if (C <= cap16) {
@@ -398,13 +413,15 @@ int dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
         else if (C <= 3) launch_bwd<16, 3, BIAS>(a, ntiles, s);
         else if (C <= 4) launch_bwd<16, 4, BIAS>(a, ntiles, s);
         else launch_bwd<16, cap16, BIAS>(a, ntiles, s);
-        return 16;
+    } else if (C <= cap32) {
+        if (C <= 12) launch_bwd<32, 12, BIAS>(a, ntiles, s);
+        else if (C <= 16) launch_bwd<32, 16, BIAS>(a, ntiles, s);
+        else if (C <= 20) launch_bwd<32, 20, BIAS>(a, ntiles, s);
+        else launch_bwd<32, cap32, BIAS>(a, ntiles, s);
+    } else {
+        if (C <= 28) launch_bwd<64, 28, BIAS>(a, ntiles, s);
+        else launch_bwd<64, 32, BIAS>(a, ntiles, s);
     }
-    if (C <= 12) launch_bwd<32, 12, BIAS>(a, ntiles, s);
-    else if (C <= 16) launch_bwd<32, 16, BIAS>(a, ntiles, s);
-    else if (C <= 20) launch_bwd<32, 20, BIAS>(a, ntiles, s);
-    else launch_bwd<32, cap32, BIAS>(a, ntiles, s);
-    return 32;
 }
 
 }  // namespace
@@ -447,7 +464,7 @@ int spv_alpha_blend_forward(int P, int C, int W, int H, int K, int enable_trunca
 
 size_t spv_alpha_blend_backward_workspace_bytes(int P, int C) {
     (void)C;
-    return (size_t)(P > 0 ? P : 1) * 32 * sizeof(float);
+    return (size_t)(P > 0 ? P : 1) * 64 * sizeof(float);
 }
 
 int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const float *conic, const float *opacity,
@@ -463,7 +480,7 @@ int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const 
     const bool has_bias = opacity_bias != nullptr;
     if (has_bias && !dL_dopacity_bias) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_backward: dL_dopacity_bias is NULL"); return (int)cudaErrorInvalidValue; }
     float *packed = (float *)workspace;
-    const int cap = has_bias ? 23 : 24;
+    const int cap = 32;  // channels per launch == the reference's chunking
     if (C <= 0 || W <= 0 || H <= 0) {
         SPV_CUDA_TRY(cudaMemsetAsync(dL_duv, 0, sizeof(float) * 2 * (size_t)P, s), "spv_alpha_blend_backward");
         SPV_CUDA_TRY(cudaMemsetAsync(dL_dabs_uv, 0, sizeof(float) * 2 * (size_t)P, s), "spv_alpha_blend_backward");
@@ -479,7 +496,7 @@ int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const 
         a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg;
         a.final_T = final_T; a.ncontrib = ncontrib; a.dL_drendered = dL_drendered + (size_t)c0 * H * W;
         a.packed = packed;
-        const int nv = (a.C <= (has_bias ? 7 : 8)) ? 16 : 32;
+        const int nv = bwd_nv(a.C, has_bias);
         SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)nv * P, s), "spv_alpha_blend_backward");
         if (has_bias) dispatch_bwd<true>(a, ntiles, s); else dispatch_bwd<false>(a, ntiles, s);
         int rc = spv::check_launch("spv_alpha_blend_backward/blend");
@@ -487,6 +504,10 @@ int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const 
         const unsigned g = spv::cdiv(P, kBlock);
         if (nv == 16)
             unpack_kernel<16><<<g, kBlock, 0, s>>>(P, a.C, C, c0, has_bias, c0 > 0, packed, (float2 *)dL_duv,
+                                                   (float2 *)dL_dabs_uv, dL_dconic, dL_dopacity, dL_dfeature,
+                                                   dL_dopacity_bias);
+        else if (nv == 64)
+            unpack_kernel<64><<<g, kBlock, 0, s>>>(P, a.C, C, c0, has_bias, c0 > 0, packed, (float2 *)dL_duv,
                                                    (float2 *)dL_dabs_uv, dL_dconic, dL_dopacity, dL_dfeature,
                                                    dL_dopacity_bias);
         else

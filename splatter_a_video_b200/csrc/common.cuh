@@ -11,7 +11,9 @@ namespace spv {
 
 // Error plumbing: every extern "C" entry returns this after its launches.
 void set_error(cudaError_t e, const char *where);
-inline int check_launch(const char *where) {
+void count_launches(int n);  // bookkeeping for spv_launch_count(): kernels this library has launched
+inline int check_launch(const char *where, int launches = 1) {
+    count_launches(launches);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
         set_error(e, where);

@@ -87,7 +87,7 @@ int spv_sort_scan(int P, const int *tiles, int *offsets, void *workspace, size_t
     cub::DeviceScan::InclusiveSum((void *)nullptr, need, tiles, offsets, P);
     if (ws_bytes < need) { spv::set_error(cudaErrorInvalidValue, "spv_sort_scan: workspace too small"); return (int)cudaErrorInvalidValue; }
     SPV_CUDA_TRY(cub::DeviceScan::InclusiveSum(workspace, need, tiles, offsets, P, (cudaStream_t)stream), "spv_sort_scan");
-    return spv::check_launch("spv_sort_scan");
+    return spv::check_launch("spv_sort_scan", 2);
 }
 
 size_t spv_sort_workspace_bytes(int P, int64_t I) {
@@ -120,7 +120,8 @@ int spv_sort_gaussian(int P, int64_t I, const float *uv, const float *depth, con
                                                  (const int *)vals_in, idx_sorted, (int)I, 0, key_end_bit(gx * gy), s),
                  "spv_sort_gaussian/sort");
     tile_range_kernel<<<spv::cdiv(I, kThreads), kThreads, 0, s>>>((long long)I, keys_out, (int2 *)tile_range);
-    return spv::check_launch("spv_sort_gaussian/range");
+    // CUB onesweep: histogram + exclusive-sum + one kernel per 8-bit digit
+    return spv::check_launch("spv_sort_gaussian/range", 1 + 2 + (key_end_bit(gx * gy) + 7) / 8);
 }
 
 }  // extern "C"

@@ -46,7 +46,7 @@ def test_ctypes_binding_matches_header(lib_path):
     assert lib.spv_abi_version() == 1
     assert sorted(_lib.EXPORTED) == declared_symbols()
     # (the CUB-backed sort/scan size queries need a device: covered by the -m gpu tests)
-    assert lib.spv_alpha_blend_backward_workspace_bytes(1000, 19) == 1000 * 32 * 4
+    assert lib.spv_alpha_blend_backward_workspace_bytes(1000, 19) == 1000 * 64 * 4
 
 
 def test_library_is_sm100a_only(lib_path):
