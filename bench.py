@@ -40,6 +40,10 @@ from splatter_a_video_b200 import synth  # noqa: E402
 K_IDX = 20
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -50,6 +54,7 @@ def parse():
     ap.add_argument("--staged", action="store_true", help="reference op sequence (3 blend passes) instead of the fused renderer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true", help="only warm-up + K train steps, no JSON (for ncu)")
     return ap.parse_args()
 
 
@@ -266,6 +271,26 @@ def stage_breakdown(wl: Workload, frame):
     return res, info, I
 
 
+def _cpu_threads():
+    """Host threads used by the CPU baselines: all cores up to 32 (more only adds atomic contention on the per-Gaussian sums)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
+def run_bounded(fn_name, *fn_args, timeout=240):
+    """Run one of the CPU baselines in a child process with a hard timeout so it can never stall the GPU measurement."""
+    code = (f"import sys, json; sys.path.insert(0, {ROOT!r}); import bench; "
+            f"print('@@' + json.dumps(bench.{fn_name}(*{list(fn_args)!r})))")
+    env = dict(os.environ, OMP_NUM_THREADS=str(_cpu_threads()), CUDA_VISIBLE_DEVICES="")
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout, env=env)
+        for line in out.stdout.splitlines():
+            if line.startswith("@@"):
+                return json.loads(line[2:])
+        return {"unavailable": (out.stderr or "no output")[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"{fn_name} exceeded {timeout}s on this host"}
+
+
 def cpu_baseline_port(cfg_name, frame=0, max_seconds=30.0):
     """The oracle port (oracle/spv_oracle.c, OpenMP) on ONE frame of the same workload: SH, projection, cov3d, EWA, sort,
     three blend passes forward + backward (+ SH / cov3d backward).  Reported, not optimised."""
@@ -304,7 +329,7 @@ def cpu_baseline_port(cfg_name, frame=0, max_seconds=30.0):
     while len(ts) < 5 and (time.time() - t_start) < max_seconds:
         t0 = time.time(); I = one(); ts.append(time.time() - t0)
     sec = float(np.median(ts))
-    return {"value": 1.0 / sec, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": 1.0 / sec, "unit": "it/s", "cores": _cpu_threads(), "host_cores": os.cpu_count(), "kind": "port",
             "sample": f"1 frame of {cfg_name} per iteration (P={P}, {W}x{H}, I={I}): oracle/spv_oracle.c forward+backward of the "
                       f"ortho chain, OpenMP on all host threads, median of {len(ts)} runs after 1 warm-up"}
 
@@ -312,17 +337,17 @@ def cpu_baseline_port(cfg_name, frame=0, max_seconds=30.0):
 def cpu_torch_cfg1():
     """BASELINE.json configs[0]: pure-PyTorch projection + alpha-blend of the tiny scene on the host cores."""
     from oracle import torch_ref as TR
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(_cpu_threads())
     sc = synth.make_config("cfg1_tiny")
     ts = []
-    for rep in range(4):
+    for rep in range(3):
         t0 = time.time()
         for f in range(sc.frames):
             TR.render_ortho_frame(sc.frame_position(f), sc.scaling, sc.rotation, sc.opacity, sc.shs, sc.attr_features(f), sc.extr,
                                   sc.W, sc.H, K=K_IDX)
         if rep:
             ts.append(time.time() - t0)
-    return {"seconds_per_2_frames": float(np.median(ts)), "fps": sc.frames / float(np.median(ts)), "cores": os.cpu_count(),
+    return {"seconds_per_2_frames": float(np.median(ts)), "fps": sc.frames / float(np.median(ts)), "cores": _cpu_threads(),
             "what": "oracle/torch_ref.py forward (SH, ortho projection, cov3d, EWA, sort, 3 blends), 1k Gaussians, 2x64x64"}
 
 
@@ -360,13 +385,20 @@ def run_ours(args):
         wl.step_e2e(frame)
         wl.flat.allreduce_grads()
 
+    if args.profile_mode:
+        time_steps(train_step, args.steps, args.warmup, None, world, rank, frames_of)
+        return
+    log(f"workload ready: P={wl.P} {wl.W}x{wl.H}, renderer={type(wl.renderer).__name__}")
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = L.query("spv_launch_count")
     total_ms, per_step = time_steps(train_step, args.steps, args.warmup, flush, world, rank, frames_of)
     launches = (L.query("spv_launch_count") - n0) / (args.steps + args.warmup)
+    log(f"train (resident): {total_ms / args.steps:.3f} ms/step")
     e2e_ms, _ = time_steps(train_step_e2e, args.steps, args.warmup, flush, world, rank, frames_of)
+    log(f"train (e2e): {e2e_ms / args.steps:.3f} ms/step")
     fps_ms, _ = time_steps(lambda f: wl.render_only(f), args.steps, args.warmup, flush, world, rank, frames_of)
     fps_e2e_ms, _ = time_steps(lambda f: wl.render_only(f, to_host=True), args.steps, args.warmup, flush, world, rank, frames_of)
+    log(f"render: {fps_ms / args.steps:.3f} ms/frame, e2e {fps_e2e_ms / args.steps:.3f}")
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -375,7 +407,9 @@ def run_ours(args):
         return
     its = world * args.steps / (total_ms * 1e-3)
     peak, peak_src = measured_peaks()
+    log("stage breakdown")
     stages, info, I = stage_breakdown(wl, 0)
+    log("stages: " + json.dumps(stages))
     dom = max((k for k in stages if k.startswith("blend_")), key=lambda k: stages[k])
     pname = dom.split("_", 2)[2]
     abytes = info[pname]["bwd_bytes" if "bwd" in dom else "fwd_bytes"]
@@ -401,8 +435,9 @@ def run_ours(args):
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_port(args.config)
-        line["cpu_torch_cfg1"] = cpu_torch_cfg1()
+        log("cpu baselines (bounded subprocesses)")
+        line["cpu_baseline"] = run_bounded("cpu_baseline_port", args.config, timeout=240)
+        line["cpu_torch_cfg1"] = run_bounded("cpu_torch_cfg1", timeout=180)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -496,7 +531,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_baseline_port(args.config, max_seconds=60.0)
+    base = run_bounded("cpu_baseline_port", args.config, 0, 60.0, timeout=400)
+    if "value" not in base:
+        print(json.dumps({"impl": "reference", "unavailable": base.get("unavailable", "cpu port failed")}))
+        return
     line = {"impl": "reference", "metric": "train_iters_per_sec", "value": base["value"], "unit": "it/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -119,6 +119,25 @@ SPV_API int spv_alpha_blend_backward(int P, int C, int W, int H,
                              float *dL_dopacity_bias /*[P,1] or NULL*/,
                              void *workspace, size_t ws_bytes, void *stream);
 
+/* ---- Fused single-traversal blending of the trainer's three passes (dptr_ortho_enhanced.py:342-376) ----
+ * feature = [rgb(3) | depth(1) | attributes(C-4)] row-major [P,C]; per-group backgrounds.  Results equal the three
+ * separate reference calls: uv/conic gradients from all channels, opacity from rgb+depth only (the attribute pass
+ * receives opacity.detach()), dL_duv_rgb / dL_dabs_uv_rgb from the RGB pass only (they feed ndc.grad / abs_ndc.grad;
+ * the other passes receive ndc.detach()).  Extension of the ABI: no single reference entry point corresponds. */
+SPV_API int spv_alpha_blend_groups_forward(int P, int C, int W, int H, int K, const float *uv, const float *conic,
+                                   const float *opacity, const float *feature, const int *idx_sorted,
+                                   const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
+                                   float *rendered /*[C,H,W]*/, float *final_T, int *ncontrib, int *gs_idx /*[H,W,K]*/,
+                                   void *stream);
+SPV_API size_t spv_alpha_blend_groups_backward_workspace_bytes(int P);
+SPV_API int spv_alpha_blend_groups_backward(int P, int C /*4..23*/, int W, int H, const float *uv, const float *conic,
+                                    const float *opacity, const float *feature, const int *idx_sorted,
+                                    const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
+                                    const float *final_T, const int *ncontrib, const float *dL_drendered,
+                                    float *dL_duv, float *dL_duv_rgb, float *dL_dabs_uv_rgb, float *dL_dconic,
+                                    float *dL_dopacity, float *dL_dfeature, void *workspace, size_t ws_bytes,
+                                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,11 @@ _SIGS = {
     "spv_alpha_blend_backward_workspace_bytes": (c_size_t, [c_int, c_int]),
     "spv_alpha_blend_backward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, P_, c_float, P_, P_, P_,
                                          P_, P_, P_, P_, P_, P_, P_, c_size_t, P_]),
+    "spv_alpha_blend_groups_forward": (c_int, [c_int, c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float,
+                                               c_float, P_, P_, P_, P_, P_]),
+    "spv_alpha_blend_groups_backward_workspace_bytes": (c_size_t, [c_int]),
+    "spv_alpha_blend_groups_backward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float, c_float,
+                                                P_, P_, P_, P_, P_, P_, P_, P_, P_, P_, c_size_t, P_]),
 }
 
 EXPORTED = sorted(_SIGS)

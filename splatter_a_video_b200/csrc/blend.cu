@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(kBlock)
 blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int trunc,
                  const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
                  const float *__restrict__ feature, const float *__restrict__ bias,
-                 const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg,
-                 float *__restrict__ rendered, float *__restrict__ final_T, int *__restrict__ ncontrib,
+                 const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg, float bgB, float bgC,
+                 int cA, int cB, float *__restrict__ rendered, float *__restrict__ final_T, int *__restrict__ ncontrib,
                  int *__restrict__ gs_idx) {
     __shared__ float2 s_xy[kBlock];
     __shared__ float4 s_co[kBlock];  // conic a,b,c + opacity
@@ -127,7 +127,7 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
         const size_t HW = (size_t)H * W;
 #pragma unroll
         for (int c = 0; c < CH; ++c)
-            if (c < C) rendered[c * HW + pix] = F[c] + T * bg;
+            if (c < C) rendered[c * HW + pix] = F[c] + T * (c < cA ? bg : (c < cB ? bgB : bgC));
     }
 }
 
@@ -357,11 +357,197 @@ unpack_kernel(int P, int C, int Cstride, int c0, int has_bias, int accumulate, c
         if (c < C) dL_dfeature[(size_t)g * Cstride + c0 + c] = r[8 + c];
 }
 
+// ------------------------------------------------------------------------------------------------ grouped backward
+// One traversal for the trainer's three blend passes (dptr_ortho_enhanced.py:342-376) over the concatenated features
+// [rgb(3) | depth(1) | attributes(CH-4)]:
+//   * uv / conic gradients come from every channel,
+//   * opacity only from rgb+depth (the attribute pass is called with opacity.detach()),
+//   * the densification statistics ndc.grad / abs_ndc.grad only from the RGB pass (the others get ndc.detach()).
+// 33 per-Gaussian sums: the 32-value halving network + one 5-step butterfly.  Packed row (stride 36 floats):
+//   0,1 dL_duv(all)  2,3 |.| of the RGB-pass uv gradient  4,5,6 dL_dconic  7 dL_dopacity  8..8+CH-1 dL_dfeature
+//   31,32 RGB-pass dL_duv (-> ndc.grad)
+constexpr int kRowG = 36;
+
+template <int CH>
+__global__ void __launch_bounds__(kBlock, 2)
+blend_bwd_groups_kernel(int C, int W, int H, int gx,
+                        const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
+                        const float *__restrict__ feature, const int *__restrict__ idx_sorted,
+                        const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
+                        const float *__restrict__ final_T, const int *__restrict__ ncontrib,
+                        const float *__restrict__ dL_drendered, float *__restrict__ packed) {
+    static_assert(CH >= 4 && CH <= 23, "grouped backward handles 4..23 channels");
+    constexpr int kG = 32;
+    __shared__ float2 s_xy[kG];
+    __shared__ float4 s_co[kG];
+    __shared__ int s_id[kG];
+    __shared__ __align__(16) float s_feat[kG * CH];
+    __shared__ float s_part[8][kG][33];
+    __shared__ int s_max;
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    int px, py;
+    thread_pixel(tile_x, tile_y, px, py);
+    const bool inside = px < W && py < H;
+    const size_t pix = (size_t)W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const int2 range = tile_range[tile];
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    const int last_contrib = inside ? ncontrib[pix] : 0;
+
+    float d[CH];
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) d[c] = (inside && c < C) ? dL_drendered[c * HW + pix] : 0.f;
+    float sumC = 0.f;
+#pragma unroll
+    for (int c = 4; c < CH; ++c) sumC += d[c];
+    const float bgdA = bgA * (d[0] + d[1] + d[2]), bgdB = bgB * d[3], bgdC = bgC * sumC;
+
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, last_contrib);
+    if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int n_eff = min(range.y - range.x, s_max);
+
+    float last_alpha = 0.f, lfA = 0.f, lfB = 0.f, lfC = 0.f, SA = 0.f, SB = 0.f, SC = 0.f;
+
+    for (int p_hi = n_eff; p_hi > 0; p_hi -= kG) {
+        const int m = min(kG, p_hi);
+        __syncthreads();
+        if ((int)threadIdx.x < m) {
+            const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];
+            s_id[threadIdx.x] = id;
+            s_xy[threadIdx.x] = uv[id];
+            s_co[threadIdx.x] = make_float4(conic[3 * id], conic[3 * id + 1], conic[3 * id + 2], opacity[id]);
+        }
+        __syncthreads();
+        if (lane < C) {
+#pragma unroll
+            for (int jj = 0; jj < kG / 8; ++jj) {
+                const int j = warp * (kG / 8) + jj;
+                if (j < m) s_feat[j * CH + lane] = feature[(size_t)s_id[j] * C + lane];
+            }
+        }
+        __syncthreads();
+
+        for (int j = 0; j < m; ++j) {
+            const int p = p_hi - 1 - j;
+            bool contrib = false;
+            float dx = 0.f, dy = 0.f, Gv = 0.f, alpha = 0.f;
+            const float4 co = s_co[j];
+            if (p < last_contrib) {
+                const float2 xy = s_xy[j];
+                dx = xy.x - pxf; dy = xy.y - pyf;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                if (power <= 0.f) {
+                    Gv = __expf(power);
+                    alpha = fminf(kAlphaMax, co.w * Gv);
+                    contrib = alpha >= kAlphaMin;
+                }
+            }
+            if (!__any_sync(0xffffffffu, contrib)) {
+                s_part[warp][j][lane] = 0.f;
+                if (lane == 0) s_part[warp][j][32] = 0.f;
+                continue;
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            float extra = 0.f;
+            if (contrib) {
+                const float rinv = __fdividef(1.f, 1.f - alpha);
+                T = T * rinv;
+                const float w = alpha * T;
+                const float *fr = s_feat + j * CH;
+                float fdA = 0.f, fdC = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { fdA = fmaf(fr[c], d[c], fdA); v[8 + c] = w * d[c]; }
+                const float fdB = fr[3] * d[3];
+                v[8 + 3] = w * d[3];
+#pragma unroll
+                for (int c = 4; c < CH; ++c) { fdC = fmaf(fr[c], d[c], fdC); v[8 + c] = w * d[c]; }
+                const float om = 1.f - last_alpha;
+                SA = last_alpha * lfA + om * SA;
+                SB = last_alpha * lfB + om * SB;
+                SC = last_alpha * lfC + om * SC;
+                last_alpha = alpha; lfA = fdA; lfB = fdB; lfC = fdC;
+                const float tb = -T_final * rinv;
+                const float daA = (fdA - SA) * T + tb * bgdA;
+                const float daB = (fdB - SB) * T + tb * bgdB;
+                const float daC = (fdC - SC) * T + tb * bgdC;
+                const float da_op = daA + daB, da_all = da_op + daC;
+                const float dL_dG = co.w * da_all, dL_dG_ndc = co.w * daA;
+                const float dGx = -Gv * dx * co.x - Gv * dy * co.y;
+                const float dGy = -Gv * dy * co.z - Gv * dx * co.y;
+                const float n0 = dL_dG_ndc * dGx, n1 = dL_dG_ndc * dGy;
+                v[0] = dL_dG * dGx; v[1] = dL_dG * dGy; v[2] = fabsf(n0); v[3] = fabsf(n1);
+                v[4] = -0.5f * Gv * dx * dx * dL_dG;
+                v[5] = -Gv * dx * dy * dL_dG;
+                v[6] = -0.5f * Gv * dy * dy * dL_dG;
+                v[7] = Gv * da_op;
+                v[31] = n0;
+                extra = n1;
+            }
+            halving_reduce<32, 0, 32>(v, lane);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, o);
+            s_part[warp][j][lane] = v[0];
+            if (lane == 0) s_part[warp][j][32] = extra;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < kG / 8; ++jj) {
+            const int j = warp * (kG / 8) + jj;
+            if (j < m) {
+                float s = 0.f, e = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][lane];
+                if (lane == 0) {
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][32];
+                }
+                float *row = packed + (size_t)s_id[j] * kRowG;
+                if (s != 0.f) atomicAdd(row + lane, s);
+                if (lane == 0 && e != 0.f) atomicAdd(row + 32, e);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+unpack_groups_kernel(int P, int C, const float *__restrict__ packed, float2 *__restrict__ dL_duv,
+                     float2 *__restrict__ dL_duv_ndc, float2 *__restrict__ dL_dabs_uv, float *__restrict__ dL_dconic,
+                     float *__restrict__ dL_dopacity, float *__restrict__ dL_dfeature) {
+    const int g = blockIdx.x * kBlock + threadIdx.x;
+    if (g >= P) return;
+    float r[kRowG];
+    const float4 *row = reinterpret_cast<const float4 *>(packed + (size_t)g * kRowG);
+#pragma unroll
+    for (int k = 0; k < kRowG / 4; ++k) {
+        const float4 q = row[k];
+        r[4 * k] = q.x; r[4 * k + 1] = q.y; r[4 * k + 2] = q.z; r[4 * k + 3] = q.w;
+    }
+    dL_duv[g] = make_float2(r[0], r[1]);
+    dL_dabs_uv[g] = make_float2(r[2], r[3]);
+    dL_duv_ndc[g] = make_float2(r[31], r[32]);
+    dL_dconic[3 * g] = r[4]; dL_dconic[3 * g + 1] = r[5]; dL_dconic[3 * g + 2] = r[6];
+    dL_dopacity[g] = r[7];
+#pragma unroll
+    for (int c = 0; c < 23; ++c)
+        if (c < C) dL_dfeature[(size_t)g * C + c] = r[8 + c];
+}
+
 // ------------------------------------------------------------------------------------------------ dispatch
 struct FwdArgs {
     int C, Cstride, c0, W, H, gx, K, trunc;
     const float2 *uv; const float *conic, *opacity, *feature, *bias;
-    const int *idx_sorted; const int2 *tile_range; float bg;
+    const int *idx_sorted; const int2 *tile_range; float bg, bgB, bgC; int cA, cB;
     float *rendered, *final_T; int *ncontrib, *gs_idx;
 };
 
@@ -369,8 +555,8 @@ template <int CH, bool IDX, bool BIAS>
 void launch_fwd(const FwdArgs &a, int ntiles, cudaStream_t s) {
     blend_fwd_kernel<CH, IDX, BIAS><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.K, a.trunc, a.uv,
                                                              a.conic, a.opacity, a.feature, a.bias, a.idx_sorted,
-                                                             a.tile_range, a.bg, a.rendered, a.final_T, a.ncontrib,
-                                                             a.gs_idx);
+                                                             a.tile_range, a.bg, a.bgB, a.bgC, a.cA, a.cB, a.rendered,
+                                                             a.final_T, a.ncontrib, a.gs_idx);
 }
 
 template <bool IDX, bool BIAS>
@@ -451,7 +637,8 @@ int spv_alpha_blend_forward(int P, int C, int W, int H, int K, int enable_trunca
         a.C = (C - c0 < 32) ? (C - c0) : 32; a.Cstride = C; a.c0 = c0; a.W = W; a.H = H; a.gx = gx; a.K = K;
         a.trunc = enable_truncation;
         a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = opacity_bias;
-        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg;
+        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg; a.bgB = bg; a.bgC = bg;
+        a.cA = a.C; a.cB = a.C;
         a.rendered = rendered + (size_t)c0 * H * W; a.final_T = final_T; a.ncontrib = ncontrib; a.gs_idx = gs_idx;
         if (has_idx) dispatch_fwd<true, false>(a, ntiles, s);
         else if (opacity_bias) dispatch_fwd<false, true>(a, ntiles, s);
@@ -518,6 +705,65 @@ int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const 
         if (rc) return rc;
     }
     return 0;
+}
+
+// ---- grouped (single-traversal) blending of [rgb(3) | depth(1) | attributes] -------------------------------------
+int spv_alpha_blend_groups_forward(int P, int C, int W, int H, int K, const float *uv, const float *conic,
+                                   const float *opacity, const float *feature, const int *idx_sorted,
+                                   const int *tile_range, float bg_rgb, float bg_depth, float bg_attr, float *rendered,
+                                   float *final_T, int *ncontrib, int *gs_idx, void *stream) {
+    (void)P;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0) return 0;
+    if (C < 4 || C > 32) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_forward: need 4 <= C <= 32"); return (int)cudaErrorInvalidValue; }
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
+    const bool has_idx = gs_idx != nullptr && K > 0;
+    if (has_idx) SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, s), "spv_alpha_blend_groups_forward");
+    FwdArgs a;
+    a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx; a.K = K; a.trunc = 0;
+    a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
+    a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range;
+    a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.cA = 3; a.cB = 4;
+    a.rendered = rendered; a.final_T = final_T; a.ncontrib = ncontrib; a.gs_idx = gs_idx;
+    if (has_idx) dispatch_fwd<true, false>(a, ntiles, s); else dispatch_fwd<false, false>(a, ntiles, s);
+    return spv::check_launch("spv_alpha_blend_groups_forward");
+}
+
+size_t spv_alpha_blend_groups_backward_workspace_bytes(int P) { return (size_t)(P > 0 ? P : 1) * kRowG * sizeof(float); }
+
+int spv_alpha_blend_groups_backward(int P, int C, int W, int H, const float *uv, const float *conic,
+                                    const float *opacity, const float *feature, const int *idx_sorted,
+                                    const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
+                                    const float *final_T, const int *ncontrib, const float *dL_drendered,
+                                    float *dL_duv, float *dL_duv_rgb, float *dL_dabs_uv_rgb, float *dL_dconic,
+                                    float *dL_dopacity, float *dL_dfeature, void *workspace, size_t ws_bytes,
+                                    void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0) return 0;
+    if (C < 4 || C > 23) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward: need 4 <= C <= 23"); return (int)cudaErrorInvalidValue; }
+    if (ws_bytes < spv_alpha_blend_groups_backward_workspace_bytes(P)) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward: workspace too small"); return (int)cudaErrorInvalidValue; }
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
+    float *packed = (float *)workspace;
+    SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)kRowG * P, s), "spv_alpha_blend_groups_backward");
+#define SPV_LAUNCH_G(CHV)                                                                                              \
+    blend_bwd_groups_kernel<CHV><<<ntiles, kBlock, 0, s>>>(C, W, H, gx, (const float2 *)uv, conic, opacity, feature,  \
+                                                          idx_sorted, (const int2 *)tile_range, bg_rgb, bg_depth,     \
+                                                          bg_attr, final_T, ncontrib, dL_drendered, packed)
+    if (W > 0 && H > 0) {
+        if (C <= 4) SPV_LAUNCH_G(4);
+        else if (C <= 8) SPV_LAUNCH_G(8);
+        else if (C <= 12) SPV_LAUNCH_G(12);
+        else if (C <= 16) SPV_LAUNCH_G(16);
+        else if (C <= 20) SPV_LAUNCH_G(20);
+        else SPV_LAUNCH_G(23);
+        int rc = spv::check_launch("spv_alpha_blend_groups_backward/blend");
+        if (rc) return rc;
+    }
+#undef SPV_LAUNCH_G
+    unpack_groups_kernel<<<spv::cdiv(P, kBlock), kBlock, 0, s>>>(P, C, packed, (float2 *)dL_duv, (float2 *)dL_duv_rgb,
+                                                                 (float2 *)dL_dabs_uv_rgb, dL_dconic, dL_dopacity,
+                                                                 dL_dfeature);
+    return spv::check_launch("spv_alpha_blend_groups_backward/unpack");
 }
 
 }  // extern "C"
