@@ -4,21 +4,27 @@
 //   /root/reference/src/submodules/dptr/dptr/gs/src/alpha_blending.cu:16-249          (plain)
 //   /root/reference/src/submodules/dptr/dptr/gs/src/alpha_blending_enhanced.cu:16-273 (first-K ids, truncation)
 //   /root/reference/src/submodules/dptr/dptr/gs/src/alpha_blending_with_bias.cu       (per-Gaussian alpha bias)
-// (thresholds 1/255, 0.99, 1e-4; `ncontrib` = 1-based list position of the last applied Gaussian; bg added as
-// T*bg to every channel; fast exp like the reference's --use_fast_math build) but the machine mapping is new:
+// (skip power>0, alpha=min(0.99, o*G [+bias]), skip alpha<1/255, stop before T*(1-alpha)<1e-4; `ncontrib` = 1-based
+// list position of the last applied Gaussian; bg added as T*bg; fast exp like the reference's --use_fast_math build).
+// The machine mapping is new:
 //
-//  forward   one CTA per 16x16 tile, each warp owns a compact 8x4 pixel footprint (fewer warps touched per
-//            splat than the reference's 16x2 rows); every 256-entry chunk of the tile's list is staged in shared
-//            memory INCLUDING the features (the reference re-reads features from global per pixel x Gaussian,
-//            alpha_blending.cu:96-97), features come straight from the caller's [P,C] layout (no [C,P] transpose
-//            pass), feature rows are read back as broadcast LDS.128.
-//  backward  the reference issues C+8 global float atomics per (pixel, Gaussian) hit (alpha_blending.cu:219-246).
-//            Here each warp reduces its C+8 partial sums with a recursive-halving shuffle network (NV-1 shuffles
-//            for NV values instead of 5*NV), parks the per-warp totals in shared memory, the CTA folds the 8
-//            warps and issues ONE coalesced atomic row (NV consecutive floats) per (tile, Gaussian) into a packed
-//            [P,NV] gradient buffer; a streaming pass then unpacks it into the reference's output tensors.
-//            The per-channel `accum_rec/last_feature` recurrences of the reference collapse into one scalar
-//            recurrence on S = <colour behind, dL_dpixel> (same sum, C fewer registers x2).
+//  * one CTA per 16x16 tile, each warp owns a compact 8x4 pixel footprint;
+//  * every chunk of the tile's list is staged in shared memory INCLUDING the features, read from the caller's [P,C]
+//    layout (the reference re-reads features from global per pixel x Gaussian and needs a [C,P] transpose pass);
+//  * TWO-PHASE inner loop.  The reference's per-pixel loop is a serial dependent chain per Gaussian (LDS -> quadratic
+//    form -> exp -> compare -> branch), which on B200 is latency-bound at ~27 cycles per (warp, Gaussian).  Here
+//    phase 1 evaluates, for 32 Gaussians at once and with no exp, WHETHER each pixel is hit -- the quadratic form is
+//    pre-scaled by log2(e) at staging time so "alpha >= 1/255" becomes "p2 + log2(opacity) >= log2(1/255)" -- and packs
+//    the answers into one 32-bit mask per lane: 12 independent instructions per (pixel, Gaussian), fully pipelined.
+//    One REDUX.OR gives the warp's union; phase 2 visits only the Gaussians that hit at least one pixel of the warp.
+//  * backward: the reference issues C+8 global float atomics per (pixel, Gaussian) hit.  Here a warp reduces its C+8
+//    partial sums with a recursive-halving shuffle network (NV-1 shuffles for NV values instead of 5*NV), parks the
+//    per-warp totals in shared memory, the CTA folds its 8 warps and issues ONE coalesced atomic row per
+//    (tile, Gaussian) into a packed [P,NV] buffer that a streaming pass unpacks into the reference's output tensors.
+//    The per-channel `accum_rec/last_feature` recurrences collapse into one scalar recurrence on
+//    S = <colour behind, dL_dpixel>.
+//  * the hit decision and alpha are produced by the same inline functions with explicit rounding intrinsics in the
+//    forward and the backward kernel, so both always agree on which Gaussians were applied.
 #include "common.cuh"
 #include "../../include/spv_b200.h"
 
@@ -28,12 +34,51 @@ constexpr int kBlock = 256;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.99f;
 constexpr float kTmin = 0.0001f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLog2AlphaMin = -7.994353436858858f;  // log2(1/255)
+constexpr unsigned kFull = 0xffffffffu;
 
 // warp w, lane l -> pixel inside the 16x16 tile: 8x4 footprint per warp, 2x4 warps per tile.
 __device__ __forceinline__ void thread_pixel(int tile_x, int tile_y, int &px, int &py) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     px = tile_x * SPV_TILE + ((warp & 1) << 3) + (lane & 7);
     py = tile_y * SPV_TILE + ((warp >> 1) << 2) + (lane >> 3);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Staged splat: g0 = {x, y, a2, b2}, g1 = {c2, log2(opacity), opacity, bias} with
+// a2 = -0.5*log2e*a, b2 = -log2e*b, c2 = -0.5*log2e*c  ->  p2 = log2e * power.
+__device__ __forceinline__ void stage_splat(float2 xy, float a, float b, float c, float o, float bias, float4 &g0,
+                                            float4 &g1) {
+    g0 = make_float4(xy.x, xy.y, __fmul_rn(-0.5f * kLog2e, a), __fmul_rn(-kLog2e, b));
+    g1 = make_float4(__fmul_rn(-0.5f * kLog2e, c), __log2f(o), o, bias);
+}
+
+__device__ __forceinline__ float splat_p2(const float4 g0, float c2, float pxf, float pyf, float &dx, float &dy) {
+    dx = __fsub_rn(g0.x, pxf);
+    dy = __fsub_rn(g0.y, pyf);
+    return __fmaf_rn(g0.z, __fmul_rn(dx, dx), __fmaf_rn(c2, __fmul_rn(dy, dy), __fmul_rn(g0.w, __fmul_rn(dx, dy))));
+}
+
+// Does this pixel take this Gaussian?  (alpha_blending.cu:82-88: power <= 0 and alpha >= 1/255)
+template <bool HAS_BIAS>
+__device__ __forceinline__ bool splat_hits(float p2, const float4 g1) {
+    if (HAS_BIAS) {
+        const float alpha = fminf(kAlphaMax, __fmaf_rn(g1.z, ex2_approx(p2), g1.w));
+        return p2 <= 0.f && alpha >= kAlphaMin;
+    }
+    return p2 <= 0.f && __fadd_rn(p2, g1.y) >= kLog2AlphaMin;
+}
+
+template <bool HAS_BIAS>
+__device__ __forceinline__ float splat_alpha(float p2, const float4 g1, float &G) {
+    G = ex2_approx(p2);
+    return fminf(kAlphaMax, HAS_BIAS ? __fmaf_rn(g1.z, G, g1.w) : __fmul_rn(g1.z, G));
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -45,10 +90,9 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
                  const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg, float bgB, float bgC,
                  int cA, int cB, float *__restrict__ rendered, float *__restrict__ final_T, int *__restrict__ ncontrib,
                  int *__restrict__ gs_idx) {
-    __shared__ float2 s_xy[kBlock];
-    __shared__ float4 s_co[kBlock];  // conic a,b,c + opacity
+    __shared__ float4 s_g0[kBlock];
+    __shared__ float4 s_g1[kBlock];
     __shared__ int s_id[kBlock];
-    __shared__ float s_bias[HAS_BIAS ? kBlock : 1];
     __shared__ __align__(16) float s_feat[kBlock * CH];
 
     const int tile = blockIdx.x;
@@ -76,9 +120,11 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
         if ((int)threadIdx.x < m) {
             const int id = idx_sorted[range.x + base + threadIdx.x];
             s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = uv[id];
-            s_co[threadIdx.x] = make_float4(conic[3 * id], conic[3 * id + 1], conic[3 * id + 2], opacity[id]);
-            if (HAS_BIAS) s_bias[threadIdx.x] = bias[id];
+            float4 g0, g1;
+            stage_splat(uv[id], conic[3 * id], conic[3 * id + 1], conic[3 * id + 2], opacity[id],
+                        HAS_BIAS ? bias[id] : 0.f, g0, g1);
+            s_g0[threadIdx.x] = g0;
+            s_g1[threadIdx.x] = g1;
         }
         __syncthreads();
         // feature rows: one coalesced row read per Gaussian, 32 Gaussians per warp
@@ -91,31 +137,49 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
         }
         __syncthreads();
 
-        for (int j = 0; !done && j < m; ++j) {
-            const float2 xy = s_xy[j];
-            const float4 co = s_co[j];
-            const float dx = xy.x - pxf, dy = xy.y - pyf;
-            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-            if (power > 0.f) continue;
-            float a = co.w * __expf(power);
-            if (HAS_BIAS) a += s_bias[j];
-            const float alpha = fminf(kAlphaMax, a);
-            if (alpha < kAlphaMin) continue;
-            const float next_T = T * (1.f - alpha);
-            if (next_T < kTmin) { done = true; continue; }
-            const float w = alpha * T;
-            const float *fr = s_feat + j * CH;
+        for (int j0 = 0; j0 < m; j0 += 32) {
+            if (__all_sync(kFull, done)) break;
+            // phase 1: hit mask of this pixel over 32 list entries (entries past m are masked off below)
+            unsigned mask = 0;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const float4 g0 = s_g0[j0 + j];
+                const float4 g1 = s_g1[j0 + j];
+                float dx, dy;
+                const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                mask |= (splat_hits<HAS_BIAS>(p2, g1) ? 1u : 0u) << j;
+            }
+            const int cnt = m - j0;
+            if (cnt < 32) mask &= (1u << cnt) - 1u;
+            if (done) mask = 0;
+            unsigned wm = __reduce_or_sync(kFull, mask);
+            // phase 2: only Gaussians that hit at least one pixel of this warp
+            while (wm) {
+                const int j = __ffs(wm) - 1;
+                wm &= wm - 1;
+                if ((mask >> j) & 1u) {
+                    const float4 g0 = s_g0[j0 + j];
+                    const float4 g1 = s_g1[j0 + j];
+                    float dx, dy, G;
+                    const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                    const float alpha = splat_alpha<HAS_BIAS>(p2, g1, G);
+                    const float next_T = T * (1.f - alpha);
+                    if (next_T < kTmin) { done = true; mask = 0; continue; }
+                    const float w = alpha * T;
+                    const float *fr = s_feat + (j0 + j) * CH;
 #pragma unroll
-            for (int c = 0; c < CH; ++c) F[c] = fmaf(fr[c], w, F[c]);
-            T = next_T;
-            last = base + j + 1;
-            if (HAS_IDX) {
-                if (trunc) {
-                    gs_idx[pix * K + layer] = s_id[j];
-                    if (++layer >= K) { done = true; continue; }
-                } else if (layer < K) {
-                    gs_idx[pix * K + layer] = s_id[j];
-                    ++layer;
+                    for (int c = 0; c < CH; ++c) F[c] = fmaf(fr[c], w, F[c]);
+                    T = next_T;
+                    last = base + j0 + j + 1;
+                    if (HAS_IDX) {
+                        if (trunc) {
+                            gs_idx[pix * K + layer] = s_id[j0 + j];
+                            if (++layer >= K) { done = true; mask = 0; }
+                        } else if (layer < K) {
+                            gs_idx[pix * K + layer] = s_id[j0 + j];
+                            ++layer;
+                        }
+                    }
                 }
             }
         }
@@ -132,8 +196,8 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// Recursive-halving multi-value warp reduction: on return lane l holds, in v[0], the warp-wide sum of the
-// value with index (l % N).  N-1 shuffles (+1 for N=16) instead of 5*N.
+// Recursive-halving multi-value warp reduction: on return lane l holds, in v[OFF], the warp-wide sum of the value with
+// index OFF + (l % N).  N-1 shuffles (+1 for N=16) instead of 5*N.
 template <int N, int OFF, int TOT>
 __device__ __forceinline__ void halving_reduce(float (&v)[TOT], int lane) {
 #pragma unroll
@@ -143,34 +207,42 @@ __device__ __forceinline__ void halving_reduce(float (&v)[TOT], int lane) {
         for (int i = 0; i < h; ++i) {
             const float send = up ? v[OFF + i] : v[OFF + i + h];
             const float keep = up ? v[OFF + i + h] : v[OFF + i];
-            v[OFF + i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            v[OFF + i] = keep + __shfl_xor_sync(kFull, send, h);
         }
     }
-    if (N == 16) v[OFF] += __shfl_xor_sync(0xffffffffu, v[OFF], 16);
+    if (N == 16) v[OFF] += __shfl_xor_sync(kFull, v[OFF], 16);
 }
 
-// Packed gradient row layout (NV floats per Gaussian):
-//   0,1 dL_duv   2,3 dL_dabs_uv   4,5,6 dL_dconic   7 dL_dopacity   8..8+CH-1 dL_dfeature   NV-1 dL_dbias (HAS_BIAS)
-// NV = 16 (C <= 8), 32 (C <= 24) or 64 (C <= 32: two 32-value networks, lane l ends up with values l and 32+l).
-// One launch covers up to 32 channels -- the same channel chunking as the reference (alpha_blending.cu:440-576), which
-// matters for dL_dabs_uv: |.| is taken of the per-chunk uv gradient.
+// Packed gradient row layouts.
+//  plain / bias (row = NV floats): 0,1 dL_duv  2,3 dL_dabs_uv  4,5,6 dL_dconic  7 dL_dopacity  8.. dL_dfeature  NV-1 dL_dbias
+//    NV = 16 (C <= 8), 32 (C <= 24) or 64 (C <= 32).  One launch covers up to 32 channels -- the reference's channel
+//    chunking (alpha_blending.cu:440-576), which matters for dL_dabs_uv: |.| is taken of the per-chunk uv gradient.
+//  groups (row = 36 floats, NV = 32 + 1 butterfly): the trainer's three passes over [rgb(3)|depth(1)|attrs] in one
+//    traversal (dptr_ortho_enhanced.py:342-376): uv/conic from every channel, opacity from rgb+depth only (the
+//    attribute pass gets opacity.detach()), 2,3 = |.| and 31,32 = value of the RGB-pass uv gradient (-> abs_ndc / ndc).
+enum BwdMode { kPlain = 0, kBias = 1, kGroups = 2 };
+constexpr int kRowG = 36;
 
-template <int NV, int CH, bool HAS_BIAS>
+template <int NV, int CH, int MODE>
 __global__ void __launch_bounds__(kBlock, NV == 64 ? 1 : 2)
 blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                  const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
                  const float *__restrict__ feature, const float *__restrict__ bias,
-                 const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg,
+                 const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg, float bgB, float bgC,
                  const float *__restrict__ final_T, const int *__restrict__ ncontrib,
                  const float *__restrict__ dL_drendered, float *__restrict__ packed) {
-    static_assert(8 + CH + (HAS_BIAS ? 1 : 0) <= NV, "packed row too small");
-    constexpr int kG = (NV == 64) ? 16 : 32;  // Gaussians per backward chunk (keeps s_part at 32 KB)
-    __shared__ float2 s_xy[kG];
-    __shared__ float4 s_co[kG];
+    constexpr bool HAS_BIAS = MODE == kBias;
+    constexpr bool GROUPS = MODE == kGroups;
+    static_assert(GROUPS ? (NV == 32 && CH >= 4 && CH <= 23) : (8 + CH + (HAS_BIAS ? 1 : 0) <= NV), "row too small");
+    constexpr int kG = (NV == 64) ? 16 : 32;       // Gaussians per chunk (keeps s_part at <= 34 KB)
+    constexpr int kRow = GROUPS ? kRowG : NV;       // packed row stride in global memory
+    constexpr int kSP = GROUPS ? 33 : NV;           // per-warp parking row in shared memory
+    __shared__ float4 s_g0[kG];
+    __shared__ float4 s_g1[kG];
+    __shared__ float4 s_con[kG];                    // unscaled conic a,b,c for the gradient formulas
     __shared__ int s_id[kG];
-    __shared__ float s_bias[HAS_BIAS ? kG : 1];
     __shared__ __align__(16) float s_feat[kG * CH];
-    __shared__ float s_part[8][kG][NV];
+    __shared__ float s_part[8][kG][kSP];
     __shared__ int s_max;
 
     const int tile = blockIdx.x;
@@ -188,24 +260,28 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     const int last_contrib = inside ? ncontrib[pix] : 0;
 
     float d[CH];
-    float dsum = 0.f;
     const size_t HW = (size_t)H * W;
 #pragma unroll
+    for (int c = 0; c < CH; ++c) d[c] = (inside && c < C) ? dL_drendered[c * HW + pix] : 0.f;
+    // <bg, dL_dpixel> per gradient group (plain: one group)
+    float bgdA = 0.f, bgdB = 0.f, bgdC = 0.f;
+#pragma unroll
     for (int c = 0; c < CH; ++c) {
-        d[c] = (inside && c < C) ? dL_drendered[c * HW + pix] : 0.f;
-        dsum += d[c];
+        if (GROUPS && c >= 4) bgdC += d[c];
+        else if (GROUPS && c == 3) bgdB += d[c];
+        else bgdA += d[c];
     }
-    const float bg_dot = bg * dsum;
+    bgdA *= bg; bgdB *= bgB; bgdC *= bgC;
 
     // positions >= max(last_contrib) are skipped by every pixel of the tile: do not even stage them
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
-    const int wmax = __reduce_max_sync(0xffffffffu, last_contrib);
+    const int wmax = __reduce_max_sync(kFull, last_contrib);
     if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
     __syncthreads();
     const int n_eff = min(range.y - range.x, s_max);
 
-    float last_alpha = 0.f, last_fd = 0.f, S = 0.f;
+    float last_alpha = 0.f, lfA = 0.f, lfB = 0.f, lfC = 0.f, SA = 0.f, SB = 0.f, SC = 0.f;
 
     for (int p_hi = n_eff; p_hi > 0; p_hi -= kG) {
         const int m = min(kG, p_hi);
@@ -213,12 +289,14 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
         if ((int)threadIdx.x < m) {
             const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];  // j = 0 is the back-most entry
             s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = uv[id];
-            s_co[threadIdx.x] = make_float4(conic[3 * id], conic[3 * id + 1], conic[3 * id + 2], opacity[id]);
-            if (HAS_BIAS) s_bias[threadIdx.x] = bias[id];
+            const float a = conic[3 * id], b = conic[3 * id + 1], c = conic[3 * id + 2];
+            float4 g0, g1;
+            stage_splat(uv[id], a, b, c, opacity[id], HAS_BIAS ? bias[id] : 0.f, g0, g1);
+            s_g0[threadIdx.x] = g0;
+            s_g1[threadIdx.x] = g1;
+            s_con[threadIdx.x] = make_float4(a, b, c, 0.f);
         }
         __syncthreads();
-        // features: warp w stages Gaussians 4w..4w+3 of the chunk (row reads, lanes = channels)
         if (lane < C) {
 #pragma unroll
             for (int jj = 0; jj < kG / 8; ++jj) {
@@ -228,57 +306,88 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
         }
         __syncthreads();
 
+        // phase 1: which of the chunk's Gaussians did this pixel apply in the forward pass?
+        unsigned mask = 0;
+#pragma unroll 8
+        for (int j = 0; j < kG; ++j) {
+            const float4 g0 = s_g0[j];
+            const float4 g1 = s_g1[j];
+            float dx, dy;
+            const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+            const bool hit = splat_hits<HAS_BIAS>(p2, g1) && (p_hi - 1 - j) < last_contrib;
+            mask |= (hit ? 1u : 0u) << j;
+        }
+        if (m < 32) mask &= (1u << m) - 1u;
+        const unsigned wmask = __reduce_or_sync(kFull, mask);
+
+        // phase 2: reduce the per-pixel partial gradients of every Gaussian that touched this warp
         for (int j = 0; j < m; ++j) {
-            const int p = p_hi - 1 - j;
-            bool contrib = false;
-            float dx = 0.f, dy = 0.f, Gv = 0.f, alpha = 0.f;
-            const float4 co = s_co[j];
-            if (p < last_contrib) {
-                const float2 xy = s_xy[j];
-                dx = xy.x - pxf; dy = xy.y - pyf;
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                if (power <= 0.f) {
-                    Gv = __expf(power);
-                    float a = co.w * Gv;
-                    if (HAS_BIAS) a += s_bias[j];
-                    alpha = fminf(kAlphaMax, a);
-                    contrib = alpha >= kAlphaMin;
-                }
-            }
-            if (!__any_sync(0xffffffffu, contrib)) {
-                if (lane < NV) s_part[warp][j][lane] = 0.f;
-                if constexpr (NV == 64) s_part[warp][j][32 + lane] = 0.f;
+            if (!((wmask >> j) & 1u)) {
+                if (lane < kSP) s_part[warp][j][lane] = 0.f;
+                if constexpr (kSP == 33) { if (lane == 0) s_part[warp][j][32] = 0.f; }
+                if constexpr (kSP == 64) s_part[warp][j][32 + lane] = 0.f;
                 continue;
             }
             float v[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) v[i] = 0.f;
-            if (contrib) {
+            float extra = 0.f;
+            if ((mask >> j) & 1u) {
+                const float4 g0 = s_g0[j];
+                const float4 g1 = s_g1[j];
+                const float4 con = s_con[j];
+                float dx, dy, Gv;
+                const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                const float alpha = splat_alpha<HAS_BIAS>(p2, g1, Gv);
                 const float rinv = __fdividef(1.f, 1.f - alpha);
                 T = T * rinv;  // transmittance in front of this Gaussian
                 const float w = alpha * T;
                 const float *fr = s_feat + j * CH;
-                float fd = 0.f;
+                const float tb = -T_final * rinv;
+                const float om = 1.f - last_alpha;
+                float da_all, da_op, da_ndc;
+                if (GROUPS) {
+                    float fdA = 0.f, fdC = 0.f;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    fd = fmaf(fr[c], d[c], fd);
-                    v[8 + c] = w * d[c];
+                    for (int c = 0; c < 3; ++c) { fdA = fmaf(fr[c], d[c], fdA); v[8 + c] = w * d[c]; }
+                    const float fdB = fr[3] * d[3];
+                    v[8 + 3] = w * d[3];
+#pragma unroll
+                    for (int c = 4; c < CH; ++c) { fdC = fmaf(fr[c], d[c], fdC); v[8 + c] = w * d[c]; }
+                    SA = last_alpha * lfA + om * SA;
+                    SB = last_alpha * lfB + om * SB;
+                    SC = last_alpha * lfC + om * SC;
+                    lfA = fdA; lfB = fdB; lfC = fdC;
+                    da_ndc = (fdA - SA) * T + tb * bgdA;
+                    da_op = da_ndc + ((fdB - SB) * T + tb * bgdB);
+                    da_all = da_op + ((fdC - SC) * T + tb * bgdC);
+                } else {
+                    float fd = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) { fd = fmaf(fr[c], d[c], fd); v[8 + c] = w * d[c]; }
+                    SA = last_alpha * lfA + om * SA;
+                    lfA = fd;
+                    da_all = da_op = da_ndc = (fd - SA) * T + tb * bgdA;
                 }
-                S = last_alpha * last_fd + (1.f - last_alpha) * S;
-                float dL_dalpha = (fd - S) * T;
                 last_alpha = alpha;
-                last_fd = fd;
-                dL_dalpha += (-T_final * rinv) * bg_dot;
-                const float dL_dG = co.w * dL_dalpha;
-                const float dGx = -Gv * dx * co.x - Gv * dy * co.y;
-                const float dGy = -Gv * dy * co.z - Gv * dx * co.y;
-                const float g0 = dL_dG * dGx, g1 = dL_dG * dGy;
-                v[0] = g0; v[1] = g1; v[2] = fabsf(g0); v[3] = fabsf(g1);
+                const float dL_dG = g1.z * da_all;
+                const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
+                const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
+                const float g0x = dL_dG * dGx, g0y = dL_dG * dGy;
+                v[0] = g0x; v[1] = g0y;
                 v[4] = -0.5f * Gv * dx * dx * dL_dG;
                 v[5] = -Gv * dx * dy * dL_dG;
                 v[6] = -0.5f * Gv * dy * dy * dL_dG;
-                v[7] = Gv * dL_dalpha;
-                if (HAS_BIAS) v[NV - 1] = dL_dalpha;
+                v[7] = Gv * da_op;
+                if (GROUPS) {
+                    const float dL_dG_ndc = g1.z * da_ndc;
+                    const float n0 = dL_dG_ndc * dGx, n1 = dL_dG_ndc * dGy;
+                    v[2] = fabsf(n0); v[3] = fabsf(n1);
+                    v[31] = n0; extra = n1;
+                } else {
+                    v[2] = fabsf(g0x); v[3] = fabsf(g0y);
+                    if (HAS_BIAS) v[NV - 1] = da_all;
+                }
             }
             if constexpr (NV == 64) {
                 halving_reduce<32, 0, NV>(v, lane);
@@ -288,6 +397,11 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
             } else {
                 halving_reduce<NV, 0, NV>(v, lane);
                 if (lane < NV) s_part[warp][j][lane] = v[0];
+                if constexpr (GROUPS) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(kFull, extra, o);
+                    if (lane == 0) s_part[warp][j][32] = extra;
+                }
             }
         }
         __syncthreads();
@@ -297,12 +411,21 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
             for (int jj = 0; jj < kG / 8; ++jj) {
                 const int j = warp * (kG / 8) + jj;
                 if (j < m) {
+                    float *row = packed + (size_t)s_id[j] * kRow;
 #pragma unroll
                     for (int half = 0; half < NV / 32; ++half) {
                         float s = 0.f;
 #pragma unroll
                         for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][half * 32 + lane];
-                        if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * NV + half * 32 + lane, s);
+                        if (s != 0.f) atomicAdd(row + half * 32 + lane, s);
+                    }
+                    if constexpr (GROUPS) {
+                        if (lane == 0) {
+                            float e = 0.f;
+#pragma unroll
+                            for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][32];
+                            if (e != 0.f) atomicAdd(row + 32, e);
+                        }
                     }
                 }
             }
@@ -315,7 +438,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                     float s = 0.f;
 #pragma unroll
                     for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][l16];
-                    if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * NV + l16, s);
+                    if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * kRow + l16, s);
                 }
             }
         }
@@ -355,169 +478,6 @@ unpack_kernel(int P, int C, int Cstride, int c0, int has_bias, int accumulate, c
 #pragma unroll
     for (int c = 0; c < (NV == 64 ? 32 : NV - 8); ++c)
         if (c < C) dL_dfeature[(size_t)g * Cstride + c0 + c] = r[8 + c];
-}
-
-// ------------------------------------------------------------------------------------------------ grouped backward
-// One traversal for the trainer's three blend passes (dptr_ortho_enhanced.py:342-376) over the concatenated features
-// [rgb(3) | depth(1) | attributes(CH-4)]:
-//   * uv / conic gradients come from every channel,
-//   * opacity only from rgb+depth (the attribute pass is called with opacity.detach()),
-//   * the densification statistics ndc.grad / abs_ndc.grad only from the RGB pass (the others get ndc.detach()).
-// 33 per-Gaussian sums: the 32-value halving network + one 5-step butterfly.  Packed row (stride 36 floats):
-//   0,1 dL_duv(all)  2,3 |.| of the RGB-pass uv gradient  4,5,6 dL_dconic  7 dL_dopacity  8..8+CH-1 dL_dfeature
-//   31,32 RGB-pass dL_duv (-> ndc.grad)
-constexpr int kRowG = 36;
-
-template <int CH>
-__global__ void __launch_bounds__(kBlock, 2)
-blend_bwd_groups_kernel(int C, int W, int H, int gx,
-                        const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
-                        const float *__restrict__ feature, const int *__restrict__ idx_sorted,
-                        const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
-                        const float *__restrict__ final_T, const int *__restrict__ ncontrib,
-                        const float *__restrict__ dL_drendered, float *__restrict__ packed) {
-    static_assert(CH >= 4 && CH <= 23, "grouped backward handles 4..23 channels");
-    constexpr int kG = 32;
-    __shared__ float2 s_xy[kG];
-    __shared__ float4 s_co[kG];
-    __shared__ int s_id[kG];
-    __shared__ __align__(16) float s_feat[kG * CH];
-    __shared__ float s_part[8][kG][33];
-    __shared__ int s_max;
-
-    const int tile = blockIdx.x;
-    const int tile_x = tile % gx, tile_y = tile / gx;
-    int px, py;
-    thread_pixel(tile_x, tile_y, px, py);
-    const bool inside = px < W && py < H;
-    const size_t pix = (size_t)W * py + px;
-    const float pxf = (float)px, pyf = (float)py;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    const int2 range = tile_range[tile];
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    const int last_contrib = inside ? ncontrib[pix] : 0;
-
-    float d[CH];
-    const size_t HW = (size_t)H * W;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) d[c] = (inside && c < C) ? dL_drendered[c * HW + pix] : 0.f;
-    float sumC = 0.f;
-#pragma unroll
-    for (int c = 4; c < CH; ++c) sumC += d[c];
-    const float bgdA = bgA * (d[0] + d[1] + d[2]), bgdB = bgB * d[3], bgdC = bgC * sumC;
-
-    if (threadIdx.x == 0) s_max = 0;
-    __syncthreads();
-    const int wmax = __reduce_max_sync(0xffffffffu, last_contrib);
-    if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
-    __syncthreads();
-    const int n_eff = min(range.y - range.x, s_max);
-
-    float last_alpha = 0.f, lfA = 0.f, lfB = 0.f, lfC = 0.f, SA = 0.f, SB = 0.f, SC = 0.f;
-
-    for (int p_hi = n_eff; p_hi > 0; p_hi -= kG) {
-        const int m = min(kG, p_hi);
-        __syncthreads();
-        if ((int)threadIdx.x < m) {
-            const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];
-            s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = uv[id];
-            s_co[threadIdx.x] = make_float4(conic[3 * id], conic[3 * id + 1], conic[3 * id + 2], opacity[id]);
-        }
-        __syncthreads();
-        if (lane < C) {
-#pragma unroll
-            for (int jj = 0; jj < kG / 8; ++jj) {
-                const int j = warp * (kG / 8) + jj;
-                if (j < m) s_feat[j * CH + lane] = feature[(size_t)s_id[j] * C + lane];
-            }
-        }
-        __syncthreads();
-
-        for (int j = 0; j < m; ++j) {
-            const int p = p_hi - 1 - j;
-            bool contrib = false;
-            float dx = 0.f, dy = 0.f, Gv = 0.f, alpha = 0.f;
-            const float4 co = s_co[j];
-            if (p < last_contrib) {
-                const float2 xy = s_xy[j];
-                dx = xy.x - pxf; dy = xy.y - pyf;
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                if (power <= 0.f) {
-                    Gv = __expf(power);
-                    alpha = fminf(kAlphaMax, co.w * Gv);
-                    contrib = alpha >= kAlphaMin;
-                }
-            }
-            if (!__any_sync(0xffffffffu, contrib)) {
-                s_part[warp][j][lane] = 0.f;
-                if (lane == 0) s_part[warp][j][32] = 0.f;
-                continue;
-            }
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            float extra = 0.f;
-            if (contrib) {
-                const float rinv = __fdividef(1.f, 1.f - alpha);
-                T = T * rinv;
-                const float w = alpha * T;
-                const float *fr = s_feat + j * CH;
-                float fdA = 0.f, fdC = 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) { fdA = fmaf(fr[c], d[c], fdA); v[8 + c] = w * d[c]; }
-                const float fdB = fr[3] * d[3];
-                v[8 + 3] = w * d[3];
-#pragma unroll
-                for (int c = 4; c < CH; ++c) { fdC = fmaf(fr[c], d[c], fdC); v[8 + c] = w * d[c]; }
-                const float om = 1.f - last_alpha;
-                SA = last_alpha * lfA + om * SA;
-                SB = last_alpha * lfB + om * SB;
-                SC = last_alpha * lfC + om * SC;
-                last_alpha = alpha; lfA = fdA; lfB = fdB; lfC = fdC;
-                const float tb = -T_final * rinv;
-                const float daA = (fdA - SA) * T + tb * bgdA;
-                const float daB = (fdB - SB) * T + tb * bgdB;
-                const float daC = (fdC - SC) * T + tb * bgdC;
-                const float da_op = daA + daB, da_all = da_op + daC;
-                const float dL_dG = co.w * da_all, dL_dG_ndc = co.w * daA;
-                const float dGx = -Gv * dx * co.x - Gv * dy * co.y;
-                const float dGy = -Gv * dy * co.z - Gv * dx * co.y;
-                const float n0 = dL_dG_ndc * dGx, n1 = dL_dG_ndc * dGy;
-                v[0] = dL_dG * dGx; v[1] = dL_dG * dGy; v[2] = fabsf(n0); v[3] = fabsf(n1);
-                v[4] = -0.5f * Gv * dx * dx * dL_dG;
-                v[5] = -Gv * dx * dy * dL_dG;
-                v[6] = -0.5f * Gv * dy * dy * dL_dG;
-                v[7] = Gv * da_op;
-                v[31] = n0;
-                extra = n1;
-            }
-            halving_reduce<32, 0, 32>(v, lane);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, o);
-            s_part[warp][j][lane] = v[0];
-            if (lane == 0) s_part[warp][j][32] = extra;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int jj = 0; jj < kG / 8; ++jj) {
-            const int j = warp * (kG / 8) + jj;
-            if (j < m) {
-                float s = 0.f, e = 0.f;
-#pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][lane];
-                if (lane == 0) {
-#pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][32];
-                }
-                float *row = packed + (size_t)s_id[j] * kRowG;
-                if (s != 0.f) atomicAdd(row + lane, s);
-                if (lane == 0 && e != 0.f) atomicAdd(row + 32, e);
-            }
-        }
-    }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -577,37 +537,49 @@ void dispatch_fwd(const FwdArgs &a, int ntiles, cudaStream_t s) {
 struct BwdArgs {
     int C, Cstride, c0, W, H, gx;
     const float2 *uv; const float *conic, *opacity, *feature, *bias;
-    const int *idx_sorted; const int2 *tile_range; float bg;
+    const int *idx_sorted; const int2 *tile_range; float bg, bgB, bgC;
     const float *final_T; const int *ncontrib; const float *dL_drendered; float *packed;
 };
 
-template <int NV, int CH, bool BIAS>
+template <int NV, int CH, int MODE>
 void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
-    blend_bwd_kernel<NV, CH, BIAS><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
+    blend_bwd_kernel<NV, CH, MODE><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
                                                             a.opacity, a.feature, a.bias, a.idx_sorted, a.tile_range,
-                                                            a.bg, a.final_T, a.ncontrib, a.dL_drendered, a.packed);
+                                                            a.bg, a.bgB, a.bgC, a.final_T, a.ncontrib, a.dL_drendered,
+                                                            a.packed);
 }
 
 inline int bwd_nv(int C, bool bias) { return C <= (bias ? 7 : 8) ? 16 : (C <= (bias ? 23 : 24) ? 32 : 64); }
 
-template <bool BIAS>
+template <int MODE>
 void dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
     const int C = a.C;
+    constexpr bool BIAS = MODE == kBias;
     constexpr int cap16 = BIAS ? 7 : 8, cap32 = BIAS ? 23 : 24;
     if (C <= cap16) {
-        if (C <= 1) launch_bwd<16, 1, BIAS>(a, ntiles, s);
-        else if (C <= 3) launch_bwd<16, 3, BIAS>(a, ntiles, s);
-        else if (C <= 4) launch_bwd<16, 4, BIAS>(a, ntiles, s);
-        else launch_bwd<16, cap16, BIAS>(a, ntiles, s);
+        if (C <= 1) launch_bwd<16, 1, MODE>(a, ntiles, s);
+        else if (C <= 3) launch_bwd<16, 3, MODE>(a, ntiles, s);
+        else if (C <= 4) launch_bwd<16, 4, MODE>(a, ntiles, s);
+        else launch_bwd<16, cap16, MODE>(a, ntiles, s);
     } else if (C <= cap32) {
-        if (C <= 12) launch_bwd<32, 12, BIAS>(a, ntiles, s);
-        else if (C <= 16) launch_bwd<32, 16, BIAS>(a, ntiles, s);
-        else if (C <= 20) launch_bwd<32, 20, BIAS>(a, ntiles, s);
-        else launch_bwd<32, cap32, BIAS>(a, ntiles, s);
+        if (C <= 12) launch_bwd<32, 12, MODE>(a, ntiles, s);
+        else if (C <= 16) launch_bwd<32, 16, MODE>(a, ntiles, s);
+        else if (C <= 20) launch_bwd<32, 20, MODE>(a, ntiles, s);
+        else launch_bwd<32, cap32, MODE>(a, ntiles, s);
     } else {
-        if (C <= 28) launch_bwd<64, 28, BIAS>(a, ntiles, s);
-        else launch_bwd<64, 32, BIAS>(a, ntiles, s);
+        if (C <= 28) launch_bwd<64, 28, MODE>(a, ntiles, s);
+        else launch_bwd<64, 32, MODE>(a, ntiles, s);
     }
+}
+
+void dispatch_bwd_groups(const BwdArgs &a, int ntiles, cudaStream_t s) {
+    const int C = a.C;
+    if (C <= 4) launch_bwd<32, 4, kGroups>(a, ntiles, s);
+    else if (C <= 8) launch_bwd<32, 8, kGroups>(a, ntiles, s);
+    else if (C <= 12) launch_bwd<32, 12, kGroups>(a, ntiles, s);
+    else if (C <= 16) launch_bwd<32, 16, kGroups>(a, ntiles, s);
+    else if (C <= 20) launch_bwd<32, 20, kGroups>(a, ntiles, s);
+    else launch_bwd<32, 23, kGroups>(a, ntiles, s);
 }
 
 }  // namespace
@@ -625,7 +597,7 @@ int spv_alpha_blend_forward(int P, int C, int W, int H, int K, int enable_trunca
     const bool has_idx = gs_idx != nullptr && K > 0;
     if (has_idx && opacity_bias) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_forward: gs_idx and opacity_bias are exclusive"); return (int)cudaErrorInvalidValue; }
     if (has_idx) SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, s), "spv_alpha_blend_forward");
-    if (C <= 0) {  // still produce final_T / ncontrib? the reference launches nothing for C == 0
+    if (C <= 0) {  // the reference launches nothing for C == 0
         SPV_CUDA_TRY(cudaMemsetAsync(final_T, 0, sizeof(float) * (size_t)H * W, s), "spv_alpha_blend_forward");
         SPV_CUDA_TRY(cudaMemsetAsync(ncontrib, 0, sizeof(int) * (size_t)H * W, s), "spv_alpha_blend_forward");
         return 0;
@@ -680,12 +652,12 @@ int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const 
         BwdArgs a;
         a.C = (C - c0 < cap) ? (C - c0) : cap; a.Cstride = C; a.c0 = c0; a.W = W; a.H = H; a.gx = gx;
         a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = opacity_bias;
-        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg;
+        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg; a.bgB = bg; a.bgC = bg;
         a.final_T = final_T; a.ncontrib = ncontrib; a.dL_drendered = dL_drendered + (size_t)c0 * H * W;
         a.packed = packed;
         const int nv = bwd_nv(a.C, has_bias);
         SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)nv * P, s), "spv_alpha_blend_backward");
-        if (has_bias) dispatch_bwd<true>(a, ntiles, s); else dispatch_bwd<false>(a, ntiles, s);
+        if (has_bias) dispatch_bwd<kBias>(a, ntiles, s); else dispatch_bwd<kPlain>(a, ntiles, s);
         int rc = spv::check_launch("spv_alpha_blend_backward/blend");
         if (rc) return rc;
         const unsigned g = spv::cdiv(P, kBlock);
@@ -745,21 +717,16 @@ int spv_alpha_blend_groups_backward(int P, int C, int W, int H, const float *uv,
     const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
     float *packed = (float *)workspace;
     SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)kRowG * P, s), "spv_alpha_blend_groups_backward");
-#define SPV_LAUNCH_G(CHV)                                                                                              \
-    blend_bwd_groups_kernel<CHV><<<ntiles, kBlock, 0, s>>>(C, W, H, gx, (const float2 *)uv, conic, opacity, feature,  \
-                                                          idx_sorted, (const int2 *)tile_range, bg_rgb, bg_depth,     \
-                                                          bg_attr, final_T, ncontrib, dL_drendered, packed)
     if (W > 0 && H > 0) {
-        if (C <= 4) SPV_LAUNCH_G(4);
-        else if (C <= 8) SPV_LAUNCH_G(8);
-        else if (C <= 12) SPV_LAUNCH_G(12);
-        else if (C <= 16) SPV_LAUNCH_G(16);
-        else if (C <= 20) SPV_LAUNCH_G(20);
-        else SPV_LAUNCH_G(23);
+        BwdArgs a;
+        a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx;
+        a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
+        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr;
+        a.final_T = final_T; a.ncontrib = ncontrib; a.dL_drendered = dL_drendered; a.packed = packed;
+        dispatch_bwd_groups(a, ntiles, s);
         int rc = spv::check_launch("spv_alpha_blend_groups_backward/blend");
         if (rc) return rc;
     }
-#undef SPV_LAUNCH_G
     unpack_groups_kernel<<<spv::cdiv(P, kBlock), kBlock, 0, s>>>(P, C, packed, (float2 *)dL_duv, (float2 *)dL_duv_rgb,
                                                                  (float2 *)dL_dabs_uv_rgb, dL_dconic, dL_dopacity,
                                                                  dL_dfeature);
