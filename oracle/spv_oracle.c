@@ -760,3 +760,31 @@ void orc_alpha_blend_bwd(int P, int C, int W, int H,
 }
 
 int orc_version(void) { return 1; }
+
+/* Diagnostics (not part of the reference): for every list entry, how many pixels of its tile pass the hit test
+ * (power <= 0 and alpha >= 1/255), ignoring transmittance termination, and how many of the tile's eight 8x4 pixel
+ * blocks contain at least one such pixel. */
+void orc_count_entry_hits(int W, int H, const float *uv, const float *conic, const float *opacity,
+                          const int *idx_sorted, const int *tile_range, int *hits, int *warp_hits) {
+    int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int tile = 0; tile < gx * gy; ++tile) {
+        int tx = tile % gx, ty = tile / gx;
+        for (int k = tile_range[2 * tile]; k < tile_range[2 * tile + 1]; ++k) {
+            int g = idx_sorted[k], n = 0, wmask = 0;
+            for (int ly = 0; ly < BLOCK_Y; ++ly)
+                for (int lx = 0; lx < BLOCK_X; ++lx) {
+                    int px = tx * BLOCK_X + lx, py = ty * BLOCK_Y + ly;
+                    if (px >= W || py >= H) continue;
+                    float vx = uv[2 * g] - (float)px, vy = uv[2 * g + 1] - (float)py;
+                    float power = -0.5f * (conic[3 * g] * vx * vx + conic[3 * g + 2] * vy * vy) - conic[3 * g + 1] * vx * vy;
+                    if (power > 0) continue;
+                    if (fminf(0.99f, opacity[g] * expf(power)) < 1.0f / 255.0f) continue;
+                    ++n;
+                    wmask |= 1 << ((ly / 4) * 2 + (lx / 8));
+                }
+            hits[k] = n;
+            warp_hits[k] = __builtin_popcount(wmask);
+        }
+    }
+}
