@@ -51,7 +51,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2_davis480p", choices=list(synth.CONFIGS))
-    ap.add_argument("--staged", action="store_true", help="reference op sequence (3 blend passes) instead of the fused renderer")
+    ap.add_argument("--mode", default="frame", choices=["frame", "fused", "staged"],
+                    help="frame: one fused C call per frame fwd/bwd + CUDA graph (default); fused: staged ops with single-traversal "
+                         "blending; staged: the reference's op sequence through the dptr.gs-compatible operators")
+    ap.add_argument("--staged", action="store_true", help="alias of --mode staged")
+    ap.add_argument("--no-graph", action="store_true", help="frame mode without CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="only warm-up + K train steps, no JSON (for ncu)")
@@ -118,85 +122,138 @@ def blend_fwd_algorithmic_bytes(I, C, H, W, K):
 
 # ----------------------------------------------------------------------------------------------------- our arm
 class Workload:
-    """Device-resident leaves (the reference's render_dict tensors) + renderer plugin + camera dict."""
+    """Device-resident trainable tensors (views of one flat buffer), the deformation op, the renderer plugin and the camera.
 
-    def __init__(self, cfg_name, device, fused):
+    Parameters follow the active reference model (dynamic_gaussian_with_base_point_cloud.py): frozen base position,
+    trainable cubic-spline coefficients pos_cubic_node[P, 4*NI*3] (NI = ceil(frames/5)), scaling, rotation, opacity, SH,
+    mask/dino attributes; pos_poly_feat is rendered but not trained -> 180 gradient floats per Gaussian at 50 frames."""
+
+    KEYS = ["rgb", "depth", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
+
+    def __init__(self, cfg_name, device, mode="frame", graph=True):
+        from splatter_a_video_b200.gs.frame import spline_interval
         from splatter_a_video_b200.parallel import FlatParams
         from splatter_a_video_b200.renderer import parse_renderer
-        self.sc_cpu = synth.make_config(cfg_name)
-        sc = self.sc_cpu
+        sc = synth.make_config(cfg_name)
         self.P, self.W, self.H, self.frames = sc.P, sc.W, sc.H, sc.frames
-        self.device = device
+        self.NI = -(-self.frames // 5)
+        self.device, self.mode = device, mode
         dev = lambda x: x.to(device)
-        # trainable per-Gaussian tensors as views of one flat buffer (one all-reduce per step at N>1)
-        self.flat = FlatParams({"position": dev(sc.position), "scaling": dev(sc.scaling), "rotation": dev(sc.rotation),
+        g = torch.Generator().manual_seed(99)
+        node = 0.02 * torch.randn(sc.P, 4 * self.NI * 3, generator=g)
+        self.flat = FlatParams({"pos_cubic_node": dev(node), "scaling": dev(sc.scaling), "rotation": dev(sc.rotation),
                                 "opacity": dev(sc.opacity), "shs": dev(sc.shs),
-                                "mask_attribute": dev(sc.attrs["mask_attribute"]), "dino_attribute": dev(sc.attrs["dino_attribute"]),
-                                "pos_poly_feat": dev(sc.attrs["pos_poly_feat"])})
-        self.nodes = dev(sc.nodes)
-        self.extr = dev(sc.extr)
-        self.intr = dev(sc.intr)
-        name = "DPTROrthoEnhancedRenderB200" if fused else "DPTROrthoEnhancedRender"
-        self.renderer = parse_renderer({"name": name}, white_bg=False, device=device)
+                                "mask_attribute": dev(sc.attrs["mask_attribute"]), "dino_attribute": dev(sc.attrs["dino_attribute"])})
+        self.base = dev(sc.position)
+        self.pos_poly_feat = dev(sc.attrs["pos_poly_feat"])
+        self.extr, self.intr = dev(sc.extr), dev(sc.intr)
+        name = {"frame": "DPTROrthoEnhancedRenderB200", "fused": "DPTROrthoEnhancedRenderB200", "staged": "DPTROrthoEnhancedRender"}[mode]
+        cfg = {"name": name}
+        if mode == "fused":
+            cfg["frame"] = False
+        self.renderer = parse_renderer(cfg, white_bg=False, device=device)
         self.batch = {"FovX": 0.0, "FovY": 0.0, "height": self.H, "width": self.W, "extrinsic_matrix": self.extr,
                       "intrinsic_matrix": self.intr, "camera_center": torch.zeros(3, device=device),
                       "render_attributes_list": ["track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"], "num_idx": K_IDX}
-        g = torch.Generator().manual_seed(99)
-        # upstream image gradients, resident in HBM (N(0,1), SURVEY.md 8d) and pinned host copies for the e2e path
-        self.g_img = {"rgb": torch.randn(3, self.H, self.W, generator=g), "depth": torch.randn(1, self.H, self.W, generator=g),
-                      "track_gs": torch.randn(3, self.H, self.W, generator=g), "mask_attribute": torch.randn(1, self.H, self.W, generator=g),
-                      "pos_poly_feat": torch.randn(12, self.H, self.W, generator=g), "dino_attribute": torch.randn(3, self.H, self.W, generator=g)}
-        self.g_dev = {k: v.to(device) for k, v in self.g_img.items()}
+        # frame time -> (interval, distance) device scalars of the deformation op, for ids1 and ids2 = ids1 + 1
+        tab = [spline_interval(t, self.frames, self.NI) for t in range(self.frames)]
+        self.tab_idx = torch.tensor([a for a, _ in tab], dtype=torch.int32).pin_memory()
+        self.tab_dist = torch.tensor([b for _, b in tab], dtype=torch.float32).pin_memory()
+        self.idx1 = torch.zeros(1, dtype=torch.int32, device=device); self.dist1 = torch.zeros(1, device=device)
+        self.idx2 = torch.zeros(1, dtype=torch.int32, device=device); self.dist2 = torch.zeros(1, device=device)
+        # upstream image gradients resident in HBM (N(0,1), SURVEY.md 8d) + pinned host buffers for the e2e path
+        chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
+        self.g_dev = {k: torch.randn(c, self.H, self.W, generator=g).to(device) for k, c in chans.items()}
         self.gt_host = torch.rand(3, self.H, self.W, generator=g).pin_memory()
-        self.w_host = torch.cat([v for v in self.g_img.values()], 0).contiguous().pin_memory()   # [23,H,W]
+        self.w_host = torch.cat([v.cpu() for v in self.g_dev.values()], 0).contiguous().pin_memory()   # [23,H,W]
         self.gt_dev = torch.empty(3, self.H, self.W, device=device)
         self.w_dev = torch.empty(23, self.H, self.W, device=device)
+        self.loss_dev = torch.zeros(1, device=device)
         self.loss_host = torch.empty(1).pin_memory()
+        self.use_graph = bool(graph) and mode == "frame"
+        self.graphs = {}
 
-    def render_dict(self, frame):
+    # ---- per-step pieces -------------------------------------------------------------------------------------------
+    def set_frame(self, frame):
+        f2 = min(frame + 1, self.frames - 1)
+        self.idx1.copy_(self.tab_idx[frame:frame + 1], non_blocking=True); self.dist1.copy_(self.tab_dist[frame:frame + 1], non_blocking=True)
+        self.idx2.copy_(self.tab_idx[f2:f2 + 1], non_blocking=True); self.dist2.copy_(self.tab_dist[f2:f2 + 1], non_blocking=True)
+
+    def render_dict(self):
+        from splatter_a_video_b200.gs.frame import deform_position
         p = self.flat.params
+        pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI)
         with torch.no_grad():
-            disp = synth.eval_spline(self.nodes, frame / 5.0)
-            disp2 = synth.eval_spline(self.nodes, min(frame + 1, self.frames - 1) / 5.0)
-        pos = p["position"] + disp
-        track = (p["position"] + disp2).detach()
+            track = deform_position(self.base, p["pos_cubic_node"], self.idx2, self.dist2, self.NI)
         return {"position": pos, "opacity": p["opacity"], "scaling": p["scaling"], "rotation": p["rotation"], "shs": p["shs"],
-                "track_gs": track, "mask_attribute": p["mask_attribute"], "pos_poly_feat": p["pos_poly_feat"],
+                "track_gs": track, "mask_attribute": p["mask_attribute"], "pos_poly_feat": self.pos_poly_feat,
                 "dino_attribute": p["dino_attribute"]}
 
-    def forward(self, frame):
-        return self.renderer.render_batch(self.render_dict(frame), [dict(self.batch)])
+    def _fwd_bwd_resident(self):
+        self.flat.zero_grad()
+        out = self.renderer.render_batch(self.render_dict(), [dict(self.batch)])
+        torch.autograd.backward([out[k][0] for k in self.KEYS], [self.g_dev[k] for k in self.KEYS])
 
-    def step_resident(self, frame):
-        out = self.forward(frame)
-        keys = ["rgb", "depth", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
-        torch.autograd.backward([out[k][0] for k in keys], [self.g_dev[k] for k in keys])
-        return out
-
-    def step_e2e(self, frame):
-        """Host-driven step: H2D of the frame's ground truth + per-pixel weights, loss gradient on device, D2H loss."""
-        self.gt_dev.copy_(self.gt_host, non_blocking=True)
-        self.w_dev.copy_(self.w_host, non_blocking=True)
-        out = self.forward(frame)
-        keys = ["rgb", "depth", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
-        imgs = torch.cat([out[k][0] for k in keys], 0)                       # [23,H,W]
+    def _fwd_bwd_from_staged_host_data(self):
+        self.flat.zero_grad()
+        out = self.renderer.render_batch(self.render_dict(), [dict(self.batch)])
+        imgs = torch.cat([out[k][0] for k in self.KEYS], 0)                   # [23,H,W]
         diff = imgs.detach().clone()
         diff[:3] -= self.gt_dev
-        loss = (diff * self.w_dev).sum() / diff.numel()
+        self.loss_dev.copy_(((diff * self.w_dev).sum() / diff.numel()).reshape(1))
         imgs.backward(self.w_dev / diff.numel())
-        self.loss_host.copy_(loss.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()                            # the D2H read of the step's result
-        return float(self.loss_host[0])
 
-    def render_only(self, frame, to_host=False):
+    def _render_only(self):
         with torch.no_grad():
             b = dict(self.batch)
             b["render_attributes_list"] = ["dino_attribute", "mask_attribute"]   # trainer_fragGS.py:1264-1306
             b["num_idx"] = 10
-            out = self.renderer.render_batch(self.render_dict(frame), [b])
-            if to_host:
-                return out["rgb"].cpu()
-        return out
+            self.last_render = self.renderer.render_batch(self.render_dict(), [b])["rgb"]
+
+    def _run(self, name, fn):
+        """Eager, or a CUDA graph captured once per step kind (frame mode: nothing on the path syncs the host)."""
+        if not self.use_graph:
+            return fn()
+        if name not in self.graphs:
+            self.renderer.observe_capacity = True
+            fn(); torch.cuda.synchronize()                      # settles the intersection capacity (the only sync, once)
+            if name == "train":
+                self.renderer.capacity.I_cap = int(self.renderer.capacity.I_cap * 1.2)   # head-room across frames
+            self.renderer.observe_capacity = False
+            s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fn(); fn()
+            torch.cuda.current_stream().wait_stream(s)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            self.graphs[name] = gr
+        self.graphs[name].replay()
+
+    # ---- the timed step kinds --------------------------------------------------------------------------------------
+    def step_resident(self, frame):
+        self.set_frame(frame)
+        self._run("train", self._fwd_bwd_resident)
+
+    def step_e2e(self, frame):
+        """Host-driven step: H2D of the frame's ground truth + per-pixel weights, loss gradient on device, D2H loss."""
+        self.set_frame(frame)
+        self.gt_dev.copy_(self.gt_host, non_blocking=True)
+        self.w_dev.copy_(self.w_host, non_blocking=True)
+        self._run("train_e2e", self._fwd_bwd_from_staged_host_data)
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                            # the D2H read of the step's result
+        return float(self.loss_host[0])
+
+    def render_only(self, frame, to_host=False):
+        self.set_frame(frame)
+        self._run("render", self._render_only)
+        if to_host:
+            return self.last_render.cpu()
+
+    def overflowed(self):
+        st = self.renderer.last_status
+        return bool(st is not None and int(st.cpu()[1]) != 0)
 
 
 def time_steps(fn, steps, warmup, flush_buf, world, rank, frames_of):
@@ -229,7 +286,8 @@ def stage_breakdown(wl: Workload, frame):
     from splatter_a_video_b200 import gs
     from splatter_a_video_b200 import _lib as L
     dev = wl.device
-    rd = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in wl.render_dict(frame).items()}
+    wl.set_frame(frame)
+    rd = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in wl.render_dict().items()}
     W, H, P = wl.W, wl.H, wl.P
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     res = {}
@@ -267,6 +325,16 @@ def stage_breakdown(wl: Workload, frame):
         g = torch.randn_like(img)
         timed(f"blend_bwd_{name}", lambda: torch.autograd.grad(img, leaves, g, retain_graph=True))
         info[name] = dict(C=C, K=K, fwd_bytes=blend_fwd_algorithmic_bytes(I, C, H, W, K), bwd_bytes=blend_bwd_algorithmic_bytes(I, C, H, W, P))
+    # the single-traversal kernels the frame / fused modes actually run (C = 3 + 1 + 19)
+    from splatter_a_video_b200.gs import fused as F_
+    leaves = [t.detach().clone().requires_grad_(True) for t in (uv, conic, rd["opacity"], rgb, depth, attrs)]
+    outs = timed("blend_fwd_fused23", lambda: F_.blend_rgb_depth_attrs(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[5],
+                                                                      idx, tr, 0.0, W, H, None, None, K=K_IDX))
+    imgs = torch.cat([outs[0], outs[1], outs[2]], 0)
+    g = torch.randn_like(imgs)
+    timed("blend_bwd_fused23", lambda: torch.autograd.grad(imgs, leaves, g, retain_graph=True))
+    info["fused23"] = dict(C=23, K=K_IDX, fwd_bytes=blend_fwd_algorithmic_bytes(I, 23, H, W, K_IDX),
+                           bwd_bytes=blend_bwd_algorithmic_bytes(I, 23, H, W, P))
     res["sort_keys_per_s"] = I / (res["sort_gaussian"] * 1e-3)
     return res, info, I
 
@@ -366,22 +434,16 @@ def run_ours(args):
     from splatter_a_video_b200.parallel import frame_for_step
     L.load()
 
-    fused = not args.staged
-    try:
-        from splatter_a_video_b200.gs import fused as _f  # noqa: F401
-    except ImportError:
-        fused = False
-    wl = Workload(args.config, device, fused=fused)
+    mode = "staged" if args.staged else args.mode
+    wl = Workload(args.config, device, mode=mode, graph=not args.no_graph)
     flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=device)
     frames_of = lambda i: frame_for_step(i, rank, world, wl.frames)
 
     def train_step(frame):
-        wl.flat.zero_grad()
         wl.step_resident(frame)
         wl.flat.allreduce_grads()
 
     def train_step_e2e(frame):
-        wl.flat.zero_grad()
         wl.step_e2e(frame)
         wl.flat.allreduce_grads()
 
@@ -389,10 +451,14 @@ def run_ours(args):
         time_steps(train_step, args.steps, args.warmup, None, world, rank, frames_of)
         return
     log(f"workload ready: P={wl.P} {wl.W}x{wl.H}, renderer={type(wl.renderer).__name__}")
-    sampler = ClockSampler(local) if rank == 0 else None
+    # kernels of this library per step, counted on one eager step (graph replays do not pass through the host counter)
+    wl.set_frame(0)
+    wl._fwd_bwd_resident(); torch.cuda.synchronize()
     n0 = L.query("spv_launch_count")
+    wl._fwd_bwd_resident(); torch.cuda.synchronize()
+    launches = L.query("spv_launch_count") - n0
+    sampler = ClockSampler(local) if rank == 0 else None
     total_ms, per_step = time_steps(train_step, args.steps, args.warmup, flush, world, rank, frames_of)
-    launches = (L.query("spv_launch_count") - n0) / (args.steps + args.warmup)
     log(f"train (resident): {total_ms / args.steps:.3f} ms/step")
     e2e_ms, _ = time_steps(train_step_e2e, args.steps, args.warmup, flush, world, rank, frames_of)
     log(f"train (e2e): {e2e_ms / args.steps:.3f} ms/step")
@@ -410,7 +476,8 @@ def run_ours(args):
     log("stage breakdown")
     stages, info, I = stage_breakdown(wl, 0)
     log("stages: " + json.dumps(stages))
-    dom = max((k for k in stages if k.startswith("blend_")), key=lambda k: stages[k])
+    cands = [k for k in stages if k.startswith("blend_") and (("fused" in k) == (wl.mode != "staged"))]
+    dom = max(cands, key=lambda k: stages[k])
     pname = dom.split("_", 2)[2]
     abytes = info[pname]["bwd_bytes" if "bwd" in dom else "fwd_bytes"]
     ach = abytes / (stages[dom] * 1e-3) / 1e9
@@ -421,7 +488,8 @@ def run_ours(args):
         "config": {"workload": f"{args.config}: P={wl.P}, {wl.W}x{wl.H}, {wl.frames} frames, I={I} tile intersections/frame; one step = "
                                "render one frame (RGB K=20 + depth + 19 attribute channels) forward+backward through "
                                f"{type(wl.renderer).__name__}.render_batch; frames sharded {world}-way, one flat-gradient all-reduce/step",
-                   "renderer": type(wl.renderer).__name__, "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
+                   "renderer": type(wl.renderer).__name__, "mode": wl.mode, "cuda_graph": wl.use_graph,
+                   "capacity_overflow": wl.overflowed(), "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
                    "grad_floats_per_gaussian": wl.flat.floats_per_gaussian(wl.P)},
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "it/s", "h2d_bytes_per_step": int(wl.gt_host.numel() * 4 + wl.w_host.numel() * 4),
                 "d2h_bytes_per_step": 4},

@@ -138,6 +138,38 @@ SPV_API int spv_alpha_blend_groups_backward(int P, int C /*4..23*/, int W, int H
                                     float *dL_dopacity, float *dL_dfeature, void *workspace, size_t ws_bytes,
                                     void *stream);
 
+/* ---- Fused per-frame entry points (no host synchronisation; CUDA-graph capturable) -------------------------------
+ * spv_bin_capacity: scan + (optionally exactly culled) key emission + radix sort + ranges for at most I_cap
+ * intersections; status[0] = intersections kept, status[1] = 1 on overflow (device ints).
+ * spv_frame_ortho_forward/backward: DPTROrthoEnhancedRender.render_iter (dptr_ortho_enhanced.py:205-383) and its full
+ * backward as one call each.  images = [rgb(3) | depth(1) | attrs(A)] x H x W; A <= 19.  The workspace filled by the
+ * forward call must be passed unchanged to the backward call. */
+SPV_API size_t spv_bin_capacity_workspace_bytes(int P, int64_t I_cap);
+SPV_API int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
+                     const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
+                     void *workspace, size_t ws_bytes, void *stream);
+SPV_API size_t spv_frame_workspace_bytes(int P, int64_t I_cap, int W, int H, int A);
+SPV_API int spv_frame_ortho_forward(int P, int W, int H, int A, int K, int64_t I_cap, int cull,
+                            const float *position, const float *scaling, const float *rotation, const float *opacity,
+                            const float *shs /*[P,16,3]*/, const float *attrs /*[P,A] or NULL*/, const float *extr,
+                            float nearest, float extent, float bg_rgb, float *images /*[4+A,H,W]*/,
+                            int *gs_idx /*[H,W,K]*/, int *radii /*[P]*/, int *status /*[2]*/, void *workspace,
+                            size_t ws_bytes, void *stream);
+SPV_API int spv_frame_ortho_backward(int P, int W, int H, int A, int64_t I_cap, const float *scaling, const float *rotation,
+                             const float *opacity, const float *shs, const float *extr, float bg_rgb,
+                             const float *dL_dimages /*[4+A,H,W]*/, float *dL_dposition, float *dL_dscaling,
+                             float *dL_drotation, float *dL_dopacity, float *dL_dshs /*[P,16,3]*/, float *dL_dattrs /*[P,A]*/,
+                             float *dL_dndc /*[P,2] or NULL*/, float *dL_dabs_ndc /*[P,2] or NULL*/, void *workspace,
+                             size_t ws_bytes, void *stream);
+
+/* ---- Per-frame deformation (next row f-1): cubic-spline position of the active model
+ * (src/dynamic_gaussian_with_base_point_cloud.py:236-250).  coeff = pos_cubic_node viewed as [P,4,NI,3]; the interval
+ * index and in-interval distance are DEVICE scalars (graph-replayable).  Backward: gradient to the coefficients. */
+SPV_API int spv_deform_spline_forward(int P, int NI, const float *base, const float *coeff, const int *idx_dev,
+                              const float *dist_dev, float *pos /*[P,3]*/, void *stream);
+SPV_API int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *dist_dev, const float *dL_dpos,
+                               float *dL_dcoeff /*[P,4,NI,3]*/, int accumulate, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

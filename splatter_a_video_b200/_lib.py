@@ -46,6 +46,15 @@ _SIGS = {
     "spv_alpha_blend_groups_backward_workspace_bytes": (c_size_t, [c_int]),
     "spv_alpha_blend_groups_backward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float, c_float,
                                                 P_, P_, P_, P_, P_, P_, P_, P_, P_, P_, c_size_t, P_]),
+    "spv_bin_capacity_workspace_bytes": (c_size_t, [c_int, c_int64]),
+    "spv_bin_capacity": (c_int, [c_int, c_int64, P_, P_, P_, P_, P_, c_int, c_int, c_int, P_, P_, P_, P_, c_size_t, P_]),
+    "spv_frame_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
+    "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int64, c_int, P_, P_, P_, P_, P_, P_, P_, c_float,
+                                        c_float, c_float, P_, P_, P_, P_, P_, c_size_t, P_]),
+    "spv_frame_ortho_backward": (c_int, [c_int, c_int, c_int, c_int, c_int64, P_, P_, P_, P_, P_, c_float, P_, P_, P_, P_, P_,
+                                         P_, P_, P_, P_, P_, c_size_t, P_]),
+    "spv_deform_spline_forward": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_spline_backward": (c_int, [c_int, c_int, P_, P_, P_, P_, c_int, P_]),
 }
 
 EXPORTED = sorted(_SIGS)

@@ -25,6 +25,8 @@
 //    S = <colour behind, dL_dpixel>.
 //  * the hit decision and alpha are produced by the same inline functions with explicit rounding intrinsics in the
 //    forward and the backward kernel, so both always agree on which Gaussians were applied.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/spv_b200.h"
 
@@ -838,6 +840,15 @@ void launch_bwd_mma(const BwdArgs &a, int ntiles, cudaStream_t s) {
                                                                  a.ncontrib, a.dL_drendered, a.packed);
 }
 
+// The tensor-core variant is numerically correct (it passes the same parity tests) but MEASURED SLOWER on the
+// DAVIS-shaped workload (C=19 pass: 1.08 ms vs 0.82 ms; only ~24 % of the (warp, Gaussian) pairs of a chunk are active, so
+// the dense per-chunk fragment building costs more than the shuffle network it replaces).  Kept selectable for
+// experiments with SPV_BWD_MMA=1; the default is the halving-shuffle kernel.
+inline bool use_mma_backward() {
+    static const bool on = [] { const char *e = getenv("SPV_BWD_MMA"); return e && e[0] == '1'; }();
+    return on;
+}
+
 inline int bwd_nv(int C, bool bias) { return C <= (bias ? 7 : 8) ? 16 : (C <= (bias ? 23 : 24) ? 32 : 64); }
 
 template <int MODE>
@@ -851,8 +862,13 @@ void dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
         else if (C <= 4) launch_bwd<16, 4, MODE>(a, ntiles, s);
         else launch_bwd<16, cap16, MODE>(a, ntiles, s);
     } else if (C <= cap32) {
-        if (C <= 16) launch_bwd_mma<16, MODE>(a, ntiles, s);
-        else launch_bwd_mma<24, MODE>(a, ntiles, s);
+        if (use_mma_backward()) {
+            if (C <= 16) launch_bwd_mma<16, MODE>(a, ntiles, s);
+            else launch_bwd_mma<24, MODE>(a, ntiles, s);
+        } else if (C <= 12) launch_bwd<32, 12, MODE>(a, ntiles, s);
+        else if (C <= 16) launch_bwd<32, 16, MODE>(a, ntiles, s);
+        else if (C <= 20) launch_bwd<32, 20, MODE>(a, ntiles, s);
+        else launch_bwd<32, cap32, MODE>(a, ntiles, s);
     } else {
         if (C <= 28) launch_bwd<64, 28, MODE>(a, ntiles, s);
         else launch_bwd<64, 32, MODE>(a, ntiles, s);
@@ -861,9 +877,18 @@ void dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
 
 void dispatch_bwd_groups(const BwdArgs &a, int ntiles, cudaStream_t s) {
     const int C = a.C;
-    if (C <= 8) launch_bwd_mma<8, kGroups>(a, ntiles, s);
-    else if (C <= 16) launch_bwd_mma<16, kGroups>(a, ntiles, s);
-    else launch_bwd_mma<24, kGroups>(a, ntiles, s);
+    if (use_mma_backward()) {
+        if (C <= 8) launch_bwd_mma<8, kGroups>(a, ntiles, s);
+        else if (C <= 16) launch_bwd_mma<16, kGroups>(a, ntiles, s);
+        else launch_bwd_mma<24, kGroups>(a, ntiles, s);
+        return;
+    }
+    if (C <= 4) launch_bwd<32, 4, kGroups>(a, ntiles, s);
+    else if (C <= 8) launch_bwd<32, 8, kGroups>(a, ntiles, s);
+    else if (C <= 12) launch_bwd<32, 12, kGroups>(a, ntiles, s);
+    else if (C <= 16) launch_bwd<32, 16, kGroups>(a, ntiles, s);
+    else if (C <= 20) launch_bwd<32, 20, kGroups>(a, ntiles, s);
+    else launch_bwd<32, 23, kGroups>(a, ntiles, s);
 }
 
 }  // namespace

@@ -1,0 +1,64 @@
+// Per-frame deformation of the active model: cubic-spline position
+//   pos(t) = base + c3 + c2*d + c1*d^2 + c0*d^3,  coeff = pos_cubic_node[P, 4, NI, 3], (interval idx, d) from the frame time
+// restating /root/reference/src/dynamic_gaussian_with_base_point_cloud.py:236-250 (get_position), and its backward
+// (gradient to the 4 coefficients of the active interval; `position` itself is frozen there, :97-99).
+// The interval index and the in-interval distance are read from DEVICE memory so a captured CUDA graph can be replayed
+// for any frame by updating two scalars.  One coalesced streaming pass: 12 B read + 48 B coefficients + 12 B written per
+// Gaussian forward; the reference evaluates it with ~10 torch kernels over [P,3].
+#include "common.cuh"
+#include "../../include/spv_b200.h"
+
+namespace {
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+deform_fwd_kernel(int P, int NI, const float *__restrict__ base, const float *__restrict__ coeff,
+                  const int *__restrict__ idx_dev, const float *__restrict__ dist_dev, float *__restrict__ pos) {
+    const int k = blockIdx.x * kThreads + threadIdx.x;   // one thread per (Gaussian, xyz component)
+    if (k >= 3 * P) return;
+    const int i = k / 3, c = k % 3;
+    const int idx = idx_dev[0];
+    const float d = dist_dev[0];
+    const float *q = coeff + (size_t)i * 4 * NI * 3 + (size_t)idx * 3 + c;   // [4][NI][3]
+    const size_t s = (size_t)NI * 3;
+    // same association as the reference: c3 + c2*d + c1*d**2 + c0*d**3, then + position
+    const float v = q[3 * s] + q[2 * s] * d + q[1 * s] * (d * d) + q[0] * (d * d * d);
+    pos[k] = v + base[k];
+}
+
+__global__ void __launch_bounds__(kThreads)
+deform_bwd_kernel(int P, int NI, const int *__restrict__ idx_dev, const float *__restrict__ dist_dev,
+                  const float *__restrict__ dL_dpos, float *__restrict__ dL_dcoeff, int accumulate) {
+    const int k = blockIdx.x * kThreads + threadIdx.x;
+    if (k >= 3 * P) return;
+    const int i = k / 3, c = k % 3;
+    const int idx = idx_dev[0];
+    const float d = dist_dev[0];
+    const float g = dL_dpos[k];
+    float *q = dL_dcoeff + (size_t)i * 4 * NI * 3 + (size_t)idx * 3 + c;
+    const size_t s = (size_t)NI * 3;
+    if (accumulate) { q[3 * s] += g; q[2 * s] += g * d; q[1 * s] += g * (d * d); q[0] += g * (d * d * d); }
+    else { q[3 * s] = g; q[2 * s] = g * d; q[1 * s] = g * (d * d); q[0] = g * (d * d * d); }
+}
+}  // namespace
+
+extern "C" {
+
+int spv_deform_spline_forward(int P, int NI, const float *base, const float *coeff, const int *idx_dev,
+                              const float *dist_dev, float *pos, void *stream) {
+    if (P <= 0) return 0;
+    deform_fwd_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, (cudaStream_t)stream>>>(P, NI, base, coeff, idx_dev, dist_dev, pos);
+    return spv::check_launch("spv_deform_spline_forward");
+}
+
+/* accumulate == 0: dL_dcoeff is cleared first (only the active interval's 12 floats per Gaussian are non-zero). */
+int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *dist_dev, const float *dL_dpos,
+                               float *dL_dcoeff, int accumulate, void *stream) {
+    if (P <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!accumulate) SPV_CUDA_TRY(cudaMemsetAsync(dL_dcoeff, 0, sizeof(float) * 12 * (size_t)NI * P, s), "spv_deform_spline_backward");
+    deform_bwd_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, s>>>(P, NI, idx_dev, dist_dev, dL_dpos, dL_dcoeff, accumulate);
+    return spv::check_launch("spv_deform_spline_backward");
+}
+
+}  // extern "C"

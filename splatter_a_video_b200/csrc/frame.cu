@@ -1,0 +1,168 @@
+// Fused per-frame entry points for the video trainer's orthographic renderer: the whole hot path of
+// DPTROrthoEnhancedRender.render_iter (/root/reference/src/pointrix/renderer/dptr_ortho_enhanced.py:205-383) forward,
+// and its whole backward, each as ONE C call that only enqueues kernels on the caller's stream:
+//   * no host synchronisation (the reference has two .item() calls per frame, sort_gaussian.cu:93,132): the number
+//     of tile intersections stays on the device, buffers are sized by a caller-chosen capacity, overflow is flagged in
+//     `status` -- so a whole training step can be captured in a CUDA graph;
+//   * exact tile culling (sort.cu) shortens every list without changing any pixel;
+//   * the three blend passes are one traversal (blend.cu, grouped kernels).
+// Intermediates live in a caller-provided workspace that the backward call reuses.
+#include "common.cuh"
+#include "../../include/spv_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct FrameWs {
+    float *dirs, *rgb, *uv, *depth, *cov3d, *conic, *feature, *final_T;
+    uint8_t *vis, *clamped;
+    int *radius, *tiles, *idx_sorted, *tile_range, *ncontrib;
+    void *bin_ws; size_t bin_bytes;
+    // backward temporaries
+    float *packed, *g_uv, *g_uv_rgb, *g_abs, *g_conic, *g_op, *g_feat, *g_rgb, *g_depth, *g_cov3d, *g_dirs;
+    void *blend_ws; size_t blend_bytes;
+    size_t total;
+};
+
+FrameWs carve(void *base, int P, int64_t I_cap, int W, int H, int A) {
+    FrameWs f;
+    char *p = (char *)base;
+    const size_t Pn = (size_t)(P > 0 ? P : 1), C = 4 + (size_t)A, T = (size_t)spv::tiles_x(W) * spv::tiles_y(H), HW = (size_t)W * H;
+    auto take = [&](size_t bytes) { char *r = p; p += al(bytes); return (void *)r; };
+    f.dirs = (float *)take(Pn * 12); f.rgb = (float *)take(Pn * 12); f.uv = (float *)take(Pn * 8); f.depth = (float *)take(Pn * 4);
+    f.cov3d = (float *)take(Pn * 24); f.conic = (float *)take(Pn * 12); f.feature = (float *)take(Pn * C * 4);
+    f.final_T = (float *)take(HW * 4);
+    f.vis = (uint8_t *)take(Pn); f.clamped = (uint8_t *)take(Pn * 3);
+    f.radius = (int *)take(Pn * 4); f.tiles = (int *)take(Pn * 4);
+    f.idx_sorted = (int *)take((size_t)(I_cap > 0 ? I_cap : 1) * 4); f.tile_range = (int *)take(T * 8);
+    f.ncontrib = (int *)take(HW * 4);
+    f.bin_bytes = spv_bin_capacity_workspace_bytes(P, I_cap); f.bin_ws = take(f.bin_bytes);
+    f.blend_bytes = spv_alpha_blend_groups_backward_workspace_bytes(P); f.blend_ws = take(f.blend_bytes);
+    f.packed = nullptr;
+    f.g_uv = (float *)take(Pn * 8); f.g_uv_rgb = (float *)take(Pn * 8); f.g_abs = (float *)take(Pn * 8);
+    f.g_conic = (float *)take(Pn * 12); f.g_op = (float *)take(Pn * 4); f.g_feat = (float *)take(Pn * C * 4);
+    f.g_rgb = (float *)take(Pn * 12); f.g_depth = (float *)take(Pn * 4); f.g_cov3d = (float *)take(Pn * 24);
+    f.g_dirs = (float *)take(Pn * 12);
+    f.total = (size_t)(p - (char *)base);
+    return f;
+}
+
+__global__ void __launch_bounds__(kThreads)
+frame_prep_kernel(int P, float *__restrict__ dirs) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    dirs[3 * i] = 0.f; dirs[3 * i + 1] = 0.f; dirs[3 * i + 2] = 1.f;   // constant view direction (0,0,1), :270-271
+}
+
+__global__ void __launch_bounds__(kThreads)
+visible_kernel(int P, const float *__restrict__ depth, uint8_t *__restrict__ vis) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < P) vis[i] = depth[i] != 0.f;
+}
+
+// feature[P, 4+A] = [rgb(3) | depth(1) | attrs(A)]
+__global__ void __launch_bounds__(kThreads)
+pack_features_kernel(int P, int A, const float *__restrict__ rgb, const float *__restrict__ depth,
+                     const float *__restrict__ attrs, float *__restrict__ feature) {
+    const int C = 4 + A;
+    const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= (long long)P * C) return;
+    const int i = (int)(k / C), c = (int)(k % C);
+    feature[k] = c < 3 ? rgb[3 * i + c] : (c == 3 ? depth[i] : attrs[(size_t)i * A + (c - 4)]);
+}
+
+// inverse of pack_features for the gradients; also folds the [W/2,H/2] scale of the ndc dummies
+__global__ void __launch_bounds__(kThreads)
+split_grads_kernel(int P, int A, const float *__restrict__ g_feat, float *__restrict__ g_rgb, float *__restrict__ g_depth,
+                   float *__restrict__ g_attrs, const float2 *__restrict__ g_uv_rgb, const float2 *__restrict__ g_abs,
+                   float2 *__restrict__ g_ndc, float2 *__restrict__ g_abs_ndc, float hw, float hh) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const int C = 4 + A;
+    const float *r = g_feat + (size_t)i * C;
+    g_rgb[3 * i] = r[0]; g_rgb[3 * i + 1] = r[1]; g_rgb[3 * i + 2] = r[2];
+    g_depth[i] = r[3];
+    for (int c = 0; c < A; ++c) g_attrs[(size_t)i * A + c] = r[4 + c];
+    if (g_ndc) { const float2 v = g_uv_rgb[i]; g_ndc[i] = make_float2(v.x * hw, v.y * hh); }
+    if (g_abs_ndc) { const float2 v = g_abs[i]; g_abs_ndc[i] = make_float2(v.x * hw, v.y * hh); }
+}
+
+#define SPV_TRY_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+}  // namespace
+
+extern "C" {
+
+size_t spv_frame_workspace_bytes(int P, int64_t I_cap, int W, int H, int A) {
+    return carve(nullptr, P, I_cap, W, H, A).total;
+}
+
+int spv_frame_ortho_forward(int P, int W, int H, int A, int K, int64_t I_cap, int cull,
+                            const float *position, const float *scaling, const float *rotation, const float *opacity,
+                            const float *shs, const float *attrs, const float *extr, float nearest, float extent,
+                            float bg_rgb, float *images, int *gs_idx, int *radii, int *status, void *workspace,
+                            size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0 || W <= 0 || H <= 0) return 0;
+    if (A < 0 || 4 + A > 23 || K <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: need 0 <= A <= 19 and K > 0"); return (int)cudaErrorInvalidValue; }
+    FrameWs f = carve(workspace, P, I_cap, W, H, A);
+    if (ws_bytes < f.total) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: workspace too small"); return (int)cudaErrorInvalidValue; }
+    const unsigned g = spv::cdiv(P, kThreads);
+    frame_prep_kernel<<<g, kThreads, 0, s>>>(P, f.dirs);
+    SPV_TRY_RC(spv_project_point_ortho_forward(P, position, extr, W, H, nearest, extent, f.uv, f.depth, stream));
+    visible_kernel<<<g, kThreads, 0, s>>>(P, f.depth, f.vis);
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep", 2));
+    // SH is evaluated for every point (the renderer passes no visibility mask to compute_sh, :272)
+    SPV_CUDA_TRY(cudaMemsetAsync(f.clamped, 1, (size_t)P * 3, s), "spv_frame_ortho_forward");
+    {
+        // all-visible mask for SH: reuse `tiles` storage as a byte mask of ones is not possible (int) -> use clamped trick:
+        // compute_sh takes a visibility array; build an all-ones byte array in the (not yet used) g_dirs scratch.
+        uint8_t *ones = (uint8_t *)f.g_dirs;
+        SPV_CUDA_TRY(cudaMemsetAsync(ones, 1, (size_t)P, s), "spv_frame_ortho_forward");
+        SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, ones, 0, f.rgb, f.clamped, stream));
+    }
+    SPV_TRY_RC(spv_compute_cov3d_forward(P, scaling, rotation, f.vis, f.cov3d, stream));
+    SPV_TRY_RC(spv_ewa_project_ortho_forward(P, f.cov3d, extr, f.uv, W, H, f.vis, f.conic, f.radius, f.tiles, stream));
+    SPV_CUDA_TRY(cudaMemcpyAsync(radii, f.radius, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, s), "spv_frame_ortho_forward");
+    SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
+                                status, f.bin_ws, f.bin_bytes, stream));
+    const int C = 4 + A;
+    pack_features_kernel<<<spv::cdiv((long long)P * C, kThreads), kThreads, 0, s>>>(P, A, f.rgb, f.depth, attrs, f.feature);
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/pack"));
+    return spv_alpha_blend_groups_forward(P, C, W, H, K, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
+                                          bg_rgb, 1.0f, 0.0f, images, f.final_T, f.ncontrib, gs_idx, stream);
+}
+
+int spv_frame_ortho_backward(int P, int W, int H, int A, int64_t I_cap, const float *scaling, const float *rotation,
+                             const float *opacity, const float *shs, const float *extr, float bg_rgb,
+                             const float *dL_dimages, float *dL_dposition, float *dL_dscaling, float *dL_drotation,
+                             float *dL_dopacity, float *dL_dshs, float *dL_dattrs, float *dL_dndc, float *dL_dabs_ndc,
+                             void *workspace, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0 || W <= 0 || H <= 0) return 0;
+    FrameWs f = carve(workspace, P, I_cap, W, H, A);
+    if (ws_bytes < f.total) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_backward: workspace too small"); return (int)cudaErrorInvalidValue; }
+    const int C = 4 + A;
+    const unsigned g = spv::cdiv(P, kThreads);
+    SPV_TRY_RC(spv_alpha_blend_groups_backward(P, C, W, H, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range, bg_rgb,
+                                               1.0f, 0.0f, f.final_T, f.ncontrib, dL_dimages, f.g_uv, f.g_uv_rgb, f.g_abs,
+                                               f.g_conic, dL_dopacity, f.g_feat, f.blend_ws, f.blend_bytes, stream));
+    split_grads_kernel<<<g, kThreads, 0, s>>>(P, A, f.g_feat, f.g_rgb, f.g_depth, dL_dattrs, (const float2 *)f.g_uv_rgb,
+                                              (const float2 *)f.g_abs, (float2 *)dL_dndc, (float2 *)dL_dabs_ndc,
+                                              0.5f * (float)W, 0.5f * (float)H);
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/split"));
+    // colours -> SH coefficients (view direction is a constant: its gradient is discarded)
+    {
+        uint8_t *ones = (uint8_t *)f.bin_ws;   // binning scratch is free again: all-visible mask for SH
+        SPV_CUDA_TRY(cudaMemsetAsync(ones, 1, (size_t)P, s), "spv_frame_ortho_backward");
+        SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, ones, f.clamped, f.g_rgb, 16, dL_dshs, f.g_dirs, stream));
+    }
+    // uv, depth -> position ; conic -> cov3d -> scaling, rotation
+    SPV_TRY_RC(spv_project_point_ortho_backward(P, extr, W, H, f.depth, f.g_uv, f.g_depth, dL_dposition, stream));
+    SPV_TRY_RC(spv_ewa_project_ortho_backward(P, f.cov3d, extr, W, H, f.radius, f.g_conic, f.g_cov3d, stream));
+    return spv_compute_cov3d_backward(P, scaling, rotation, f.vis, f.g_cov3d, dL_dscaling, dL_drotation, stream);
+}
+
+}  // extern "C"

@@ -56,6 +56,95 @@ tile_range_kernel(long long I, const unsigned long long *__restrict__ keys_sorte
     if (k == I - 1) tile_range[cur].y = (int)I;
 }
 
+// ---- exact tile culling + capacity-bounded emission (fused frame path; no host synchronisation) -----------------------
+// The reference bins a splat into every tile of the bounding square of radius ceil(3*sigma_max) (utils.h:17-37); 31 % of
+// those (tile, splat) pairs contain no pixel with alpha >= 1/255 on the DAVIS-shaped workload.  Dropping them cannot change
+// any pixel: a pixel takes a splat only if power >= -tau with tau = ln(255*opacity), i.e. only inside the ellipse
+// q(d) = 0.5*(a dx^2 + c dy^2) + b dx dy <= tau, and the test below keeps every tile whose pixel-centre rectangle
+// intersects that ellipse (minimum of the convex quadratic over the rectangle, with a relative safety margin).
+__device__ __forceinline__ float quad_min_on_segment(float A, float B, float C0, float lo, float hi) {
+    // min over t in [lo,hi] of A t^2 + B t + C0, A >= 0
+    float t = (A > 0.f) ? fminf(fmaxf(-B / (2.f * A), lo), hi) : ((B > 0.f) ? lo : hi);
+    return (A * t + B) * t + C0;
+}
+
+__device__ __forceinline__ bool tile_may_hit(float cx, float cy, float a, float b, float c, float tau, float x0, float y0,
+                                             float x1, float y1) {
+    // rectangle of pixel centres [x0,x1] x [y0,y1]; d = centre - pixel
+    if (cx >= x0 && cx <= x1 && cy >= y0 && cy <= y1) return true;
+    const float dxl = cx - x0, dxh = cx - x1, dyl = cy - y0, dyh = cy - y1;   // dx in [dxh, dxl], dy in [dyh, dyl]
+    // q(dx,dy) = 0.5 a dx^2 + b dx dy + 0.5 c dy^2 ; the minimum over the box lies on its boundary here
+    float m = quad_min_on_segment(0.5f * a, b * dyl, 0.5f * c * dyl * dyl, dxh, dxl);
+    m = fminf(m, quad_min_on_segment(0.5f * a, b * dyh, 0.5f * c * dyh * dyh, dxh, dxl));
+    m = fminf(m, quad_min_on_segment(0.5f * c, b * dxl, 0.5f * a * dxl * dxl, dyh, dyl));
+    m = fminf(m, quad_min_on_segment(0.5f * c, b * dxh, 0.5f * a * dxh * dxh, dyh, dyl));
+    return m <= tau * 1.0005f + 1e-4f;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kThreads)
+cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__restrict__ depth, const int *__restrict__ radius,
+                       const float *__restrict__ conic, const float *__restrict__ opacity, int cull, int W, int H, int gx,
+                       int gy, int *__restrict__ counts, const int *__restrict__ offsets, long long cap,
+                       unsigned long long *__restrict__ keys, int *__restrict__ vals, int *__restrict__ status) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const int r = radius[i];
+    int n = 0;
+    if (r > 0) {
+        int x0, y0, x1, y1;
+        const float2 c = uv[i];
+        spv::tile_rect(c.x, c.y, r, gx, gy, x0, y0, x1, y1);
+        const float o = opacity[i];
+        const float ka = conic[3 * i], kb = conic[3 * i + 1], kc = conic[3 * i + 2];
+        const float tau = __logf(255.f * o);   // alpha = min(.99, o G) >= 1/255  <=>  o G >= 1/255  <=>  power >= -ln(255 o)
+        const bool any = !cull || (o * 255.f >= 0.999f);
+        long long cur = 0;
+        unsigned long long dbits = 0;
+        if (EMIT) {
+            cur = (i == 0) ? 0 : offsets[i - 1];
+            dbits = (unsigned long long)__float_as_uint(depth[i]);
+        }
+        if (any)
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) {
+                    if (cull) {
+                        const float px0 = (float)(x * 16), py0 = (float)(y * 16);
+                        const float px1 = fminf(px0 + 15.f, (float)(W - 1)), py1 = fminf(py0 + 15.f, (float)(H - 1));
+                        if (!tile_may_hit(c.x, c.y, ka, kb, kc, tau, px0, py0, px1, py1)) continue;
+                    }
+                    if (EMIT) {
+                        if (cur + n < cap) {
+                            keys[cur + n] = ((unsigned long long)(y * gx + x) << 32) | dbits;
+                            vals[cur + n] = i;
+                        }
+                    }
+                    ++n;
+                }
+    }
+    if (!EMIT) counts[i] = n;
+    if (EMIT && i == P - 1) {
+        const long long total = (long long)offsets[P - 1];
+        status[0] = (int)(total < cap ? total : cap);
+        status[1] = total > cap ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+tile_range_dev_kernel(long long cap, const int *__restrict__ status, const unsigned long long *__restrict__ keys_sorted,
+                      int2 *__restrict__ tile_range) {
+    const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long I = status[0];
+    if (k >= I || k >= cap) return;
+    const int cur = (int)(keys_sorted[k] >> 32);
+    if (k == 0) tile_range[cur].x = 0;
+    else {
+        const int prev = (int)(keys_sorted[k - 1] >> 32);
+        if (prev != cur) { tile_range[prev].y = (int)k; tile_range[cur].x = (int)k; }
+    }
+    if (k == I - 1) tile_range[cur].y = (int)I;
+}
+
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 inline int key_end_bit(int ntiles) {
@@ -122,6 +211,59 @@ int spv_sort_gaussian(int P, int64_t I, const float *uv, const float *depth, con
     tile_range_kernel<<<spv::cdiv(I, kThreads), kThreads, 0, s>>>((long long)I, keys_out, (int2 *)tile_range);
     // CUB onesweep: histogram + exclusive-sum + one kernel per 8-bit digit
     return spv::check_launch("spv_sort_gaussian/range", 1 + 2 + (key_end_bit(gx * gy) + 7) / 8);
+}
+
+// ---- capacity-bounded binning without host synchronisation (fused frame path) -------------------------------------
+size_t spv_bin_capacity_workspace_bytes(int P, int64_t I_cap) {
+    if (I_cap <= 0) I_cap = 1;
+    size_t scan = 0;
+    cub::DeviceScan::InclusiveSum((void *)nullptr, scan, (const int *)nullptr, (int *)nullptr, P > 0 ? P : 1);
+    size_t temp = sort_temp_bytes(I_cap);
+    if (scan > temp) temp = scan;
+    return align_up(8 * (size_t)I_cap) * 2 + align_up(4 * (size_t)I_cap) + align_up(4 * (size_t)(P > 0 ? P : 1)) * 2 +
+           align_up(temp);
+}
+
+/* Bins the splats of one frame with at most I_cap intersections.  status[0] = number of intersections kept,
+ * status[1] = 1 if I_cap was too small (device memory, read it asynchronously).  cull != 0 enables exact tile culling. */
+int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
+                     const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
+                     void *workspace, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H);
+    SPV_CUDA_TRY(cudaMemsetAsync(tile_range, 0, sizeof(int) * 2 * (size_t)gx * gy, s), "spv_bin_capacity");
+    SPV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * 2, s), "spv_bin_capacity");
+    if (P <= 0 || I_cap <= 0) return 0;
+    if (I_cap >= (1ll << 31)) { spv::set_error(cudaErrorInvalidValue, "spv_bin_capacity: capacity too large"); return (int)cudaErrorInvalidValue; }
+    if (ws_bytes < spv_bin_capacity_workspace_bytes(P, I_cap)) { spv::set_error(cudaErrorInvalidValue, "spv_bin_capacity: workspace too small"); return (int)cudaErrorInvalidValue; }
+    char *w = (char *)workspace;
+    unsigned long long *keys_in = (unsigned long long *)w; w += align_up(8 * (size_t)I_cap);
+    unsigned long long *keys_out = (unsigned long long *)w; w += align_up(8 * (size_t)I_cap);
+    int *vals_in = (int *)w; w += align_up(4 * (size_t)I_cap);
+    int *counts = (int *)w; w += align_up(4 * (size_t)P);
+    int *offsets = (int *)w; w += align_up(4 * (size_t)P);
+    size_t scan = 0;
+    cub::DeviceScan::InclusiveSum((void *)nullptr, scan, counts, offsets, P);
+    size_t temp = sort_temp_bytes(I_cap);
+    const unsigned g = spv::cdiv(P, kThreads);
+    cull_count_emit_kernel<false><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx,
+                                                        gy, counts, nullptr, (long long)I_cap, nullptr, nullptr, nullptr);
+    int rc = spv::check_launch("spv_bin_capacity/count");
+    if (rc) return rc;
+    SPV_CUDA_TRY(cub::DeviceScan::InclusiveSum((void *)w, scan, counts, offsets, P, s), "spv_bin_capacity/scan");
+    // unused slots keep an all-ones key: they sort behind every real (tile, depth) key
+    SPV_CUDA_TRY(cudaMemsetAsync(keys_in, 0xFF, 8 * (size_t)I_cap, s), "spv_bin_capacity");
+    cull_count_emit_kernel<true><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
+                                                       nullptr, offsets, (long long)I_cap, keys_in, vals_in, status);
+    rc = spv::check_launch("spv_bin_capacity/emit", 3);
+    if (rc) return rc;
+    int tb = 1;
+    while ((1 << tb) < gx * gy + 1) ++tb;   // room for the all-ones sentinel above the largest tile id
+    SPV_CUDA_TRY(cub::DeviceRadixSort::SortPairs((void *)w, temp, (const unsigned long long *)keys_in, keys_out,
+                                                 (const int *)vals_in, idx_sorted, (int)I_cap, 0, 32 + tb, s),
+                 "spv_bin_capacity/sort");
+    tile_range_dev_kernel<<<spv::cdiv(I_cap, kThreads), kThreads, 0, s>>>((long long)I_cap, status, keys_out, (int2 *)tile_range);
+    return spv::check_launch("spv_bin_capacity/range", 1 + 2 + (32 + tb + 7) / 8);
 }
 
 }  // extern "C"

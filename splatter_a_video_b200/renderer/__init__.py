@@ -121,10 +121,16 @@ class DPTROrthoEnhancedRender(_BaseRender):
     -> RGB blend with first-K ids -> depth blend (bg 1) -> attribute blend (bg 0, opacity detached)."""
 
     fused_default = False
+    frame_default = False
 
     def __init__(self, cfg=None, white_bg: bool = False, device="cuda", **kwargs):
         super().__init__(cfg, white_bg, device, **kwargs)
         self.fused = bool(self.cfg.pop("fused", self.fused_default))
+        self.frame = bool(self.cfg.pop("frame", self.frame_default))
+        self.cull = bool(self.cfg.pop("cull", True))
+        self.capacity = None          # gs.frame.Capacity, created on first use
+        self.observe_capacity = True  # set False while capturing a CUDA graph
+        self.last_status = None
 
     def project_point(self, xyz, extr, W, H, nearest: float = 0.2, extent: float = 1.3):
         """Called directly by the trainer too (src/trainer_fragGS.py:781-793)."""
@@ -135,6 +141,8 @@ class DPTROrthoEnhancedRender(_BaseRender):
                     scaling_modifier=1.0, render_xyz=False, **kwargs) -> dict:
         dev = position.device
         extr = extrinsic_matrix.to(dev)
+        if self.frame and kwargs.get("enable_ortho_projection", True) and shs.shape[1] == 16:
+            return self._render_iter_frame(height, width, extr, position, opacity, scaling, rotation, shs, **kwargs)
         direction = torch.zeros_like(position)
         direction[:, 2] = 1.0
         rgb = _gs.compute_sh(shs, 3, direction)
@@ -182,10 +190,48 @@ class DPTROrthoEnhancedRender(_BaseRender):
                 "visibility_filter": radius > 0, "radii": radius, "gs_idx": gs_idx}
 
 
+    # --- one-call-per-frame path (gs.frame): no host sync, exact tile culling, CUDA-graph capturable
+    def _render_iter_frame(self, height, width, extr, position, opacity, scaling, rotation, shs, **kwargs):
+        from ..gs import frame as _frame
+        P = position.shape[0]
+        attr_names = kwargs.get("render_attributes_list", [])
+        attrs = RenderFeatures(**{x: kwargs[x] for x in attr_names}) if len(attr_names) > 0 else None
+        if attrs is not None and attrs.combine().shape[1] > 19:
+            raise ValueError("the fused frame path handles at most 19 attribute channels")
+        if self.capacity is None:
+            self.capacity = _frame.Capacity(initial=8 * P)
+        cap = self.capacity
+        first = cap.last_I == 0 and self.observe_capacity
+        ndc = torch.zeros(P, 2, device=position.device, requires_grad=True)
+        abs_ndc = torch.zeros(P, 2, device=position.device, requires_grad=True)
+        bg_color = kwargs.get("bg_color", self.bg_color)
+        while True:
+            images, gs_idx, radii, status = _frame.render_ortho_frame(
+                position, scaling, rotation, opacity, shs, attrs.combine() if attrs is not None else None, extr, width, height,
+                kwargs.get("num_idx", 10), bg_color, cap.I_cap, self.cull, 0.01, 1.3, ndc, abs_ndc)
+            self.last_status = status
+            if not self.observe_capacity:
+                break
+            cap.observe(status)
+            if cap.check(wait=first):
+                if first and cap.last_I > 0:   # first frame: settle on measured size + slack
+                    cap.I_cap = int(cap.slack * cap.last_I) + 4096
+                break
+            first = True                        # overflow: capacity has grown, render again
+        split = {"rgb": images[:3], "depth": images[3:4]}
+        if attrs is not None:
+            split.update(attrs.split(images[4:]))
+        return {"rendered_features_split": split,
+                "viewspace_points": abs_ndc if self.cfg["densify_abs_grad_enable"] else ndc,
+                "visibility_filter": radii > 0, "radii": radii, "gs_idx": gs_idx}
+
+
 @RENDERER_REGISTRY.register()
 class DPTROrthoEnhancedRenderB200(DPTROrthoEnhancedRender):
-    """Same contract, fused single-traversal blending (new registry name; the reference classes stay selectable)."""
+    """Same contract through the fused per-frame entry points (new registry name; the reference classes stay selectable).
+    cfg: frame (default True) -> one C call per frame; fused -> single-traversal blending on the staged ops; cull."""
     fused_default = True
+    frame_default = True
 
 
 @RENDERER_REGISTRY.register()

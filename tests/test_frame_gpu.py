@@ -1,0 +1,152 @@
+"""-m gpu: the fused per-frame path (one C call forward, one backward, no host sync, exact tile culling) against the staged
+`dptr.gs` op sequence (already pinned to the oracle / reference by the other suites), the deformation op against torch,
+and CUDA-graph replay of a whole step against eager execution."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as Hh
+from helpers import n
+from splatter_a_video_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ATTRS = ["track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
+LEAVES = ["position", "opacity", "scaling", "rotation", "shs", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
+
+
+def _batch(sc, dev, K=20):
+    return {"height": sc.H, "width": sc.W, "extrinsic_matrix": sc.extr.to(dev), "intrinsic_matrix": sc.intr.to(dev),
+            "camera_center": torch.zeros(3, device=dev), "render_attributes_list": list(ATTRS), "num_idx": K}
+
+
+def _rd(sc, dev, frame=0):
+    d = {"position": sc.frame_position(frame), "opacity": sc.opacity, "scaling": sc.scaling, "rotation": sc.rotation, "shs": sc.shs,
+         "track_gs": sc.frame_position(frame + 1), "mask_attribute": sc.attrs["mask_attribute"],
+         "pos_poly_feat": sc.attrs["pos_poly_feat"], "dino_attribute": sc.attrs["dino_attribute"]}
+    return {k: v.to(dev).clone().requires_grad_(True) for k, v in d.items()}
+
+
+def _run(rnd, sc, dev, gimgs):
+    rd = _rd(sc, dev)
+    out = rnd.render_batch(rd, [_batch(sc, dev)])
+    keys = ["rgb", "depth"] + ATTRS
+    torch.autograd.backward([out[k][0] for k in keys], [gimgs[k] for k in keys])
+    return out, rd
+
+
+@pytest.mark.parametrize("P,W,H", [(1000, 64, 64), (40_000, 333, 250)])
+@pytest.mark.parametrize("cull", [False, True])
+def test_frame_path_equals_staged_ops(cuda, P, W, H, cull):
+    from splatter_a_video_b200.renderer import parse_renderer
+    sc = synth.make_scene(P, 6, W, H, seed=3)
+    g = torch.Generator().manual_seed(1)
+    chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
+    gimgs = {k: torch.randn(c, H, W, generator=g).to(cuda) for k, c in chans.items()}
+    staged = parse_renderer({"name": "DPTROrthoEnhancedRender"}, white_bg=False, device=cuda)
+    frame = parse_renderer({"name": "DPTROrthoEnhancedRenderB200", "cull": cull}, white_bg=False, device=cuda)
+    o1, r1 = _run(staged, sc, cuda, gimgs)
+    o2, r2 = _run(frame, sc, cuda, gimgs)
+    for k in ["rgb", "depth"] + ATTRS:
+        assert float((o1[k] - o2[k]).abs().max()) <= 1e-6, k     # same kernels, shorter lists: images must not move
+    assert torch.equal(o1["gs_idx"], o2["gs_idx"]) and torch.equal(o1["radii"], o2["radii"]) and torch.equal(o1["visibility"], o2["visibility"])
+    for k in LEAVES:
+        Hh.assert_grad_close(n(r2[k].grad), n(r1[k].grad), f"frame d/d{k}", norm_tol=2e-5)
+    Hh.assert_grad_close(n(o2["viewspace_points"][0].grad), n(o1["viewspace_points"][0].grad), "ndc.grad", norm_tol=2e-5)
+    st = frame.last_status.cpu()
+    assert int(st[1]) == 0
+    if cull:
+        from splatter_a_video_b200 import gs
+        assert int(st[0]) < 0.95 * int(frame.capacity.I_cap)   # lists got shorter than the un-culled count + slack
+
+
+def test_capacity_overflow_recovers(cuda):
+    from splatter_a_video_b200.gs.frame import Capacity
+    from splatter_a_video_b200.renderer import parse_renderer
+    sc = synth.make_scene(5000, 4, 128, 96, seed=9)
+    ref = parse_renderer({"name": "DPTROrthoEnhancedRender"}, white_bg=False, device=cuda)
+    small = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+    small.capacity = Capacity(initial=100)          # far too small: must grow and re-render
+    rd = {k: v.detach() for k, v in _rd(sc, cuda).items()}
+    o1 = ref.render_batch(dict(rd), [_batch(sc, cuda)])
+    o2 = small.render_batch(dict(rd), [_batch(sc, cuda)])
+    assert small.capacity.I_cap > 100
+    assert float((o1["rgb"] - o2["rgb"]).abs().max()) <= 1e-6 and torch.equal(o1["gs_idx"], o2["gs_idx"])
+
+
+def test_deform_position_matches_reference_formula(cuda):
+    from splatter_a_video_b200.gs.frame import deform_position, spline_interval
+    P, T = 3000, 50
+    NI = -(-T // 5)
+    g = torch.Generator().manual_seed(4)
+    base = torch.randn(P, 3, generator=g)
+    node = 0.1 * torch.randn(P, 4 * NI * 3, generator=g)
+    for time in (0, 1, 7, 24, 25, 49):
+        idx, dist = spline_interval(time, T, NI)
+        # the reference formula on CPU (dynamic_gaussian_with_base_point_cloud.py:239-250)
+        cpu_node = node.clone().requires_grad_(True)
+        coeff = cpu_node.reshape(-1, 4, NI, 3)
+        want = coeff[:, 3, idx] + coeff[:, 2, idx] * dist + coeff[:, 1, idx] * dist ** 2 + coeff[:, 0, idx] * dist ** 3 + base
+        gnode = node.to(cuda).requires_grad_(True)
+        got = deform_position(base.to(cuda), gnode, torch.tensor([idx], dtype=torch.int32, device=cuda),
+                              torch.tensor([dist], dtype=torch.float32, device=cuda), NI)
+        np.testing.assert_allclose(n(got), want.detach().numpy(), rtol=1e-6, atol=1e-6)
+        gp = torch.randn(P, 3, generator=g)
+        want.backward(gp); got.backward(gp.to(cuda))
+        np.testing.assert_allclose(n(gnode.grad), cpu_node.grad.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_cuda_graph_replay_of_a_full_step(cuda):
+    """No host synchronisation on the frame path => a whole forward+backward captures into a CUDA graph and replays for
+    other frames by updating two device scalars."""
+    from splatter_a_video_b200.gs.frame import deform_position, spline_interval
+    from splatter_a_video_b200.renderer import parse_renderer
+    P, W, H, T = 8000, 160, 128, 20
+    NI = -(-T // 5)
+    sc = synth.make_scene(P, T, W, H, seed=2).to(cuda)
+    g = torch.Generator().manual_seed(7)
+    node = (0.02 * torch.randn(P, 4 * NI * 3, generator=g)).to(cuda).requires_grad_(True)
+    leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("opacity", "scaling", "rotation", "shs")}
+    idx_dev = torch.zeros(1, dtype=torch.int32, device=cuda); dist_dev = torch.zeros(1, device=cuda)
+    gimg = torch.randn(4, H, W, generator=g).to(cuda)
+    rnd = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+    batch = {"height": H, "width": W, "extrinsic_matrix": sc.extr, "intrinsic_matrix": sc.intr, "camera_center": torch.zeros(3, device=cuda),
+             "num_idx": 8}
+
+    def step():
+        for p in [node, *leaves.values()]:
+            p.grad = None
+        pos = deform_position(sc.position, node, idx_dev, dist_dev, NI)
+        out = rnd.render_batch({"position": pos, **leaves}, [dict(batch)])
+        torch.autograd.backward([out["rgb"][0], out["depth"][0]], [gimg[:3], gimg[3:]])
+        return out["rgb"]
+
+    def set_frame(t):
+        i, d = spline_interval(t, T, NI)
+        idx_dev.fill_(i); dist_dev.fill_(d)
+
+    set_frame(3)
+    step()                                   # settles the capacity (one sync, outside the graph)
+    rnd.capacity.I_cap = int(rnd.capacity.I_cap * 1.5)
+    rnd.observe_capacity = False
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        img_static = step()
+    grads_static = {"node": node.grad, **{k: v.grad for k, v in leaves.items()}}
+    for t in (11, 0, 19):
+        set_frame(t)
+        graph.replay()
+        torch.cuda.synchronize()
+        got_img = img_static.clone(); got = {k: v.clone() for k, v in grads_static.items()}
+        assert int(rnd.last_status.cpu()[1]) == 0
+        eager_img = step().clone()
+        want = {"node": node.grad.clone(), **{k: v.grad.clone() for k, v in leaves.items()}}
+        assert float((got_img - eager_img).abs().max()) <= 1e-6
+        for k in want:
+            Hh.assert_grad_close(n(got[k]), n(want[k]), f"graph replay d/d{k}", norm_tol=2e-5)
