@@ -111,6 +111,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(key):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]["bytes"]
+    except Exception:
+        return None
+
+
 def blend_bwd_algorithmic_bytes(I, C, H, W, P):
     """reads I*(28+4C) + H*W*(4C+8); writes P*4*(2+2+3+1+C)."""
     return I * (28 + 4 * C) + H * W * (4 * C + 8) + P * 4 * (8 + C)
@@ -497,7 +505,9 @@ def run_ours(args):
         "render_fps": world * args.steps / (fps_ms * 1e-3),
         "render_fps_e2e": {"value": world * args.steps / (fps_e2e_ms * 1e-3), "d2h_bytes_per_frame": 3 * wl.H * wl.W * 4},
         "roofline": {"bound": "hbm", "kernel": f"spv_alpha_blend_{'backward' if 'bwd' in dom else 'forward'} ({pname} pass, C={info[pname]['C']})",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": ncu_traffic(("blend_groups_" if "fused" in dom else "blend_") + ("backward" if "bwd" in dom else "forward")),
+                     "peak_source": peak_src,
                      "algorithmic_bytes": abytes, "ms": stages[dom]},
         "stages_ms": stages,
         "clocks": clocks,
