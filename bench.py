@@ -180,6 +180,11 @@ class Workload:
         self.loss_host = torch.empty(1).pin_memory()
         self.use_graph = bool(graph) and mode == "frame"
         self.graphs = {}
+        # frame mode: the fused backward writes these gradients straight into their slices of the flat buffer
+        self.sink_names = ["scaling", "rotation", "opacity", "shs"] if mode == "frame" else []
+        self.sinks = self.flat.grad_sinks(self.sink_names) if self.sink_names else None
+        self.node_sink = self.flat.params["pos_cubic_node"].grad if mode == "frame" else None
+        self.autograd_names = [k for k in self.flat.names if k not in self.sink_names and not (mode == "frame" and k == "pos_cubic_node")]
 
     # ---- per-step pieces -------------------------------------------------------------------------------------------
     def set_frame(self, frame):
@@ -190,21 +195,27 @@ class Workload:
     def render_dict(self):
         from splatter_a_video_b200.gs.frame import deform_position
         p = self.flat.params
-        pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI)
+        pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI, self.node_sink)
         with torch.no_grad():
             track = deform_position(self.base, p["pos_cubic_node"], self.idx2, self.dist2, self.NI)
         return {"position": pos, "opacity": p["opacity"], "scaling": p["scaling"], "rotation": p["rotation"], "shs": p["shs"],
                 "track_gs": track, "mask_attribute": p["mask_attribute"], "pos_poly_feat": self.pos_poly_feat,
                 "dino_attribute": p["dino_attribute"]}
 
+    def _batch(self):
+        b = dict(self.batch)
+        if self.sinks:
+            b["grad_sinks"] = self.sinks
+        return b
+
     def _fwd_bwd_resident(self):
-        self.flat.zero_grad()
-        out = self.renderer.render_batch(self.render_dict(), [dict(self.batch)])
+        self.flat.zero_grad(self.autograd_names if self.sinks else None)
+        out = self.renderer.render_batch(self.render_dict(), [self._batch()])
         torch.autograd.backward([out[k][0] for k in self.KEYS], [self.g_dev[k] for k in self.KEYS])
 
     def _fwd_bwd_from_staged_host_data(self):
-        self.flat.zero_grad()
-        out = self.renderer.render_batch(self.render_dict(), [dict(self.batch)])
+        self.flat.zero_grad(self.autograd_names if self.sinks else None)
+        out = self.renderer.render_batch(self.render_dict(), [self._batch()])
         imgs = torch.cat([out[k][0] for k in self.KEYS], 0)                   # [23,H,W]
         diff = imgs.detach().clone()
         diff[:3] -= self.gt_dev
@@ -447,13 +458,16 @@ def run_ours(args):
     flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=device)
     frames_of = lambda i: frame_for_step(i, rank, world, wl.frames)
 
+    # spline coefficients: each rank's gradient lives in one interval -> exchanged as N slices, the rest all-reduced
+    sparse = {"pos_cubic_node": ((wl.P, 4, wl.NI, 3), 2, wl.idx1)}
+
     def train_step(frame):
         wl.step_resident(frame)
-        wl.flat.allreduce_grads()
+        wl.flat.allreduce_grads(sparse=sparse)
 
     def train_step_e2e(frame):
         wl.step_e2e(frame)
-        wl.flat.allreduce_grads()
+        wl.flat.allreduce_grads(sparse=sparse)
 
     if args.profile_mode:
         time_steps(train_step, args.steps, args.warmup, None, world, rank, frames_of)

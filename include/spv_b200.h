@@ -170,6 +170,11 @@ SPV_API int spv_deform_spline_forward(int P, int NI, const float *base, const fl
 SPV_API int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *dist_dev, const float *dL_dpos,
                                float *dL_dcoeff /*[P,4,NI,3]*/, int accumulate, void *stream);
 
+/* ---- Fused Adam over the flat parameter buffer (next row f-3, optimizer half; torch.optim.Adam arithmetic) ---------- */
+SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,
+                  const long long *seg_end_host, const float *seg_lr_host, float beta1, float beta2, float eps, int step,
+                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

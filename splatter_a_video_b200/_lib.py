@@ -55,6 +55,7 @@ _SIGS = {
                                          P_, P_, P_, P_, P_, c_size_t, P_]),
     "spv_deform_spline_forward": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_]),
     "spv_deform_spline_backward": (c_int, [c_int, c_int, P_, P_, P_, P_, c_int, P_]),
+    "spv_adam_step": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, c_int, P_]),
 }
 
 EXPORTED = sorted(_SIGS)

@@ -516,18 +516,63 @@ __constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.3153
 __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                                -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
 
+// SH kernels move 192 B (deg 3) per Gaussian each way -- the fattest per-Gaussian stream.  A
+// thread-per-Gaussian access pattern strides by 192 B, so the coefficient rows go through shared memory: the CTA's
+// contiguous [128 x NB*3] slab is loaded / stored with coalesced 16-byte accesses and each thread works on its own row
+// (row pitch NB*3+1 words: conflict-free).  The arithmetic is unchanged (bit-exact against the oracle).
+constexpr int kShThreads = 128;     // forward: one 25 KB slab
+constexpr int kShBwdThreads = 64;   // backward: coefficient slab + gradient slab
+
+template <int ROW, int NT>
+__device__ __forceinline__ void sh_slab_load(const float *__restrict__ g, float *s, int rows_valid) {
+    const int nfl = rows_valid * ROW;                       // floats in this CTA's slab
+    const float4 *g4 = reinterpret_cast<const float4 *>(g); // slab base is 16-byte aligned (128*ROW*4 bytes per CTA)
+    for (int q = threadIdx.x; q * 4 < nfl; q += NT) {
+        float v[4];
+        if (q * 4 + 3 < nfl) { const float4 t = g4[q]; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else { for (int k = 0; k < 4; ++k) v[k] = (q * 4 + k < nfl) ? g[q * 4 + k] : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = q * 4 + k;
+            if (e < nfl) s[(e / ROW) * (ROW + 1) + e % ROW] = v[k];
+        }
+    }
+}
+
+template <int ROW, int NT>
+__device__ __forceinline__ void sh_slab_store(float *__restrict__ g, const float *s, int rows_valid) {
+    const int nfl = rows_valid * ROW;
+    float4 *g4 = reinterpret_cast<float4 *>(g);
+    for (int q = threadIdx.x; q * 4 < nfl; q += NT) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = q * 4 + k;
+            v[k] = e < nfl ? s[(e / ROW) * (ROW + 1) + e % ROW] : 0.f;
+        }
+        if (q * 4 + 3 < nfl) g4[q] = make_float4(v[0], v[1], v[2], v[3]);
+        else { for (int k = 0; k < 4; ++k) if (q * 4 + k < nfl) g[q * 4 + k] = v[k]; }
+    }
+}
+
 template <int DEG>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kShThreads)
 sh_fwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ dirs,
               const uint8_t *__restrict__ visible, int free_variant, float *__restrict__ colors,
               uint8_t *__restrict__ clamped) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
-    const int i = blockIdx.x * kThreads + threadIdx.x;
+    constexpr int ROW = NB * 3;
+    __shared__ float s_sh[kShThreads * (ROW + 1)];
+    const int base = blockIdx.x * kShThreads;
+    const int rows = min(kShThreads, P - base);
+    sh_slab_load<ROW, kShThreads>(shs + (size_t)base * ROW, s_sh, rows);
+    __syncthreads();
+    const int i = base + threadIdx.x;
     if (i >= P) return;
     float out[3] = {0.f, 0.f, 0.f};
     uint8_t cl[3] = {1, 1, 1};  // torch::ones for rows the kernel skips (compute_sh.cu:245)
     if (visible[i]) {
-        const float *sh = shs + (size_t)i * NB * 3;
+        const float *sh = s_sh + threadIdx.x * (ROW + 1);
         const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -563,62 +608,74 @@ sh_fwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
 }
 
 template <int DEG>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kShBwdThreads)
 sh_bwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ dirs,
               const uint8_t *__restrict__ visible, const uint8_t *__restrict__ clamped,
               const float *__restrict__ dL_dcolors, float *__restrict__ dL_dshs, float *__restrict__ dL_ddirs) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P) return;
+    constexpr int ROW = NB * 3;
+    __shared__ float s_sh[kShBwdThreads * (ROW + 1)];
+    __shared__ float s_g[kShBwdThreads * (ROW + 1)];
+    const int base = blockIdx.x * kShBwdThreads;
+    const int rows = min(kShBwdThreads, P - base);
+    sh_slab_load<ROW, kShBwdThreads>(shs + (size_t)base * ROW, s_sh, rows);
+    __syncthreads();
+    const int i = base + threadIdx.x;
     float gdir[3] = {0.f, 0.f, 0.f};
-    if (visible[i]) {
-        const float *sh = shs + (size_t)i * NB * 3;
-        float *dsh = dL_dshs + (size_t)i * NB * 3;
-        const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
+    if (i < P) {
+        float *dsh = s_g + threadIdx.x * (ROW + 1);
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float g = dL_dcolors[3 * i + ch];
-            if (clamped) g *= clamped[3 * i + ch] ? 0.0f : 1.0f;
+        for (int k = 0; k < ROW; ++k) dsh[k] = 0.f;     // invisible rows stay zero (torch::zeros in the reference)
+        if (visible[i]) {
+            const float *sh = s_sh + threadIdx.x * (ROW + 1);
+            const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float g = dL_dcolors[3 * i + ch];
+                if (clamped) g *= clamped[3 * i + ch] ? 0.0f : 1.0f;
 #define S(k) sh[(k) * 3 + ch]
 #define DS(k) dsh[(k) * 3 + ch]
-            float dx = 0, dy = 0, dz = 0;
-            DS(0) = SH_C0 * g;
-            if (DEG > 0) {
-                DS(1) = (-SH_C1 * y) * g; DS(2) = (SH_C1 * z) * g; DS(3) = (-SH_C1 * x) * g;
-                dx = -SH_C1 * S(3); dy = -SH_C1 * S(1); dz = SH_C1 * S(2);
-                if (DEG > 1) {
-                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                    DS(4) = (SH_C2[0] * xy) * g; DS(5) = (SH_C2[1] * yz) * g;
-                    DS(6) = (SH_C2[2] * (2.f * zz - xx - yy)) * g;
-                    DS(7) = (SH_C2[3] * xz) * g; DS(8) = (SH_C2[4] * (xx - yy)) * g;
-                    dx += SH_C2[0] * y * S(4) + SH_C2[2] * 2.f * -x * S(6) + SH_C2[3] * z * S(7) + SH_C2[4] * 2.f * x * S(8);
-                    dy += SH_C2[0] * x * S(4) + SH_C2[1] * z * S(5) + SH_C2[2] * 2.f * -y * S(6) + SH_C2[4] * 2.f * -y * S(8);
-                    dz += SH_C2[1] * y * S(5) + SH_C2[2] * 2.f * 2.f * z * S(6) + SH_C2[3] * x * S(7);
-                    if (DEG > 2) {
-                        DS(9) = (SH_C3[0] * y * (3.f * xx - yy)) * g; DS(10) = (SH_C3[1] * xy * z) * g;
-                        DS(11) = (SH_C3[2] * y * (4.f * zz - xx - yy)) * g;
-                        DS(12) = (SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g;
-                        DS(13) = (SH_C3[4] * x * (4.f * zz - xx - yy)) * g;
-                        DS(14) = (SH_C3[5] * z * (xx - yy)) * g; DS(15) = (SH_C3[6] * x * (xx - 3.f * yy)) * g;
-                        dx += (SH_C3[0] * S(9) * 3.f * 2.f * xy + SH_C3[1] * S(10) * yz + SH_C3[2] * S(11) * -2.f * xy +
-                               SH_C3[3] * S(12) * -3.f * 2.f * xz + SH_C3[4] * S(13) * (-3.f * xx + 4.f * zz - yy) +
-                               SH_C3[5] * S(14) * 2.f * xz + SH_C3[6] * S(15) * 3.f * (xx - yy));
-                        dy += (SH_C3[0] * S(9) * 3.f * (xx - yy) + SH_C3[1] * S(10) * xz +
-                               SH_C3[2] * S(11) * (-3.f * yy + 4.f * zz - xx) + SH_C3[3] * S(12) * -3.f * 2.f * yz +
-                               SH_C3[4] * S(13) * -2.f * xy + SH_C3[5] * S(14) * -2.f * yz +
-                               SH_C3[6] * S(15) * -3.f * 2.f * xy);
-                        dz += (SH_C3[1] * S(10) * xy + SH_C3[2] * S(11) * 4.f * 2.f * yz +
-                               SH_C3[3] * S(12) * 3.f * (2.f * zz - xx - yy) + SH_C3[4] * S(13) * 4.f * 2.f * xz +
-                               SH_C3[5] * S(14) * (xx - yy));
+                float dx = 0, dy = 0, dz = 0;
+                DS(0) = SH_C0 * g;
+                if (DEG > 0) {
+                    DS(1) = (-SH_C1 * y) * g; DS(2) = (SH_C1 * z) * g; DS(3) = (-SH_C1 * x) * g;
+                    dx = -SH_C1 * S(3); dy = -SH_C1 * S(1); dz = SH_C1 * S(2);
+                    if (DEG > 1) {
+                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                        DS(4) = (SH_C2[0] * xy) * g; DS(5) = (SH_C2[1] * yz) * g;
+                        DS(6) = (SH_C2[2] * (2.f * zz - xx - yy)) * g;
+                        DS(7) = (SH_C2[3] * xz) * g; DS(8) = (SH_C2[4] * (xx - yy)) * g;
+                        dx += SH_C2[0] * y * S(4) + SH_C2[2] * 2.f * -x * S(6) + SH_C2[3] * z * S(7) + SH_C2[4] * 2.f * x * S(8);
+                        dy += SH_C2[0] * x * S(4) + SH_C2[1] * z * S(5) + SH_C2[2] * 2.f * -y * S(6) + SH_C2[4] * 2.f * -y * S(8);
+                        dz += SH_C2[1] * y * S(5) + SH_C2[2] * 2.f * 2.f * z * S(6) + SH_C2[3] * x * S(7);
+                        if (DEG > 2) {
+                            DS(9) = (SH_C3[0] * y * (3.f * xx - yy)) * g; DS(10) = (SH_C3[1] * xy * z) * g;
+                            DS(11) = (SH_C3[2] * y * (4.f * zz - xx - yy)) * g;
+                            DS(12) = (SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g;
+                            DS(13) = (SH_C3[4] * x * (4.f * zz - xx - yy)) * g;
+                            DS(14) = (SH_C3[5] * z * (xx - yy)) * g; DS(15) = (SH_C3[6] * x * (xx - 3.f * yy)) * g;
+                            dx += (SH_C3[0] * S(9) * 3.f * 2.f * xy + SH_C3[1] * S(10) * yz + SH_C3[2] * S(11) * -2.f * xy +
+                                   SH_C3[3] * S(12) * -3.f * 2.f * xz + SH_C3[4] * S(13) * (-3.f * xx + 4.f * zz - yy) +
+                                   SH_C3[5] * S(14) * 2.f * xz + SH_C3[6] * S(15) * 3.f * (xx - yy));
+                            dy += (SH_C3[0] * S(9) * 3.f * (xx - yy) + SH_C3[1] * S(10) * xz +
+                                   SH_C3[2] * S(11) * (-3.f * yy + 4.f * zz - xx) + SH_C3[3] * S(12) * -3.f * 2.f * yz +
+                                   SH_C3[4] * S(13) * -2.f * xy + SH_C3[5] * S(14) * -2.f * yz +
+                                   SH_C3[6] * S(15) * -3.f * 2.f * xy);
+                            dz += (SH_C3[1] * S(10) * xy + SH_C3[2] * S(11) * 4.f * 2.f * yz +
+                                   SH_C3[3] * S(12) * 3.f * (2.f * zz - xx - yy) + SH_C3[4] * S(13) * 4.f * 2.f * xz +
+                                   SH_C3[5] * S(14) * (xx - yy));
+                        }
                     }
                 }
-            }
 #undef S
 #undef DS
-            gdir[0] += dx * g; gdir[1] += dy * g; gdir[2] += dz * g;
+                gdir[0] += dx * g; gdir[1] += dy * g; gdir[2] += dz * g;
+            }
         }
+        dL_ddirs[3 * i] = gdir[0]; dL_ddirs[3 * i + 1] = gdir[1]; dL_ddirs[3 * i + 2] = gdir[2];
     }
-    dL_ddirs[3 * i] = gdir[0]; dL_ddirs[3 * i + 1] = gdir[1]; dL_ddirs[3 * i + 2] = gdir[2];
+    __syncthreads();
+    sh_slab_store<ROW, kShBwdThreads>(dL_dshs + (size_t)base * ROW, s_g, rows);
 }
 
 inline dim3 grid_for(int P) { return dim3(spv::cdiv(P, kThreads)); }
@@ -726,12 +783,12 @@ int spv_compute_sh_forward(int P, const float *shs, int deg, const float *dirs, 
     if (P <= 0) return 0;
     if (deg < 0 || deg > 3) { spv::set_error(cudaErrorInvalidValue, "spv_compute_sh_forward: deg must be 0..3"); return (int)cudaErrorInvalidValue; }
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 g = grid_for(P);
+    dim3 g(spv::cdiv(P, kShThreads));
     switch (deg) {
-        case 0: sh_fwd_kernel<0><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
-        case 1: sh_fwd_kernel<1><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
-        case 2: sh_fwd_kernel<2><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
-        default: sh_fwd_kernel<3><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
+        case 0: sh_fwd_kernel<0><<<g, kShThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
+        case 1: sh_fwd_kernel<1><<<g, kShThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
+        case 2: sh_fwd_kernel<2><<<g, kShThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
+        default: sh_fwd_kernel<3><<<g, kShThreads, 0, s>>>(P, shs, dirs, visible, free_variant, colors, clamped); break;
     }
     return spv::check_launch("spv_compute_sh_forward");
 }
@@ -742,14 +799,18 @@ int spv_compute_sh_backward(int P, const float *shs, int deg, const float *dirs,
     if (P <= 0) return 0;
     if (deg < 0 || deg > 3) { spv::set_error(cudaErrorInvalidValue, "spv_compute_sh_backward: deg must be 0..3"); return (int)cudaErrorInvalidValue; }
     cudaStream_t s = (cudaStream_t)stream;
-    // invisible rows (and the tail when S_alloc > (deg+1)^2) stay zero like torch::zeros in the reference
-    SPV_CUDA_TRY(cudaMemsetAsync(dL_dshs, 0, sizeof(float) * 3 * (size_t)S_alloc * (size_t)P, s), "spv_compute_sh_backward");
-    dim3 g = grid_for(P);
+    // the kernel writes every (deg+1)^2-row (zeros for invisible points); only the tail of an over-allocated gradient
+    // tensor (S_alloc > (deg+1)^2, the reference's stride quirk) needs the torch::zeros-like clear
+    const int nb = (deg + 1) * (deg + 1);
+    if (S_alloc > nb)
+        SPV_CUDA_TRY(cudaMemsetAsync(dL_dshs + (size_t)P * nb * 3, 0, sizeof(float) * 3 * (size_t)(S_alloc - nb) * (size_t)P, s),
+                     "spv_compute_sh_backward");
+    dim3 g(spv::cdiv(P, kShBwdThreads));
     switch (deg) {
-        case 0: sh_bwd_kernel<0><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
-        case 1: sh_bwd_kernel<1><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
-        case 2: sh_bwd_kernel<2><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
-        default: sh_bwd_kernel<3><<<g, kThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
+        case 0: sh_bwd_kernel<0><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
+        case 1: sh_bwd_kernel<1><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
+        case 2: sh_bwd_kernel<2><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
+        default: sh_bwd_kernel<3><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
     }
     return spv::check_launch("spv_compute_sh_backward");
 }

@@ -8,7 +8,7 @@ Works with any torch.distributed backend (NCCL over NVLink on the B200 box, gloo
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Sequence, Tuple
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -37,7 +37,9 @@ class FlatParams:
         self.names = list(tensors)
         self.shapes = {k: tuple(v.shape) for k, v in tensors.items()}
         sizes = [tensors[k].numel() for k in self.names]
+        self.sizes = sizes
         total = sum(sizes)
+        total = (total + 3) // 4 * 4      # float4-friendly tail for the fused optimizer
         dev = next(iter(tensors.values())).device
         self.flat = torch.empty(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -54,20 +56,88 @@ class FlatParams:
     def __getitem__(self, k: str) -> torch.Tensor:
         return self.params[k]
 
-    def zero_grad(self):
-        self.flat_grad.zero_()
+    def zero_grad(self, names: Sequence[str] = None):
+        """Zero the whole flat gradient buffer, or only the named parameters' slices."""
+        if names is None:
+            self.flat_grad.zero_()
+        else:
+            for k in names:
+                self.params[k].grad.zero_()
+
+    def grad_sinks(self, names: Sequence[str]) -> Dict[str, torch.Tensor]:
+        """The named parameters' slices of the flat gradient buffer, for operators that can write gradients in place
+        (gs.frame.render_ortho_frame(grad_sinks=...)): no zero-fill and no accumulation pass for those parameters."""
+        return {k: self.params[k].grad for k in names}
 
     def floats_per_gaussian(self, P: int) -> float:
         return self.flat.numel() / max(P, 1)
 
-    def allreduce_grads(self, average: bool = True, async_op: bool = False):
-        """One collective per step over the whole flat gradient buffer."""
+    def allreduce_grads(self, average: bool = True, async_op: bool = False, sparse: Optional[dict] = None):
+        """The step's gradient exchange: ONE all-reduce over the flat gradient buffer.
+
+        sparse (optional) = {name: (view_shape, dim, index_tensor)} marks parameters whose gradient is non-zero only in
+        ONE slice along `dim` per rank -- the cubic-spline coefficients: a frame touches the 12 coefficients of its own
+        interval out of 4*NI*3 (dynamic_gaussian_with_base_point_cloud.py:239-247).  Those parameters must be the LEADING
+        entries of the flat buffer; their active slices travel through an all-gather (N*P*12 floats instead of
+        P*4*NI*3) and are scatter-added locally, the rest of the buffer is all-reduced.  The result is exactly the dense
+        all-reduce sum."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
-        work = dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, async_op=async_op)
+        world, rank = dist.get_world_size(), dist.get_rank()
+        start = 0
+        if sparse:
+            off = 0
+            for k in self.names:
+                if k not in sparse:
+                    break
+                shape, dim, index = sparse[k]
+                n = self.params[k].numel()
+                g = self.flat_grad[off:off + n].view(shape)
+                idx_all = [torch.empty_like(index) for _ in range(world)]
+                dist.all_gather(idx_all, index)
+                mine = g.index_select(dim, index.to(torch.long)).contiguous()
+                parts = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(parts, mine)
+                for r in range(world):
+                    if r != rank:
+                        g.index_add_(dim, idx_all[r].to(torch.long), parts[r])
+                off += n
+            start = off
+            assert all(k not in sparse for k in self.names[len([k for k in self.names if k in sparse]):]), \
+                "sparse parameters must lead the flat buffer"
+        work = dist.all_reduce(self.flat_grad[start:], op=dist.ReduceOp.SUM, async_op=async_op)
         if average and not async_op:
-            self.flat_grad.div_(dist.get_world_size())
+            self.flat_grad.div_(world)
         return work
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (betas, eps, per-parameter learning rates) as ONE fused kernel over FlatParams
+    (`spv_adam_step`).  Role of the per-attribute param groups of src/pointrix/optimizer/__init__.py:27-62."""
+
+    def __init__(self, flat: FlatParams, lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-15):
+        import ctypes
+        self.flat, self.betas, self.eps = flat, betas, eps
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        ends, off = [], 0
+        for k, n in zip(flat.names, flat.sizes):
+            off += n
+            ends.append(off)
+        ends[-1] = flat.flat.numel()
+        self._ends = (ctypes.c_longlong * len(ends))(*ends)
+        self._lrs = (ctypes.c_float * len(ends))(*[float(lrs[k]) for k in flat.names])
+        self.nseg = len(ends)
+        self.t = 0
+
+    def step(self):
+        from . import _lib as L
+        import ctypes
+        self.t += 1
+        f = self.flat
+        L.call("spv_adam_step", f.flat.numel(), L.ptr(f.flat), L.ptr(f.flat_grad), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+               self.nseg, ctypes.cast(self._ends, ctypes.c_void_p), ctypes.cast(self._lrs, ctypes.c_void_p), float(self.betas[0]),
+               float(self.betas[1]), float(self.eps), int(self.t), L.stream())
 
 
 def reduce_densify_stats(grad_norm_sum: torch.Tensor, visible_count: torch.Tensor, max_radius: torch.Tensor):

@@ -208,7 +208,8 @@ class DPTROrthoEnhancedRender(_BaseRender):
         while True:
             images, gs_idx, radii, status = _frame.render_ortho_frame(
                 position, scaling, rotation, opacity, shs, attrs.combine() if attrs is not None else None, extr, width, height,
-                kwargs.get("num_idx", 10), bg_color, cap.I_cap, self.cull, 0.01, 1.3, ndc, abs_ndc)
+                kwargs.get("num_idx", 10), bg_color, cap.I_cap, self.cull, 0.01, 1.3, ndc, abs_ndc,
+                grad_sinks=kwargs.get("grad_sinks"))
             self.last_status = status
             if not self.observe_capacity:
                 break

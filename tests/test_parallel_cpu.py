@@ -56,6 +56,40 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _sparse_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, NI = 50, 6
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = FlatParams({"node": torch.zeros(P, 4 * NI * 3), "other": torch.zeros(P, 7)})
+    idx = torch.tensor([2 if rank == 0 else 5], dtype=torch.int32)       # each rank touched one interval
+    gn = torch.zeros(P, 4, NI, 3); gn[:, :, int(idx)] = torch.randn(P, 4, 3, generator=g)
+    go = torch.randn(P, 7, generator=g)
+    flat["node"].grad.copy_(gn.reshape(P, -1)); flat["other"].grad.copy_(go)
+    dense = flat.flat_grad.clone()
+    dist.all_reduce(dense)
+    flat.allreduce_grads(average=False, sparse={"node": ((P, 4, NI, 3), 2, idx)})
+    if rank == 0:
+        q.put((flat.flat_grad.numpy().copy(), dense.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sparse_interval_exchange_equals_dense_allreduce():
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, want = q.get(timeout=200)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+
+
 def test_shard_frames_partition():
     for n, w in ((50, 4), (80, 8), (7, 2), (3, 8)):
         seen = []

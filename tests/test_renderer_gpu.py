@@ -130,3 +130,37 @@ def test_full_size_frame_properties_and_oracle(cuda):
                                   fo["final_T"], fo["ncontrib"], g_np)
     for name, got in zip(("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature"), leaves):
         Hh.assert_grad_close(n(got.grad), b[name], f"full-size {name}")
+
+
+def test_diff_gaussian_rasterization_shim(cuda):
+    """Boundary B2 (call site only, parity unpinned): the shim must behave like the B1 perspective pipeline with a colour
+    background, return int radii and deliver screen-space gradients through means2D.grad."""
+    import math
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from splatter_a_video_b200 import gs
+    s = Hh.scene_np(3000, 96, 64, seed=21)
+    W, H = 96, 64
+    fx = fy = W / 2.0
+    view = torch.eye(4)
+    settings = GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=W / (2 * fx), tanfovy=H / (2 * fy),
+                                             bg=torch.tensor([0.2, 0.4, 0.6], device=cuda), scale_modifier=1.0, viewmatrix=view.to(cuda),
+                                             projmatrix=torch.eye(4, device=cuda), sh_degree=3, campos=torch.zeros(3, device=cuda))
+    means3D = t(s["xyz"], cuda).requires_grad_(True)
+    means2D = torch.zeros(s["P"], 3, device=cuda, requires_grad=True)
+    img, radii = GaussianRasterizer(settings)(means3D=means3D, means2D=means2D, shs=t(s["shs"], cuda), colors_precomp=None,
+                                              opacities=t(s["opacity"], cuda), scales=t(s["scaling"], cuda), rotations=t(s["rotation"], cuda),
+                                              cov3D_precomp=None)
+    assert img.shape == (3, H, W) and radii.dtype == torch.int32 and radii.shape == (s["P"],)
+    # same thing through the B1 operators
+    intr = torch.tensor([fx, fy, W / 2.0, H / 2.0], device=cuda)
+    extr = torch.eye(4, device=cuda)[:3]
+    d = means3D.detach(); d = d / d.norm(dim=1, keepdim=True)
+    col = gs.compute_sh(t(s["shs"], cuda), 3, d)
+    ones = torch.ones(s["P"], 1, device=cuda)
+    ref = gs.rasterization(means3D.detach(), t(s["scaling"], cuda), t(s["rotation"], cuda), t(s["opacity"], cuda),
+                           torch.cat([col, ones], 1), intr, extr, W, H, 0.0)
+    want = ref[:3] + (1 - ref[3:4]) * settings.bg.reshape(3, 1, 1)
+    assert float((img - want).abs().max()) <= 1e-6
+    img.sum().backward()
+    assert means2D.grad is not None and float(means2D.grad[:, :2].abs().sum()) > 0 and float(means2D.grad[:, 2].abs().sum()) == 0
+    assert torch.isfinite(means3D.grad).all()
