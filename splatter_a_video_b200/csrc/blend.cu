@@ -257,11 +257,12 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     constexpr int kG = (NV == 64) ? 16 : 32;       // Gaussians per chunk (keeps s_part at <= 34 KB)
     constexpr int kRow = GROUPS ? kRowG : NV;       // packed row stride in global memory
     constexpr int kSP = GROUPS ? 33 : NV;           // per-warp parking row in shared memory
+    constexpr int FS = (CH + 3) & ~3;               // feature row pitch: 16-byte rows -> LDS.128 broadcasts
     __shared__ float4 s_g0[kG];
     __shared__ float4 s_g1[kG];
     __shared__ float4 s_con[kG];                    // unscaled conic a,b,c for the gradient formulas
     __shared__ int s_id[kG];
-    __shared__ __align__(16) float s_feat[kG * CH];
+    __shared__ __align__(16) float s_feat[kG * FS];
     __shared__ float s_part[8][kG][kSP];
     __shared__ int s_max;
 
@@ -317,11 +318,11 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
             s_con[threadIdx.x] = make_float4(a, b, c, 0.f);
         }
         __syncthreads();
-        if (lane < CH) {  // padding channels (C <= c < CH) are zero-filled: they meet d[c] == 0 but must stay finite
+        if (lane < FS) {  // padding channels (C <= c < FS) are zero-filled: they meet d[c] == 0 but must stay finite
 #pragma unroll
             for (int jj = 0; jj < kG / 8; ++jj) {
                 const int j = warp * (kG / 8) + jj;
-                if (j < m) s_feat[j * CH + lane] = lane < C ? feature[(size_t)s_id[j] * Cstride + c0 + lane] : 0.f;
+                if (j < m) s_feat[j * FS + lane] = lane < C ? feature[(size_t)s_id[j] * Cstride + c0 + lane] : 0.f;
             }
         }
         __syncthreads();
@@ -340,7 +341,9 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
         if (m < 32) mask &= (1u << m) - 1u;
         const unsigned wmask = __reduce_or_sync(kFull, mask);
 
-        // phase 2: reduce the per-pixel partial gradients of every Gaussian that touched this warp
+        // phase 2: reduce the per-pixel partial gradients of every Gaussian that touched this warp.  The body is
+        // branch-free: a lane that did not take the Gaussian runs it with p2 = -inf, i.e. G = alpha = w = 0, so every
+        // partial sum it contributes is an exact zero and only the recurrence state needs selects.
         for (int j = 0; j < m; ++j) {
             if (!((wmask >> j) & 1u)) {
                 if (lane < kSP) s_part[warp][j][lane] = 0.f;
@@ -349,20 +352,21 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                 continue;
             }
             float v[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i) v[i] = 0.f;
             float extra = 0.f;
-            if ((mask >> j) & 1u) {
+            {
+                const bool hit = (mask >> j) & 1u;
                 const float4 g0 = s_g0[j];
                 const float4 g1 = s_g1[j];
                 const float4 con = s_con[j];
                 float dx, dy, Gv;
-                const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-                const float alpha = splat_alpha<HAS_BIAS>(p2, g1, Gv);
+                float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                p2 = hit ? p2 : -INFINITY;
+                float alpha = splat_alpha<HAS_BIAS>(p2, g1, Gv);
+                if (HAS_BIAS) alpha = hit ? alpha : 0.f;
                 const float rinv = __fdividef(1.f, 1.f - alpha);
-                T = T * rinv;  // transmittance in front of this Gaussian
+                T = T * rinv;  // transmittance in front of this Gaussian (unchanged when alpha == 0)
                 const float w = alpha * T;
-                const float *fr = s_feat + j * CH;
+                const float *fr = s_feat + j * FS;
                 const float tb = -T_final * rinv;
                 const float om = 1.f - last_alpha;
                 float da_all, da_op, da_ndc;
@@ -374,22 +378,28 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                     v[8 + 3] = w * d[3];
 #pragma unroll
                     for (int c = 4; c < CH; ++c) { fdC = fmaf(fr[c], d[c], fdC); v[8 + c] = w * d[c]; }
-                    SA = last_alpha * lfA + om * SA;
-                    SB = last_alpha * lfB + om * SB;
-                    SC = last_alpha * lfC + om * SC;
-                    lfA = fdA; lfB = fdB; lfC = fdC;
-                    da_ndc = (fdA - SA) * T + tb * bgdA;
-                    da_op = da_ndc + ((fdB - SB) * T + tb * bgdB);
-                    da_all = da_op + ((fdC - SC) * T + tb * bgdC);
+                    const float nSA = last_alpha * lfA + om * SA;
+                    const float nSB = last_alpha * lfB + om * SB;
+                    const float nSC = last_alpha * lfC + om * SC;
+                    da_ndc = (fdA - nSA) * T + tb * bgdA;
+                    da_op = da_ndc + ((fdB - nSB) * T + tb * bgdB);
+                    da_all = da_op + ((fdC - nSC) * T + tb * bgdC);
+                    SA = hit ? nSA : SA; SB = hit ? nSB : SB; SC = hit ? nSC : SC;
+                    lfA = hit ? fdA : lfA; lfB = hit ? fdB : lfB; lfC = hit ? fdC : lfC;
+#pragma unroll
+                    for (int c = 8 + CH; c < 31; ++c) v[c] = 0.f;
                 } else {
                     float fd = 0.f;
 #pragma unroll
                     for (int c = 0; c < CH; ++c) { fd = fmaf(fr[c], d[c], fd); v[8 + c] = w * d[c]; }
-                    SA = last_alpha * lfA + om * SA;
-                    lfA = fd;
-                    da_all = da_op = da_ndc = (fd - SA) * T + tb * bgdA;
+                    const float nSA = last_alpha * lfA + om * SA;
+                    da_all = da_op = da_ndc = (fd - nSA) * T + tb * bgdA;
+                    SA = hit ? nSA : SA;
+                    lfA = hit ? fd : lfA;
+#pragma unroll
+                    for (int c = 8 + CH; c < NV; ++c) v[c] = 0.f;
                 }
-                last_alpha = alpha;
+                last_alpha = hit ? alpha : last_alpha;
                 const float dL_dG = g1.z * da_all;
                 const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
                 const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
@@ -406,7 +416,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                     v[31] = n0; extra = n1;
                 } else {
                     v[2] = fabsf(g0x); v[3] = fabsf(g0y);
-                    if (HAS_BIAS) v[NV - 1] = da_all;
+                    if (HAS_BIAS) v[NV - 1] = hit ? da_all : 0.f;
                 }
             }
             if constexpr (NV == 64) {
