@@ -149,18 +149,26 @@ SPV_API int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float 
                      const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
                      void *workspace, size_t ws_bytes, void *stream);
 SPV_API size_t spv_frame_workspace_bytes(int P, int64_t I_cap, int W, int H, int A);
-SPV_API int spv_frame_ortho_forward(int P, int W, int H, int A, int K, int64_t I_cap, int cull,
-                            const float *position, const float *scaling, const float *rotation, const float *opacity,
-                            const float *shs /*[P,16,3]*/, const float *attrs /*[P,A] or NULL*/, const float *extr,
-                            float nearest, float extent, float bg_rgb, float *images /*[4+A,H,W]*/,
+SPV_API int spv_frame_ortho_forward(int P, int W, int H, int n_groups /*<= 8*/, const float *const *attr_ptrs /*host array of device ptrs*/,
+                            const int *attr_channels /*host*/, int K, int64_t I_cap, int cull, const float *position,
+                            const float *scaling, const float *rotation, const float *opacity, const float *shs /*[P,16,3]*/,
+                            const float *extr, float nearest, float extent, float bg_rgb, float *images /*[4+A,H,W]*/,
                             int *gs_idx /*[H,W,K]*/, int *radii /*[P]*/, int *status /*[2]*/, void *workspace,
                             size_t ws_bytes, void *stream);
-SPV_API int spv_frame_ortho_backward(int P, int W, int H, int A, int64_t I_cap, const float *scaling, const float *rotation,
-                             const float *opacity, const float *shs, const float *extr, float bg_rgb,
-                             const float *dL_dimages /*[4+A,H,W]*/, float *dL_dposition, float *dL_dscaling,
-                             float *dL_drotation, float *dL_dopacity, float *dL_dshs /*[P,16,3]*/, float *dL_dattrs /*[P,A]*/,
-                             float *dL_dndc /*[P,2] or NULL*/, float *dL_dabs_ndc /*[P,2] or NULL*/, void *workspace,
-                             size_t ws_bytes, void *stream);
+/* dL_dimage_planes: host array of 4+A device pointers, one [H,W] gradient plane per image channel (NULL = no gradient);
+ * dL_dattr_ptrs: host array of n_groups device pointers receiving each attribute group's gradient (NULL = not needed). */
+SPV_API int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int64_t I_cap,
+                             const float *scaling, const float *rotation, const float *opacity, const float *shs,
+                             const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
+                             float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs /*[P,16,3]*/,
+                             float *const *dL_dattr_ptrs, float *dL_dndc /*[P,2] or NULL*/, float *dL_dabs_ndc /*[P,2] or NULL*/,
+                             void *workspace, size_t ws_bytes, void *stream);
+/* Blend stage of the grouped backward with per-channel gradient planes; leaves 36-float packed rows in `packed`. */
+SPV_API int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, const float *uv, const float *conic,
+                                           const float *opacity, const float *feature, const int *idx_sorted,
+                                           const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
+                                           const float *final_T, const int *ncontrib, const float *const *planes_host,
+                                           float *packed, void *stream);
 
 /* ---- Per-frame deformation (next row f-1): cubic-spline position of the active model
  * (src/dynamic_gaussian_with_base_point_cloud.py:236-250).  coeff = pos_cubic_node viewed as [P,4,NI,3]; the interval
@@ -169,6 +177,14 @@ SPV_API int spv_deform_spline_forward(int P, int NI, const float *base, const fl
                               const float *dist_dev, float *pos /*[P,3]*/, void *stream);
 SPV_API int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *dist_dev, const float *dL_dpos,
                                float *dL_dcoeff /*[P,4,NI,3]*/, int accumulate, void *stream);
+
+/* Rotation at frame time t (get_rotation, :184-198): normalize(rotation + detached poly/Fourier offsets); basis_dev holds
+ * [t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] on the device.  Backward: through the normalisation to `rotation`. */
+SPV_API int spv_deform_rotation_forward(int P, const float *rotation, const float *rot_poly_feat /*[P,4,4]*/,
+                                const float *rot_fourier_feat /*[P,8,4]*/, const float *basis_dev /*[12]*/,
+                                float *out /*[P,4]*/, float *inv_norm /*[P]*/, void *stream);
+SPV_API int spv_deform_rotation_backward(int P, const float *out, const float *inv_norm, const float *dL_dout,
+                                 float *dL_drotation, void *stream);
 
 /* ---- Fused Adam over the flat parameter buffer (next row f-3, optimizer half; torch.optim.Adam arithmetic) ---------- */
 SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,

@@ -49,12 +49,16 @@ _SIGS = {
     "spv_bin_capacity_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "spv_bin_capacity": (c_int, [c_int, c_int64, P_, P_, P_, P_, P_, c_int, c_int, c_int, P_, P_, P_, P_, c_size_t, P_]),
     "spv_frame_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
-    "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int64, c_int, P_, P_, P_, P_, P_, P_, P_, c_float,
+    "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, c_int, c_int64, c_int, P_, P_, P_, P_, P_, P_, c_float,
                                         c_float, c_float, P_, P_, P_, P_, P_, c_size_t, P_]),
-    "spv_frame_ortho_backward": (c_int, [c_int, c_int, c_int, c_int, c_int64, P_, P_, P_, P_, P_, c_float, P_, P_, P_, P_, P_,
+    "spv_frame_ortho_backward": (c_int, [c_int, c_int, c_int, c_int, P_, c_int64, P_, P_, P_, P_, P_, c_float, P_, P_, P_, P_, P_,
                                          P_, P_, P_, P_, P_, c_size_t, P_]),
+    "spv_alpha_blend_groups_backward_packed": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float, c_float,
+                                                       P_, P_, P_, P_, P_]),
     "spv_deform_spline_forward": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_]),
     "spv_deform_spline_backward": (c_int, [c_int, c_int, P_, P_, P_, P_, c_int, P_]),
+    "spv_deform_rotation_forward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_rotation_backward": (c_int, [c_int, P_, P_, P_, P_, P_]),
     "spv_adam_step": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, c_int, P_]),
 }
 

@@ -241,7 +241,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 //    traversal (dptr_ortho_enhanced.py:342-376): uv/conic from every channel, opacity from rgb+depth only (the
 //    attribute pass gets opacity.detach()), 2,3 = |.| and 31,32 = value of the RGB-pass uv gradient (-> abs_ndc / ndc).
 enum BwdMode { kPlain = 0, kBias = 1, kGroups = 2 };
-constexpr int kRowG = 36;
+constexpr int kRowG = spv::kPackedRowGroups;
 
 template <int NV, int CH, int MODE>
 __global__ void __launch_bounds__(kBlock, NV == 64 ? 1 : 2)
@@ -250,7 +250,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                  const float *__restrict__ feature, const float *__restrict__ bias,
                  const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg, float bgB, float bgC,
                  const float *__restrict__ final_T, const int *__restrict__ ncontrib,
-                 const float *__restrict__ dL_drendered, float *__restrict__ packed) {
+                 const spv::ChanPlanes planes, float *__restrict__ packed) {
     constexpr bool HAS_BIAS = MODE == kBias;
     constexpr bool GROUPS = MODE == kGroups;
     static_assert(GROUPS ? (NV == 32 && CH >= 4 && CH <= 23) : (8 + CH + (HAS_BIAS ? 1 : 0) <= NV), "row too small");
@@ -283,7 +283,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     float d[CH];
     const size_t HW = (size_t)H * W;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) d[c] = (inside && c < C) ? dL_drendered[c * HW + pix] : 0.f;
+    for (int c = 0; c < CH; ++c) d[c] = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
     // <bg, dL_dpixel> per gradient group (plain: one group)
     float bgdA = 0.f, bgdB = 0.f, bgdC = 0.f;
 #pragma unroll
@@ -488,7 +488,7 @@ blend_bwd_mma_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                      const float *__restrict__ feature, const float *__restrict__ bias,
                      const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg, float bgB,
                      float bgC, const float *__restrict__ final_T, const int *__restrict__ ncontrib,
-                     const float *__restrict__ dL_drendered, float *__restrict__ packed) {
+                     const spv::ChanPlanes planes, float *__restrict__ packed) {
     constexpr bool HAS_BIAS = MODE == kBias;
     constexpr bool GROUPS = MODE == kGroups;
     static_assert(CH % 8 == 0 && CH <= 24, "MMA backward handles 8/16/24 padded channels");
@@ -530,7 +530,7 @@ blend_bwd_mma_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     const size_t HW = (size_t)H * W;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-        d[c] = (inside && c < C) ? dL_drendered[c * HW + pix] : 0.f;
+        d[c] = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
         my_d[lane * CH + c] = d[c];
     }
     float bgdA = 0.f, bgdB = 0.f, bgdC = 0.f;
@@ -825,14 +825,20 @@ struct BwdArgs {
     int C, Cstride, c0, W, H, gx;
     const float2 *uv; const float *conic, *opacity, *feature, *bias;
     const int *idx_sorted; const int2 *tile_range; float bg, bgB, bgC;
-    const float *final_T; const int *ncontrib; const float *dL_drendered; float *packed;
+    const float *final_T; const int *ncontrib; spv::ChanPlanes planes; float *packed;
 };
+
+inline spv::ChanPlanes contiguous_planes(const float *base, int C, int W, int H) {
+    spv::ChanPlanes pl;
+    for (int c = 0; c < 32; ++c) pl.p[c] = (base && c < C) ? base + (size_t)c * H * W : nullptr;
+    return pl;
+}
 
 template <int NV, int CH, int MODE>
 void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
     blend_bwd_kernel<NV, CH, MODE><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
                                                             a.opacity, a.feature, a.bias, a.idx_sorted, a.tile_range,
-                                                            a.bg, a.bgB, a.bgC, a.final_T, a.ncontrib, a.dL_drendered,
+                                                            a.bg, a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes,
                                                             a.packed);
 }
 
@@ -847,7 +853,7 @@ void launch_bwd_mma(const BwdArgs &a, int ntiles, cudaStream_t s) {
     blend_bwd_mma_kernel<CH, MODE><<<ntiles, kBlock, bytes, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
                                                                  a.opacity, a.feature, a.bias, a.idx_sorted,
                                                                  a.tile_range, a.bg, a.bgB, a.bgC, a.final_T,
-                                                                 a.ncontrib, a.dL_drendered, a.packed);
+                                                                 a.ncontrib, a.planes, a.packed);
 }
 
 // The tensor-core variant is numerically correct (it passes the same parity tests) but MEASURED SLOWER on the
@@ -972,7 +978,7 @@ int spv_alpha_blend_backward(int P, int C, int W, int H, const float *uv, const 
         a.C = (C - c0 < cap) ? (C - c0) : cap; a.Cstride = C; a.c0 = c0; a.W = W; a.H = H; a.gx = gx;
         a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = opacity_bias;
         a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg; a.bgB = bg; a.bgC = bg;
-        a.final_T = final_T; a.ncontrib = ncontrib; a.dL_drendered = dL_drendered + (size_t)c0 * H * W;
+        a.final_T = final_T; a.ncontrib = ncontrib; a.planes = contiguous_planes(dL_drendered + (size_t)c0 * H * W, a.C, W, H);
         a.packed = packed;
         const int nv = bwd_nv(a.C, has_bias);
         SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)nv * P, s), "spv_alpha_blend_backward");
@@ -1041,7 +1047,7 @@ int spv_alpha_blend_groups_backward(int P, int C, int W, int H, const float *uv,
         a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx;
         a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
         a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr;
-        a.final_T = final_T; a.ncontrib = ncontrib; a.dL_drendered = dL_drendered; a.packed = packed;
+        a.final_T = final_T; a.ncontrib = ncontrib; a.planes = contiguous_planes(dL_drendered, C, W, H); a.packed = packed;
         dispatch_bwd_groups(a, ntiles, s);
         int rc = spv::check_launch("spv_alpha_blend_groups_backward/blend");
         if (rc) return rc;
@@ -1050,6 +1056,30 @@ int spv_alpha_blend_groups_backward(int P, int C, int W, int H, const float *uv,
                                                                  (float2 *)dL_dabs_uv_rgb, dL_dconic, dL_dopacity,
                                                                  dL_dfeature);
     return spv::check_launch("spv_alpha_blend_groups_backward/unpack");
+}
+
+/* Grouped backward, blend stage only: upstream gradients as per-channel planes (host array of C device pointers, NULL
+ * entries allowed), result left as packed rows (spv::kPackedRowGroups floats per Gaussian) in `packed` for a caller-side
+ * unpack (frame.cu).  `packed` must hold P*36 floats. */
+int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, const float *uv, const float *conic,
+                                           const float *opacity, const float *feature, const int *idx_sorted,
+                                           const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
+                                           const float *final_T, const int *ncontrib, const float *const *planes_host,
+                                           float *packed, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0) return 0;
+    if (C < 4 || C > 23) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward_packed: need 4 <= C <= 23"); return (int)cudaErrorInvalidValue; }
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
+    SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)kRowG * P, s), "spv_alpha_blend_groups_backward_packed");
+    if (W <= 0 || H <= 0) return 0;
+    BwdArgs a;
+    a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx;
+    a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
+    a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr;
+    a.final_T = final_T; a.ncontrib = ncontrib; a.packed = packed;
+    for (int c = 0; c < 32; ++c) a.planes.p[c] = c < C ? planes_host[c] : nullptr;
+    dispatch_bwd_groups(a, ntiles, s);
+    return spv::check_launch("spv_alpha_blend_groups_backward_packed");
 }
 
 }  // extern "C"

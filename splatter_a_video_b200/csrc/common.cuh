@@ -46,4 +46,12 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
     y1 = min(gy, max(0, (int)((py + r + 16.0f - 1.0f) / 16.0f)));
 }
 
+// Upstream image gradients given as one [H,W] plane per channel (NULL = that channel has no gradient).  Lets the fused
+// frame path hand the autograd engine's separate per-image gradients to the kernel without concatenating them.
+struct ChanPlanes { const float *p[32]; };
+
+// Packed per-Gaussian gradient row of the grouped blend backward (stride kPackedRowGroups floats):
+//   0,1 dL_duv(all)  2,3 |RGB-pass dL_duv|  4,5,6 dL_dconic  7 dL_dopacity  8..8+C-1 dL_dfeature  31,32 RGB-pass dL_duv
+constexpr int kPackedRowGroups = 36;
+
 }  // namespace spv

@@ -40,6 +40,42 @@ deform_bwd_kernel(int P, int NI, const int *__restrict__ idx_dev, const float *_
     if (accumulate) { q[3 * s] += g; q[2 * s] += g * d; q[1 * s] += g * (d * d); q[0] += g * (d * d * d); }
     else { q[3 * s] = g; q[2 * s] = g * d; q[1 * s] = g * (d * d); q[0] = g * (d * d * d); }
 }
+// Rotation of the active model at frame time t (dynamic_gaussian_with_base_point_cloud.py:184-198, get_rotation):
+//   q = rotation + sum_k rot_poly_feat[:,k,:] * t^k + sum_l rot_fourier_feat[:,l,:] * basis_l(t)   (both feature sums are
+//   .detach()ed there), returned through F.normalize.  basis = [t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] is read from
+//   DEVICE memory (12 floats) so a captured graph can be replayed for any frame.
+__global__ void __launch_bounds__(kThreads)
+deform_rot_fwd_kernel(int P, const float4 *__restrict__ rot, const float4 *__restrict__ poly /*[P,4]*/,
+                      const float4 *__restrict__ fourier /*[P,8]*/, const float *__restrict__ basis, float4 *__restrict__ out,
+                      float *__restrict__ inv_norm) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    float4 q = rot[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 f = poly[4 * (size_t)i + k]; const float b = basis[k];
+        q.x += f.x * b; q.y += f.y * b; q.z += f.z * b; q.w += f.w * b;
+    }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        const float4 f = fourier[8 * (size_t)i + l]; const float b = basis[4 + l];
+        q.x += f.x * b; q.y += f.y * b; q.z += f.z * b; q.w += f.w * b;
+    }
+    const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);   // F.normalize eps
+    const float r = 1.0f / n;
+    out[i] = make_float4(q.x * r, q.y * r, q.z * r, q.w * r);
+    inv_norm[i] = r;
+}
+
+__global__ void __launch_bounds__(kThreads)
+deform_rot_bwd_kernel(int P, const float4 *__restrict__ qhat, const float *__restrict__ inv_norm,
+                      const float4 *__restrict__ g, float4 *__restrict__ g_rot) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const float4 q = qhat[i], d = g[i];
+    const float dot = q.x * d.x + q.y * d.y + q.z * d.z + q.w * d.w, r = inv_norm[i];
+    g_rot[i] = make_float4((d.x - q.x * dot) * r, (d.y - q.y * dot) * r, (d.z - q.z * dot) * r, (d.w - q.w * dot) * r);
+}
 }  // namespace
 
 extern "C" {
@@ -59,6 +95,22 @@ int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *d
     if (!accumulate) SPV_CUDA_TRY(cudaMemsetAsync(dL_dcoeff, 0, sizeof(float) * 12 * (size_t)NI * P, s), "spv_deform_spline_backward");
     deform_bwd_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, s>>>(P, NI, idx_dev, dist_dev, dL_dpos, dL_dcoeff, accumulate);
     return spv::check_launch("spv_deform_spline_backward");
+}
+
+int spv_deform_rotation_forward(int P, const float *rotation, const float *rot_poly_feat, const float *rot_fourier_feat,
+                                const float *basis_dev /*[12]*/, float *out /*[P,4]*/, float *inv_norm /*[P]*/, void *stream) {
+    if (P <= 0) return 0;
+    deform_rot_fwd_kernel<<<spv::cdiv(P, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        P, (const float4 *)rotation, (const float4 *)rot_poly_feat, (const float4 *)rot_fourier_feat, basis_dev, (float4 *)out, inv_norm);
+    return spv::check_launch("spv_deform_rotation_forward");
+}
+
+int spv_deform_rotation_backward(int P, const float *out, const float *inv_norm, const float *dL_dout, float *dL_drotation,
+                                 void *stream) {
+    if (P <= 0) return 0;
+    deform_rot_bwd_kernel<<<spv::cdiv(P, kThreads), kThreads, 0, (cudaStream_t)stream>>>(P, (const float4 *)out, inv_norm,
+                                                                                     (const float4 *)dL_dout, (float4 *)dL_drotation);
+    return spv::check_launch("spv_deform_rotation_backward");
 }
 
 }  // extern "C"

@@ -62,31 +62,76 @@ visible_kernel(int P, const float *__restrict__ depth, uint8_t *__restrict__ vis
     if (i < P) vis[i] = depth[i] != 0.f;
 }
 
-// feature[P, 4+A] = [rgb(3) | depth(1) | attrs(A)]
+// Attribute groups: the renderer receives the attribute stack as separately named per-Gaussian tensors
+// (render_attributes_list, trainer_fragGS.py:510-512); they are consumed / differentiated in place, no torch.cat.
+constexpr int kMaxGroups = 8;
+struct AttrGroups { const float *in[kMaxGroups]; float *grad[kMaxGroups]; int ch[kMaxGroups]; int start[kMaxGroups]; int n; };
+
+// feature[P, 4+A] = [rgb(3) | depth(1) | attribute groups]
 __global__ void __launch_bounds__(kThreads)
-pack_features_kernel(int P, int A, const float *__restrict__ rgb, const float *__restrict__ depth,
-                     const float *__restrict__ attrs, float *__restrict__ feature) {
+pack_features_kernel(int P, int A, const float *__restrict__ rgb, const float *__restrict__ depth, const AttrGroups gr,
+                     float *__restrict__ feature) {
     const int C = 4 + A;
     const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
     if (k >= (long long)P * C) return;
     const int i = (int)(k / C), c = (int)(k % C);
-    feature[k] = c < 3 ? rgb[3 * i + c] : (c == 3 ? depth[i] : attrs[(size_t)i * A + (c - 4)]);
+    float v;
+    if (c < 3) v = rgb[3 * i + c];
+    else if (c == 3) v = depth[i];
+    else {
+        int gi = 0;
+#pragma unroll
+        for (int q = 1; q < kMaxGroups; ++q) if (q < gr.n && c - 4 >= gr.start[q]) gi = q;
+        v = gr.in[gi][(size_t)i * gr.ch[gi] + (c - 4 - gr.start[gi])];
+    }
+    feature[k] = v;
 }
 
-// inverse of pack_features for the gradients; also folds the [W/2,H/2] scale of the ndc dummies
+// Packed gradient rows of the grouped blend backward (spv::kPackedRowGroups layout) -> everything the rest of the chain and
+// the caller need, in one pass: uv / conic (workspace), opacity, colour and depth gradients (workspace), the attribute
+// groups' gradients straight into their own tensors, and the ndc dummies' gradients with their [W/2,H/2] scale.
 __global__ void __launch_bounds__(kThreads)
-split_grads_kernel(int P, int A, const float *__restrict__ g_feat, float *__restrict__ g_rgb, float *__restrict__ g_depth,
-                   float *__restrict__ g_attrs, const float2 *__restrict__ g_uv_rgb, const float2 *__restrict__ g_abs,
-                   float2 *__restrict__ g_ndc, float2 *__restrict__ g_abs_ndc, float hw, float hh) {
+unpack_frame_kernel(int P, int A, const float *__restrict__ packed, float2 *__restrict__ g_uv, float *__restrict__ g_conic,
+                    float *__restrict__ g_op, float *__restrict__ g_rgb, float *__restrict__ g_depth, const AttrGroups gr,
+                    float2 *__restrict__ g_ndc, float2 *__restrict__ g_abs_ndc, float hw, float hh) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= P) return;
-    const int C = 4 + A;
-    const float *r = g_feat + (size_t)i * C;
-    g_rgb[3 * i] = r[0]; g_rgb[3 * i + 1] = r[1]; g_rgb[3 * i + 2] = r[2];
-    g_depth[i] = r[3];
-    for (int c = 0; c < A; ++c) g_attrs[(size_t)i * A + c] = r[4 + c];
-    if (g_ndc) { const float2 v = g_uv_rgb[i]; g_ndc[i] = make_float2(v.x * hw, v.y * hh); }
-    if (g_abs_ndc) { const float2 v = g_abs[i]; g_abs_ndc[i] = make_float2(v.x * hw, v.y * hh); }
+    float r[spv::kPackedRowGroups];
+    const float4 *row = reinterpret_cast<const float4 *>(packed + (size_t)i * spv::kPackedRowGroups);
+#pragma unroll
+    for (int k = 0; k < spv::kPackedRowGroups / 4; ++k) {
+        const float4 q = row[k];
+        r[4 * k] = q.x; r[4 * k + 1] = q.y; r[4 * k + 2] = q.z; r[4 * k + 3] = q.w;
+    }
+    g_uv[i] = make_float2(r[0], r[1]);
+    g_conic[3 * i] = r[4]; g_conic[3 * i + 1] = r[5]; g_conic[3 * i + 2] = r[6];
+    g_op[i] = r[7];
+    g_rgb[3 * i] = r[8]; g_rgb[3 * i + 1] = r[9]; g_rgb[3 * i + 2] = r[10];
+    g_depth[i] = r[11];
+#pragma unroll
+    for (int q = 0; q < kMaxGroups; ++q) {
+        if (q < gr.n && gr.grad[q]) {
+            float *o = gr.grad[q] + (size_t)i * gr.ch[q];
+#pragma unroll
+            for (int c = 0; c < 19; ++c)
+                if (c >= gr.start[q] && c < gr.start[q] + gr.ch[q]) o[c - gr.start[q]] = r[12 + c];
+        }
+    }
+    if (g_ndc) g_ndc[i] = make_float2(r[31] * hw, r[32] * hh);
+    if (g_abs_ndc) g_abs_ndc[i] = make_float2(r[2] * hw, r[3] * hh);
+}
+
+inline int make_groups(AttrGroups &g, int n, const float *const *in, float *const *grad, const int *ch) {
+    g.n = n;
+    int A = 0;
+    for (int q = 0; q < kMaxGroups; ++q) {
+        g.in[q] = (q < n && in) ? in[q] : nullptr;
+        g.grad[q] = (q < n && grad) ? grad[q] : nullptr;
+        g.ch[q] = q < n ? ch[q] : 0;
+        g.start[q] = A;
+        A += g.ch[q];
+    }
+    return A;
 }
 
 #define SPV_TRY_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
@@ -99,14 +144,17 @@ size_t spv_frame_workspace_bytes(int P, int64_t I_cap, int W, int H, int A) {
     return carve(nullptr, P, I_cap, W, H, A).total;
 }
 
-int spv_frame_ortho_forward(int P, int W, int H, int A, int K, int64_t I_cap, int cull,
-                            const float *position, const float *scaling, const float *rotation, const float *opacity,
-                            const float *shs, const float *attrs, const float *extr, float nearest, float extent,
-                            float bg_rgb, float *images, int *gs_idx, int *radii, int *status, void *workspace,
-                            size_t ws_bytes, void *stream) {
+int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *const *attr_ptrs, const int *attr_channels,
+                            int K, int64_t I_cap, int cull, const float *position, const float *scaling,
+                            const float *rotation, const float *opacity, const float *shs, const float *extr,
+                            float nearest, float extent, float bg_rgb, float *images, int *gs_idx, int *radii,
+                            int *status, void *workspace, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0 || W <= 0 || H <= 0) return 0;
-    if (A < 0 || 4 + A > 23 || K <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: need 0 <= A <= 19 and K > 0"); return (int)cudaErrorInvalidValue; }
+    if (n_groups < 0 || n_groups > kMaxGroups) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: at most 8 attribute groups"); return (int)cudaErrorInvalidValue; }
+    AttrGroups gr;
+    const int A = make_groups(gr, n_groups, attr_ptrs, nullptr, attr_channels);
+    if (4 + A > 23 || K <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: need at most 19 attribute channels and K > 0"); return (int)cudaErrorInvalidValue; }
     FrameWs f = carve(workspace, P, I_cap, W, H, A);
     if (ws_bytes < f.total) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: workspace too small"); return (int)cudaErrorInvalidValue; }
     const unsigned g = spv::cdiv(P, kThreads);
@@ -129,30 +177,32 @@ int spv_frame_ortho_forward(int P, int W, int H, int A, int K, int64_t I_cap, in
     SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
                                 status, f.bin_ws, f.bin_bytes, stream));
     const int C = 4 + A;
-    pack_features_kernel<<<spv::cdiv((long long)P * C, kThreads), kThreads, 0, s>>>(P, A, f.rgb, f.depth, attrs, f.feature);
+    pack_features_kernel<<<spv::cdiv((long long)P * C, kThreads), kThreads, 0, s>>>(P, A, f.rgb, f.depth, gr, f.feature);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/pack"));
     return spv_alpha_blend_groups_forward(P, C, W, H, K, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
                                           bg_rgb, 1.0f, 0.0f, images, f.final_T, f.ncontrib, gs_idx, stream);
 }
 
-int spv_frame_ortho_backward(int P, int W, int H, int A, int64_t I_cap, const float *scaling, const float *rotation,
-                             const float *opacity, const float *shs, const float *extr, float bg_rgb,
-                             const float *dL_dimages, float *dL_dposition, float *dL_dscaling, float *dL_drotation,
-                             float *dL_dopacity, float *dL_dshs, float *dL_dattrs, float *dL_dndc, float *dL_dabs_ndc,
-                             void *workspace, size_t ws_bytes, void *stream) {
+int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int64_t I_cap,
+                             const float *scaling, const float *rotation, const float *opacity, const float *shs,
+                             const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
+                             float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs,
+                             float *const *dL_dattr_ptrs, float *dL_dndc, float *dL_dabs_ndc, void *workspace,
+                             size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0 || W <= 0 || H <= 0) return 0;
+    AttrGroups gr;
+    const int A = make_groups(gr, n_groups, nullptr, dL_dattr_ptrs, attr_channels);
     FrameWs f = carve(workspace, P, I_cap, W, H, A);
     if (ws_bytes < f.total) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_backward: workspace too small"); return (int)cudaErrorInvalidValue; }
     const int C = 4 + A;
     const unsigned g = spv::cdiv(P, kThreads);
-    SPV_TRY_RC(spv_alpha_blend_groups_backward(P, C, W, H, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range, bg_rgb,
-                                               1.0f, 0.0f, f.final_T, f.ncontrib, dL_dimages, f.g_uv, f.g_uv_rgb, f.g_abs,
-                                               f.g_conic, dL_dopacity, f.g_feat, f.blend_ws, f.blend_bytes, stream));
-    split_grads_kernel<<<g, kThreads, 0, s>>>(P, A, f.g_feat, f.g_rgb, f.g_depth, dL_dattrs, (const float2 *)f.g_uv_rgb,
-                                              (const float2 *)f.g_abs, (float2 *)dL_dndc, (float2 *)dL_dabs_ndc,
-                                              0.5f * (float)W, 0.5f * (float)H);
-    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/split"));
+    float *packed = (float *)f.blend_ws;
+    SPV_TRY_RC(spv_alpha_blend_groups_backward_packed(P, C, W, H, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
+                                                      bg_rgb, 1.0f, 0.0f, f.final_T, f.ncontrib, dL_dimage_planes, packed, stream));
+    unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, (float2 *)f.g_uv, f.g_conic, dL_dopacity, f.g_rgb, f.g_depth, gr,
+                                               (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));
     // colours -> SH coefficients (view direction is a constant: its gradient is discarded)
     {
         uint8_t *ones = (uint8_t *)f.bin_ws;   // binning scratch is free again: all-visible mask for SH

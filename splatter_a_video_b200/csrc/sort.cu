@@ -81,48 +81,61 @@ __device__ __forceinline__ bool tile_may_hit(float cx, float cy, float a, float 
     return m <= tau * 1.0005f + 1e-4f;
 }
 
+// Pass 1 (EMIT = false): per-splat count of surviving tiles + a 64-bit survival mask over its candidate rectangle (row-major;
+// rectangles with more than 64 tiles -- rare -- are simply re-tested in pass 2).  Pass 2 (EMIT = true): write (key, id) at
+// the scanned offsets.
 template <bool EMIT>
 __global__ void __launch_bounds__(kThreads)
 cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__restrict__ depth, const int *__restrict__ radius,
                        const float *__restrict__ conic, const float *__restrict__ opacity, int cull, int W, int H, int gx,
-                       int gy, int *__restrict__ counts, const int *__restrict__ offsets, long long cap,
-                       unsigned long long *__restrict__ keys, int *__restrict__ vals, int *__restrict__ status) {
+                       int gy, int *__restrict__ counts, unsigned long long *__restrict__ masks,
+                       const int *__restrict__ offsets, long long cap, unsigned long long *__restrict__ keys,
+                       int *__restrict__ vals, int *__restrict__ status) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= P) return;
     const int r = radius[i];
     int n = 0;
+    unsigned long long m = 0ull;
     if (r > 0) {
         int x0, y0, x1, y1;
         const float2 c = uv[i];
         spv::tile_rect(c.x, c.y, r, gx, gy, x0, y0, x1, y1);
+        const int area = (x1 - x0) * (y1 - y0);
         const float o = opacity[i];
-        const float ka = conic[3 * i], kb = conic[3 * i + 1], kc = conic[3 * i + 2];
-        const float tau = __logf(255.f * o);   // alpha = min(.99, o G) >= 1/255  <=>  o G >= 1/255  <=>  power >= -ln(255 o)
         const bool any = !cull || (o * 255.f >= 0.999f);
         long long cur = 0;
         unsigned long long dbits = 0;
+        bool retest = cull != 0;
         if (EMIT) {
             cur = (i == 0) ? 0 : offsets[i - 1];
             dbits = (unsigned long long)__float_as_uint(depth[i]);
+            if (cull && area <= 64) { m = masks[i]; retest = false; }
         }
-        if (any)
+        if (any && area > 0) {
+            const float ka = conic[3 * i], kb = conic[3 * i + 1], kc = conic[3 * i + 2];
+            const float tau = __logf(255.f * o);   // alpha = min(.99, o G) >= 1/255  <=>  o G >= 1/255  <=>  power >= -ln(255 o)
+            int k = 0;
             for (int y = y0; y < y1; ++y)
-                for (int x = x0; x < x1; ++x) {
-                    if (cull) {
+                for (int x = x0; x < x1; ++x, ++k) {
+                    bool keep = true;
+                    if (EMIT && cull && !retest) keep = (m >> k) & 1ull;
+                    else if (retest) {
                         const float px0 = (float)(x * 16), py0 = (float)(y * 16);
                         const float px1 = fminf(px0 + 15.f, (float)(W - 1)), py1 = fminf(py0 + 15.f, (float)(H - 1));
-                        if (!tile_may_hit(c.x, c.y, ka, kb, kc, tau, px0, py0, px1, py1)) continue;
+                        keep = tile_may_hit(c.x, c.y, ka, kb, kc, tau, px0, py0, px1, py1);
                     }
+                    if (!keep) continue;
                     if (EMIT) {
                         if (cur + n < cap) {
                             keys[cur + n] = ((unsigned long long)(y * gx + x) << 32) | dbits;
                             vals[cur + n] = i;
                         }
-                    }
+                    } else if (k < 64) m |= 1ull << k;
                     ++n;
                 }
+        }
     }
-    if (!EMIT) counts[i] = n;
+    if (!EMIT) { counts[i] = n; masks[i] = m; }
     if (EMIT && i == P - 1) {
         const long long total = (long long)offsets[P - 1];
         status[0] = (int)(total < cap ? total : cap);
@@ -221,7 +234,7 @@ size_t spv_bin_capacity_workspace_bytes(int P, int64_t I_cap) {
     size_t temp = sort_temp_bytes(I_cap);
     if (scan > temp) temp = scan;
     return align_up(8 * (size_t)I_cap) * 2 + align_up(4 * (size_t)I_cap) + align_up(4 * (size_t)(P > 0 ? P : 1)) * 2 +
-           align_up(temp);
+           align_up(8 * (size_t)(P > 0 ? P : 1)) + align_up(temp);
 }
 
 /* Bins the splats of one frame with at most I_cap intersections.  status[0] = number of intersections kept,
@@ -242,19 +255,20 @@ int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float *depth, 
     int *vals_in = (int *)w; w += align_up(4 * (size_t)I_cap);
     int *counts = (int *)w; w += align_up(4 * (size_t)P);
     int *offsets = (int *)w; w += align_up(4 * (size_t)P);
+    unsigned long long *masks = (unsigned long long *)w; w += align_up(8 * (size_t)P);
     size_t scan = 0;
     cub::DeviceScan::InclusiveSum((void *)nullptr, scan, counts, offsets, P);
     size_t temp = sort_temp_bytes(I_cap);
     const unsigned g = spv::cdiv(P, kThreads);
     cull_count_emit_kernel<false><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx,
-                                                        gy, counts, nullptr, (long long)I_cap, nullptr, nullptr, nullptr);
+                                                        gy, counts, masks, nullptr, (long long)I_cap, nullptr, nullptr, nullptr);
     int rc = spv::check_launch("spv_bin_capacity/count");
     if (rc) return rc;
     SPV_CUDA_TRY(cub::DeviceScan::InclusiveSum((void *)w, scan, counts, offsets, P, s), "spv_bin_capacity/scan");
     // unused slots keep an all-ones key: they sort behind every real (tile, depth) key
     SPV_CUDA_TRY(cudaMemsetAsync(keys_in, 0xFF, 8 * (size_t)I_cap, s), "spv_bin_capacity");
     cull_count_emit_kernel<true><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
-                                                       nullptr, offsets, (long long)I_cap, keys_in, vals_in, status);
+                                                       nullptr, masks, offsets, (long long)I_cap, keys_in, vals_in, status);
     rc = spv::check_launch("spv_bin_capacity/emit", 3);
     if (rc) return rc;
     int tb = 1;

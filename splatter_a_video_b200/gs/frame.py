@@ -50,18 +50,30 @@ class Capacity:
         return True
 
 
+def _ptr_array(ptrs):
+    import ctypes
+    return (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
+
+
 class _FrameOrtho(torch.autograd.Function):
+    """inputs: position, scaling, rotation, opacity, shs, extr, <scalars>, ndc, abs_ndc, sinks, *attribute groups
+    outputs: rgb[3,H,W], depth[1,H,W], one image per attribute group, gs_idx, radii, status."""
+
     @staticmethod
-    def forward(ctx, position, scaling, rotation, opacity, shs, attrs, extr, W, H, K, bg_rgb, nearest, extent, I_cap, cull,
-                ndc, abs_ndc, sinks):
-        L.need_cuda(position, scaling, rotation, opacity, shs, attrs, extr)
+    def forward(ctx, position, scaling, rotation, opacity, shs, extr, W, H, K, bg_rgb, nearest, extent, I_cap, cull,
+                ndc, abs_ndc, sinks, *attr_groups):
+        import ctypes
+        L.need_cuda(position, scaling, rotation, opacity, shs, extr, *attr_groups)
         pos, sc, rot, op, sh = (L.f32c(x) for x in (position, scaling, rotation, opacity, shs))
-        at = L.f32c(attrs) if attrs is not None else None
+        groups = [L.f32c(a) for a in attr_groups]
         ex = L.f32c(extr)
         P = pos.shape[0]
-        A = 0 if at is None else at.shape[1]
+        chans = [int(g.shape[1]) for g in groups]
+        A = sum(chans)
         if sh.shape[1] != 16:
             raise ValueError("render_ortho_frame needs degree-3 SH coefficients [P,16,3]")
+        if len(groups) > 8 or A > 19:
+            raise ValueError("render_ortho_frame handles at most 8 attribute groups / 19 attribute channels")
         dev = pos.device
         images = torch.empty(4 + A, H, W, dtype=torch.float32, device=dev)
         gs_idx = torch.empty(H, W, K, dtype=torch.int32, device=dev)
@@ -69,21 +81,36 @@ class _FrameOrtho(torch.autograd.Function):
         status = torch.empty(2, dtype=torch.int32, device=dev)
         nbytes = L.query("spv_frame_workspace_bytes", P, int(I_cap), int(W), int(H), A)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        L.call("spv_frame_ortho_forward", P, int(W), int(H), A, int(K), int(I_cap), int(bool(cull)), L.ptr(pos), L.ptr(sc),
-               L.ptr(rot), L.ptr(op), L.ptr(sh), L.ptr(at), L.ptr(ex), float(nearest), float(extent), float(bg_rgb),
-               L.ptr(images), L.ptr(gs_idx), L.ptr(radii), L.ptr(status), L.ptr(ws), nbytes, L.stream())
-        ctx.meta = (P, int(W), int(H), A, int(I_cap), float(bg_rgb), ndc is not None, abs_ndc is not None)
+        ch_arr = (ctypes.c_int * max(len(chans), 1))(*chans)
+        L.call("spv_frame_ortho_forward", P, int(W), int(H), len(groups), ctypes.cast(_ptr_array([g.data_ptr() for g in groups]), ctypes.c_void_p),
+               ctypes.cast(ch_arr, ctypes.c_void_p), int(K), int(I_cap), int(bool(cull)), L.ptr(pos), L.ptr(sc), L.ptr(rot), L.ptr(op),
+               L.ptr(sh), L.ptr(ex), float(nearest), float(extent), float(bg_rgb), L.ptr(images), L.ptr(gs_idx), L.ptr(radii),
+               L.ptr(status), L.ptr(ws), nbytes, L.stream())
+        ctx.meta = (P, int(W), int(H), chans, int(I_cap), float(bg_rgb), ndc is not None, abs_ndc is not None)
         ctx.sinks = dict(sinks) if sinks else {}
+        ctx.attr_needs = [bool(a.requires_grad) for a in attr_groups]
         ctx.save_for_backward(sc, rot, op, sh, ex, ws)
         ctx.mark_non_differentiable(gs_idx, radii, status)
-        return images, gs_idx, radii, status
+        # the per-image views are created inside forward: autograd hands their gradients to backward one by one, so no
+        # zero-filled [C,H,W] gradient image is ever assembled
+        outs, c = [images[:3], images[3:4]], 4
+        for n in chans:
+            outs.append(images[c:c + n]); c += n
+        return (*outs, gs_idx, radii, status)
 
     @staticmethod
-    def backward(ctx, g_images, _g, _r, _s):
-        P, W, H, A, I_cap, bg_rgb, has_ndc, has_abs = ctx.meta
+    def backward(ctx, *grads):
+        import ctypes
+        P, W, H, chans, I_cap, bg_rgb, has_ndc, has_abs = ctx.meta
         sc, rot, op, sh, ex, ws = ctx.saved_tensors
         dev = sc.device
         sinks = ctx.sinks
+        ng = len(chans)
+        img_grads = [None if g is None else L.f32c(g) for g in grads[:2 + ng]]
+        planes, HW = [], H * W * 4
+        for g, n in zip(img_grads, [3, 1] + chans):
+            for k in range(n):
+                planes.append(None if g is None else g.data_ptr() + k * HW)
 
         def out(name, *shape):
             """Gradient buffer: a caller-provided sink (written in place, `None` returned to autograd so nothing is
@@ -100,28 +127,39 @@ class _FrameOrtho(torch.autograd.Function):
         g_rot, r_rot = out("rotation", P, 4)
         g_op, r_op = out("opacity", P, 1)
         g_sh, r_sh = out("shs", P, 16, 3)
-        g_at = torch.empty(P, max(A, 1), dtype=torch.float32, device=dev)
+        g_attr = [torch.empty(P, n, dtype=torch.float32, device=dev) if need else None for n, need in zip(chans, ctx.attr_needs)]
         g_ndc = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_ndc else None
         g_abs = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_abs else None
-        L.call("spv_frame_ortho_backward", P, W, H, A, I_cap, L.ptr(sc), L.ptr(rot), L.ptr(op), L.ptr(sh), L.ptr(ex), bg_rgb,
-               L.ptr(L.f32c(g_images)), L.ptr(g_pos), L.ptr(g_sc), L.ptr(g_rot), L.ptr(g_op), L.ptr(g_sh), L.ptr(g_at),
+        ch_arr = (ctypes.c_int * max(ng, 1))(*chans)
+        L.call("spv_frame_ortho_backward", P, W, H, ng, ctypes.cast(ch_arr, ctypes.c_void_p), I_cap, L.ptr(sc), L.ptr(rot), L.ptr(op),
+               L.ptr(sh), L.ptr(ex), bg_rgb, ctypes.cast(_ptr_array(planes), ctypes.c_void_p), L.ptr(g_pos), L.ptr(g_sc), L.ptr(g_rot),
+               L.ptr(g_op), L.ptr(g_sh), ctypes.cast(_ptr_array([None if t is None else t.data_ptr() for t in g_attr]), ctypes.c_void_p),
                L.ptr(g_ndc), L.ptr(g_abs), L.ptr(ws), ws.numel(), L.stream())
-        return (g_pos, r_sc, r_rot, r_op, r_sh, g_at if A > 0 else None, None, None, None, None, None, None, None, None, None,
-                g_ndc, g_abs, None)
+        return (g_pos, r_sc, r_rot, r_op, r_sh, None, None, None, None, None, None, None, None, None, g_ndc, g_abs, None, *g_attr)
 
 
 def render_ortho_frame(position: Tensor, scaling: Tensor, rotation: Tensor, opacity: Tensor, shs: Tensor,
-                       attrs: Optional[Tensor], extr: Tensor, W: int, H: int, K: int, bg_rgb: float, I_cap: int,
+                       attrs, extr: Tensor, W: int, H: int, K: int, bg_rgb: float, I_cap: int,
                        cull: bool = True, nearest: float = 0.01, extent: float = 1.3, ndc: Optional[Tensor] = None,
-                       abs_ndc: Optional[Tensor] = None, grad_sinks: Optional[dict] = None
-                       ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """-> (images[4+A,H,W] = rgb|depth|attrs, gs_idx[H,W,K], radii[P], status[2] = (intersections, overflow) on device).
+                       abs_ndc: Optional[Tensor] = None, grad_sinks: Optional[dict] = None):
+    """One frame of DPTROrthoEnhancedRender.render_iter as one autograd node.
+
+    attrs: None, one [P,A] tensor, or a list/tuple of per-Gaussian attribute tensors (<= 8 groups, <= 19 channels in total);
+    they are read in place (no concatenation) and each receives its own gradient.
+    Returns (images, gs_idx[H,W,K], radii[P], status[2] = (intersections, overflow) on device) where `images` is the
+    [4+A,H,W] stack rgb|depth|attrs when `attrs` is a tensor / None, or a list [rgb, depth, attr_0, ...] when it is a list.
 
     grad_sinks (optional): {"scaling"|"rotation"|"opacity"|"shs": tensor}.  The backward pass WRITES (not accumulates)
     that input's gradient straight into the given buffer -- e.g. the parameter's slice of a flat gradient buffer -- and
     returns no gradient to autograd for it: no zero-fill, no accumulation pass (one backward per step)."""
-    return _FrameOrtho.apply(position, scaling, rotation, opacity, shs, attrs, extr, W, H, K, bg_rgb, nearest, extent, I_cap,
-                             cull, ndc, abs_ndc, grad_sinks)
+    as_list = isinstance(attrs, (list, tuple))
+    groups = list(attrs) if as_list else ([attrs] if attrs is not None else [])
+    res = _FrameOrtho.apply(position, scaling, rotation, opacity, shs, extr, W, H, K, bg_rgb, nearest, extent, I_cap, cull,
+                            ndc, abs_ndc, grad_sinks, *groups)
+    imgs, (gs_idx, radii, status) = list(res[:-3]), res[-3:]
+    if as_list:
+        return imgs, gs_idx, radii, status
+    return torch.cat(imgs, 0), gs_idx, radii, status
 
 
 # ------------------------------------------------------------------------------------------------ deformation
@@ -165,3 +203,38 @@ def deform_position(base: Tensor, pos_cubic_node: Tensor, idx_dev: Tensor, dist_
     (float32[1]) are device scalars produced from `spline_interval` (update them in place to replay a CUDA graph).
     grad_sink: optional buffer the coefficient gradient is written into (see render_ortho_frame)."""
     return _DeformSpline.apply(base, pos_cubic_node, idx_dev, dist_dev, interval_num, grad_sink)
+
+
+def rotation_basis(time: float, start_frame_id: int, time_len: int) -> Tensor:
+    """[t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] with t = (time - start)/time_len (get_rotation, :186-193)."""
+    t = (time - start_frame_id) / time_len
+    k = torch.arange(1, 5, dtype=torch.float32)
+    return torch.cat([torch.pow(torch.tensor(float(t)), torch.arange(4, dtype=torch.float32)), torch.cos(t * k * math.pi),
+                      torch.sin(t * k * math.pi)])
+
+
+class _DeformRotation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rotation, rot_poly_feat, rot_fourier_feat, basis_dev):
+        L.need_cuda(rotation, rot_poly_feat, rot_fourier_feat, basis_dev)
+        r, pf, ff = L.f32c(rotation), L.f32c(rot_poly_feat), L.f32c(rot_fourier_feat)
+        P = r.shape[0]
+        out = torch.empty(P, 4, dtype=torch.float32, device=r.device)
+        inv = torch.empty(P, dtype=torch.float32, device=r.device)
+        L.call("spv_deform_rotation_forward", P, L.ptr(r), L.ptr(pf), L.ptr(ff), L.ptr(basis_dev), L.ptr(out), L.ptr(inv), L.stream())
+        ctx.save_for_backward(out, inv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, inv = ctx.saved_tensors
+        P = out.shape[0]
+        gr = torch.empty(P, 4, dtype=torch.float32, device=out.device)
+        L.call("spv_deform_rotation_backward", P, L.ptr(out), L.ptr(inv), L.ptr(L.f32c(g)), L.ptr(gr), L.stream())
+        return gr, None, None, None
+
+
+def deform_rotation(rotation: Tensor, rot_poly_feat: Tensor, rot_fourier_feat: Tensor, basis_dev: Tensor) -> Tensor:
+    """Unit quaternion of every Gaussian at frame time t (src/dynamic_gaussian_with_base_point_cloud.py:184-198); the
+    poly / Fourier features enter detached, as in the reference.  `basis_dev` = rotation_basis(...).cuda()."""
+    return _DeformRotation.apply(rotation, rot_poly_feat, rot_fourier_feat, basis_dev)

@@ -131,6 +131,7 @@ class DPTROrthoEnhancedRender(_BaseRender):
         self.capacity = None          # gs.frame.Capacity, created on first use
         self.observe_capacity = True  # set False while capturing a CUDA graph
         self.last_status = None
+        self._ndc_zero = None
 
     def project_point(self, xyz, extr, W, H, nearest: float = 0.2, extent: float = 1.3):
         """Called directly by the trainer too (src/trainer_fragGS.py:781-793)."""
@@ -194,22 +195,24 @@ class DPTROrthoEnhancedRender(_BaseRender):
     def _render_iter_frame(self, height, width, extr, position, opacity, scaling, rotation, shs, **kwargs):
         from ..gs import frame as _frame
         P = position.shape[0]
-        attr_names = kwargs.get("render_attributes_list", [])
-        attrs = RenderFeatures(**{x: kwargs[x] for x in attr_names}) if len(attr_names) > 0 else None
-        if attrs is not None and attrs.combine().shape[1] > 19:
-            raise ValueError("the fused frame path handles at most 19 attribute channels")
+        attr_names = list(kwargs.get("render_attributes_list", []))
+        groups = [kwargs[x] for x in attr_names]
+        if len(groups) > 8 or sum(g.shape[1] for g in groups) > 19:
+            raise ValueError("the fused frame path handles at most 8 attribute tensors / 19 attribute channels")
         if self.capacity is None:
             self.capacity = _frame.Capacity(initial=8 * P)
         cap = self.capacity
         first = cap.last_I == 0 and self.observe_capacity
-        ndc = torch.zeros(P, 2, device=position.device, requires_grad=True)
-        abs_ndc = torch.zeros(P, 2, device=position.device, requires_grad=True)
+        if self._ndc_zero is None or self._ndc_zero.shape[0] != P or self._ndc_zero.device != position.device:
+            self._ndc_zero = torch.zeros(P, 2, device=position.device)
+        # fresh leaves over one persistent zero buffer: the dummies' values are never read, only their .grad
+        ndc = self._ndc_zero.detach().requires_grad_(True)
+        abs_ndc = self._ndc_zero.detach().requires_grad_(True)
         bg_color = kwargs.get("bg_color", self.bg_color)
         while True:
-            images, gs_idx, radii, status = _frame.render_ortho_frame(
-                position, scaling, rotation, opacity, shs, attrs.combine() if attrs is not None else None, extr, width, height,
-                kwargs.get("num_idx", 10), bg_color, cap.I_cap, self.cull, 0.01, 1.3, ndc, abs_ndc,
-                grad_sinks=kwargs.get("grad_sinks"))
+            imgs, gs_idx, radii, status = _frame.render_ortho_frame(
+                position, scaling, rotation, opacity, shs, groups, extr, width, height, kwargs.get("num_idx", 10), bg_color,
+                cap.I_cap, self.cull, 0.01, 1.3, ndc, abs_ndc, grad_sinks=kwargs.get("grad_sinks"))
             self.last_status = status
             if not self.observe_capacity:
                 break
@@ -219,9 +222,9 @@ class DPTROrthoEnhancedRender(_BaseRender):
                     cap.I_cap = int(cap.slack * cap.last_I) + 4096
                 break
             first = True                        # overflow: capacity has grown, render again
-        split = {"rgb": images[:3], "depth": images[3:4]}
-        if attrs is not None:
-            split.update(attrs.split(images[4:]))
+        split = {"rgb": imgs[0], "depth": imgs[1]}
+        for name, img in zip(attr_names, imgs[2:]):
+            split[name] = img
         return {"rendered_features_split": split,
                 "viewspace_points": abs_ndc if self.cfg["densify_abs_grad_enable"] else ndc,
                 "visibility_filter": radii > 0, "radii": radii, "gs_idx": gs_idx}

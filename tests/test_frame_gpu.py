@@ -197,3 +197,25 @@ def test_grad_sinks_write_in_place(cuda):
 
     a, b = run(False), run(True)
     Hh.assert_grad_close(n(b), n(a), "sinks vs autograd accumulation", norm_tol=2e-5)
+
+
+def test_deform_rotation_matches_reference_formula(cuda):
+    from splatter_a_video_b200.gs.frame import deform_rotation, rotation_basis
+    P = 2000
+    g = torch.Generator().manual_seed(8)
+    rot = torch.randn(P, 4, generator=g); poly = 0.1 * torch.randn(P, 16, generator=g); four = 0.1 * torch.randn(P, 32, generator=g)
+    for time in (0, 13, 49):
+        normed = (time - 0) / 49
+        # reference (dynamic_gaussian_with_base_point_cloud.py:184-198) on CPU
+        r = rot.clone().requires_grad_(True)
+        pb = torch.pow(torch.tensor(normed), torch.arange(4).float())[None, :, None]
+        k = torch.arange(4).float() + 1
+        fb = torch.cat([torch.cos(normed * k * np.pi), torch.sin(normed * k * np.pi)], 0)[None, :, None]
+        want = torch.nn.functional.normalize(r + torch.sum(poly.reshape(P, 4, 4) * pb, dim=1).detach()
+                                             + torch.sum(four.reshape(P, 8, 4) * fb, dim=1).detach())
+        gr = rot.to(cuda).requires_grad_(True)
+        got = deform_rotation(gr, poly.to(cuda), four.to(cuda), rotation_basis(time, 0, 49).to(cuda))
+        np.testing.assert_allclose(n(got), want.detach().numpy(), rtol=1e-5, atol=1e-6)
+        go = torch.randn(P, 4, generator=g)
+        want.backward(go); got.backward(go.to(cuda))
+        np.testing.assert_allclose(n(gr.grad), r.grad.numpy(), rtol=1e-4, atol=1e-6)
