@@ -172,10 +172,12 @@ class Workload:
         # upstream image gradients resident in HBM (N(0,1)) + pinned host buffers for the e2e path
         chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
         self.g_dev = {k: torch.randn(c, self.H, self.W, generator=g).to(device) for k, c in chans.items()}
+        # the reference's per-step batch is {ids1, ids2, gt_rgb1, weights} (src/loaders/gs_data2.py:24-88): ground-truth frame +
+        # per-pixel weights travel H2D every step; depth / attribute supervision gradients stay device-resident
         self.gt_host = torch.rand(3, self.H, self.W, generator=g).pin_memory()
-        self.w_host = torch.cat([v.cpu() for v in self.g_dev.values()], 0).contiguous().pin_memory()   # [23,H,W]
+        self.w_host = torch.rand(1, self.H, self.W, generator=g).pin_memory()
         self.gt_dev = torch.empty(3, self.H, self.W, device=device)
-        self.w_dev = torch.empty(23, self.H, self.W, device=device)
+        self.w_dev = torch.empty(1, self.H, self.W, device=device)
         self.loss_dev = torch.zeros(1, device=device)
         self.loss_host = torch.empty(1).pin_memory()
         self.use_graph = bool(graph) and mode == "frame"
@@ -216,11 +218,11 @@ class Workload:
     def _fwd_bwd_from_staged_host_data(self):
         self.flat.zero_grad(self.autograd_names if self.sinks else None)
         out = self.renderer.render_batch(self.render_dict(), [self._batch()])
-        imgs = torch.cat([out[k][0] for k in self.KEYS], 0)                   # [23,H,W]
-        diff = imgs.detach().clone()
-        diff[:3] -= self.gt_dev
-        self.loss_dev.copy_(((diff * self.w_dev).sum() / diff.numel()).reshape(1))
-        imgs.backward(self.w_dev / diff.numel())
+        rgb = out["rgb"][0]
+        resid = (rgb.detach() - self.gt_dev) * self.w_dev                     # weighted residual of the frame just uploaded
+        self.loss_dev.copy_((resid * resid).mean().reshape(1) * 0.5)          # weighted L2 photometric loss (scalar read back)
+        g_rgb = resid * self.w_dev / resid.numel()
+        torch.autograd.backward([rgb] + [out[k][0] for k in self.KEYS[1:]], [g_rgb] + [self.g_dev[k] for k in self.KEYS[1:]])
 
     def _render_only(self):
         with torch.no_grad():

@@ -244,7 +244,7 @@ enum BwdMode { kPlain = 0, kBias = 1, kGroups = 2 };
 constexpr int kRowG = spv::kPackedRowGroups;
 
 template <int NV, int CH, int MODE>
-__global__ void __launch_bounds__(kBlock, NV == 64 ? 1 : 2)
+__global__ void __launch_bounds__(kBlock, NV == 64 ? 1 : (NV == 32 ? 3 : 2))
 blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                  const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
                  const float *__restrict__ feature, const float *__restrict__ bias,
@@ -258,6 +258,11 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     constexpr int kRow = GROUPS ? kRowG : NV;       // packed row stride in global memory
     constexpr int kSP = GROUPS ? 33 : NV;           // per-warp parking row in shared memory
     constexpr int FS = (CH + 3) & ~3;               // feature row pitch: 16-byte rows -> LDS.128 broadcasts
+    // NV == 32 variants keep each pixel's dL_dpixel row in (dynamic) shared memory instead of 23 registers: 113 -> ~85
+    // registers, 3 instead of 2 resident CTAs per SM.  Row pitch 20 / 28 words: conflict-free 16-byte row reads.
+    constexpr bool D_SMEM = (NV == 32);
+    constexpr int DS = (FS <= 20) ? 20 : 28;
+    extern __shared__ __align__(16) float s_dyn[];
     __shared__ float4 s_g0[kG];
     __shared__ float4 s_g1[kG];
     __shared__ float4 s_con[kG];                    // unscaled conic a,b,c for the gradient formulas
@@ -280,17 +285,17 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     float T = T_final;
     const int last_contrib = inside ? ncontrib[pix] : 0;
 
-    float d[CH];
-    const size_t HW = (size_t)H * W;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) d[c] = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
+    float d[D_SMEM ? 1 : FS];
+    float *dq = s_dyn + threadIdx.x * DS;           // this pixel's dL_dpixel row (D_SMEM)
     // <bg, dL_dpixel> per gradient group (plain: one group)
     float bgdA = 0.f, bgdB = 0.f, bgdC = 0.f;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        if (GROUPS && c >= 4) bgdC += d[c];
-        else if (GROUPS && c == 3) bgdB += d[c];
-        else bgdA += d[c];
+    for (int c = 0; c < FS; ++c) {
+        const float dv = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
+        if (D_SMEM) dq[c] = dv; else d[c] = dv;
+        if (GROUPS && c >= 4) bgdC += dv;
+        else if (GROUPS && c == 3) bgdB += dv;
+        else bgdA += dv;
     }
     bgdA *= bg; bgdB *= bgB; bgdC *= bgC;
 
@@ -370,14 +375,28 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                 const float tb = -T_final * rinv;
                 const float om = 1.f - last_alpha;
                 float da_all, da_op, da_ndc;
+                // <feature, dL_dpixel> per gradient group and the per-channel feature-gradient partials, 4 channels per
+                // 16-byte read of the feature row (and of the pixel's gradient row when it lives in shared memory)
+                float fdA = 0.f, fdB = 0.f, fdC = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < FS / 4; ++c4) {
+                    const float4 ff = *reinterpret_cast<const float4 *>(fr + 4 * c4);
+                    float4 dd;
+                    if (D_SMEM) dd = *reinterpret_cast<const float4 *>(dq + 4 * c4);
+                    else dd = make_float4(d[4 * c4], d[4 * c4 + 1], d[4 * c4 + 2], d[4 * c4 + 3]);
+                    const float fv[4] = {ff.x, ff.y, ff.z, ff.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = 4 * c4 + k;
+                        if (c < CH) {
+                            if (GROUPS && c >= 4) fdC = fmaf(fv[k], dv[k], fdC);
+                            else if (GROUPS && c == 3) fdB = fmaf(fv[k], dv[k], fdB);
+                            else fdA = fmaf(fv[k], dv[k], fdA);
+                            v[8 + c] = w * dv[k];
+                        }
+                    }
+                }
                 if (GROUPS) {
-                    float fdA = 0.f, fdC = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) { fdA = fmaf(fr[c], d[c], fdA); v[8 + c] = w * d[c]; }
-                    const float fdB = fr[3] * d[3];
-                    v[8 + 3] = w * d[3];
-#pragma unroll
-                    for (int c = 4; c < CH; ++c) { fdC = fmaf(fr[c], d[c], fdC); v[8 + c] = w * d[c]; }
                     const float nSA = last_alpha * lfA + om * SA;
                     const float nSB = last_alpha * lfB + om * SB;
                     const float nSC = last_alpha * lfC + om * SC;
@@ -389,13 +408,10 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
 #pragma unroll
                     for (int c = 8 + CH; c < 31; ++c) v[c] = 0.f;
                 } else {
-                    float fd = 0.f;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) { fd = fmaf(fr[c], d[c], fd); v[8 + c] = w * d[c]; }
                     const float nSA = last_alpha * lfA + om * SA;
-                    da_all = da_op = da_ndc = (fd - nSA) * T + tb * bgdA;
+                    da_all = da_op = da_ndc = (fdA - nSA) * T + tb * bgdA;
                     SA = hit ? nSA : SA;
-                    lfA = hit ? fd : lfA;
+                    lfA = hit ? fdA : lfA;
 #pragma unroll
                     for (int c = 8 + CH; c < NV; ++c) v[c] = 0.f;
                 }
@@ -836,7 +852,14 @@ inline spv::ChanPlanes contiguous_planes(const float *base, int C, int W, int H)
 
 template <int NV, int CH, int MODE>
 void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
-    blend_bwd_kernel<NV, CH, MODE><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
+    constexpr int FS = (CH + 3) & ~3;
+    constexpr size_t dyn = (NV == 32) ? sizeof(float) * kBlock * ((FS <= 20) ? 20 : 28) : 0;
+    static bool configured = false;   // static (36 KB) + dynamic (<= 28 KB) shared memory exceeds the 48 KB default
+    if (dyn && !configured) {
+        cudaFuncSetAttribute(blend_bwd_kernel<NV, CH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        configured = true;
+    }
+    blend_bwd_kernel<NV, CH, MODE><<<ntiles, kBlock, dyn, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
                                                             a.opacity, a.feature, a.bias, a.idx_sorted, a.tile_range,
                                                             a.bg, a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes,
                                                             a.packed);
