@@ -462,14 +462,16 @@ def run_ours(args):
 
     # spline coefficients: each rank's gradient lives in one interval -> exchanged as N slices, the rest all-reduced
     sparse = {"pos_cubic_node": ((wl.P, 4, wl.NI, 3), 2, wl.idx1)}
+    # SH under the renderer's constant view direction (0,0,1): only bases 0, 2, 6, 12 ever receive gradient
+    subset = {"shs": ((wl.P, 16, 3), 1, torch.tensor([0, 2, 6, 12], device=device))}
 
     def train_step(frame):
         wl.step_resident(frame)
-        wl.flat.allreduce_grads(sparse=sparse)
+        wl.flat.allreduce_grads(sparse=sparse, subset=subset)
 
     def train_step_e2e(frame):
         wl.step_e2e(frame)
-        wl.flat.allreduce_grads(sparse=sparse)
+        wl.flat.allreduce_grads(sparse=sparse, subset=subset)
 
     if args.profile_mode:
         time_steps(train_step, args.steps, args.warmup, None, world, rank, frames_of)

@@ -72,26 +72,38 @@ class FlatParams:
     def floats_per_gaussian(self, P: int) -> float:
         return self.flat.numel() / max(P, 1)
 
-    def allreduce_grads(self, average: bool = True, async_op: bool = False, sparse: Optional[dict] = None):
-        """The step's gradient exchange: ONE all-reduce over the flat gradient buffer.
+    def allreduce_grads(self, average: bool = True, sparse: Optional[dict] = None, subset: Optional[dict] = None):
+        """The step's gradient exchange over the flat gradient buffer; the result always equals the dense all-reduce sum.
 
-        sparse (optional) = {name: (view_shape, dim, index_tensor)} marks parameters whose gradient is non-zero only in
-        ONE slice along `dim` per rank -- the cubic-spline coefficients: a frame touches the 12 coefficients of its own
-        interval out of 4*NI*3 (dynamic_gaussian_with_base_point_cloud.py:239-247).  Those parameters must be the LEADING
-        entries of the flat buffer; their active slices travel through an all-gather (N*P*12 floats instead of
-        P*4*NI*3) and are scatter-added locally, the rest of the buffer is all-reduced.  The result is exactly the dense
-        all-reduce sum."""
+        Without hints: ONE all-reduce of the whole buffer.  Two exact volume reductions for this model:
+
+        sparse = {name: (view_shape, dim, index_tensor)}: the gradient is non-zero only in ONE slice along `dim`, a
+            different one per rank -- the cubic-spline coefficients: a frame touches the 12 coefficients of its own interval
+            out of 4*NI*3 (dynamic_gaussian_with_base_point_cloud.py:239-247).  The active slices travel through an
+            all-gather (N*P*12 floats instead of P*4*NI*3) and are scatter-added locally.
+        subset = {name: (view_shape, dim, index_tensor)}: the gradient is non-zero only in the SAME slices on every rank --
+            the SH coefficients under the renderer's constant view direction (0,0,1) (dptr_ortho_enhanced.py:270-271): only
+            bases 0, 2, 6, 12 have a non-zero basis value, 12 of 48 floats.  Only those slices are all-reduced.
+        Every other parameter is all-reduced in place, one collective per maximal contiguous run."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
         world, rank = dist.get_world_size(), dist.get_rank()
-        start = 0
-        if sparse:
-            off = 0
-            for k in self.names:
-                if k not in sparse:
-                    break
+        sparse, subset = sparse or {}, subset or {}
+        off, run_start = 0, None
+        runs = []
+        for k, n in zip(self.names, self.sizes):
+            if k in sparse or k in subset:
+                if run_start is not None:
+                    runs.append((run_start, off)); run_start = None
+            elif run_start is None:
+                run_start = off
+            off += n
+        if run_start is not None:
+            runs.append((run_start, self.flat_grad.numel()))
+        off = 0
+        for k, n in zip(self.names, self.sizes):
+            if k in sparse:
                 shape, dim, index = sparse[k]
-                n = self.params[k].numel()
                 g = self.flat_grad[off:off + n].view(shape)
                 idx_all = [torch.empty_like(index) for _ in range(world)]
                 dist.all_gather(idx_all, index)
@@ -101,14 +113,18 @@ class FlatParams:
                 for r in range(world):
                     if r != rank:
                         g.index_add_(dim, idx_all[r].to(torch.long), parts[r])
-                off += n
-            start = off
-            assert all(k not in sparse for k in self.names[len([k for k in self.names if k in sparse]):]), \
-                "sparse parameters must lead the flat buffer"
-        work = dist.all_reduce(self.flat_grad[start:], op=dist.ReduceOp.SUM, async_op=async_op)
-        if average and not async_op:
+            elif k in subset:
+                shape, dim, index = subset[k]
+                g = self.flat_grad[off:off + n].view(shape)
+                sel = g.index_select(dim, index.to(torch.long)).contiguous()
+                dist.all_reduce(sel, op=dist.ReduceOp.SUM)
+                g.index_copy_(dim, index.to(torch.long), sel)
+            off += n
+        for a, b in runs:
+            dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM)
+        if average:
             self.flat_grad.div_(world)
-        return work
+        return None
 
 
 class FlatAdam:

@@ -61,14 +61,18 @@ def _sparse_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     P, NI = 50, 6
     g = torch.Generator().manual_seed(100 + rank)
-    flat = FlatParams({"node": torch.zeros(P, 4 * NI * 3), "other": torch.zeros(P, 7)})
+    flat = FlatParams({"node": torch.zeros(P, 4 * NI * 3), "other": torch.zeros(P, 7), "shs": torch.zeros(P, 16, 3),
+                       "tail": torch.zeros(P, 2)})
     idx = torch.tensor([2 if rank == 0 else 5], dtype=torch.int32)       # each rank touched one interval
     gn = torch.zeros(P, 4, NI, 3); gn[:, :, int(idx)] = torch.randn(P, 4, 3, generator=g)
     go = torch.randn(P, 7, generator=g)
-    flat["node"].grad.copy_(gn.reshape(P, -1)); flat["other"].grad.copy_(go)
+    sh_idx = torch.tensor([0, 2, 6, 12])
+    gsh = torch.zeros(P, 16, 3); gsh[:, sh_idx] = torch.randn(P, 4, 3, generator=g)
+    flat["node"].grad.copy_(gn.reshape(P, -1)); flat["other"].grad.copy_(go); flat["shs"].grad.copy_(gsh)
+    flat["tail"].grad.copy_(torch.randn(P, 2, generator=g))
     dense = flat.flat_grad.clone()
     dist.all_reduce(dense)
-    flat.allreduce_grads(average=False, sparse={"node": ((P, 4, NI, 3), 2, idx)})
+    flat.allreduce_grads(average=False, sparse={"node": ((P, 4, NI, 3), 2, idx)}, subset={"shs": ((P, 16, 3), 1, sh_idx)})
     if rank == 0:
         q.put((flat.flat_grad.numpy().copy(), dense.numpy().copy()))
     dist.barrier()
