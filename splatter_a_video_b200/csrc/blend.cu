@@ -83,6 +83,16 @@ __device__ __forceinline__ float splat_alpha(float p2, const float4 g1, float &G
     return fminf(kAlphaMax, HAS_BIAS ? __fmaf_rn(g1.z, G, g1.w) : __fmul_rn(g1.z, G));
 }
 
+// Per-warp pre-filter: can ANY pixel of the warp's 8x4 block take this splat?  Same hit condition as splat_hits, evaluated
+// conservatively over the block rectangle: -p2 = A dx^2 + B dx dy + C dy^2 must reach lo - log2(1/255) somewhere on it.
+template <bool HAS_BIAS>
+__device__ __forceinline__ bool block_may_hit(const float4 g0, const float4 g1, float bx0, float by0) {
+    if (HAS_BIAS) return true;   // alpha = o*G + bias: no closed-form bound; the per-pixel test decides
+    const float tau2 = g1.y - kLog2AlphaMin;
+    if (!(tau2 >= 0.f)) return false;   // opacity below 1/255 (or NaN): never taken
+    return spv::tile_may_hit(g0.x, g0.y, -2.f * g0.z, -g0.w, -2.f * g1.x, tau2, bx0, by0, bx0 + 7.f, by0 + 3.f);
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int CH, bool HAS_IDX, bool HAS_BIAS>
 __global__ void __launch_bounds__(kBlock)
@@ -105,6 +115,7 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
     const size_t pix = (size_t)W * py + px;
     const float pxf = (float)px, pyf = (float)py;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float bx0 = (float)(tile_x * SPV_TILE + ((warp & 1) << 3)), by0 = (float)(tile_y * SPV_TILE + ((warp >> 1) << 2));
 
     const int2 range = tile_range[tile];
     const int n = range.y - range.x;
@@ -141,32 +152,24 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
 
         for (int j0 = 0; j0 < m; j0 += 32) {
             if (__all_sync(kFull, done)) break;
-            // phase 1: hit mask of this pixel over 32 list entries (entries past m are masked off below)
-            unsigned mask = 0;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const float4 g0 = s_g0[j0 + j];
-                const float4 g1 = s_g1[j0 + j];
-                float dx, dy;
-                const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-                mask |= (splat_hits<HAS_BIAS>(p2, g1) ? 1u : 0u) << j;
-            }
-            const int cnt = m - j0;
-            if (cnt < 32) mask &= (1u << cnt) - 1u;
-            if (done) mask = 0;
-            unsigned wm = __reduce_or_sync(kFull, mask);
-            // phase 2: only Gaussians that hit at least one pixel of this warp
+            // stage 1: one list entry per lane -- can the warp's pixel block take it at all?
+            bool maybe = false;
+            if (j0 + lane < m) maybe = block_may_hit<HAS_BIAS>(s_g0[j0 + lane], s_g1[j0 + lane], bx0, by0);
+            unsigned wm = __ballot_sync(kFull, maybe);
+            // stage 2: visit the survivors in list order; every lane decides for its own pixel
             while (wm) {
                 const int j = __ffs(wm) - 1;
                 wm &= wm - 1;
-                if ((mask >> j) & 1u) {
-                    const float4 g0 = s_g0[j0 + j];
-                    const float4 g1 = s_g1[j0 + j];
-                    float dx, dy, G;
-                    const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                const float4 g0 = s_g0[j0 + j];
+                const float4 g1 = s_g1[j0 + j];
+                float dx, dy, G;
+                const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                const bool hit = !done && splat_hits<HAS_BIAS>(p2, g1);
+                if (!__any_sync(kFull, hit)) continue;
+                if (hit) {
                     const float alpha = splat_alpha<HAS_BIAS>(p2, g1, G);
                     const float next_T = T * (1.f - alpha);
-                    if (next_T < kTmin) { done = true; mask = 0; continue; }
+                    if (next_T < kTmin) { done = true; continue; }
                     const float w = alpha * T;
                     const float *fr = s_feat + (j0 + j) * CH;
 #pragma unroll
@@ -176,7 +179,7 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
                     if (HAS_IDX) {
                         if (trunc) {
                             gs_idx[pix * K + layer] = s_id[j0 + j];
-                            if (++layer >= K) { done = true; mask = 0; }
+                            if (++layer >= K) done = true;
                         } else if (layer < K) {
                             gs_idx[pix * K + layer] = s_id[j0 + j];
                             ++layer;
@@ -279,6 +282,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     const size_t pix = (size_t)W * py + px;
     const float pxf = (float)px, pyf = (float)py;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float bx0 = (float)(tile_x * SPV_TILE + ((warp & 1) << 3)), by0 = (float)(tile_y * SPV_TILE + ((warp >> 1) << 2));
 
     const int2 range = tile_range[tile];
     const float T_final = inside ? final_T[pix] : 0.f;
@@ -332,25 +336,25 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
         }
         __syncthreads();
 
-        // phase 1: which of the chunk's Gaussians did this pixel apply in the forward pass?
-        unsigned mask = 0;
-#pragma unroll 8
-        for (int j = 0; j < kG; ++j) {
-            const float4 g0 = s_g0[j];
-            const float4 g1 = s_g1[j];
-            float dx, dy;
-            const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-            const bool hit = splat_hits<HAS_BIAS>(p2, g1) && (p_hi - 1 - j) < last_contrib;
-            mask |= (hit ? 1u : 0u) << j;
-        }
-        if (m < 32) mask &= (1u << m) - 1u;
-        const unsigned wmask = __reduce_or_sync(kFull, mask);
+        // stage 1: one chunk entry per lane -- can the warp's 8x4 pixel block have taken it at all?
+        bool maybe = false;
+        if (lane < m) maybe = block_may_hit<HAS_BIAS>(s_g0[lane], s_g1[lane], bx0, by0);
+        const unsigned wmask = __ballot_sync(kFull, maybe);
 
         // phase 2: reduce the per-pixel partial gradients of every Gaussian that touched this warp.  The body is
         // branch-free: a lane that did not take the Gaussian runs it with p2 = -inf, i.e. G = alpha = w = 0, so every
         // partial sum it contributes is an exact zero and only the recurrence state needs selects.
         for (int j = 0; j < m; ++j) {
-            if (!((wmask >> j) & 1u)) {
+            bool hit = false;
+            float dx = 0.f, dy = 0.f, p2 = 0.f;
+            const float4 g0 = s_g0[j];
+            const float4 g1 = s_g1[j];
+            if ((wmask >> j) & 1u) {   // warp-uniform
+                p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                // did this pixel apply the Gaussian in the forward pass?  (same test, and before the last contributor)
+                hit = splat_hits<HAS_BIAS>(p2, g1) && (p_hi - 1 - j) < last_contrib;
+            }
+            if (!__any_sync(kFull, hit)) {
                 if (lane < kSP) s_part[warp][j][lane] = 0.f;
                 if constexpr (kSP == 33) { if (lane == 0) s_part[warp][j][32] = 0.f; }
                 if constexpr (kSP == 64) s_part[warp][j][32 + lane] = 0.f;
@@ -359,12 +363,8 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
             float v[NV];
             float extra = 0.f;
             {
-                const bool hit = (mask >> j) & 1u;
-                const float4 g0 = s_g0[j];
-                const float4 g1 = s_g1[j];
                 const float4 con = s_con[j];
-                float dx, dy, Gv;
-                float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                float Gv;
                 p2 = hit ? p2 : -INFINITY;
                 float alpha = splat_alpha<HAS_BIAS>(p2, g1, Gv);
                 if (HAS_BIAS) alpha = hit ? alpha : 0.f;

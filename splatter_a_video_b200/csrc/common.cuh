@@ -46,6 +46,29 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
     y1 = min(gy, max(0, (int)((py + r + 16.0f - 1.0f) / 16.0f)));
 }
 
+// Conservative ellipse-vs-pixel-rectangle test shared by the tile culling (sort.cu) and the per-warp pre-filter of the blend
+// kernels: can q(d) = 0.5 a dx^2 + b dx dy + 0.5 c dy^2 (d = centre - pixel) drop to <= tau somewhere on the rectangle of
+// pixel centres [x0,x1] x [y0,y1]?  q is a convex quadratic: zero if the centre is inside, else its minimum is on an edge.
+__device__ __forceinline__ float quad_min_on_segment(float A, float B, float C0, float lo, float hi) {
+    // min over t in [lo,hi] of A t^2 + B t + C0, A >= 0
+    float t = (A > 0.f) ? fminf(fmaxf(-B / (2.f * A), lo), hi) : ((B > 0.f) ? lo : hi);
+    return (A * t + B) * t + C0;
+}
+
+__device__ __forceinline__ bool tile_may_hit(float cx, float cy, float a, float b, float c, float tau, float x0, float y0,
+                                             float x1, float y1) {
+    // rectangle of pixel centres [x0,x1] x [y0,y1]; d = centre - pixel
+    if (cx >= x0 && cx <= x1 && cy >= y0 && cy <= y1) return true;
+    const float dxl = cx - x0, dxh = cx - x1, dyl = cy - y0, dyh = cy - y1;   // dx in [dxh, dxl], dy in [dyh, dyl]
+    // q(dx,dy) = 0.5 a dx^2 + b dx dy + 0.5 c dy^2 ; the minimum over the box lies on its boundary here
+    float m = quad_min_on_segment(0.5f * a, b * dyl, 0.5f * c * dyl * dyl, dxh, dxl);
+    m = fminf(m, quad_min_on_segment(0.5f * a, b * dyh, 0.5f * c * dyh * dyh, dxh, dxl));
+    m = fminf(m, quad_min_on_segment(0.5f * c, b * dxl, 0.5f * a * dxl * dxl, dyh, dyl));
+    m = fminf(m, quad_min_on_segment(0.5f * c, b * dxh, 0.5f * a * dxh * dxh, dyh, dyl));
+    return m <= tau * 1.0005f + 1e-4f;
+}
+
+
 // Upstream image gradients given as one [H,W] plane per channel (NULL = that channel has no gradient).  Lets the fused
 // frame path hand the autograd engine's separate per-image gradients to the kernel without concatenating them.
 struct ChanPlanes { const float *p[32]; };

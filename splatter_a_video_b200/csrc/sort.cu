@@ -62,28 +62,12 @@ tile_range_kernel(long long I, const unsigned long long *__restrict__ keys_sorte
 // any pixel: a pixel takes a splat only if power >= -tau with tau = ln(255*opacity), i.e. only inside the ellipse
 // q(d) = 0.5*(a dx^2 + c dy^2) + b dx dy <= tau, and the test below keeps every tile whose pixel-centre rectangle
 // intersects that ellipse (minimum of the convex quadratic over the rectangle, with a relative safety margin).
-__device__ __forceinline__ float quad_min_on_segment(float A, float B, float C0, float lo, float hi) {
-    // min over t in [lo,hi] of A t^2 + B t + C0, A >= 0
-    float t = (A > 0.f) ? fminf(fmaxf(-B / (2.f * A), lo), hi) : ((B > 0.f) ? lo : hi);
-    return (A * t + B) * t + C0;
-}
-
-__device__ __forceinline__ bool tile_may_hit(float cx, float cy, float a, float b, float c, float tau, float x0, float y0,
-                                             float x1, float y1) {
-    // rectangle of pixel centres [x0,x1] x [y0,y1]; d = centre - pixel
-    if (cx >= x0 && cx <= x1 && cy >= y0 && cy <= y1) return true;
-    const float dxl = cx - x0, dxh = cx - x1, dyl = cy - y0, dyh = cy - y1;   // dx in [dxh, dxl], dy in [dyh, dyl]
-    // q(dx,dy) = 0.5 a dx^2 + b dx dy + 0.5 c dy^2 ; the minimum over the box lies on its boundary here
-    float m = quad_min_on_segment(0.5f * a, b * dyl, 0.5f * c * dyl * dyl, dxh, dxl);
-    m = fminf(m, quad_min_on_segment(0.5f * a, b * dyh, 0.5f * c * dyh * dyh, dxh, dxl));
-    m = fminf(m, quad_min_on_segment(0.5f * c, b * dxl, 0.5f * a * dxl * dxl, dyh, dyl));
-    m = fminf(m, quad_min_on_segment(0.5f * c, b * dxh, 0.5f * a * dxh * dxh, dyh, dyl));
-    return m <= tau * 1.0005f + 1e-4f;
-}
-
 // Pass 1 (EMIT = false): per-splat count of surviving tiles + a 64-bit survival mask over its candidate rectangle (row-major;
 // rectangles with more than 64 tiles -- rare -- are simply re-tested in pass 2).  Pass 2 (EMIT = true): write (key, id) at
-// the scanned offsets.
+// the scanned offsets.  EIGHT lanes share one splat and stride over its candidate tiles: tile rectangles are heavy-tailed
+// (2 % of the splats cover 36+ tiles), and with one thread per splat half of all warps wait on such a lane.
+constexpr int kLanesPerSplat = 8;
+
 template <bool EMIT>
 __global__ void __launch_bounds__(kThreads)
 cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__restrict__ depth, const int *__restrict__ radius,
@@ -91,52 +75,67 @@ cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__rest
                        int gy, int *__restrict__ counts, unsigned long long *__restrict__ masks,
                        const int *__restrict__ offsets, long long cap, unsigned long long *__restrict__ keys,
                        int *__restrict__ vals, int *__restrict__ status) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P) return;
-    const int r = radius[i];
-    int n = 0;
+    const int t = blockIdx.x * kThreads + threadIdx.x;
+    const int i = t / kLanesPerSplat, sub = t % kLanesPerSplat;          // splat, lane within the splat's group
+    const int lane = threadIdx.x & 31, gshift = lane & ~(kLanesPerSplat - 1);
+    const bool live = i < P;
+    const int r = live ? radius[i] : 0;
+    int n = 0;                       // tiles kept so far (identical on the 8 lanes of a group)
     unsigned long long m = 0ull;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0, area = 0;
+    float2 c = make_float2(0.f, 0.f);
+    float ka = 0.f, kb = 0.f, kc = 0.f, tau = 0.f;
+    bool any = false, retest = cull != 0;
+    long long cur = 0;
+    unsigned long long dbits = 0;
     if (r > 0) {
-        int x0, y0, x1, y1;
-        const float2 c = uv[i];
+        c = uv[i];
         spv::tile_rect(c.x, c.y, r, gx, gy, x0, y0, x1, y1);
-        const int area = (x1 - x0) * (y1 - y0);
+        area = (x1 - x0) * (y1 - y0);
         const float o = opacity[i];
-        const bool any = !cull || (o * 255.f >= 0.999f);
-        long long cur = 0;
-        unsigned long long dbits = 0;
-        bool retest = cull != 0;
+        any = (!cull || (o * 255.f >= 0.999f)) && area > 0;
+        ka = conic[3 * i]; kb = conic[3 * i + 1]; kc = conic[3 * i + 2];
+        tau = __logf(255.f * o);    // alpha = min(.99, o G) >= 1/255  <=>  o G >= 1/255  <=>  power >= -ln(255 o)
         if (EMIT) {
             cur = (i == 0) ? 0 : offsets[i - 1];
             dbits = (unsigned long long)__float_as_uint(depth[i]);
             if (cull && area <= 64) { m = masks[i]; retest = false; }
         }
-        if (any && area > 0) {
-            const float ka = conic[3 * i], kb = conic[3 * i + 1], kc = conic[3 * i + 2];
-            const float tau = __logf(255.f * o);   // alpha = min(.99, o G) >= 1/255  <=>  o G >= 1/255  <=>  power >= -ln(255 o)
-            int k = 0;
-            for (int y = y0; y < y1; ++y)
-                for (int x = x0; x < x1; ++x, ++k) {
-                    bool keep = true;
-                    if (EMIT && cull && !retest) keep = (m >> k) & 1ull;
-                    else if (retest) {
-                        const float px0 = (float)(x * 16), py0 = (float)(y * 16);
-                        const float px1 = fminf(px0 + 15.f, (float)(W - 1)), py1 = fminf(py0 + 15.f, (float)(H - 1));
-                        keep = tile_may_hit(c.x, c.y, ka, kb, kc, tau, px0, py0, px1, py1);
-                    }
-                    if (!keep) continue;
-                    if (EMIT) {
-                        if (cur + n < cap) {
-                            keys[cur + n] = ((unsigned long long)(y * gx + x) << 32) | dbits;
-                            vals[cur + n] = i;
-                        }
-                    } else if (k < 64) m |= 1ull << k;
-                    ++n;
-                }
-        }
     }
-    if (!EMIT) { counts[i] = n; masks[i] = m; }
-    if (EMIT && i == P - 1) {
+    // every lane of the warp runs the same number of rounds (the ballots below are warp-wide)
+    int rounds = any ? (area + kLanesPerSplat - 1) / kLanesPerSplat : 0;
+    rounds = __reduce_max_sync(0xffffffffu, rounds);
+    const int w = max(x1 - x0, 1);
+    for (int it = 0; it < rounds; ++it) {
+        const int k = it * kLanesPerSplat + sub;
+        bool keep = any && k < area;
+        int x = 0, y = 0;
+        if (keep) {
+            y = y0 + k / w; x = x0 + k % w;
+            if (EMIT && cull && !retest) keep = (m >> k) & 1ull;
+            else if (retest) {
+                const float px0 = (float)(x * 16), py0 = (float)(y * 16);
+                const float px1 = fminf(px0 + 15.f, (float)(W - 1)), py1 = fminf(py0 + 15.f, (float)(H - 1));
+                keep = spv::tile_may_hit(c.x, c.y, ka, kb, kc, tau, px0, py0, px1, py1);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const unsigned grp = (bal >> gshift) & ((1u << kLanesPerSplat) - 1u);
+        if (EMIT) {
+            if (keep) {
+                const long long pos = cur + n + __popc(grp & ((1u << sub) - 1u));
+                if (pos < cap) {
+                    keys[pos] = ((unsigned long long)(y * gx + x) << 32) | dbits;
+                    vals[pos] = i;
+                }
+            }
+        } else if (it < 64 / kLanesPerSplat) {
+            m |= (unsigned long long)grp << (it * kLanesPerSplat);
+        }
+        n += __popc(grp);
+    }
+    if (!EMIT && live && sub == 0) { counts[i] = n; masks[i] = m; }
+    if (EMIT && live && i == P - 1 && sub == 0) {
         const long long total = (long long)offsets[P - 1];
         status[0] = (int)(total < cap ? total : cap);
         status[1] = total > cap ? 1 : 0;
@@ -259,7 +258,7 @@ int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float *depth, 
     size_t scan = 0;
     cub::DeviceScan::InclusiveSum((void *)nullptr, scan, counts, offsets, P);
     size_t temp = sort_temp_bytes(I_cap);
-    const unsigned g = spv::cdiv(P, kThreads);
+    const unsigned g = spv::cdiv((long long)P * kLanesPerSplat, kThreads);
     cull_count_emit_kernel<false><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx,
                                                         gy, counts, masks, nullptr, (long long)I_cap, nullptr, nullptr, nullptr);
     int rc = spv::check_launch("spv_bin_capacity/count");

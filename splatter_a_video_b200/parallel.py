@@ -89,41 +89,64 @@ class FlatParams:
             return None
         world, rank = dist.get_world_size(), dist.get_rank()
         sparse, subset = sparse or {}, subset or {}
-        off, run_start = 0, None
-        runs = []
+        if not sparse and not subset:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            if average:
+                self.flat_grad.div_(world)
+            return None
+        scale = 1.0 / world if average else 1.0
+        # ---- one packed all-reduce: [every dense parameter | the fixed slices of the `subset` parameters]
+        pieces, writeback, off = [], [], 0
+        gathers = []
         for k, n in zip(self.names, self.sizes):
-            if k in sparse or k in subset:
-                if run_start is not None:
-                    runs.append((run_start, off)); run_start = None
-            elif run_start is None:
-                run_start = off
-            off += n
-        if run_start is not None:
-            runs.append((run_start, self.flat_grad.numel()))
-        off = 0
-        for k, n in zip(self.names, self.sizes):
+            g = self.flat_grad[off:off + n]
             if k in sparse:
                 shape, dim, index = sparse[k]
-                g = self.flat_grad[off:off + n].view(shape)
-                idx_all = [torch.empty_like(index) for _ in range(world)]
-                dist.all_gather(idx_all, index)
-                mine = g.index_select(dim, index.to(torch.long)).contiguous()
-                parts = [torch.empty_like(mine) for _ in range(world)]
-                dist.all_gather(parts, mine)
-                for r in range(world):
-                    if r != rank:
-                        g.index_add_(dim, idx_all[r].to(torch.long), parts[r])
+                gathers.append((g.view(shape), dim, index))
             elif k in subset:
                 shape, dim, index = subset[k]
-                g = self.flat_grad[off:off + n].view(shape)
-                sel = g.index_select(dim, index.to(torch.long)).contiguous()
-                dist.all_reduce(sel, op=dist.ReduceOp.SUM)
-                g.index_copy_(dim, index.to(torch.long), sel)
+                gv = g.view(shape)
+                idx = index.to(torch.long)
+                pieces.append(gv.index_select(dim, idx).reshape(-1))
+                writeback.append(("subset", gv, dim, idx))
+            else:
+                pieces.append(g)
+                writeback.append(("dense", g, None, None))
             off += n
-        for a, b in runs:
-            dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM)
-        if average:
-            self.flat_grad.div_(world)
+        tail = self.flat_grad[off:]                       # float4 padding of the flat buffer
+        if pieces:
+            comm = torch.cat(pieces)
+            if scale != 1.0:
+                comm.mul_(scale)
+            dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+            o = 0
+            for (kind, gv, dim, idx), src in zip(writeback, pieces):
+                m = src.numel()
+                if kind == "dense":
+                    gv.copy_(comm[o:o + m])
+                else:
+                    sel_shape = list(gv.shape); sel_shape[dim] = idx.numel()
+                    gv.index_copy_(dim, idx, comm[o:o + m].view(sel_shape))
+                o += m
+        # ---- one all-gather per sparse parameter: [own active slice | its index]
+        for gv, dim, index in gathers:
+            idx = index.to(torch.long)
+            mine = gv.index_select(dim, idx)
+            if scale != 1.0:
+                mine = mine * scale
+                gv.index_copy_(dim, idx, mine)
+            payload = torch.cat([mine.reshape(-1), index.to(torch.float32).reshape(-1)])
+            allp = torch.empty(world, payload.numel(), dtype=torch.float32, device=payload.device)
+            if dist.get_backend() == "nccl":
+                dist.all_gather_into_tensor(allp, payload)
+            else:                                           # gloo (CPU tests) has no flat all-gather
+                dist.all_gather(list(allp.unbind(0)), payload)
+            nsl = mine.numel()
+            for r in range(world):
+                if r != rank:
+                    gv.index_add_(dim, allp[r, nsl:].to(torch.long), allp[r, :nsl].view(mine.shape))
+        if tail.numel():
+            tail.zero_()
         return None
 
 
