@@ -157,7 +157,10 @@ SPV_API int spv_frame_ortho_forward(int P, int W, int H, int n_groups /*<= 8*/, 
                             size_t ws_bytes, void *stream);
 /* dL_dimage_planes: host array of 4+A device pointers, one [H,W] gradient plane per image channel (NULL = no gradient);
  * dL_dattr_ptrs: host array of n_groups device pointers receiving each attribute group's gradient (NULL = not needed). */
-SPV_API int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int64_t I_cap,
+SPV_API int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels,
+                             int n_grad_channels /* leading image channels (rgb, depth, then attribute groups) whose feature
+                                                    gradient is wanted; gradient-free groups must come last */,
+                             int64_t I_cap,
                              const float *scaling, const float *rotation, const float *opacity, const float *shs,
                              const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
                              float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs /*[P,16,3]*/,
@@ -168,7 +171,7 @@ SPV_API int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, c
                                            const float *opacity, const float *feature, const int *idx_sorted,
                                            const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
                                            const float *final_T, const int *ncontrib, const float *const *planes_host,
-                                           float *packed, void *stream);
+                                           int n_grad_channels, float *packed, void *stream);
 
 /* ---- Per-frame deformation (next row f-1): cubic-spline position of the active model
  * (src/dynamic_gaussian_with_base_point_cloud.py:236-250).  coeff = pos_cubic_node viewed as [P,4,NI,3]; the interval

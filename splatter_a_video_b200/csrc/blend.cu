@@ -246,8 +246,10 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 enum BwdMode { kPlain = 0, kBias = 1, kGroups = 2 };
 constexpr int kRowG = spv::kPackedRowGroups;
 
-template <int NV, int CH, int MODE>
-__global__ void __launch_bounds__(kBlock, NV == 64 ? 1 : (NV == 32 ? 3 : 2))
+// CG = number of leading feature channels whose dL_dfeature is wanted (the caller orders gradient-free attribute groups
+// last): only 8 + CG sums go through the reduction network.
+template <int NV, int CH, int MODE, int CG>
+__global__ void __launch_bounds__(kBlock, NV == 64 ? 1 : ((CH > 8) ? 3 : 2))
 blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                  const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
                  const float *__restrict__ feature, const float *__restrict__ bias,
@@ -256,14 +258,15 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                  const spv::ChanPlanes planes, float *__restrict__ packed) {
     constexpr bool HAS_BIAS = MODE == kBias;
     constexpr bool GROUPS = MODE == kGroups;
-    static_assert(GROUPS ? (NV == 32 && CH >= 4 && CH <= 23) : (8 + CH + (HAS_BIAS ? 1 : 0) <= NV), "row too small");
+    static_assert(GROUPS ? (CH >= 4 && CH <= 23 && 8 + CG <= NV && NV <= 32) : (CG == CH && 8 + CH + (HAS_BIAS ? 1 : 0) <= NV),
+                  "row too small");
     constexpr int kG = (NV == 64) ? 16 : 32;       // Gaussians per chunk (keeps s_part at <= 34 KB)
     constexpr int kRow = GROUPS ? kRowG : NV;       // packed row stride in global memory
-    constexpr int kSP = GROUPS ? 33 : NV;           // per-warp parking row in shared memory
+    constexpr int kSP = GROUPS ? NV + 2 : NV;       // per-warp parking row (+2: the RGB-pass uv gradient of the groups mode)
     constexpr int FS = (CH + 3) & ~3;               // feature row pitch: 16-byte rows -> LDS.128 broadcasts
     // NV == 32 variants keep each pixel's dL_dpixel row in (dynamic) shared memory instead of 23 registers: 113 -> ~85
     // registers, 3 instead of 2 resident CTAs per SM.  Row pitch 20 / 28 words: conflict-free 16-byte row reads.
-    constexpr bool D_SMEM = (NV == 32);
+    constexpr bool D_SMEM = (CH > 8) && NV <= 32;
     constexpr int DS = (FS <= 20) ? 20 : 28;
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ float4 s_g0[kG];
@@ -356,12 +359,11 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
             }
             if (!__any_sync(kFull, hit)) {
                 if (lane < kSP) s_part[warp][j][lane] = 0.f;
-                if constexpr (kSP == 33) { if (lane == 0) s_part[warp][j][32] = 0.f; }
-                if constexpr (kSP == 64) s_part[warp][j][32 + lane] = 0.f;
+                if constexpr (kSP > 32) { if (lane < kSP - 32) s_part[warp][j][32 + lane] = 0.f; }
                 continue;
             }
             float v[NV];
-            float extra = 0.f;
+            float n0 = 0.f, n1 = 0.f;
             {
                 const float4 con = s_con[j];
                 float Gv;
@@ -392,7 +394,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                             if (GROUPS && c >= 4) fdC = fmaf(fv[k], dv[k], fdC);
                             else if (GROUPS && c == 3) fdB = fmaf(fv[k], dv[k], fdB);
                             else fdA = fmaf(fv[k], dv[k], fdA);
-                            v[8 + c] = w * dv[k];
+                            if (c < CG) v[8 + c] = w * dv[k];
                         }
                     }
                 }
@@ -406,7 +408,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                     SA = hit ? nSA : SA; SB = hit ? nSB : SB; SC = hit ? nSC : SC;
                     lfA = hit ? fdA : lfA; lfB = hit ? fdB : lfB; lfC = hit ? fdC : lfC;
 #pragma unroll
-                    for (int c = 8 + CH; c < 31; ++c) v[c] = 0.f;
+                    for (int c = 8 + CG; c < NV; ++c) v[c] = 0.f;
                 } else {
                     const float nSA = last_alpha * lfA + om * SA;
                     da_all = da_op = da_ndc = (fdA - nSA) * T + tb * bgdA;
@@ -427,9 +429,8 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                 v[7] = Gv * da_op;
                 if (GROUPS) {
                     const float dL_dG_ndc = g1.z * da_ndc;
-                    const float n0 = dL_dG_ndc * dGx, n1 = dL_dG_ndc * dGy;
+                    n0 = dL_dG_ndc * dGx; n1 = dL_dG_ndc * dGy;
                     v[2] = fabsf(n0); v[3] = fabsf(n1);
-                    v[31] = n0; extra = n1;
                 } else {
                     v[2] = fabsf(g0x); v[3] = fabsf(g0y);
                     if (HAS_BIAS) v[NV - 1] = hit ? da_all : 0.f;
@@ -445,8 +446,11 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                 if (lane < NV) s_part[warp][j][lane] = v[0];
                 if constexpr (GROUPS) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(kFull, extra, o);
-                    if (lane == 0) s_part[warp][j][32] = extra;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        n0 += __shfl_xor_sync(kFull, n0, o);
+                        n1 += __shfl_xor_sync(kFull, n1, o);
+                    }
+                    if (lane == 0) { s_part[warp][j][NV] = n0; s_part[warp][j][NV + 1] = n1; }
                 }
             }
         }
@@ -466,11 +470,11 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                         if (s != 0.f) atomicAdd(row + half * 32 + lane, s);
                     }
                     if constexpr (GROUPS) {
-                        if (lane == 0) {
+                        if (lane < 2) {
                             float e = 0.f;
 #pragma unroll
-                            for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][32];
-                            if (e != 0.f) atomicAdd(row + 32, e);
+                            for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][NV + lane];
+                            if (e != 0.f) atomicAdd(row + 31 + lane, e);
                         }
                     }
                 }
@@ -481,10 +485,19 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
             for (int jj = 0; jj < kG / 16; ++jj) {
                 const int j = warp * (kG / 8) + jj * 2 + half;
                 if (j < m) {
+                    float *row = packed + (size_t)s_id[j] * kRow;
                     float s = 0.f;
 #pragma unroll
                     for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][l16];
-                    if (s != 0.f) atomicAdd(packed + (size_t)s_id[j] * kRow + l16, s);
+                    if (s != 0.f) atomicAdd(row + l16, s);
+                    if constexpr (GROUPS) {
+                        if (l16 < 2) {
+                            float e = 0.f;
+#pragma unroll
+                            for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][NV + l16];
+                            if (e != 0.f) atomicAdd(row + 31 + l16, e);
+                        }
+                    }
                 }
             }
         }
@@ -842,6 +855,7 @@ struct BwdArgs {
     const float2 *uv; const float *conic, *opacity, *feature, *bias;
     const int *idx_sorted; const int2 *tile_range; float bg, bgB, bgC;
     const float *final_T; const int *ncontrib; spv::ChanPlanes planes; float *packed;
+    int n_grad_channels = 1 << 30;   // groups mode: leading channels whose dL_dfeature is wanted
 };
 
 inline spv::ChanPlanes contiguous_planes(const float *base, int C, int W, int H) {
@@ -850,16 +864,16 @@ inline spv::ChanPlanes contiguous_planes(const float *base, int C, int W, int H)
     return pl;
 }
 
-template <int NV, int CH, int MODE>
+template <int NV, int CH, int MODE, int CG = CH>
 void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
     constexpr int FS = (CH + 3) & ~3;
-    constexpr size_t dyn = (NV == 32) ? sizeof(float) * kBlock * ((FS <= 20) ? 20 : 28) : 0;
-    static bool configured = false;   // static (36 KB) + dynamic (<= 28 KB) shared memory exceeds the 48 KB default
+    constexpr size_t dyn = (CH > 8 && NV <= 32) ? sizeof(float) * kBlock * ((FS <= 20) ? 20 : 28) : 0;
+    static bool configured = false;   // static (<= 38 KB) + dynamic (<= 28 KB) shared memory exceeds the 48 KB default
     if (dyn && !configured) {
-        cudaFuncSetAttribute(blend_bwd_kernel<NV, CH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(blend_bwd_kernel<NV, CH, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         configured = true;
     }
-    blend_bwd_kernel<NV, CH, MODE><<<ntiles, kBlock, dyn, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
+    blend_bwd_kernel<NV, CH, MODE, CG><<<ntiles, kBlock, dyn, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
                                                             a.opacity, a.feature, a.bias, a.idx_sorted, a.tile_range,
                                                             a.bg, a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes,
                                                             a.packed);
@@ -922,9 +936,16 @@ void dispatch_bwd_groups(const BwdArgs &a, int ntiles, cudaStream_t s) {
         else launch_bwd_mma<24, kGroups>(a, ntiles, s);
         return;
     }
-    if (C <= 4) launch_bwd<32, 4, kGroups>(a, ntiles, s);
-    else if (C <= 8) launch_bwd<32, 8, kGroups>(a, ntiles, s);
-    else if (C <= 12) launch_bwd<32, 12, kGroups>(a, ntiles, s);
+    if (a.n_grad_channels <= 8) {   // <= 8 feature-gradient channels: 16-wide network + the two RGB-pass butterflies
+        if (C <= 4) launch_bwd<16, 4, kGroups, 4>(a, ntiles, s);
+        else if (C <= 8) launch_bwd<16, 8, kGroups, 8>(a, ntiles, s);
+        else if (C <= 12) launch_bwd<16, 12, kGroups, 8>(a, ntiles, s);
+        else if (C <= 16) launch_bwd<16, 16, kGroups, 8>(a, ntiles, s);
+        else if (C <= 20) launch_bwd<16, 20, kGroups, 8>(a, ntiles, s);
+        else launch_bwd<16, 23, kGroups, 8>(a, ntiles, s);
+        return;
+    }
+    if (C <= 12) launch_bwd<32, 12, kGroups>(a, ntiles, s);
     else if (C <= 16) launch_bwd<32, 16, kGroups>(a, ntiles, s);
     else if (C <= 20) launch_bwd<32, 20, kGroups>(a, ntiles, s);
     else launch_bwd<32, 23, kGroups>(a, ntiles, s);
@@ -1088,7 +1109,7 @@ int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, const flo
                                            const float *opacity, const float *feature, const int *idx_sorted,
                                            const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
                                            const float *final_T, const int *ncontrib, const float *const *planes_host,
-                                           float *packed, void *stream) {
+                                           int n_grad_channels, float *packed, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0) return 0;
     if (C < 4 || C > 23) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward_packed: need 4 <= C <= 23"); return (int)cudaErrorInvalidValue; }
@@ -1101,6 +1122,7 @@ int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, const flo
     a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr;
     a.final_T = final_T; a.ncontrib = ncontrib; a.packed = packed;
     for (int c = 0; c < 32; ++c) a.planes.p[c] = c < C ? planes_host[c] : nullptr;
+    a.n_grad_channels = n_grad_channels;
     dispatch_bwd_groups(a, ntiles, s);
     return spv::check_launch("spv_alpha_blend_groups_backward_packed");
 }

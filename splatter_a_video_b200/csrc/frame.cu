@@ -183,7 +183,7 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
                                           bg_rgb, 1.0f, 0.0f, images, f.final_T, f.ncontrib, gs_idx, stream);
 }
 
-int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int64_t I_cap,
+int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int n_grad_channels, int64_t I_cap,
                              const float *scaling, const float *rotation, const float *opacity, const float *shs,
                              const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
                              float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs,
@@ -199,7 +199,7 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     const unsigned g = spv::cdiv(P, kThreads);
     float *packed = (float *)f.blend_ws;
     SPV_TRY_RC(spv_alpha_blend_groups_backward_packed(P, C, W, H, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
-                                                      bg_rgb, 1.0f, 0.0f, f.final_T, f.ncontrib, dL_dimage_planes, packed, stream));
+                                                      bg_rgb, 1.0f, 0.0f, f.final_T, f.ncontrib, dL_dimage_planes, n_grad_channels, packed, stream));
     unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, (float2 *)f.g_uv, f.g_conic, dL_dopacity, f.g_rgb, f.g_depth, gr,
                                                (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));

@@ -65,7 +65,10 @@ class _FrameOrtho(torch.autograd.Function):
         import ctypes
         L.need_cuda(position, scaling, rotation, opacity, shs, extr, *attr_groups)
         pos, sc, rot, op, sh = (L.f32c(x) for x in (position, scaling, rotation, opacity, shs))
-        groups = [L.f32c(a) for a in attr_groups]
+        # internal channel order: attribute groups that need a gradient first -- the backward kernel then reduces feature
+        # gradients only for the leading 4 + (their channels) image channels
+        order = sorted(range(len(attr_groups)), key=lambda i: not attr_groups[i].requires_grad)
+        groups = [L.f32c(attr_groups[i]) for i in order]
         ex = L.f32c(extr)
         P = pos.shape[0]
         chans = [int(g.shape[1]) for g in groups]
@@ -88,15 +91,16 @@ class _FrameOrtho(torch.autograd.Function):
                L.ptr(status), L.ptr(ws), nbytes, L.stream())
         ctx.meta = (P, int(W), int(H), chans, int(I_cap), float(bg_rgb), ndc is not None, abs_ndc is not None)
         ctx.sinks = dict(sinks) if sinks else {}
-        ctx.attr_needs = [bool(a.requires_grad) for a in attr_groups]
+        ctx.order = order
+        ctx.attr_needs = [bool(attr_groups[i].requires_grad) for i in order]
         ctx.save_for_backward(sc, rot, op, sh, ex, ws)
         ctx.mark_non_differentiable(gs_idx, radii, status)
         # the per-image views are created inside forward: autograd hands their gradients to backward one by one, so no
         # zero-filled [C,H,W] gradient image is ever assembled
-        outs, c = [images[:3], images[3:4]], 4
-        for n in chans:
-            outs.append(images[c:c + n]); c += n
-        return (*outs, gs_idx, radii, status)
+        views, c = [None] * len(order), 4
+        for slot, n in zip(order, chans):
+            views[slot] = images[c:c + n]; c += n
+        return (images[:3], images[3:4], *views, gs_idx, radii, status)
 
     @staticmethod
     def backward(ctx, *grads):
@@ -106,11 +110,13 @@ class _FrameOrtho(torch.autograd.Function):
         dev = sc.device
         sinks = ctx.sinks
         ng = len(chans)
-        img_grads = [None if g is None else L.f32c(g) for g in grads[:2 + ng]]
+        user_grads = [None if g is None else L.f32c(g) for g in grads[:2 + ng]]
+        img_grads = user_grads[:2] + [user_grads[2 + slot] for slot in ctx.order]      # internal channel order
         planes, HW = [], H * W * 4
         for g, n in zip(img_grads, [3, 1] + chans):
             for k in range(n):
                 planes.append(None if g is None else g.data_ptr() + k * HW)
+        n_grad_channels = 4 + sum(n for n, need in zip(chans, ctx.attr_needs) if need)
 
         def out(name, *shape):
             """Gradient buffer: a caller-provided sink (written in place, `None` returned to autograd so nothing is
@@ -131,11 +137,14 @@ class _FrameOrtho(torch.autograd.Function):
         g_ndc = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_ndc else None
         g_abs = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_abs else None
         ch_arr = (ctypes.c_int * max(ng, 1))(*chans)
-        L.call("spv_frame_ortho_backward", P, W, H, ng, ctypes.cast(ch_arr, ctypes.c_void_p), I_cap, L.ptr(sc), L.ptr(rot), L.ptr(op),
+        L.call("spv_frame_ortho_backward", P, W, H, ng, ctypes.cast(ch_arr, ctypes.c_void_p), n_grad_channels, I_cap, L.ptr(sc), L.ptr(rot), L.ptr(op),
                L.ptr(sh), L.ptr(ex), bg_rgb, ctypes.cast(_ptr_array(planes), ctypes.c_void_p), L.ptr(g_pos), L.ptr(g_sc), L.ptr(g_rot),
                L.ptr(g_op), L.ptr(g_sh), ctypes.cast(_ptr_array([None if t is None else t.data_ptr() for t in g_attr]), ctypes.c_void_p),
                L.ptr(g_ndc), L.ptr(g_abs), L.ptr(ws), ws.numel(), L.stream())
-        return (g_pos, r_sc, r_rot, r_op, r_sh, None, None, None, None, None, None, None, None, None, g_ndc, g_abs, None, *g_attr)
+        g_user = [None] * ng
+        for slot, t in zip(ctx.order, g_attr):
+            g_user[slot] = t
+        return (g_pos, r_sc, r_rot, r_op, r_sh, None, None, None, None, None, None, None, None, None, g_ndc, g_abs, None, *g_user)
 
 
 def render_ortho_frame(position: Tensor, scaling: Tensor, rotation: Tensor, opacity: Tensor, shs: Tensor,

@@ -219,3 +219,36 @@ def test_deform_rotation_matches_reference_formula(cuda):
         go = torch.randn(P, 4, generator=g)
         want.backward(go); got.backward(go.to(cuda))
         np.testing.assert_allclose(n(gr.grad), r.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_frame_path_with_gradient_free_attribute_groups(cuda):
+    """The trainer's real situation: track_gs is detached and pos_poly_feat frozen, only mask/dino (4 channels) carry a
+    gradient -> the backward reduces 8 feature channels (16-wide network); results must equal the staged ops."""
+    from splatter_a_video_b200.renderer import parse_renderer
+    P, W, H = 20_000, 256, 160
+    sc = synth.make_scene(P, 6, W, H, seed=17)
+    g = torch.Generator().manual_seed(2)
+    chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
+    gimgs = {k: torch.randn(c, H, W, generator=g).to(cuda) for k, c in chans.items()}
+    frozen = ("track_gs", "pos_poly_feat")
+
+    def run(name):
+        rd = _rd(sc, cuda)
+        for k in frozen:
+            rd[k] = rd[k].detach()
+        rnd = parse_renderer({"name": name}, white_bg=False, device=cuda)
+        out = rnd.render_batch(rd, [_batch(sc, cuda)])
+        keys = ["rgb", "depth"] + ATTRS
+        torch.autograd.backward([out[k][0] for k in keys], [gimgs[k] for k in keys])
+        return out, rd
+
+    o1, r1 = run("DPTROrthoEnhancedRender")
+    o2, r2 = run("DPTROrthoEnhancedRenderB200")
+    for k in ["rgb", "depth"] + ATTRS:
+        assert float((o1[k] - o2[k]).abs().max()) <= 1e-6, k
+    for k in LEAVES:
+        if k in frozen:
+            assert r2[k].grad is None
+        else:
+            Hh.assert_grad_close(n(r2[k].grad), n(r1[k].grad), f"d/d{k}", norm_tol=2e-5)
+    Hh.assert_grad_close(n(o2["viewspace_points"][0].grad), n(o1["viewspace_points"][0].grad), "ndc.grad", norm_tol=2e-5)
