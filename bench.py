@@ -488,6 +488,19 @@ def run_ours(args):
     log(f"train (resident): {total_ms / args.steps:.3f} ms/step")
     e2e_ms, _ = time_steps(train_step_e2e, args.steps, args.warmup, flush, world, rank, frames_of)
     log(f"train (e2e): {e2e_ms / args.steps:.3f} ms/step")
+    # the same step followed by the fused Adam update of every trainable tensor ("full train loop" of BASELINE configs[1])
+    from splatter_a_video_b200.parallel import FlatAdam
+    # learning rates of the reference config (src/configs/frag_gs_v10.yaml:41-66)
+    lrs = {"pos_cubic_node": 6e-5, "scaling": 5e-3, "rotation": 1e-3, "opacity": 5e-2, "shs": 2.5e-3, "mask_attribute": 1e-3,
+           "dino_attribute": 1e-3}
+    opt = FlatAdam(wl.flat, lrs)
+
+    def train_step_adam(frame):
+        train_step(frame)
+        opt.step()
+
+    adam_ms, _ = time_steps(train_step_adam, args.steps, args.warmup, flush, world, rank, frames_of)
+    log(f"train + fused Adam: {adam_ms / args.steps:.3f} ms/step")
     fps_ms, _ = time_steps(lambda f: wl.render_only(f), args.steps, args.warmup, flush, world, rank, frames_of)
     fps_e2e_ms, _ = time_steps(lambda f: wl.render_only(f, to_host=True), args.steps, args.warmup, flush, world, rank, frames_of)
     log(f"render: {fps_ms / args.steps:.3f} ms/frame, e2e {fps_e2e_ms / args.steps:.3f}")
@@ -520,6 +533,8 @@ def run_ours(args):
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "it/s", "h2d_bytes_per_step": int(wl.gt_host.numel() * 4 + wl.w_host.numel() * 4),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
+        "train_with_adam": {"value": world * args.steps / (adam_ms * 1e-3), "unit": "it/s",
+                            "what": "same step + one fused Adam kernel over the flat parameter buffer (parallel.FlatAdam)"},
         "render_fps": world * args.steps / (fps_ms * 1e-3),
         "render_fps_e2e": {"value": world * args.steps / (fps_e2e_ms * 1e-3), "d2h_bytes_per_frame": 3 * wl.H * wl.W * 4},
         "roofline": {"bound": "hbm", "kernel": f"spv_alpha_blend_{'backward' if 'bwd' in dom else 'forward'} ({pname} pass, C={info[pname]['C']})",
