@@ -43,6 +43,11 @@ SPV_API int spv_abi_version(void);
 SPV_API const char *spv_last_error(void);
 /* number of CUDA kernels this library has launched since load (bench.py reports it as `gpu_launches`) */
 SPV_API long long spv_launch_count(void);
+/* Measurement hook (no reference counterpart): when enabled, every blend kernel launch is bracketed by a pair of CUDA events
+ * on its own stream (slot 0 = forward kernel, 1 = backward kernel; also inside a captured graph).  `read` waits for the
+ * slot's closing event and returns the device time of the most recent launch.  Disabled (default): no cost. */
+SPV_API int spv_kernel_timer_enable(int on);
+SPV_API int spv_kernel_timer_read(int slot, float *ms);
 
 /* ---- K1/K2: project_point_forward/backward (ext.cpp:15-16; src/project_point.cu:13-145) ---------- */
 /* intr = [fx,fy,cx,cy]; extr = 12 floats, row-major 3x4 [R|t] (a 4x4 matrix's first 12 floats work). */

@@ -20,6 +20,8 @@ _SIGS = {
     "spv_abi_version": (c_int, []),
     "spv_last_error": (ctypes.c_char_p, []),
     "spv_launch_count": (ctypes.c_longlong, []),
+    "spv_kernel_timer_enable": (c_int, [c_int]),
+    "spv_kernel_timer_read": (c_int, [c_int, P_]),
     "spv_project_point_forward": (c_int, [c_int, P_, P_, P_, c_int, c_int, c_float, c_float, P_, P_, P_]),
     "spv_project_point_backward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
     "spv_project_point_ortho_forward": (c_int, [c_int, P_, P_, c_int, c_int, c_float, c_float, P_, P_, P_]),

@@ -829,10 +829,12 @@ struct FwdArgs {
 
 template <int CH, bool IDX, bool BIAS>
 void launch_fwd(const FwdArgs &a, int ntiles, cudaStream_t s) {
+    spv::timer_mark(0, 0, s);
     blend_fwd_kernel<CH, IDX, BIAS><<<ntiles, kBlock, 0, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.K, a.trunc, a.uv,
                                                              a.conic, a.opacity, a.feature, a.bias, a.idx_sorted,
                                                              a.tile_range, a.bg, a.bgB, a.bgC, a.cA, a.cB, a.rendered,
                                                              a.final_T, a.ncontrib, a.gs_idx);
+    spv::timer_mark(0, 1, s);
 }
 
 template <bool IDX, bool BIAS>
@@ -873,10 +875,12 @@ void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
         cudaFuncSetAttribute(blend_bwd_kernel<NV, CH, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         configured = true;
     }
+    spv::timer_mark(1, 0, s);
     blend_bwd_kernel<NV, CH, MODE, CG><<<ntiles, kBlock, dyn, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
                                                             a.opacity, a.feature, a.bias, a.idx_sorted, a.tile_range,
                                                             a.bg, a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes,
                                                             a.packed);
+    spv::timer_mark(1, 1, s);
 }
 
 template <int CH, int MODE>

@@ -11,9 +11,41 @@ void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed);
 void set_error(cudaError_t e, const char *where) {
     snprintf(g_err, sizeof g_err, "%s: %s (%d)", where, cudaGetErrorString(e), (int)e);
 }
+
+// Optional CUDA-event bracket around the blend kernels (slot 0: forward, 1: backward) so a caller can time the dominant
+// kernel INSIDE a real step (also inside a captured graph: external event-record nodes).  Off by default: zero cost.
+static std::atomic<int> g_timer_on{0};
+static cudaEvent_t g_timer_ev[2][2];
+static bool g_timer_made = false;
+void timer_mark(int slot, int edge, cudaStream_t s) {
+    if (!g_timer_on.load(std::memory_order_relaxed) || slot < 0 || slot > 1) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &st);
+    cudaEventRecordWithFlags(g_timer_ev[slot][edge], s,
+                             st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 }  // namespace spv
 
 extern "C" {
+int spv_kernel_timer_enable(int on) {
+    if (on && !spv::g_timer_made) {
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                cudaError_t e = cudaEventCreate(&spv::g_timer_ev[i][j]);
+                if (e != cudaSuccess) { spv::set_error(e, "spv_kernel_timer_enable"); return (int)e; }
+            }
+        spv::g_timer_made = true;
+    }
+    spv::g_timer_on.store(on ? 1 : 0, std::memory_order_relaxed);
+    return 0;
+}
+int spv_kernel_timer_read(int slot, float *ms) {
+    if (!spv::g_timer_made || slot < 0 || slot > 1 || !ms) { spv::set_error(cudaErrorInvalidValue, "spv_kernel_timer_read: timer not enabled"); return (int)cudaErrorInvalidValue; }
+    cudaError_t e = cudaEventSynchronize(spv::g_timer_ev[slot][1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms, spv::g_timer_ev[slot][0], spv::g_timer_ev[slot][1]);
+    if (e != cudaSuccess) { spv::set_error(e, "spv_kernel_timer_read"); return (int)e; }
+    return 0;
+}
 int spv_abi_version(void) { return SPV_ABI_VERSION; }
 const char *spv_last_error(void) { return spv::g_err; }
 long long spv_launch_count(void) { return spv::g_launches.load(std::memory_order_relaxed); }

@@ -252,3 +252,32 @@ def test_frame_path_with_gradient_free_attribute_groups(cuda):
         else:
             Hh.assert_grad_close(n(r2[k].grad), n(r1[k].grad), f"d/d{k}", norm_tol=2e-5)
     Hh.assert_grad_close(n(o2["viewspace_points"][0].grad), n(o1["viewspace_points"][0].grad), "ndc.grad", norm_tol=2e-5)
+
+
+def test_kernel_timer_brackets_the_blend_kernels(cuda):
+    """spv_kernel_timer_*: off by default; when on, one frame step leaves a positive device time for both blend kernels that
+    is smaller than the event-timed step around it."""
+    import ctypes
+    from splatter_a_video_b200 import _lib as L
+    from splatter_a_video_b200.renderer import parse_renderer
+    sc = synth.make_scene(20_000, 4, 256, 192, seed=5)
+    g = torch.Generator().manual_seed(2)
+    chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
+    gimgs = {k: torch.randn(c, 192, 256, generator=g).to(cuda) for k, c in chans.items()}
+    rnd = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+    _run(rnd, sc, cuda, gimgs)
+    ms = ctypes.c_float()
+    with pytest.raises(RuntimeError):
+        L.call("spv_kernel_timer_read", 0, ctypes.byref(ms))       # never enabled: no events exist
+    L.call("spv_kernel_timer_enable", 1)
+    try:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); _run(rnd, sc, cuda, gimgs); e1.record()
+        torch.cuda.synchronize()
+        got = []
+        for slot in (0, 1):
+            L.call("spv_kernel_timer_read", slot, ctypes.byref(ms))
+            got.append(ms.value)
+        assert 0.0 < got[0] < e0.elapsed_time(e1) and 0.0 < got[1] < e0.elapsed_time(e1)
+    finally:
+        L.call("spv_kernel_timer_enable", 0)
