@@ -199,6 +199,32 @@ SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *e
                   const long long *seg_end_host, const float *seg_lr_host, float beta1, float beta2, float eps, int step,
                   void *stream);
 
+/* ---- Fused image losses (next row f-2): scalar loss + dL/d(rendered image), no host sync --------------------------- */
+/* RGB: weight * ((1-lambda) * mean|p-g| + lambda * (1 - SSIM)) as the trainer computes it (trainer_fragGS.py:573-578 with
+ * pointrix/model/loss.py:22-38 l1_loss and :62-112 ssim).  pred_chw = rendered rgb [3,H,W]; gt_hwc = ground truth [H,W,3]
+ * (the trainer's layout).  The trainer passes [1,H,W,3] tensors to `ssim`, which therefore takes H as the channel count
+ * (loss.py:83): the 11x11 window runs over (x, colour) inside every row -- reproduced exactly.  loss = [total, l1, ssim];
+ * dL_dpred_chw [3,H,W] may be NULL (evaluation). */
+SPV_API size_t spv_loss_rgb_workspace_bytes(int W, int H);
+SPV_API int spv_loss_rgb(int W, int H, const float *pred_chw, const float *gt_hwc, float weight, float lambda_dssim,
+                         float *loss /*[3]*/, float *dL_dpred_chw, void *workspace, size_t ws_bytes, void *stream);
+/* Depth: depth_loss_dpt without weights (src/loss.py:184-206; trainer_fragGS.py:599-601): both maps shifted by their median
+ * (torch.median: lower middle) and scaled by their mean absolute deviation, then MSE.  The gradient flows through the median
+ * element and the deviation like autograd's; among elements tied at the median the lowest index receives it. */
+SPV_API size_t spv_loss_depth_workspace_bytes(int n);
+SPV_API int spv_loss_depth_dpt(int n, const float *pred, const float *gt, float weight, float *loss /*[1]*/,
+                               float *dL_dpred /*[n] or NULL*/, void *workspace, size_t ws_bytes, void *stream);
+/* Track: the "optical flow" loss of trainer_fragGS.py:531-571: rendered track image [>=2,H,W] (normalised x,y in channels
+ * 0,1) sampled at the integer query pixels, denormalised (src/util.py:82), per-point mean |.| against target_xy, trimmed at
+ * torch.quantile(q) over the visible points and weighted (src/criterion.py:46-51), divided by max(H,W).  Point i of
+ * query_xy pairs with point i of target_xy/visible/weights (the reference relies on raster-ordered unique query pixels).
+ * dL_dtrack_chw [2,H,W] is zero-filled by the call (may be NULL). */
+SPV_API size_t spv_loss_track_workspace_bytes(int n_points);
+SPV_API int spv_loss_track(int n_points, int W, int H, const float *track_chw, const int *query_xy /*[n,2] (x,y)*/,
+                           const float *target_xy /*[n,2] pixels*/, const unsigned char *visible /*[n]*/,
+                           const float *weights /*[n]*/, float quantile, float weight, float *loss /*[1]*/,
+                           float *dL_dtrack_chw, void *workspace, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,12 @@ _SIGS = {
     "spv_deform_rotation_forward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
     "spv_deform_rotation_backward": (c_int, [c_int, P_, P_, P_, P_, P_]),
     "spv_adam_step": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, c_int, P_]),
+    "spv_loss_rgb_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
+    "spv_loss_rgb": (c_int, [c_int, c_int, P_, P_, c_float, c_float, P_, P_, P_, ctypes.c_size_t, P_]),
+    "spv_loss_depth_workspace_bytes": (ctypes.c_size_t, [c_int]),
+    "spv_loss_depth_dpt": (c_int, [c_int, P_, P_, c_float, P_, P_, P_, ctypes.c_size_t, P_]),
+    "spv_loss_track_workspace_bytes": (ctypes.c_size_t, [c_int]),
+    "spv_loss_track": (c_int, [c_int, c_int, c_int, P_, P_, P_, P_, P_, c_float, c_float, P_, P_, P_, ctypes.c_size_t, P_]),
 }
 
 EXPORTED = sorted(_SIGS)

@@ -1,0 +1,417 @@
+// Fused image losses of the training step: the step immediately after the rasterizer.  Each entry
+// produces the scalar loss AND dL/d(rendered image) in a handful of launches, with no host synchronisation, so the whole
+// render -> loss -> backward chain stays on one stream (and inside one CUDA graph).
+//
+//   spv_loss_rgb        0.8 L1 + 0.2 (1 - SSIM)     trainer_fragGS.py:573-578, pointrix/model/loss.py:22-112
+//   spv_loss_depth_dpt  median/MAD-normalised MSE   trainer_fragGS.py:599-601, src/loss.py:184-206
+//   spv_loss_track      quantile-trimmed, confidence-weighted L1 on the rendered track image at the query pixels
+//                                                   trainer_fragGS.py:531-571, src/criterion.py:46-51, src/util.py:75-82
+//
+// SSIM quirk kept on purpose: the trainer hands `ssim` tensors of shape [1,H,W,3], and the reference takes
+// `channel = img.size(-3)` = H, so its depthwise 11x11 Gaussian window slides over the (x, colour) plane of every image ROW:
+// 11 taps along x and 11 taps along the 3-wide colour axis (zero padded), rows never mix.
+#include "common.cuh"
+#include "../../include/spv_b200.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+
+constexpr int kRow = 128;               // pixels of one image row per CTA
+constexpr int kHalo = 5;                // window_size // 2
+constexpr int kSpan = kRow + 2 * kHalo;
+constexpr int kRed = 256;               // threads of the streaming reduction kernels
+constexpr int kRedBlocks = 296;         // 2 CTAs per SM
+constexpr float kC1 = 0.01f * 0.01f, kC2 = 0.03f * 0.03f;
+
+// gaussian(11, 1.5) of pointrix/model/loss.py:58-60, evaluated in float32 like the reference (exp in double, sum in float)
+__constant__ float kG[11] = {1.028380124e-03f, 7.598758209e-03f, 3.600077331e-02f, 1.093606874e-01f, 2.130055279e-01f,
+                             2.660117149e-01f, 2.130055279e-01f, 1.093606874e-01f, 3.600077331e-02f, 7.598758209e-03f,
+                             1.028380124e-03f};
+
+__device__ __forceinline__ float sgnf(float d) { return (float)((d > 0.f) - (d < 0.f)); }
+
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+    // fixed-order tree: warp shuffles, then warp 0 over the per-warp sums; every thread of warp 0 gets the total
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < NT / 32 ? scratch[threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        t = __shfl_sync(0xffffffffu, t, 0);
+    }
+    __syncthreads();
+    return t;
+}
+
+// Sums `k` interleaved columns of a [n][k] array of per-CTA partials in a fixed order; result valid in every thread.
+template <int NT, int K>
+__device__ __forceinline__ void total_of_partials(const double *__restrict__ part, int n, double (&out)[K], double *scratch,
+                                                  double *bcast) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < n; i += NT) v += part[(size_t)i * K + j];
+        v = block_sum<NT>(v, scratch);
+        if (threadIdx.x == 0) bcast[j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j) out[j] = bcast[j];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ RGB: L1 + SSIM
+// forward: per (row, x, colour) SSIM value and its derivatives w.r.t. the three window sums that depend on the prediction
+// (E[p], E[p^2], E[p g]), pre-multiplied by dLoss/dSSIM; per-CTA partial sums of SSIM and |p - g|.
+__global__ void __launch_bounds__(kRow)
+ssim_fwd_kernel(int W, int H, const float *__restrict__ pred, const float *__restrict__ gt, float dscale,
+                float *__restrict__ fmaps, double *__restrict__ partials) {
+    __shared__ float sp[3][kSpan], sg[3][kSpan];
+    __shared__ double scratch[kRow / 32];
+    const int y = blockIdx.y, x0 = blockIdx.x * kRow;
+    const size_t HW = (size_t)H * W, row = (size_t)y * W;
+    for (int i = threadIdx.x; i < 3 * kSpan; i += kRow) {
+        const int c = i / kSpan, k = i - c * kSpan, x = x0 + k - kHalo;
+        const bool in = x >= 0 && x < W;
+        sp[c][k] = in ? pred[c * HW + row + x] : 0.f;
+        sg[c][k] = in ? gt[(row + x) * 3 + c] : 0.f;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x, x = x0 + tx;
+    float ssim_sum = 0.f, l1_sum = 0.f;
+    if (x < W) {
+        float h[3][5];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                const float w = kG[k], p = sp[c][tx + k], g = sg[c][tx + k];
+                a0 += w * p; a1 += w * g; a2 += w * (p * p); a3 += w * (g * g); a4 += w * (p * g);
+            }
+            h[c][0] = a0; h[c][1] = a1; h[c][2] = a2; h[c][3] = a3; h[c][4] = a4;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                const float w = kG[5 + cc - c];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) m[q] += w * h[cc][q];
+            }
+            const float mu1 = m[0], mu2 = m[1];
+            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+            const float s1 = m[2] - mu1_sq, s2 = m[3] - mu2_sq, s12 = m[4] - mu12;
+            const float a1 = 2.f * mu12 + kC1, a2 = 2.f * s12 + kC2, b1 = mu1_sq + mu2_sq + kC1, b2 = s1 + s2 + kC2;
+            const float inv = 1.f / (b1 * b2);
+            ssim_sum += (a1 * a2) * inv;
+            // partials with (mu1, s1, s12) independent, then chained onto the raw window sums A=E[p], B=E[p^2], C=E[p g]
+            const float d_s12 = 2.f * a1 * inv;
+            const float d_s1 = -(a1 * a2) * inv / b2;
+            const float d_mu1 = 2.f * mu2 * a2 * inv - 2.f * mu1 * (a1 * a2) * inv / b1;
+            const size_t o = row + x;
+            fmaps[(0 * 3 + c) * HW + o] = dscale * (d_mu1 - 2.f * mu1 * d_s1 - mu2 * d_s12);
+            fmaps[(1 * 3 + c) * HW + o] = dscale * d_s1;
+            fmaps[(2 * 3 + c) * HW + o] = dscale * d_s12;
+            l1_sum += fabsf(sp[c][tx + kHalo] - sg[c][tx + kHalo]);
+        }
+    }
+    const double t0 = block_sum<kRow>((double)ssim_sum, scratch);
+    const double t1 = block_sum<kRow>((double)l1_sum, scratch);
+    if (tx == 0) {
+        const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        partials[2 * b] = t0; partials[2 * b + 1] = t1;
+    }
+}
+
+// backward: the transposed depthwise convolution of the three derivative maps (the window is symmetric, so it is the same
+// zero-padded convolution) + the L1 sign term.  dL/dp = G*fA + 2 p (G*fB) + g (G*fC) + l1scale sign(p - g).
+__global__ void __launch_bounds__(kRow)
+ssim_bwd_kernel(int W, int H, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ fmaps,
+                float l1scale, float *__restrict__ dL_dpred) {
+    __shared__ float sf[9][kSpan];
+    const int y = blockIdx.y, x0 = blockIdx.x * kRow;
+    const size_t HW = (size_t)H * W, row = (size_t)y * W;
+    for (int i = threadIdx.x; i < 9 * kSpan; i += kRow) {
+        const int m = i / kSpan, k = i - m * kSpan, x = x0 + k - kHalo;
+        sf[m][k] = (x >= 0 && x < W) ? fmaps[m * HW + row + x] : 0.f;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x, x = x0 + tx;
+    if (x >= W) return;
+    float h[3][3];   // [kind][colour]: horizontal pass
+#pragma unroll
+    for (int m = 0; m < 9; ++m) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) a += kG[k] * sf[m][tx + k];
+        h[m / 3][m % 3] = a;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float GA = 0.f, GB = 0.f, GC = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            const float w = kG[5 + cc - c];
+            GA += w * h[0][cc]; GB += w * h[1][cc]; GC += w * h[2][cc];
+        }
+        const float p = pred[c * HW + row + x], g = gt[(row + x) * 3 + c];
+        dL_dpred[c * HW + row + x] = GA + 2.f * p * GB + g * GC + l1scale * sgnf(p - g);
+    }
+}
+
+__global__ void __launch_bounds__(kRed)
+rgb_finalize_kernel(const double *__restrict__ partials, int nblk, double n_elems, float weight, float lambda,
+                    float *__restrict__ loss) {
+    __shared__ double scratch[kRed / 32], bcast[2];
+    double t[2];
+    total_of_partials<kRed, 2>(partials, nblk, t, scratch, bcast);
+    if (threadIdx.x == 0) {
+        const float ssim = (float)(t[0] / n_elems), l1 = (float)(t[1] / n_elems);
+        loss[0] = weight * ((1.f - lambda) * l1 + lambda * (1.f - ssim));
+        loss[1] = l1;
+        loss[2] = ssim;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ depth: depth_loss_dpt
+// A: sum |p - t_p|, sum sign(p - t_p), sum |g - t_g|; index of the (first) element that equals the median of p
+__global__ void __launch_bounds__(kRed)
+depth_stats_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ sorted_p,
+                   const float *__restrict__ sorted_g, double *__restrict__ partA, int *__restrict__ med_idx) {
+    __shared__ double scratch[kRed / 32];
+    const float tp = sorted_p[(n - 1) / 2], tg = sorted_g[(n - 1) / 2];   // torch.median: the lower of the two middles
+    float a = 0.f, sg = 0.f, b = 0.f;
+    int first = 0x7fffffff;
+    for (int i = blockIdx.x * kRed + threadIdx.x; i < n; i += gridDim.x * kRed) {
+        const float p = pred[i], d = p - tp;
+        a += fabsf(d); sg += sgnf(d); b += fabsf(gt[i] - tg);
+        if (p == tp) first = min(first, i);
+    }
+    first = __reduce_min_sync(0xffffffffu, first);   // background pixels tie at the median: one atomic per warp, not per pixel
+    if ((threadIdx.x & 31) == 0 && first != 0x7fffffff) atomicMin(med_idx, first);
+    const double t0 = block_sum<kRed>((double)a, scratch), t1 = block_sum<kRed>((double)sg, scratch),
+                 t2 = block_sum<kRed>((double)b, scratch);
+    if (threadIdx.x == 0) { partA[3 * blockIdx.x] = t0; partA[3 * blockIdx.x + 1] = t1; partA[3 * blockIdx.x + 2] = t2; }
+}
+
+// B: residuals r = (p - t_p)/s_p - (g - t_g)/s_g: sum r^2, sum r, sum r * (p - t_p)/s_p
+__global__ void __launch_bounds__(kRed)
+depth_resid_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ sorted_p,
+                   const float *__restrict__ sorted_g, const double *__restrict__ partA, double *__restrict__ partB) {
+    __shared__ double scratch[kRed / 32], bcast[3];
+    double A[3];
+    total_of_partials<kRed, 3>(partA, gridDim.x, A, scratch, bcast);
+    const float tp = sorted_p[(n - 1) / 2], tg = sorted_g[(n - 1) / 2];
+    const float sp = (float)(A[0] / n), sg = (float)(A[2] / n);
+    float r2 = 0.f, r1 = 0.f, rd = 0.f;
+    for (int i = blockIdx.x * kRed + threadIdx.x; i < n; i += gridDim.x * kRed) {
+        const float dn = (pred[i] - tp) / sp, gn = (gt[i] - tg) / sg, r = dn - gn;
+        r2 += r * r; r1 += r; rd += r * dn;
+    }
+    const double t0 = block_sum<kRed>((double)r2, scratch), t1 = block_sum<kRed>((double)r1, scratch),
+                 t2 = block_sum<kRed>((double)rd, scratch);
+    if (threadIdx.x == 0) { partB[3 * blockIdx.x] = t0; partB[3 * blockIdx.x + 1] = t1; partB[3 * blockIdx.x + 2] = t2; }
+}
+
+// C: loss and gradient.  With a_j = 2 r_j / N, S_a = sum a_j, S_ad = sum a_j dn_j, m = median index:
+//   dL/dp_i = a_i/s - [i==m] S_a/s - (S_ad/s) * (1/N) (sign(p_i - t) - [i==m] sum_k sign(p_k - t))
+__global__ void __launch_bounds__(kRed)
+depth_grad_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ sorted_p,
+                  const float *__restrict__ sorted_g, const double *__restrict__ partA, const double *__restrict__ partB,
+                  const int *__restrict__ med_idx, float weight, float *__restrict__ loss, float *__restrict__ dL_dpred) {
+    __shared__ double scratch[kRed / 32], bcast[3];
+    double A[3], B[3];
+    total_of_partials<kRed, 3>(partA, gridDim.x, A, scratch, bcast);
+    total_of_partials<kRed, 3>(partB, gridDim.x, B, scratch, bcast);
+    const float tp = sorted_p[(n - 1) / 2], tg = sorted_g[(n - 1) / 2];
+    const float sp = (float)(A[0] / n), sg = (float)(A[2] / n);
+    const float invn = 1.f / (float)n;
+    const float Sa = (float)(2.0 * B[1] / n), Sad = (float)(2.0 * B[2] / n), Ssgn = (float)A[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) loss[0] = weight * (float)(B[0] / n);
+    if (dL_dpred == nullptr) return;
+    const int m = *med_idx;
+    for (int i = blockIdx.x * kRed + threadIdx.x; i < n; i += gridDim.x * kRed) {
+        const float p = pred[i], dn = (p - tp) / sp, gn = (gt[i] - tg) / sg;
+        const float a = 2.f * (dn - gn) * invn;
+        float g = a / sp - (Sad / sp) * (sgnf(p - tp) * invn);
+        if (i == m) g += -Sa / sp + (Sad / sp) * (Ssgn * invn);
+        dL_dpred[i] = weight * g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ track: trimmed masked L1
+// per point: mean_c |denormalised rendered track - target| (invisible points: +inf so they sort last); count of visible
+__global__ void __launch_bounds__(kRed)
+track_point_kernel(int n, int W, int H, const float *__restrict__ track, const int *__restrict__ query_xy,
+                   const float *__restrict__ gt_xy, const uint8_t *__restrict__ visible, float *__restrict__ vals,
+                   int *__restrict__ n_visible) {
+    const int i = blockIdx.x * kRed + threadIdx.x;
+    if (i >= n) return;
+    float v = __int_as_float(0x7f800000);
+    const int qx = query_xy[2 * i], qy = query_xy[2 * i + 1];
+    if (visible[i] && qx >= 0 && qx < W && qy >= 0 && qy < H) {
+        const size_t o = (size_t)qy * W + qx, HW = (size_t)H * W;
+        const float px = (track[o] + 1.f) * (float)W / 2.f, py = (track[HW + o] + 1.f) * (float)H / 2.f;   // util.py:82
+        v = (fabsf(px - gt_xy[2 * i]) + fabsf(py - gt_xy[2 * i + 1])) / 2.f;
+        atomicAdd(n_visible, 1);
+    }
+    vals[i] = v;
+}
+
+// one CTA: quantile threshold (torch.quantile, linear interpolation, float32 rank), the two masked sums in a fixed order,
+// the loss, then the scatter of the gradient onto the two coordinate planes (atomics: query pixels may repeat)
+__global__ void __launch_bounds__(1024)
+track_reduce_kernel(int n, int W, int H, const float *__restrict__ track, const int *__restrict__ query_xy,
+                    const float *__restrict__ gt_xy, const float *__restrict__ weights, const float *__restrict__ vals,
+                    const float *__restrict__ sorted, const int *__restrict__ n_visible, float quantile, float weight,
+                    float *__restrict__ loss, float *__restrict__ dL_dtrack) {
+    __shared__ double scratch[32], bcast[2];
+    const int M = *n_visible;
+    if (M <= 0) {   // trainer_fragGS.py:569-570: no visible track -> zero loss, no gradient
+        if (threadIdx.x == 0) loss[0] = 0.f;
+        return;
+    }
+    const float pos = quantile * (float)(M - 1);
+    const int lo = (int)floorf(pos), hi = (int)ceilf(pos);
+    const float fr = pos - (float)lo, a = sorted[lo], b = sorted[hi];
+    const float thr = fr < 0.5f ? a + fr * (b - a) : b - (b - a) * (1.f - fr);   // at::lerp
+    double num = 0.0, den = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float v = vals[i];
+        if (v <= thr) { num += (double)(v * weights[i]); den += (double)weights[i]; }
+    }
+    num = block_sum<1024>(num, scratch);
+    if (threadIdx.x == 0) bcast[0] = num;
+    den = block_sum<1024>(den, scratch);
+    if (threadIdx.x == 0) bcast[1] = den;
+    __syncthreads();
+    const float numf = (float)bcast[0], denf = (float)bcast[1] + 1e-8f;     // ndim = 1 (criterion.py:49-51)
+    const float hw = (float)max(H, W);
+    if (threadIdx.x == 0) loss[0] = weight * (numf / denf) / hw;
+    if (dL_dtrack == nullptr) return;
+    const size_t HW = (size_t)H * W;
+    const float k = weight / (denf * hw);
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float v = vals[i];
+        if (!(v <= thr)) continue;
+        const int qx = query_xy[2 * i], qy = query_xy[2 * i + 1];
+        const size_t o = (size_t)qy * W + qx;
+        const float px = (track[o] + 1.f) * (float)W / 2.f, py = (track[HW + o] + 1.f) * (float)H / 2.f;
+        const float w = k * weights[i] * 0.5f;
+        atomicAdd(&dL_dtrack[o], w * sgnf(px - gt_xy[2 * i]) * ((float)W / 2.f));
+        atomicAdd(&dL_dtrack[HW + o], w * sgnf(py - gt_xy[2 * i + 1]) * ((float)H / 2.f));
+    }
+}
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+inline unsigned row_blocks(int W) { return spv::cdiv(W, kRow); }
+
+struct DepthWs { float *sorted_p, *sorted_g; double *partA, *partB; int *med_idx; void *cub; size_t cub_bytes, total; };
+DepthWs carve_depth(void *base, int n) {
+    DepthWs w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void *p = base ? (char *)base + off : nullptr; off += align256(bytes); return p; };
+    w.sorted_p = (float *)take(sizeof(float) * (size_t)n);
+    w.sorted_g = (float *)take(sizeof(float) * (size_t)n);
+    w.partA = (double *)take(sizeof(double) * 3 * kRedBlocks);
+    w.partB = (double *)take(sizeof(double) * 3 * kRedBlocks);
+    w.med_idx = (int *)take(sizeof(int));
+    size_t cb = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cb, (const float *)nullptr, (float *)nullptr, n);
+    w.cub_bytes = cb > 0 ? cb : ((size_t)n * 16 + (1 << 20));   // no device at query time (CPU-side probe): generous bound
+    w.cub = take(w.cub_bytes);
+    w.total = off;
+    return w;
+}
+
+struct TrackWs { float *vals, *sorted; int *n_visible; void *cub; size_t cub_bytes, total; };
+TrackWs carve_track(void *base, int n) {
+    TrackWs w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void *p = base ? (char *)base + off : nullptr; off += align256(bytes); return p; };
+    w.vals = (float *)take(sizeof(float) * (size_t)n);
+    w.sorted = (float *)take(sizeof(float) * (size_t)n);
+    w.n_visible = (int *)take(sizeof(int));
+    size_t cb = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cb, (const float *)nullptr, (float *)nullptr, n);
+    w.cub_bytes = cb > 0 ? cb : ((size_t)n * 16 + (1 << 20));
+    w.cub = take(w.cub_bytes);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t spv_loss_rgb_workspace_bytes(int W, int H) {
+    if (W <= 0 || H <= 0) return 0;
+    return align256(sizeof(float) * 9 * (size_t)H * W) + align256(sizeof(double) * 2 * (size_t)row_blocks(W) * H);
+}
+
+int spv_loss_rgb(int W, int H, const float *pred_chw, const float *gt_hwc, float weight, float lambda_dssim, float *loss,
+                 float *dL_dpred_chw, void *workspace, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_loss_rgb: empty image"); return (int)cudaErrorInvalidValue; }
+    if (ws_bytes < spv_loss_rgb_workspace_bytes(W, H)) { spv::set_error(cudaErrorInvalidValue, "spv_loss_rgb: workspace too small"); return (int)cudaErrorInvalidValue; }
+    float *fmaps = (float *)workspace;
+    double *partials = (double *)((char *)workspace + align256(sizeof(float) * 9 * (size_t)H * W));
+    const dim3 grid(row_blocks(W), H);
+    const double n_elems = 3.0 * (double)H * (double)W;
+    // d(loss)/d(ssim_map element) = -weight * lambda / N ; d(loss)/d|p-g| = weight * (1 - lambda) / N
+    ssim_fwd_kernel<<<grid, kRow, 0, s>>>(W, H, pred_chw, gt_hwc, (float)(-(double)weight * lambda_dssim / n_elems), fmaps, partials);
+    int launches = 2;
+    if (dL_dpred_chw) {
+        ssim_bwd_kernel<<<grid, kRow, 0, s>>>(W, H, pred_chw, gt_hwc, fmaps, (float)((double)weight * (1.0 - lambda_dssim) / n_elems), dL_dpred_chw);
+        ++launches;
+    }
+    rgb_finalize_kernel<<<1, kRed, 0, s>>>(partials, (int)(grid.x * grid.y), n_elems, weight, lambda_dssim, loss);
+    return spv::check_launch("spv_loss_rgb", launches);
+}
+
+size_t spv_loss_depth_workspace_bytes(int n) { return n > 0 ? carve_depth(nullptr, n).total : 0; }
+
+int spv_loss_depth_dpt(int n, const float *pred, const float *gt, float weight, float *loss, float *dL_dpred,
+                       void *workspace, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_loss_depth_dpt: empty image"); return (int)cudaErrorInvalidValue; }
+    DepthWs w = carve_depth(workspace, n);
+    if (ws_bytes < w.total) { spv::set_error(cudaErrorInvalidValue, "spv_loss_depth_dpt: workspace too small"); return (int)cudaErrorInvalidValue; }
+    SPV_CUDA_TRY(cub::DeviceRadixSort::SortKeys(w.cub, w.cub_bytes, pred, w.sorted_p, n, 0, 32, s), "spv_loss_depth_dpt/sort");
+    SPV_CUDA_TRY(cub::DeviceRadixSort::SortKeys(w.cub, w.cub_bytes, gt, w.sorted_g, n, 0, 32, s), "spv_loss_depth_dpt/sort");
+    SPV_CUDA_TRY(cudaMemsetAsync(w.med_idx, 0x7f, sizeof(int), s), "spv_loss_depth_dpt");
+    depth_stats_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.sorted_p, w.sorted_g, w.partA, w.med_idx);
+    depth_resid_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.sorted_p, w.sorted_g, w.partA, w.partB);
+    depth_grad_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.sorted_p, w.sorted_g, w.partA, w.partB, w.med_idx, weight, loss, dL_dpred);
+    return spv::check_launch("spv_loss_depth_dpt", 3 + 2 * 4);   // + the radix-sort passes of the two CUB calls
+}
+
+size_t spv_loss_track_workspace_bytes(int n_points) { return n_points > 0 ? carve_track(nullptr, n_points).total : 0; }
+
+int spv_loss_track(int n_points, int W, int H, const float *track_chw, const int *query_xy, const float *target_xy,
+                   const unsigned char *visible, const float *weights, float quantile, float weight, float *loss,
+                   float *dL_dtrack_chw, void *workspace, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_loss_track: empty image"); return (int)cudaErrorInvalidValue; }
+    if (dL_dtrack_chw) SPV_CUDA_TRY(cudaMemsetAsync(dL_dtrack_chw, 0, sizeof(float) * 2 * (size_t)H * W, s), "spv_loss_track");
+    if (n_points <= 0) {
+        SPV_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), s), "spv_loss_track");
+        return 0;
+    }
+    TrackWs w = carve_track(workspace, n_points);
+    if (ws_bytes < w.total) { spv::set_error(cudaErrorInvalidValue, "spv_loss_track: workspace too small"); return (int)cudaErrorInvalidValue; }
+    SPV_CUDA_TRY(cudaMemsetAsync(w.n_visible, 0, sizeof(int), s), "spv_loss_track");
+    track_point_kernel<<<spv::cdiv(n_points, kRed), kRed, 0, s>>>(n_points, W, H, track_chw, query_xy, target_xy, visible, w.vals, w.n_visible);
+    SPV_CUDA_TRY(cub::DeviceRadixSort::SortKeys(w.cub, w.cub_bytes, w.vals, w.sorted, n_points, 0, 32, s), "spv_loss_track/sort");
+    track_reduce_kernel<<<1, 1024, 0, s>>>(n_points, W, H, track_chw, query_xy, target_xy, weights, w.vals, w.sorted, w.n_visible,
+                                           quantile, weight, loss, dL_dtrack_chw);
+    return spv::check_launch("spv_loss_track", 2 + 4);
+}
+
+}  // extern "C"

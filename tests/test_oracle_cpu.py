@@ -186,3 +186,48 @@ def test_oracle_matches_real_reference_goldens(tiny):
                                       g["final_T"], g["ncontrib"], g["g"])
         for k in ("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature", "dL_dabs_uv"):
             Hh.assert_grad_close(b[k], g[k], f"oracle {k} vs reference golden C={C}", norm_tol=2e-4)
+
+
+# ----------------------------------------------------------------------------- image losses (next row f-2)
+def _loss_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_losses.npz"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_loss_oracle_rgb_matches_reference_golden(tag):
+    """oracle/loss_ref.rgb_loss against values + autograd gradients of the reference's own l1_loss / ssim (row-wise window quirk)."""
+    from oracle import loss_ref as LR
+    G = _loss_golden()
+    pred = torch.from_numpy(G[f"rgb_{tag}_pred"]).requires_grad_(True)
+    loss, l1, ssim = LR.rgb_loss(pred, torch.from_numpy(G[f"rgb_{tag}_gt"]), 0.2)
+    (grad,) = torch.autograd.grad(loss, pred)
+    assert abs(float(loss) - float(G[f"rgb_{tag}_loss"])) <= 2e-6
+    assert abs(float(l1) - float(G[f"rgb_{tag}_l1"])) <= 2e-6 and abs(float(ssim) - float(G[f"rgb_{tag}_ssim"])) <= 2e-6
+    ref = G[f"rgb_{tag}_grad"]
+    assert np.abs(grad.numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_loss_oracle_depth_matches_reference_golden(tag):
+    from oracle import loss_ref as LR
+    G = _loss_golden()
+    pred = torch.from_numpy(G[f"depth_{tag}_pred"]).requires_grad_(True)
+    loss = LR.depth_loss_dpt(pred, torch.from_numpy(G[f"depth_{tag}_gt"]))
+    (grad,) = torch.autograd.grad(loss, pred)
+    assert abs(float(loss) - float(G[f"depth_{tag}_loss"])) <= 1e-5 * max(1.0, float(G[f"depth_{tag}_loss"]))
+    ref = G[f"depth_{tag}_grad"]
+    assert np.abs(grad.numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+def test_loss_oracle_track_matches_reference_golden():
+    from oracle import loss_ref as LR
+    G = _loss_golden()
+    img = torch.from_numpy(G["track_img"]).requires_grad_(True)
+    loss = LR.track_loss(img, torch.from_numpy(G["track_query"]), torch.from_numpy(G["track_target"]),
+                         torch.from_numpy(G["track_visible"]), torch.from_numpy(G["track_weights"]), 0.98)
+    (grad,) = torch.autograd.grad(loss, img)
+    assert abs(float(loss) - float(G["track_loss"])) <= 1e-6 * max(1.0, float(G["track_loss"]))
+    ref = G["track_grad"]
+    assert np.abs(grad.numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert np.count_nonzero(grad.numpy()[2]) == 0                  # the track's depth channel is not part of the loss
