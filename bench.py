@@ -213,7 +213,9 @@ class Workload:
     def _fwd_bwd_resident(self):
         self.flat.zero_grad(self.autograd_names if self.sinks else None)
         out = self.renderer.render_batch(self.render_dict(), [self._batch()])
-        torch.autograd.backward([out[k][0] for k in self.KEYS], [self.g_dev[k] for k in self.KEYS])
+        # gradients handed over on the batched [1,C,H,W] outputs: indexing `out[k][0]` first would make autograd rebuild a
+        # zero-filled batched gradient per image (select_backward), 2 x 37 MB of fills and copies per step
+        torch.autograd.backward([out[k] for k in self.KEYS], [self.g_dev[k][None] for k in self.KEYS])
 
     def _fwd_bwd_from_staged_host_data(self):
         self.flat.zero_grad(self.autograd_names if self.sinks else None)
@@ -222,7 +224,7 @@ class Workload:
         resid = (rgb.detach() - self.gt_dev) * self.w_dev                     # weighted residual of the frame just uploaded
         self.loss_dev.copy_((resid * resid).mean().reshape(1) * 0.5)          # weighted L2 photometric loss (scalar read back)
         g_rgb = resid * self.w_dev / resid.numel()
-        torch.autograd.backward([rgb] + [out[k][0] for k in self.KEYS[1:]], [g_rgb] + [self.g_dev[k] for k in self.KEYS[1:]])
+        torch.autograd.backward([out["rgb"]] + [out[k] for k in self.KEYS[1:]], [g_rgb[None]] + [self.g_dev[k][None] for k in self.KEYS[1:]])
 
     def _render_only(self):
         with torch.no_grad():
@@ -298,8 +300,8 @@ def live_kernel_times(wl, steps, warmup, flush_buf, frames_of):
         L.call("spv_kernel_timer_read", 0, ctypes.byref(ms)); fwd.append(ms.value)
         L.call("spv_kernel_timer_read", 1, ctypes.byref(ms)); bwd.append(ms.value)
     L.call("spv_kernel_timer_enable", 0)
+    I = int(wl.renderer.last_status.cpu()[0])      # read before the graph (and its memory pool) goes away
     wl.graphs.pop("train", None)
-    I = int(wl.renderer.last_status.cpu()[0])
     return {"fwd_ms": sum(fwd) / len(fwd), "bwd_ms": sum(bwd) / len(bwd), "step_ms": sum(step) / len(step), "I": I}
 
 
@@ -511,7 +513,7 @@ def run_ours(args):
     launches = L.query("spv_launch_count") - n0
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms, per_step = time_steps(train_step, args.steps, args.warmup, flush, world, rank, frames_of)
-    log(f"train (resident): {total_ms / args.steps:.3f} ms/step")
+    log(f"train (resident): {total_ms / args.steps:.3f} ms/step (per step min {min(per_step):.3f} / median {float(np.median(per_step)):.3f} / max {max(per_step):.3f})")
     e2e_ms, _ = time_steps(train_step_e2e, args.steps, args.warmup, flush, world, rank, frames_of)
     log(f"train (e2e): {e2e_ms / args.steps:.3f} ms/step")
     # the same step followed by the fused Adam update of every trainable tensor ("full train loop" of BASELINE configs[1])
@@ -520,12 +522,15 @@ def run_ours(args):
     lrs = {"pos_cubic_node": 6e-5, "scaling": 5e-3, "rotation": 1e-3, "opacity": 5e-2, "shs": 2.5e-3, "mask_attribute": 1e-3,
            "dino_attribute": 1e-3}
     opt = FlatAdam(wl.flat, lrs)
+    snapshot = wl.flat.flat.clone()          # the optimizer moves the scene: every other measurement runs on the initial one
 
     def train_step_adam(frame):
         train_step(frame)
         opt.step()
 
     adam_ms, _ = time_steps(train_step_adam, args.steps, args.warmup, flush, world, rank, frames_of)
+    wl.flat.flat.copy_(snapshot)
+    del snapshot, opt
     log(f"train + fused Adam: {adam_ms / args.steps:.3f} ms/step")
     fps_ms, _ = time_steps(lambda f: wl.render_only(f), args.steps, args.warmup, flush, world, rank, frames_of)
     fps_e2e_ms, _ = time_steps(lambda f: wl.render_only(f, to_host=True), args.steps, args.warmup, flush, world, rank, frames_of)

@@ -106,6 +106,14 @@ class _BaseRender:
             radii.append(r["radii"].unsqueeze(0))
             if "gs_idx" in r:
                 gs_idx.append(r["gs_idx"].unsqueeze(0))
+        if len(batch) == 1:
+            # the trainer's case (one camera per step): the same [1,...] tensors as views -- no 70 MB of stack/cat copies, no
+            # reductions over a batch axis of length one
+            out = {k: v[0].unsqueeze(0) for k, v in feats.items()}
+            out.update(viewspace_points=viewspace, visibility=vis[0].squeeze(0), radii=radii[0].squeeze(0))
+            if gs_idx:
+                out["gs_idx"] = gs_idx[0]
+            return out
         out = {k: torch.stack(v, dim=0) for k, v in feats.items()}
         out.update(viewspace_points=viewspace, visibility=torch.cat(vis).any(dim=0),
                    radii=torch.cat(radii, 0).max(dim=0).values)
