@@ -180,6 +180,7 @@ class Workload:
         self.w_dev = torch.empty(1, self.H, self.W, device=device)
         self.loss_dev = torch.zeros(1, device=device)
         self.loss_host = torch.empty(1).pin_memory()
+        self.copy_stream = self.dl_stream = None                # created on first use by the e2e paths
         self.use_graph = bool(graph) and mode == "frame"
         self.graphs = {}
         # frame mode: the fused backward writes these gradients straight into their slices of the flat buffer
@@ -258,21 +259,67 @@ class Workload:
         self.set_frame(frame)
         self._run("train", self._fwd_bwd_resident)
 
+    def _prefetch_batch(self, buf):
+        """Next step's batch (ground-truth frame + per-pixel weights) pinned host -> staging buffer `buf` on the copy stream."""
+        cs = self.copy_stream
+        cs.wait_stream(torch.cuda.current_stream())            # not before this point of the step (stays inside its time bracket)
+        with torch.cuda.stream(cs):
+            self.gt_stage[buf].copy_(self.gt_host, non_blocking=True)
+            self.w_stage[buf].copy_(self.w_host, non_blocking=True)
+            self.pf_event[buf].record(cs)
+
     def step_e2e(self, frame):
-        """Host-driven step: H2D of the frame's ground truth + per-pixel weights, loss gradient on device, D2H loss."""
+        """Host-driven step: the batch of step i+1 travels H2D on a copy stream WHILE step i computes (what a pinned-memory
+        DataLoader gives the reference trainer); the step itself starts from the staged copy, computes the loss gradient on
+        the device and reads the scalar loss back.  Every time bracket contains one full H2D batch copy and one D2H read."""
         self.set_frame(frame)
-        self.gt_dev.copy_(self.gt_host, non_blocking=True)
-        self.w_dev.copy_(self.w_host, non_blocking=True)
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream()
+            self.gt_stage = [torch.empty_like(self.gt_dev) for _ in range(2)]
+            self.w_stage = [torch.empty_like(self.w_dev) for _ in range(2)]
+            self.pf_event = [torch.cuda.Event() for _ in range(2)]
+            self.pf_buf = 0
+            self._prefetch_batch(0)
+        cur = self.pf_buf
+        main = torch.cuda.current_stream()
+        self._prefetch_batch(cur ^ 1)                           # overlaps this step's kernels
+        main.wait_event(self.pf_event[cur])
+        self.gt_dev.copy_(self.gt_stage[cur], non_blocking=True)
+        self.w_dev.copy_(self.w_stage[cur], non_blocking=True)
         self._run("train_e2e", self._fwd_bwd_from_staged_host_data)
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                            # the D2H read of the step's result
+        main.wait_event(self.pf_event[cur ^ 1])                 # the bracket ends only after the prefetch it started
+        self.pf_buf = cur ^ 1
+        main.synchronize()                                      # the D2H read of the step's result
         return float(self.loss_host[0])
 
     def render_only(self, frame, to_host=False):
+        """to_host: the frame rendered by call i-1 is copied D2H on the copy stream while call i renders; every time bracket
+        contains one full frame download (the consumer sees frames one call late, like a double-buffered video sink)."""
         self.set_frame(frame)
+        if not to_host:
+            self._run("render", self._render_only)
+            return None
+        main = torch.cuda.current_stream()
+        if self.dl_stream is None:
+            self.dl_stream = torch.cuda.Stream()
+            self.dl_stage = [torch.empty(1, 3, self.H, self.W, device=self.device) for _ in range(2)]
+            self.dl_host = [torch.empty(1, 3, self.H, self.W).pin_memory() for _ in range(2)]
+            self.dl_event = torch.cuda.Event()
+            self.dl_buf, self.dl_pending = 0, False
+        if self.dl_pending:                                     # download of the previous frame, overlapping this render
+            prev = self.dl_buf ^ 1
+            self.dl_stream.wait_stream(main)
+            with torch.cuda.stream(self.dl_stream):
+                self.dl_host[prev].copy_(self.dl_stage[prev], non_blocking=True)
+                self.dl_event.record(self.dl_stream)
         self._run("render", self._render_only)
-        if to_host:
-            return self.last_render.cpu()
+        self.dl_stage[self.dl_buf].copy_(self.last_render, non_blocking=True)
+        if self.dl_pending:
+            main.wait_event(self.dl_event)
+        self.dl_pending = True
+        self.dl_buf ^= 1
+        return self.dl_host[self.dl_buf]                         # valid after the next call / a synchronize
 
     def overflowed(self):
         st = self.renderer.last_status
@@ -575,12 +622,15 @@ def run_ours(args):
                    "capacity_overflow": wl.overflowed(), "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
                    "grad_floats_per_gaussian": wl.flat.floats_per_gaussian(wl.P)},
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "it/s", "h2d_bytes_per_step": int(wl.gt_host.numel() * 4 + wl.w_host.numel() * 4),
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4,
+                "pipeline": "double-buffered H2D: the batch of step i+1 is copied on a second stream while step i runs; every per-step "
+                            "event bracket contains one full batch copy, the loss read-back and a host synchronize"},
         "gpu_launches": launches,
         "train_with_adam": {"value": world * args.steps / (adam_ms * 1e-3), "unit": "it/s",
                             "what": "same step + one fused Adam kernel over the flat parameter buffer (parallel.FlatAdam)"},
         "render_fps": world * args.steps / (fps_ms * 1e-3),
-        "render_fps_e2e": {"value": world * args.steps / (fps_e2e_ms * 1e-3), "d2h_bytes_per_frame": 3 * wl.H * wl.W * 4},
+        "render_fps_e2e": {"value": world * args.steps / (fps_e2e_ms * 1e-3), "d2h_bytes_per_frame": 3 * wl.H * wl.W * 4,
+                           "pipeline": "double-buffered D2H: frame i-1 downloads on a second stream while frame i renders"},
         "roofline": {"bound": "hbm", "kernel": dom_label,
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": ncu_traffic(("blend_groups_" if "fused" in dom else "blend_") + ("backward" if "bwd" in dom else "forward")),

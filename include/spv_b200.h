@@ -88,7 +88,8 @@ SPV_API int spv_ewa_project_ortho_backward(int P, const float *cov3d, const floa
 
 /* ---- K7-K10: compute_sh(_free)_forward/backward (ext.cpp:23-24,29-30; src/compute_sh*.cu) --------- */
 /* shs is read with a per-point stride of (deg+1)^2 * 3 floats exactly like the reference
- * (compute_sh.cu:45); S_alloc = shs.size(1) only sizes the zero-filled dL_dshs[P,S_alloc,3].          */
+ * (compute_sh.cu:45); S_alloc = shs.size(1) only sizes the zero-filled dL_dshs[P,S_alloc,3].
+ * visible == NULL means "every point visible" (what the renderers pass, dptr_ortho_enhanced.py:272).   */
 SPV_API int spv_compute_sh_forward(int P, const float *shs, int deg, const float *dirs, const uint8_t *visible,
                            int free_variant, float *colors /*[P,3]*/, uint8_t *clamped /*[P,3], NULL if free*/,
                            void *stream);

@@ -275,6 +275,7 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     __shared__ int s_id[kG];
     __shared__ __align__(16) float s_feat[kG * FS];
     __shared__ float s_part[8][kG][kSP];
+    __shared__ unsigned s_hit[8];                   // per warp: which chunk entries it parked a row for
     __shared__ int s_max;
 
     const int tile = blockIdx.x;
@@ -347,21 +348,19 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
         // phase 2: reduce the per-pixel partial gradients of every Gaussian that touched this warp.  The body is
         // branch-free: a lane that did not take the Gaussian runs it with p2 = -inf, i.e. G = alpha = w = 0, so every
         // partial sum it contributes is an exact zero and only the recurrence state needs selects.
-        for (int j = 0; j < m; ++j) {
-            bool hit = false;
-            float dx = 0.f, dy = 0.f, p2 = 0.f;
+        // only the entries that passed the block test are visited (in chunk order: the recurrence needs back-to-front)
+        unsigned todo = wmask, hmask = 0u;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            float dx = 0.f, dy = 0.f;
             const float4 g0 = s_g0[j];
             const float4 g1 = s_g1[j];
-            if ((wmask >> j) & 1u) {   // warp-uniform
-                p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-                // did this pixel apply the Gaussian in the forward pass?  (same test, and before the last contributor)
-                hit = splat_hits<HAS_BIAS>(p2, g1) && (p_hi - 1 - j) < last_contrib;
-            }
-            if (!__any_sync(kFull, hit)) {
-                if (lane < kSP) s_part[warp][j][lane] = 0.f;
-                if constexpr (kSP > 32) { if (lane < kSP - 32) s_part[warp][j][32 + lane] = 0.f; }
-                continue;
-            }
+            float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+            // did this pixel apply the Gaussian in the forward pass?  (same test, and before the last contributor)
+            const bool hit = splat_hits<HAS_BIAS>(p2, g1) && (p_hi - 1 - j) < last_contrib;
+            if (!__any_sync(kFull, hit)) continue;
+            hmask |= 1u << j;
             float v[NV];
             float n0 = 0.f, n1 = 0.f;
             {
@@ -445,35 +444,41 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
                 halving_reduce<NV, 0, NV>(v, lane);
                 if (lane < NV) s_part[warp][j][lane] = v[0];
                 if constexpr (GROUPS) {
+                    // the two RGB-pass sums: one halving step (odd lanes take n1, even lanes n0), then 4 butterfly steps
+                    const bool up = (lane & 1) != 0;
+                    float r = (up ? n1 : n0) + __shfl_xor_sync(kFull, up ? n0 : n1, 1);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        n0 += __shfl_xor_sync(kFull, n0, o);
-                        n1 += __shfl_xor_sync(kFull, n1, o);
-                    }
-                    if (lane == 0) { s_part[warp][j][NV] = n0; s_part[warp][j][NV + 1] = n1; }
+                    for (int o = 2; o <= 16; o <<= 1) r += __shfl_xor_sync(kFull, r, o);
+                    if (lane < 2) s_part[warp][j][NV + lane] = r;
                 }
             }
         }
+        if (lane == 0) s_hit[warp] = hmask;
         __syncthreads();
-        // fold the 8 warps and push one packed row per (tile, Gaussian)
+        // fold the warps that parked a row and push one packed row per (tile, Gaussian)
+        unsigned hm[8], hany = 0u;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) { hm[w8] = s_hit[w8]; hany |= hm[w8]; }
         if constexpr (NV >= 32) {
 #pragma unroll
             for (int jj = 0; jj < kG / 8; ++jj) {
                 const int j = warp * (kG / 8) + jj;
-                if (j < m) {
+                if (j < m && ((hany >> j) & 1u)) {
                     float *row = packed + (size_t)s_id[j] * kRow;
 #pragma unroll
                     for (int half = 0; half < NV / 32; ++half) {
                         float s = 0.f;
 #pragma unroll
-                        for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][half * 32 + lane];
+                        for (int w8 = 0; w8 < 8; ++w8)
+                            if ((hm[w8] >> j) & 1u) s += s_part[w8][j][half * 32 + lane];
                         if (s != 0.f) atomicAdd(row + half * 32 + lane, s);
                     }
                     if constexpr (GROUPS) {
                         if (lane < 2) {
                             float e = 0.f;
 #pragma unroll
-                            for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][NV + lane];
+                            for (int w8 = 0; w8 < 8; ++w8)
+                                if ((hm[w8] >> j) & 1u) e += s_part[w8][j][NV + lane];
                             if (e != 0.f) atomicAdd(row + 31 + lane, e);
                         }
                     }
@@ -484,17 +489,19 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
 #pragma unroll
             for (int jj = 0; jj < kG / 16; ++jj) {
                 const int j = warp * (kG / 8) + jj * 2 + half;
-                if (j < m) {
+                if (j < m && ((hany >> j) & 1u)) {
                     float *row = packed + (size_t)s_id[j] * kRow;
                     float s = 0.f;
 #pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) s += s_part[w8][j][l16];
+                    for (int w8 = 0; w8 < 8; ++w8)
+                        if ((hm[w8] >> j) & 1u) s += s_part[w8][j][l16];
                     if (s != 0.f) atomicAdd(row + l16, s);
                     if constexpr (GROUPS) {
                         if (l16 < 2) {
                             float e = 0.f;
 #pragma unroll
-                            for (int w8 = 0; w8 < 8; ++w8) e += s_part[w8][j][NV + l16];
+                            for (int w8 = 0; w8 < 8; ++w8)
+                                if ((hm[w8] >> j) & 1u) e += s_part[w8][j][NV + l16];
                             if (e != 0.f) atomicAdd(row + 31 + l16, e);
                         }
                     }
@@ -957,6 +964,29 @@ void dispatch_bwd_groups(const BwdArgs &a, int ntiles, cudaStream_t s) {
 
 }  // namespace
 
+namespace spv {
+// Grouped forward; fill_idx = false when the caller has already filled gs_idx with -1 (frame.cu does it on its side stream).
+int blend_groups_forward(int P, int C, int W, int H, int K, const float *uv, const float *conic, const float *opacity,
+                         const float *feature, const int *idx_sorted, const int *tile_range, float bg_rgb, float bg_depth,
+                         float bg_attr, float *rendered, float *final_T, int *ncontrib, int *gs_idx, bool fill_idx, void *stream) {
+    (void)P;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W <= 0 || H <= 0) return 0;
+    if (C < 4 || C > 32) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_forward: need 4 <= C <= 32"); return (int)cudaErrorInvalidValue; }
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
+    const bool has_idx = gs_idx != nullptr && K > 0;
+    if (has_idx && fill_idx) SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, s), "spv_alpha_blend_groups_forward");
+    FwdArgs a;
+    a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx; a.K = K; a.trunc = 0;
+    a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
+    a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range;
+    a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.cA = 3; a.cB = 4;
+    a.rendered = rendered; a.final_T = final_T; a.ncontrib = ncontrib; a.gs_idx = gs_idx;
+    if (has_idx) dispatch_fwd<true, false>(a, ntiles, s); else dispatch_fwd<false, false>(a, ntiles, s);
+    return spv::check_launch("spv_alpha_blend_groups_forward");
+}
+}  // namespace spv
+
 extern "C" {
 
 int spv_alpha_blend_forward(int P, int C, int W, int H, int K, int enable_truncation, const float *uv,
@@ -1057,53 +1087,8 @@ int spv_alpha_blend_groups_forward(int P, int C, int W, int H, int K, const floa
                                    const float *opacity, const float *feature, const int *idx_sorted,
                                    const int *tile_range, float bg_rgb, float bg_depth, float bg_attr, float *rendered,
                                    float *final_T, int *ncontrib, int *gs_idx, void *stream) {
-    (void)P;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (W <= 0 || H <= 0) return 0;
-    if (C < 4 || C > 32) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_forward: need 4 <= C <= 32"); return (int)cudaErrorInvalidValue; }
-    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
-    const bool has_idx = gs_idx != nullptr && K > 0;
-    if (has_idx) SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, s), "spv_alpha_blend_groups_forward");
-    FwdArgs a;
-    a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx; a.K = K; a.trunc = 0;
-    a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
-    a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range;
-    a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.cA = 3; a.cB = 4;
-    a.rendered = rendered; a.final_T = final_T; a.ncontrib = ncontrib; a.gs_idx = gs_idx;
-    if (has_idx) dispatch_fwd<true, false>(a, ntiles, s); else dispatch_fwd<false, false>(a, ntiles, s);
-    return spv::check_launch("spv_alpha_blend_groups_forward");
-}
-
-size_t spv_alpha_blend_groups_backward_workspace_bytes(int P) { return (size_t)(P > 0 ? P : 1) * kRowG * sizeof(float); }
-
-int spv_alpha_blend_groups_backward(int P, int C, int W, int H, const float *uv, const float *conic,
-                                    const float *opacity, const float *feature, const int *idx_sorted,
-                                    const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
-                                    const float *final_T, const int *ncontrib, const float *dL_drendered,
-                                    float *dL_duv, float *dL_duv_rgb, float *dL_dabs_uv_rgb, float *dL_dconic,
-                                    float *dL_dopacity, float *dL_dfeature, void *workspace, size_t ws_bytes,
-                                    void *stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    if (P <= 0) return 0;
-    if (C < 4 || C > 23) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward: need 4 <= C <= 23"); return (int)cudaErrorInvalidValue; }
-    if (ws_bytes < spv_alpha_blend_groups_backward_workspace_bytes(P)) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward: workspace too small"); return (int)cudaErrorInvalidValue; }
-    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
-    float *packed = (float *)workspace;
-    SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)kRowG * P, s), "spv_alpha_blend_groups_backward");
-    if (W > 0 && H > 0) {
-        BwdArgs a;
-        a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx;
-        a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
-        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr;
-        a.final_T = final_T; a.ncontrib = ncontrib; a.planes = contiguous_planes(dL_drendered, C, W, H); a.packed = packed;
-        dispatch_bwd_groups(a, ntiles, s);
-        int rc = spv::check_launch("spv_alpha_blend_groups_backward/blend");
-        if (rc) return rc;
-    }
-    unpack_groups_kernel<<<spv::cdiv(P, kBlock), kBlock, 0, s>>>(P, C, packed, (float2 *)dL_duv, (float2 *)dL_duv_rgb,
-                                                                 (float2 *)dL_dabs_uv_rgb, dL_dconic, dL_dopacity,
-                                                                 dL_dfeature);
-    return spv::check_launch("spv_alpha_blend_groups_backward/unpack");
+    return spv::blend_groups_forward(P, C, W, H, K, uv, conic, opacity, feature, idx_sorted, tile_range, bg_rgb, bg_depth, bg_attr,
+                                     rendered, final_T, ncontrib, gs_idx, /*fill_idx=*/true, stream);
 }
 
 /* Grouped backward, blend stage only: upstream gradients as per-channel planes (host array of C device pointers, NULL

@@ -74,6 +74,11 @@ __device__ __forceinline__ bool tile_may_hit(float cx, float cy, float a, float 
 // frame path hand the autograd engine's separate per-image gradients to the kernel without concatenating them.
 struct ChanPlanes { const float *p[32]; };
 
+// blend.cu: grouped forward with the -1 fill of the id image optional (frame.cu fills it on its side stream)
+int blend_groups_forward(int P, int C, int W, int H, int K, const float *uv, const float *conic, const float *opacity,
+                         const float *feature, const int *idx_sorted, const int *tile_range, float bg_rgb, float bg_depth,
+                         float bg_attr, float *rendered, float *final_T, int *ncontrib, int *gs_idx, bool fill_idx, void *stream);
+
 // Packed per-Gaussian gradient row of the grouped blend backward (stride kPackedRowGroups floats):
 //   0,1 dL_duv(all)  2,3 |RGB-pass dL_duv|  4,5,6 dL_dconic  7 dL_dopacity  8..8+C-1 dL_dfeature  31,32 RGB-pass dL_duv
 constexpr int kPackedRowGroups = 36;

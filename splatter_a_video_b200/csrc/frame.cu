@@ -136,6 +136,22 @@ inline int make_groups(AttrGroups &g, int n, const float *const *in, float *cons
 
 #define SPV_TRY_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
+// A second stream for the branches of a frame that do not depend on each other (forward: SH colours + feature packing +
+// the id-image fill next to the projection / binning / sort chain, whose radix passes leave most SMs idle; backward: the SH
+// gradient next to the covariance chain).  Forked from and joined back into the caller's stream with events, so the caller
+// still sees one in-order stream -- and a stream capture records the branches as parallel graph nodes.
+struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+static thread_local SideLane g_side;
+SideLane *side_lane() {
+    if (!g_side.ok) {
+        if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        g_side.ok = true;
+    }
+    return &g_side;
+}
+
 }  // namespace
 
 extern "C" {
@@ -162,25 +178,27 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     SPV_TRY_RC(spv_project_point_ortho_forward(P, position, extr, W, H, nearest, extent, f.uv, f.depth, stream));
     visible_kernel<<<g, kThreads, 0, s>>>(P, f.depth, f.vis);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep", 2));
-    // SH is evaluated for every point (the renderer passes no visibility mask to compute_sh, :272)
-    SPV_CUDA_TRY(cudaMemsetAsync(f.clamped, 1, (size_t)P * 3, s), "spv_frame_ortho_forward");
-    {
-        // all-visible mask for SH: reuse `tiles` storage as a byte mask of ones is not possible (int) -> use clamped trick:
-        // compute_sh takes a visibility array; build an all-ones byte array in the (not yet used) g_dirs scratch.
-        uint8_t *ones = (uint8_t *)f.g_dirs;
-        SPV_CUDA_TRY(cudaMemsetAsync(ones, 1, (size_t)P, s), "spv_frame_ortho_forward");
-        SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, ones, 0, f.rgb, f.clamped, stream));
-    }
+    const int C = 4 + A;
+    // ---- side branch: SH colours (evaluated for every point: the renderer passes no visibility mask, :272), the packed
+    //      [rgb | depth | attributes] feature rows and the -1 fill of the id image
+    SideLane *lane = side_lane();
+    if (!lane) { spv::set_error(cudaGetLastError(), "spv_frame_ortho_forward: side stream"); return (int)cudaErrorUnknown; }
+    SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_forward/fork");
+    SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_forward/fork");
+    SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
+    pack_features_kernel<<<spv::cdiv((long long)P * C, kThreads), kThreads, 0, lane->stream>>>(P, A, f.rgb, f.depth, gr, f.feature);
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/pack"));
+    SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, lane->stream), "spv_frame_ortho_forward");
+    SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_forward/join");
+    // ---- main branch: covariance, conic / radius / tile rectangle, culled binning + sort
     SPV_TRY_RC(spv_compute_cov3d_forward(P, scaling, rotation, f.vis, f.cov3d, stream));
     SPV_TRY_RC(spv_ewa_project_ortho_forward(P, f.cov3d, extr, f.uv, W, H, f.vis, f.conic, f.radius, f.tiles, stream));
     SPV_CUDA_TRY(cudaMemcpyAsync(radii, f.radius, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, s), "spv_frame_ortho_forward");
     SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
                                 status, f.bin_ws, f.bin_bytes, stream));
-    const int C = 4 + A;
-    pack_features_kernel<<<spv::cdiv((long long)P * C, kThreads), kThreads, 0, s>>>(P, A, f.rgb, f.depth, gr, f.feature);
-    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/pack"));
-    return spv_alpha_blend_groups_forward(P, C, W, H, K, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
-                                          bg_rgb, 1.0f, 0.0f, images, f.final_T, f.ncontrib, gs_idx, stream);
+    SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0), "spv_frame_ortho_forward/join");
+    return spv::blend_groups_forward(P, C, W, H, K, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
+                                     bg_rgb, 1.0f, 0.0f, images, f.final_T, f.ncontrib, gs_idx, /*fill_idx=*/false, stream);
 }
 
 int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int n_grad_channels, int64_t I_cap,
@@ -203,16 +221,19 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, (float2 *)f.g_uv, f.g_conic, dL_dopacity, f.g_rgb, f.g_depth, gr,
                                                (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));
-    // colours -> SH coefficients (view direction is a constant: its gradient is discarded)
-    {
-        uint8_t *ones = (uint8_t *)f.bin_ws;   // binning scratch is free again: all-visible mask for SH
-        SPV_CUDA_TRY(cudaMemsetAsync(ones, 1, (size_t)P, s), "spv_frame_ortho_backward");
-        SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, ones, f.clamped, f.g_rgb, 16, dL_dshs, f.g_dirs, stream));
-    }
-    // uv, depth -> position ; conic -> cov3d -> scaling, rotation
+    // colours -> SH coefficients (view direction is a constant: its gradient is discarded) on the side stream, next to
+    // uv, depth -> position ; conic -> cov3d -> scaling, rotation on the caller's
+    SideLane *lane = side_lane();
+    if (!lane) { spv::set_error(cudaGetLastError(), "spv_frame_ortho_backward: side stream"); return (int)cudaErrorUnknown; }
+    SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_backward/fork");
+    SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_backward/fork");
+    SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, nullptr, f.clamped, f.g_rgb, 16, dL_dshs, f.g_dirs, (void *)lane->stream));
+    SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_backward/join");
     SPV_TRY_RC(spv_project_point_ortho_backward(P, extr, W, H, f.depth, f.g_uv, f.g_depth, dL_dposition, stream));
     SPV_TRY_RC(spv_ewa_project_ortho_backward(P, f.cov3d, extr, W, H, f.radius, f.g_conic, f.g_cov3d, stream));
-    return spv_compute_cov3d_backward(P, scaling, rotation, f.vis, f.g_cov3d, dL_dscaling, dL_drotation, stream);
+    SPV_TRY_RC(spv_compute_cov3d_backward(P, scaling, rotation, f.vis, f.g_cov3d, dL_dscaling, dL_drotation, stream));
+    SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0), "spv_frame_ortho_backward/join");
+    return 0;
 }
 
 }  // extern "C"

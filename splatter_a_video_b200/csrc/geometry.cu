@@ -571,7 +571,7 @@ sh_fwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
     if (i >= P) return;
     float out[3] = {0.f, 0.f, 0.f};
     uint8_t cl[3] = {1, 1, 1};  // torch::ones for rows the kernel skips (compute_sh.cu:245)
-    if (visible[i]) {
+    if (visible == nullptr || visible[i]) {   // NULL mask = every point visible
         const float *sh = s_sh + threadIdx.x * (ROW + 1);
         const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
 #pragma unroll
@@ -626,7 +626,7 @@ sh_bwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
         float *dsh = s_g + threadIdx.x * (ROW + 1);
 #pragma unroll
         for (int k = 0; k < ROW; ++k) dsh[k] = 0.f;     // invisible rows stay zero (torch::zeros in the reference)
-        if (visible[i]) {
+        if (visible == nullptr || visible[i]) {   // NULL mask = every point visible
             const float *sh = s_sh + threadIdx.x * (ROW + 1);
             const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
 #pragma unroll
