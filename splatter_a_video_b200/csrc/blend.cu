@@ -1091,6 +1091,38 @@ int spv_alpha_blend_groups_forward(int P, int C, int W, int H, int K, const floa
                                      rendered, final_T, ncontrib, gs_idx, /*fill_idx=*/true, stream);
 }
 
+size_t spv_alpha_blend_groups_backward_workspace_bytes(int P) { return (size_t)(P > 0 ? P : 1) * kRowG * sizeof(float); }
+
+int spv_alpha_blend_groups_backward(int P, int C, int W, int H, const float *uv, const float *conic,
+                                    const float *opacity, const float *feature, const int *idx_sorted,
+                                    const int *tile_range, float bg_rgb, float bg_depth, float bg_attr,
+                                    const float *final_T, const int *ncontrib, const float *dL_drendered,
+                                    float *dL_duv, float *dL_duv_rgb, float *dL_dabs_uv_rgb, float *dL_dconic,
+                                    float *dL_dopacity, float *dL_dfeature, void *workspace, size_t ws_bytes,
+                                    void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0) return 0;
+    if (C < 4 || C > 23) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward: need 4 <= C <= 23"); return (int)cudaErrorInvalidValue; }
+    if (ws_bytes < spv_alpha_blend_groups_backward_workspace_bytes(P)) { spv::set_error(cudaErrorInvalidValue, "spv_alpha_blend_groups_backward: workspace too small"); return (int)cudaErrorInvalidValue; }
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
+    float *packed = (float *)workspace;
+    SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)kRowG * P, s), "spv_alpha_blend_groups_backward");
+    if (W > 0 && H > 0) {
+        BwdArgs a;
+        a.C = C; a.Cstride = C; a.c0 = 0; a.W = W; a.H = H; a.gx = gx;
+        a.uv = (const float2 *)uv; a.conic = conic; a.opacity = opacity; a.feature = feature; a.bias = nullptr;
+        a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range; a.bg = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr;
+        a.final_T = final_T; a.ncontrib = ncontrib; a.planes = contiguous_planes(dL_drendered, C, W, H); a.packed = packed;
+        dispatch_bwd_groups(a, ntiles, s);
+        int rc = spv::check_launch("spv_alpha_blend_groups_backward/blend");
+        if (rc) return rc;
+    }
+    unpack_groups_kernel<<<spv::cdiv(P, kBlock), kBlock, 0, s>>>(P, C, packed, (float2 *)dL_duv, (float2 *)dL_duv_rgb,
+                                                                 (float2 *)dL_dabs_uv_rgb, dL_dconic, dL_dopacity,
+                                                                 dL_dfeature);
+    return spv::check_launch("spv_alpha_blend_groups_backward/unpack");
+}
+
 /* Grouped backward, blend stage only: upstream gradients as per-channel planes (host array of C device pointers, NULL
  * entries allowed), result left as packed rows (spv::kPackedRowGroups floats per Gaussian) in `packed` for a caller-side
  * unpack (frame.cu).  `packed` must hold P*36 floats. */
