@@ -83,4 +83,17 @@ int blend_groups_forward(int P, int C, int W, int H, int K, const float *uv, con
 //   0,1 dL_duv(all)  2,3 |RGB-pass dL_duv|  4,5,6 dL_dconic  7 dL_dopacity  8..8+C-1 dL_dfeature  31,32 RGB-pass dL_duv
 constexpr int kPackedRowGroups = 36;
 
+// blend_rec.cu: record-staged blending of the fused frame path.  One record of kRecordFloats floats per Gaussian:
+//   [x y a2 b2 | c2 log2(o) o id | feature[0..23] = rgb(3) depth(1) attributes, zero padded | a b c 0]
+constexpr int kRecordFloats = 36;
+int pack_records(int P, int A, const float *uv, const float *conic, const float *opacity, const int *radius, const float *rgb,
+                 const float *depth, int n_groups, const float *const *attr_ptrs, const int *attr_channels, float *rec,
+                 void *stream);
+int blend_records_forward(int C, int W, int H, int K, const float *rec, const int *idx_sorted, const int *tile_range,
+                          float bg_rgb, float bg_depth, float bg_attr, float *rendered, float *final_T, int *ncontrib,
+                          int *gs_idx, void *stream);
+int blend_records_backward(int P, int C, int W, int H, const float *rec, const int *idx_sorted, const int *tile_range,
+                           float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
+                           const float *const *planes_host, int n_grad_channels, float *packed, void *stream);
+
 }  // namespace spv

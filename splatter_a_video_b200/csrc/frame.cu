@@ -32,7 +32,7 @@ FrameWs carve(void *base, int P, int64_t I_cap, int W, int H, int A) {
     const size_t Pn = (size_t)(P > 0 ? P : 1), C = 4 + (size_t)A, T = (size_t)spv::tiles_x(W) * spv::tiles_y(H), HW = (size_t)W * H;
     auto take = [&](size_t bytes) { char *r = p; p += al(bytes); return (void *)r; };
     f.dirs = (float *)take(Pn * 12); f.rgb = (float *)take(Pn * 12); f.uv = (float *)take(Pn * 8); f.depth = (float *)take(Pn * 4);
-    f.cov3d = (float *)take(Pn * 24); f.conic = (float *)take(Pn * 12); f.feature = (float *)take(Pn * C * 4);
+    f.cov3d = (float *)take(Pn * 24); f.conic = (float *)take(Pn * 12); f.feature = (float *)take(Pn * spv::kRecordFloats * 4);   // records
     f.final_T = (float *)take(HW * 4);
     f.vis = (uint8_t *)take(Pn); f.clamped = (uint8_t *)take(Pn * 3);
     f.radius = (int *)take(Pn * 4); f.tiles = (int *)take(Pn * 4);
@@ -66,26 +66,6 @@ visible_kernel(int P, const float *__restrict__ depth, uint8_t *__restrict__ vis
 // (render_attributes_list, trainer_fragGS.py:510-512); they are consumed / differentiated in place, no torch.cat.
 constexpr int kMaxGroups = 8;
 struct AttrGroups { const float *in[kMaxGroups]; float *grad[kMaxGroups]; int ch[kMaxGroups]; int start[kMaxGroups]; int n; };
-
-// feature[P, 4+A] = [rgb(3) | depth(1) | attribute groups]
-__global__ void __launch_bounds__(kThreads)
-pack_features_kernel(int P, int A, const float *__restrict__ rgb, const float *__restrict__ depth, const AttrGroups gr,
-                     float *__restrict__ feature) {
-    const int C = 4 + A;
-    const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (k >= (long long)P * C) return;
-    const int i = (int)(k / C), c = (int)(k % C);
-    float v;
-    if (c < 3) v = rgb[3 * i + c];
-    else if (c == 3) v = depth[i];
-    else {
-        int gi = 0;
-#pragma unroll
-        for (int q = 1; q < kMaxGroups; ++q) if (q < gr.n && c - 4 >= gr.start[q]) gi = q;
-        v = gr.in[gi][(size_t)i * gr.ch[gi] + (c - 4 - gr.start[gi])];
-    }
-    feature[k] = v;
-}
 
 // Packed gradient rows of the grouped blend backward (spv::kPackedRowGroups layout) -> everything the rest of the chain and
 // the caller need, in one pass: uv / conic (workspace), opacity, colour and depth gradients (workspace), the attribute
@@ -140,12 +120,13 @@ inline int make_groups(AttrGroups &g, int n, const float *const *in, float *cons
 // the id-image fill next to the projection / binning / sort chain, whose radix passes leave most SMs idle; backward: the SH
 // gradient next to the covariance chain).  Forked from and joined back into the caller's stream with events, so the caller
 // still sees one in-order stream -- and a stream capture records the branches as parallel graph nodes.
-struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, mid = nullptr, join = nullptr; bool ok = false; };
 static thread_local SideLane g_side;
 SideLane *side_lane() {
     if (!g_side.ok) {
         if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&g_side.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         g_side.ok = true;
     }
@@ -179,26 +160,28 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     visible_kernel<<<g, kThreads, 0, s>>>(P, f.depth, f.vis);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep", 2));
     const int C = 4 + A;
-    // ---- side branch: SH colours (evaluated for every point: the renderer passes no visibility mask, :272), the packed
-    //      [rgb | depth | attributes] feature rows and the -1 fill of the id image
+    // ---- side branch: SH colours (evaluated for every point: the renderer passes no visibility mask, :272), then -- once
+    //      the main branch has the conics -- the per-Gaussian blend records and the -1 fill of the id image
     SideLane *lane = side_lane();
     if (!lane) { spv::set_error(cudaGetLastError(), "spv_frame_ortho_forward: side stream"); return (int)cudaErrorUnknown; }
     SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_forward/fork");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_forward/fork");
     SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
-    pack_features_kernel<<<spv::cdiv((long long)P * C, kThreads), kThreads, 0, lane->stream>>>(P, A, f.rgb, f.depth, gr, f.feature);
-    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/pack"));
     SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, lane->stream), "spv_frame_ortho_forward");
-    SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_forward/join");
     // ---- main branch: covariance, conic / radius / tile rectangle, culled binning + sort
     SPV_TRY_RC(spv_compute_cov3d_forward(P, scaling, rotation, f.vis, f.cov3d, stream));
     SPV_TRY_RC(spv_ewa_project_ortho_forward(P, f.cov3d, extr, f.uv, W, H, f.vis, f.conic, f.radius, f.tiles, stream));
+    SPV_CUDA_TRY(cudaEventRecord(lane->mid, s), "spv_frame_ortho_forward/mid");
+    SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->mid, 0), "spv_frame_ortho_forward/mid");
+    SPV_TRY_RC(spv::pack_records(P, A, f.uv, f.conic, opacity, f.radius, f.rgb, f.depth, n_groups, attr_ptrs, attr_channels,
+                                 f.feature, (void *)lane->stream));
+    SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_forward/join");
     SPV_CUDA_TRY(cudaMemcpyAsync(radii, f.radius, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, s), "spv_frame_ortho_forward");
     SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
                                 status, f.bin_ws, f.bin_bytes, stream));
     SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0), "spv_frame_ortho_forward/join");
-    return spv::blend_groups_forward(P, C, W, H, K, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
-                                     bg_rgb, 1.0f, 0.0f, images, f.final_T, f.ncontrib, gs_idx, /*fill_idx=*/false, stream);
+    return spv::blend_records_forward(C, W, H, K, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, images, f.final_T,
+                                      f.ncontrib, gs_idx, stream);
 }
 
 int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int n_grad_channels, int64_t I_cap,
@@ -216,8 +199,8 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     const int C = 4 + A;
     const unsigned g = spv::cdiv(P, kThreads);
     float *packed = (float *)f.blend_ws;
-    SPV_TRY_RC(spv_alpha_blend_groups_backward_packed(P, C, W, H, f.uv, f.conic, opacity, f.feature, f.idx_sorted, f.tile_range,
-                                                      bg_rgb, 1.0f, 0.0f, f.final_T, f.ncontrib, dL_dimage_planes, n_grad_channels, packed, stream));
+    SPV_TRY_RC(spv::blend_records_backward(P, C, W, H, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, f.final_T,
+                                           f.ncontrib, dL_dimage_planes, n_grad_channels, packed, stream));
     unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, (float2 *)f.g_uv, f.g_conic, dL_dopacity, f.g_rgb, f.g_depth, gr,
                                                (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));
