@@ -50,6 +50,8 @@ _SIGS = {
                                                 P_, P_, P_, P_, P_, P_, P_, P_, P_, P_, c_size_t, P_]),
     "spv_bin_capacity_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "spv_bin_capacity": (c_int, [c_int, c_int64, P_, P_, P_, P_, P_, c_int, c_int, c_int, P_, P_, P_, P_, c_size_t, P_]),
+    "spv_bin_tiles_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
+    "spv_bin_tiles": (c_int, [c_int, c_int64, P_, P_, P_, P_, P_, c_int, c_int, c_int, P_, P_, P_, P_, c_size_t, P_]),
     "spv_frame_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
     "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, c_int, c_int64, c_int, P_, P_, P_, P_, P_, P_, c_float,
                                         c_float, c_float, P_, P_, P_, P_, P_, c_size_t, P_]),

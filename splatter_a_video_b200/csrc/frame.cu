@@ -7,6 +7,8 @@
 //   * exact tile culling (sort.cu) shortens every list without changing any pixel;
 //   * the three blend passes are one traversal (blend.cu, grouped kernels).
 // Intermediates live in a caller-provided workspace that the backward call reuses.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/spv_b200.h"
 
@@ -38,7 +40,9 @@ FrameWs carve(void *base, int P, int64_t I_cap, int W, int H, int A) {
     f.radius = (int *)take(Pn * 4); f.tiles = (int *)take(Pn * 4);
     f.idx_sorted = (int *)take((size_t)(I_cap > 0 ? I_cap : 1) * 4); f.tile_range = (int *)take(T * 8);
     f.ncontrib = (int *)take(HW * 4);
-    f.bin_bytes = spv_bin_capacity_workspace_bytes(P, I_cap); f.bin_ws = take(f.bin_bytes);
+    f.bin_bytes = spv_bin_capacity_workspace_bytes(P, I_cap);
+    { const size_t tb = spv_bin_tiles_workspace_bytes(P, I_cap, W, H); if (tb > f.bin_bytes) f.bin_bytes = tb; }
+    f.bin_ws = take(f.bin_bytes);
     f.blend_bytes = spv_alpha_blend_groups_backward_workspace_bytes(P); f.blend_ws = take(f.blend_bytes);
     f.packed = nullptr;
     f.g_uv = (float *)take(Pn * 8); f.g_uv_rgb = (float *)take(Pn * 8); f.g_abs = (float *)take(Pn * 8);
@@ -177,8 +181,12 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
                                  f.feature, (void *)lane->stream));
     SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_forward/join");
     SPV_CUDA_TRY(cudaMemcpyAsync(radii, f.radius, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, s), "spv_frame_ortho_forward");
-    SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
-                                status, f.bin_ws, f.bin_bytes, stream));
+    // binning: per-tile segments + shared-memory tile sort (SPV_BIN_RADIX=1 selects the global radix sort for A/B runs)
+    static const bool radix = [] { const char *e = getenv("SPV_BIN_RADIX"); return e && e[0] == '1'; }();
+    if (radix) SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
+                                           status, f.bin_ws, f.bin_bytes, stream));
+    else SPV_TRY_RC(spv_bin_tiles(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
+                                  status, f.bin_ws, f.bin_bytes, stream));
     SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0), "spv_frame_ortho_forward/join");
     return spv::blend_records_forward(C, W, H, K, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, images, f.final_T,
                                       f.ncontrib, gs_idx, stream);

@@ -68,13 +68,17 @@ tile_range_kernel(long long I, const unsigned long long *__restrict__ keys_sorte
 // (2 % of the splats cover 36+ tiles), and with one thread per splat half of all warps wait on such a lane.
 constexpr int kLanesPerSplat = 8;
 
-template <bool EMIT>
+// MODE 0: count (per-splat counts + masks)   1: emit at the scanned per-splat offsets (radix path)
+// MODE 2: count + per-tile histogram          3: emit (depth|id) keys into the per-tile segments (tile-sort path)
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__restrict__ depth, const int *__restrict__ radius,
                        const float *__restrict__ conic, const float *__restrict__ opacity, int cull, int W, int H, int gx,
                        int gy, int *__restrict__ counts, unsigned long long *__restrict__ masks,
                        const int *__restrict__ offsets, long long cap, unsigned long long *__restrict__ keys,
-                       int *__restrict__ vals, int *__restrict__ status) {
+                       int *__restrict__ vals, int *__restrict__ status, int *__restrict__ tile_count,
+                       const int2 *__restrict__ tile_seg) {
+    constexpr bool EMIT = (MODE & 1) != 0, TILES = MODE >= 2;
     const int t = blockIdx.x * kThreads + threadIdx.x;
     const int i = t / kLanesPerSplat, sub = t % kLanesPerSplat;          // splat, lane within the splat's group
     const int lane = threadIdx.x & 31, gshift = lane & ~(kLanesPerSplat - 1);
@@ -97,7 +101,7 @@ cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__rest
         ka = conic[3 * i]; kb = conic[3 * i + 1]; kc = conic[3 * i + 2];
         tau = __logf(255.f * o);    // alpha = min(.99, o G) >= 1/255  <=>  o G >= 1/255  <=>  power >= -ln(255 o)
         if (EMIT) {
-            cur = (i == 0) ? 0 : offsets[i - 1];
+            if (!TILES) cur = (i == 0) ? 0 : offsets[i - 1];
             dbits = (unsigned long long)__float_as_uint(depth[i]);
             if (cull && area <= 64) { m = masks[i]; retest = false; }
         }
@@ -121,7 +125,13 @@ cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__rest
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         const unsigned grp = (bal >> gshift) & ((1u << kLanesPerSplat) - 1u);
-        if (EMIT) {
+        if (EMIT && TILES) {
+            if (keep) {   // slot order inside a tile's segment is arbitrary: the tile sort orders by (depth, id)
+                const int tl = y * gx + x;
+                const long long pos = (long long)tile_seg[tl].x + atomicAdd(&tile_count[tl], 1);
+                if (pos < cap) keys[pos] = (dbits << 32) | (unsigned long long)(unsigned)i;
+            }
+        } else if (EMIT) {
             if (keep) {
                 const long long pos = cur + n + __popc(grp & ((1u << sub) - 1u));
                 if (pos < cap) {
@@ -129,13 +139,14 @@ cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__rest
                     vals[pos] = i;
                 }
             }
-        } else if (it < 64 / kLanesPerSplat) {
-            m |= (unsigned long long)grp << (it * kLanesPerSplat);
+        } else {
+            if (it < 64 / kLanesPerSplat) m |= (unsigned long long)grp << (it * kLanesPerSplat);
+            if (TILES && keep) atomicAdd(&tile_count[y * gx + x], 1);
         }
         n += __popc(grp);
     }
-    if (!EMIT && live && sub == 0) { counts[i] = n; masks[i] = m; }
-    if (EMIT && live && i == P - 1 && sub == 0) {
+    if (!EMIT && live && sub == 0) { if (!TILES) counts[i] = n; masks[i] = m; }
+    if (EMIT && !TILES && live && i == P - 1 && sub == 0) {
         const long long total = (long long)offsets[P - 1];
         status[0] = (int)(total < cap ? total : cap);
         status[1] = total > cap ? 1 : 0;
@@ -155,6 +166,133 @@ tile_range_dev_kernel(long long cap, const int *__restrict__ status, const unsig
         if (prev != cur) { tile_range[prev].y = (int)k; tile_range[cur].x = (int)k; }
     }
     if (k == I - 1) tile_range[cur].y = (int)I;
+}
+
+// ---- tile-segment binning: per-tile histogram -> scan over tiles -> scatter -> per-tile sort in shared memory --------
+// The global radix sort orders (tile | depth) keys although the tile of every entry is known when it is emitted.  Here the
+// count pass also histograms the tiles, one CTA scans the T tile counts into segment ranges, the emit pass scatters
+// (depth bits << 32 | Gaussian id) keys into the segments (slot order arbitrary), and every tile sorts its own segment in
+// shared memory (bitonic network over 64-bit keys; ids are unique, so the result is the unique (depth, id) order -- exactly
+// what the stable radix sort over emission order yields).  12 B/intersection of global traffic instead of 6 radix passes.
+constexpr int kScanThreads = 1024;
+constexpr int kSortSmall = 4096;          // keys a 256-thread CTA sorts in static shared memory (32 KB)
+constexpr int kSortBig = 25600;           // keys a 1024-thread CTA sorts in 200 KB of dynamic shared memory
+
+__global__ void __launch_bounds__(kScanThreads)
+tile_scan_kernel(int T, long long cap, int *__restrict__ tile_count, int2 *__restrict__ tile_range, int *__restrict__ status,
+                 int *__restrict__ big_queue /*[0] = count, [1] = head, [2..] = tile ids*/) {
+    __shared__ long long s_warp[kScanThreads / 32];
+    __shared__ long long s_total;
+    const int per = (T + kScanThreads - 1) / kScanThreads;
+    const int lo = min(T, (int)threadIdx.x * per), hi = min(T, lo + per);
+    long long sum = 0;
+    for (int t = lo; t < hi; ++t) sum += tile_count[t];
+    // block-wide exclusive scan of the per-thread sums
+    long long incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_warp[lane] = w;
+        if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    long long run = (incl - sum) + (warp > 0 ? s_warp[warp - 1] : 0);
+    for (int t = lo; t < hi; ++t) {
+        const int n = tile_count[t];
+        const long long a = run < cap ? run : cap, b = (run + n) < cap ? (run + n) : cap;
+        tile_range[t] = (n > 0 && b > a) ? make_int2((int)a, (int)b) : make_int2(0, 0);
+        if (b - a > kSortSmall) big_queue[2 + atomicAdd(&big_queue[0], 1)] = t;
+        tile_count[t] = 0;   // becomes the emit pass's cursor
+        run += n;
+    }
+    if (threadIdx.x == 0) {
+        status[0] = (int)(s_total < cap ? s_total : cap);
+        status[1] = s_total > cap ? 1 : 0;
+    }
+}
+
+// Bitonic network in its "flip" form (every compare-exchange moves the minimum to the lower index), so positions >= n
+// behave as +inf padding without being stored.  keys: shared or global memory.
+template <int THREADS>
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long *keys, int n) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int i = threadIdx.x; i < np2 / 2; i += THREADS) {   // flip step: partner = mirror inside the k-block
+            const int h = k >> 1, blk = i / h, off = i % h;
+            const int a = blk * k + off, b = blk * k + (k - 1 - off);
+            if (b < n) {
+                const unsigned long long x = keys[a], y = keys[b];
+                if (x > y) { keys[a] = y; keys[b] = x; }
+            }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2 / 2; i += THREADS) {
+                const int a = (i / j) * 2 * j + (i % j), b = a + j;
+                if (b < n) {
+                    const unsigned long long x = keys[a], y = keys[b];
+                    if (x > y) { keys[a] = y; keys[b] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+tile_sort_small_kernel(const int2 *__restrict__ tile_range, const unsigned long long *__restrict__ keys,
+                       int *__restrict__ idx_sorted) {
+    __shared__ unsigned long long s_keys[kSortSmall];
+    const int2 r = tile_range[blockIdx.x];
+    const int n = r.y - r.x;
+    if (n <= 0 || n > kSortSmall) return;   // larger segments: tile_sort_big_kernel
+    for (int i = threadIdx.x; i < n; i += kThreads) s_keys[i] = keys[r.x + i];
+    __syncthreads();
+    bitonic_sort_u64<kThreads>(s_keys, n);
+    for (int i = threadIdx.x; i < n; i += kThreads) idx_sorted[r.x + i] = (int)(unsigned)(s_keys[i] & 0xffffffffull);
+}
+
+// Persistent CTAs over the queue of segments with more than kSortSmall keys (none on the DAVIS-shaped workload; every tile
+// at 5 M Gaussians x 480p).  Up to kSortBig keys in shared memory, beyond that in place in global memory (L2).
+__global__ void __launch_bounds__(kScanThreads)
+tile_sort_big_kernel(const int2 *__restrict__ tile_range, unsigned long long *__restrict__ keys, int *__restrict__ idx_sorted,
+                     int *__restrict__ big_queue) {
+    extern __shared__ __align__(16) unsigned long long s_big[];
+    __shared__ int s_item;
+    const int count = big_queue[0];
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(&big_queue[1], 1);
+        __syncthreads();
+        const int item = s_item;
+        __syncthreads();
+        if (item >= count) return;
+        const int2 r = tile_range[big_queue[2 + item]];
+        const int n = r.y - r.x;
+        if (n <= kSortBig) {
+            for (int i = threadIdx.x; i < n; i += kScanThreads) s_big[i] = keys[r.x + i];
+            __syncthreads();
+            bitonic_sort_u64<kScanThreads>(s_big, n);
+            for (int i = threadIdx.x; i < n; i += kScanThreads) idx_sorted[r.x + i] = (int)(unsigned)(s_big[i] & 0xffffffffull);
+        } else {
+            __syncthreads();
+            bitonic_sort_u64<kScanThreads>(keys + r.x, n);   // __syncthreads orders this CTA's global accesses
+            for (int i = threadIdx.x; i < n; i += kScanThreads) idx_sorted[r.x + i] = (int)(unsigned)(keys[r.x + i] & 0xffffffffull);
+        }
+        __syncthreads();
+    }
 }
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -259,15 +397,15 @@ int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float *depth, 
     cub::DeviceScan::InclusiveSum((void *)nullptr, scan, counts, offsets, P);
     size_t temp = sort_temp_bytes(I_cap);
     const unsigned g = spv::cdiv((long long)P * kLanesPerSplat, kThreads);
-    cull_count_emit_kernel<false><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx,
-                                                        gy, counts, masks, nullptr, (long long)I_cap, nullptr, nullptr, nullptr);
+    cull_count_emit_kernel<0><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx,
+                                                    gy, counts, masks, nullptr, (long long)I_cap, nullptr, nullptr, nullptr, nullptr, nullptr);
     int rc = spv::check_launch("spv_bin_capacity/count");
     if (rc) return rc;
     SPV_CUDA_TRY(cub::DeviceScan::InclusiveSum((void *)w, scan, counts, offsets, P, s), "spv_bin_capacity/scan");
     // unused slots keep an all-ones key: they sort behind every real (tile, depth) key
     SPV_CUDA_TRY(cudaMemsetAsync(keys_in, 0xFF, 8 * (size_t)I_cap, s), "spv_bin_capacity");
-    cull_count_emit_kernel<true><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
-                                                       nullptr, masks, offsets, (long long)I_cap, keys_in, vals_in, status);
+    cull_count_emit_kernel<1><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
+                                                    nullptr, masks, offsets, (long long)I_cap, keys_in, vals_in, status, nullptr, nullptr);
     rc = spv::check_launch("spv_bin_capacity/emit", 3);
     if (rc) return rc;
     int tb = 1;
@@ -277,6 +415,55 @@ int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float *depth, 
                  "spv_bin_capacity/sort");
     tile_range_dev_kernel<<<spv::cdiv(I_cap, kThreads), kThreads, 0, s>>>((long long)I_cap, status, keys_out, (int2 *)tile_range);
     return spv::check_launch("spv_bin_capacity/range", 1 + 2 + (32 + tb + 7) / 8);
+}
+
+// ---- capacity-bounded binning by tile segments + per-tile shared-memory sort (fused frame path) ---------------------
+size_t spv_bin_tiles_workspace_bytes(int P, int64_t I_cap, int W, int H) {
+    if (I_cap <= 0) I_cap = 1;
+    const size_t T = (size_t)spv::tiles_x(W > 0 ? W : 1) * spv::tiles_y(H > 0 ? H : 1);
+    return align_up(8 * (size_t)I_cap) + align_up(8 * (size_t)(P > 0 ? P : 1)) + align_up(4 * T) + align_up(4 * (T + 2));
+}
+
+/* Same contract as spv_bin_capacity (idx_sorted / tile_range / status are bit-identical when nothing overflows). */
+int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
+                  const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
+                  void *workspace, size_t ws_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), T = gx * gy;
+    SPV_CUDA_TRY(cudaMemsetAsync(tile_range, 0, sizeof(int) * 2 * (size_t)T, s), "spv_bin_tiles");
+    SPV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * 2, s), "spv_bin_tiles");
+    if (P <= 0 || I_cap <= 0 || T <= 0) return 0;
+    if (I_cap >= (1ll << 31)) { spv::set_error(cudaErrorInvalidValue, "spv_bin_tiles: capacity too large"); return (int)cudaErrorInvalidValue; }
+    if (ws_bytes < spv_bin_tiles_workspace_bytes(P, I_cap, W, H)) { spv::set_error(cudaErrorInvalidValue, "spv_bin_tiles: workspace too small"); return (int)cudaErrorInvalidValue; }
+    char *w = (char *)workspace;
+    unsigned long long *keys = (unsigned long long *)w; w += align_up(8 * (size_t)I_cap);
+    unsigned long long *masks = (unsigned long long *)w; w += align_up(8 * (size_t)P);
+    int *tile_count = (int *)w; w += align_up(4 * (size_t)T);
+    int *big_queue = (int *)w;
+    SPV_CUDA_TRY(cudaMemsetAsync(tile_count, 0, align_up(4 * (size_t)T) + 8, s), "spv_bin_tiles");   // counts + queue count/head
+    const unsigned g = spv::cdiv((long long)P * kLanesPerSplat, kThreads);
+    cull_count_emit_kernel<2><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
+                                                    nullptr, masks, nullptr, (long long)I_cap, nullptr, nullptr, nullptr, tile_count,
+                                                    nullptr);
+    tile_scan_kernel<<<1, kScanThreads, 0, s>>>(T, (long long)I_cap, tile_count, (int2 *)tile_range, status, big_queue);
+    cull_count_emit_kernel<3><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
+                                                    nullptr, masks, nullptr, (long long)I_cap, keys, nullptr, nullptr, tile_count,
+                                                    (const int2 *)tile_range);
+    int rc = spv::check_launch("spv_bin_tiles/emit", 3);
+    if (rc) return rc;
+    tile_sort_small_kernel<<<T, kThreads, 0, s>>>((const int2 *)tile_range, keys, idx_sorted);
+    static bool configured = false;
+    static int n_sms = 0;
+    if (!configured) {
+        cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortBig * 8);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sms <= 0) n_sms = 148;
+        configured = true;
+    }
+    tile_sort_big_kernel<<<n_sms, kScanThreads, kSortBig * 8, s>>>((const int2 *)tile_range, keys, idx_sorted, big_queue);
+    return spv::check_launch("spv_bin_tiles/sort", 2);
 }
 
 }  // extern "C"

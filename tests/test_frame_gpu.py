@@ -281,3 +281,57 @@ def test_kernel_timer_brackets_the_blend_kernels(cuda):
         assert 0.0 < got[0] < e0.elapsed_time(e1) and 0.0 < got[1] < e0.elapsed_time(e1)
     finally:
         L.call("spv_kernel_timer_enable", 0)
+
+
+def _bin(name, uv, depth, radius, conic, opacity, cull, W, H, I_cap):
+    """Direct C-ABI call of one of the two capacity-bounded binning entry points."""
+    from splatter_a_video_b200 import _lib as L
+    P, dev = uv.shape[0], uv.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    idx = torch.full((I_cap,), -7, dtype=torch.int32, device=dev)
+    tr = torch.empty(T, 2, dtype=torch.int32, device=dev)
+    st = torch.empty(2, dtype=torch.int32, device=dev)
+    nb = (L.query("spv_bin_tiles_workspace_bytes", P, I_cap, W, H) if name == "spv_bin_tiles"
+          else L.query("spv_bin_capacity_workspace_bytes", P, I_cap))
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    L.call(name, P, I_cap, L.ptr(uv), L.ptr(depth), L.ptr(radius), L.ptr(conic), L.ptr(opacity), int(cull), W, H, L.ptr(idx),
+           L.ptr(tr), L.ptr(st), L.ptr(ws), nb, L.stream())
+    torch.cuda.synchronize()
+    return idx, tr, st.cpu()
+
+
+# (P, W, H, scale multiplier): the last two make every tile segment exceed 4096 keys (200 KB shared-memory sort) and
+# 25600 keys (in-place global sort) respectively
+@pytest.mark.parametrize("P,W,H,big", [(3000, 96, 80, 1.0), (60_000, 333, 250, 1.0), (12_000, 48, 32, 6.0), (150_000, 32, 32, 8.0)])
+@pytest.mark.parametrize("cull", [0, 1])
+def test_tile_segment_binning_equals_radix_binning(cuda, P, W, H, big, cull):
+    """spv_bin_tiles (per-tile histogram + scan + scatter + per-tile shared-memory sort) must give bit-identical idx_sorted /
+    tile_range / status to spv_bin_capacity (global radix sort), and without culling to gs.sort_gaussian."""
+    from splatter_a_video_b200 import gs
+    sc = synth.make_scene(P, 2, W, H, seed=11)
+    pos, scaling = sc.frame_position(0).to(cuda), (sc.scaling * big).to(cuda)
+    # duplicate depths inside tiles: ties must fall back to ascending Gaussian id
+    pos[1::7, 2] = pos[0::7, 2][: pos[1::7].shape[0]]
+    uv, depth = gs.project_point_ortho(pos, sc.extr.to(cuda), W, H, 0.01)
+    vis = depth != 0
+    cov3d = gs.compute_cov3d(scaling, sc.rotation.to(cuda), vis)
+    conic, radius, tiles = gs.ewa_project_ortho(cov3d, sc.extr.to(cuda), uv, W, H, vis.squeeze(-1))
+    opacity = sc.opacity.to(cuda)
+    total = int(tiles.sum())
+    I_cap = total + 1000
+    a_idx, a_tr, a_st = _bin("spv_bin_capacity", uv, depth, radius, conic, opacity, cull, W, H, I_cap)
+    b_idx, b_tr, b_st = _bin("spv_bin_tiles", uv, depth, radius, conic, opacity, cull, W, H, I_cap)
+    I = int(a_st[0])
+    assert int(b_st[0]) == I and int(a_st[1]) == 0 and int(b_st[1]) == 0
+    assert torch.equal(a_tr, b_tr)
+    assert torch.equal(a_idx[:I], b_idx[:I])
+    if big > 1:
+        assert int((a_tr[:, 1] - a_tr[:, 0]).max()) > (25600 if big >= 8 else 4096)
+    if not cull:
+        assert I == total
+        r_idx, r_tr = gs.sort_gaussian(uv, depth, W, H, radius, tiles)
+        assert torch.equal(r_idx, b_idx[:I]) and torch.equal(r_tr, b_tr)
+    # overflow: flagged, nothing written out of bounds, ranges clipped to the capacity
+    small = max(I // 3, 1)
+    c_idx, c_tr, c_st = _bin("spv_bin_tiles", uv, depth, radius, conic, opacity, cull, W, H, small)
+    assert int(c_st[1]) == 1 and int(c_st[0]) == small and int(c_tr.max()) <= small
