@@ -187,6 +187,7 @@ class Workload:
         self.sink_names = ["scaling", "rotation", "opacity", "shs"] if mode == "frame" else []
         self.sinks = self.flat.grad_sinks(self.sink_names) if self.sink_names else None
         self.node_sink = self.flat.params["pos_cubic_node"].grad if mode == "frame" else None
+        self.node_dirty = torch.zeros(17, dtype=torch.int32, device=device) if mode == "frame" else None
         self.autograd_names = [k for k in self.flat.names if k not in self.sink_names and not (mode == "frame" and k == "pos_cubic_node")]
 
     # ---- per-step pieces -------------------------------------------------------------------------------------------
@@ -196,10 +197,15 @@ class Workload:
         self.idx2.copy_(self.tab_idx[f2:f2 + 1], non_blocking=True); self.dist2.copy_(self.tab_dist[f2:f2 + 1], non_blocking=True)
 
     def render_dict(self):
-        from splatter_a_video_b200.gs.frame import deform_position
+        from splatter_a_video_b200.gs.frame import deform_position, deform_position_pair
         p = self.flat.params
-        pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI, self.node_sink)
-        with torch.no_grad():
+        if self.node_sink is not None:
+            # frame mode: both frame times from one pass over the coefficients; `track_gs` = position at ids2 carries gradient
+            # like the reference's render_dict2["position"] (trainer_fragGS.py:487,506)
+            pos, track = deform_position_pair(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.idx2, self.dist2, self.NI,
+                                              self.node_sink, self.node_dirty)
+        else:
+            pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI)
             track = deform_position(self.base, p["pos_cubic_node"], self.idx2, self.dist2, self.NI)
         return {"position": pos, "opacity": p["opacity"], "scaling": p["scaling"], "rotation": p["rotation"], "shs": p["shs"],
                 "track_gs": track, "mask_attribute": p["mask_attribute"], "pos_poly_feat": self.pos_poly_feat,
@@ -535,18 +541,19 @@ def run_ours(args):
     flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=device)
     frames_of = lambda i: frame_for_step(i, rank, world, wl.frames)
 
-    # spline coefficients: each rank's gradient lives in one interval -> exchanged as N slices, the rest all-reduced
-    sparse = {"pos_cubic_node": ((wl.P, 4, wl.NI, 3), 2, wl.idx1)}
-    # SH under the renderer's constant view direction (0,0,1): only bases 0, 2, 6, 12 ever receive gradient
-    subset = {"shs": ((wl.P, 16, 3), 1, torch.tensor([0, 2, 6, 12], device=device))}
+    # gradient exchange: spline coefficients travel as each rank's two active intervals (all-gather), SH only in the 4 bases
+    # that receive gradient under the renderer's constant view direction (0,0,1), everything else in one all-reduce
+    from splatter_a_video_b200.parallel import GradExchange
+    exchange = GradExchange(wl.flat, wl.P, subset={"shs": ((wl.P, 16, 3), 1, [0, 2, 6, 12])},
+                            sparse={"pos_cubic_node": ((wl.P, 4, wl.NI, 3), 2, [wl.idx1, wl.idx2])}, dirty=wl.node_dirty)
 
     def train_step(frame):
         wl.step_resident(frame)
-        wl.flat.allreduce_grads(sparse=sparse, subset=subset)
+        exchange.run()
 
     def train_step_e2e(frame):
         wl.step_e2e(frame)
-        wl.flat.allreduce_grads(sparse=sparse, subset=subset)
+        exchange.run()
 
     if args.profile_mode:
         time_steps(train_step, args.steps, args.warmup, None, world, rank, frames_of)

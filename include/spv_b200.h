@@ -194,6 +194,17 @@ SPV_API int spv_deform_spline_forward(int P, int NI, const float *base, const fl
 SPV_API int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *dist_dev, const float *dL_dpos,
                                float *dL_dcoeff /*[P,4,NI,3]*/, int accumulate, void *stream);
 
+/* Both frame times of a training step (ids1 rendered, ids2 as the `track_gs` attribute, trainer_fragGS.py:486-508) in one
+ * pass.  backward2 writes into a gradient sink kept clean incrementally: `dirty` = int[17] on the device ([0] = count,
+ * then interval indices holding non-zero gradient from earlier calls or gradient exchanges; zero-initialise it together
+ * with the sink); listed intervals are zeroed unless re-written, afterwards the list is {idx1, idx2}. */
+SPV_API int spv_deform_spline_forward2(int P, int NI, const float *base, const float *coeff, const int *idx1_dev,
+                               const float *dist1_dev, const int *idx2_dev, const float *dist2_dev, float *pos1,
+                               float *pos2, void *stream);
+SPV_API int spv_deform_spline_backward2(int P, int NI, const int *idx1_dev, const float *dist1_dev, const int *idx2_dev,
+                                const float *dist2_dev, const float *dL_dpos1, const float *dL_dpos2 /*or NULL*/,
+                                int *dirty, float *dL_dcoeff /*[P,4,NI,3] sink*/, void *stream);
+
 /* Rotation at frame time t (get_rotation, :184-198): normalize(rotation + detached poly/Fourier offsets); basis_dev holds
  * [t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] on the device.  Backward: through the normalisation to `rotation`. */
 SPV_API int spv_deform_rotation_forward(int P, const float *rotation, const float *rot_poly_feat /*[P,4,4]*/,
@@ -206,6 +217,33 @@ SPV_API int spv_deform_rotation_backward(int P, const float *out, const float *i
 SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,
                   const long long *seg_end_host, const float *seg_lr_host, float beta1, float beta2, float eps, int step,
                   void *stream);
+
+/* ---- Gradient exchange packing for frame-parallel training (the reference has no gradient collective,
+ * src/train.py:19-31,210-213) ----
+ * The flat gradient buffer is described by a table of per-parameter segments; each parameter's per-Gaussian row is viewed as
+ * [A, B, C] and slices are taken along B: mode 0 = dense (all of B, B <= 16), 1 = subset (sel[0..nsel) fixed, e.g. the 4 SH
+ * bases that receive gradient under the constant view direction), 2 = sparse (at most one such segment; nsel <= 2 slice
+ * indices read from device scalars, e.g. the spline intervals of this rank's two frame times).
+ * pack: flat_grad -> comm_allreduce [n_allreduce floats] and comm_allgather [n_allgather floats = payload + 16 index words],
+ * scaled.  The caller all-reduces the first and all-gathers the second (NCCL).  unpack: writes the reduced values back,
+ * adds every rank's sparse slices at their intervals in rank order, and lists the touched intervals in `dirty`
+ * (int[17], see spv_deform_spline_backward2; may be NULL). */
+#define SPV_EXCHANGE_MAX_SEGMENTS 16
+#define SPV_EXCHANGE_MAX_SELECT 16
+typedef struct spv_exchange_segment {
+    long long flat_offset;
+    int A, B, C;
+    int mode;
+    int nsel;
+    int sel[SPV_EXCHANGE_MAX_SELECT];
+} spv_exchange_segment;
+SPV_API int spv_exchange_sizes(int P, int nseg, const spv_exchange_segment *segs /*host*/, long long *n_allreduce,
+                       long long *n_allgather);
+SPV_API int spv_exchange_pack(int P, int nseg, const spv_exchange_segment *segs, const int *const *sparse_idx_dev /*host array of
+                      nsel device pointers*/, const float *flat_grad, float scale, float *comm_allreduce,
+                      float *comm_allgather, void *stream);
+SPV_API int spv_exchange_unpack(int P, int nseg, const spv_exchange_segment *segs, int world, const float *comm_allreduce,
+                        const float *gathered /*[world, n_allgather]*/, float *flat_grad, int *dirty, void *stream);
 
 /* ---- Fused image losses (next row f-2): scalar loss + dL/d(rendered image), no host sync --------------------------- */
 /* RGB: weight * ((1-lambda) * mean|p-g| + lambda * (1 - SSIM)) as the trainer computes it (trainer_fragGS.py:573-578 with

@@ -68,7 +68,7 @@ __device__ __forceinline__ bool block_may_hit(const float4 g0, const float4 g1, 
 }
 
 // Recursive-halving multi-value warp reduction: on return lane l holds, in v[OFF], the warp-wide sum of the value with
-// index OFF + (l % N).  N-1 shuffles (+1 for N=16) instead of 5*N.
+// index OFF + (l % N).  N-1 shuffles (+ log2(32/N) butterfly steps for N < 32) instead of 5*N.
 template <int N, int OFF, int TOT>
 __device__ __forceinline__ void halving_reduce(float (&v)[TOT], int lane) {
 #pragma unroll
@@ -81,7 +81,9 @@ __device__ __forceinline__ void halving_reduce(float (&v)[TOT], int lane) {
             v[OFF + i] = keep + __shfl_xor_sync(kFull, send, h);
         }
     }
-    if (N == 16) v[OFF] += __shfl_xor_sync(kFull, v[OFF], 16);
+    // N < 32: the sums are still split over the 32/N lane groups
+#pragma unroll
+    for (int o = N; o < 32; o <<= 1) v[OFF] += __shfl_xor_sync(kFull, v[OFF], o);
 }
 
 }  // namespace spv_blend

@@ -208,14 +208,17 @@ blend_rec_fwd_kernel(int C, int W, int H, int gx, int K, const float *__restrict
 // ---- backward -----------------------------------------------------------------------------------------------------------
 // Packed gradient row (kRowG = 36 floats per Gaussian): 0,1 dL_duv (all channels)  2,3 |RGB-pass dL_duv|  4,5,6 dL_dconic
 // 7 dL_dopacity (rgb + depth passes: the attribute pass gets opacity.detach(), dptr_ortho_enhanced.py:362)
-// 8.. dL_dfeature  31,32 RGB-pass dL_duv.  CG = leading feature channels whose gradient is wanted; NV = 16 (CG <= 8) or 32.
+// 8.. dL_dfeature  31,32 RGB-pass dL_duv.  CG = leading feature channels whose gradient is wanted.  Reduction networks:
+// CG <= 8: 16-wide (8 geometric sums + 8 features) + the RGB-pass pair on a 2-wide one (21 shuffles);
+// CG <= 14: 16-wide + an 8-wide one carrying features 8..13 and the RGB-pass pair (25 shuffles); else 32-wide + the pair (36).
 template <int CH, int CG>
 __global__ void __launch_bounds__(kBlock, 3)
 blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
                      const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
                      const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
                      float *__restrict__ packed) {
-    constexpr int NV = (8 + CG <= 16) ? 16 : 32;
+    constexpr int NV = (CG <= 14) ? 16 : 32;
+    constexpr bool MID = CG > 8 && CG <= 14;
     static_assert(CH % 4 == 0 && CH >= 4 && CH <= 24 && 8 + CG <= 32 && CG <= CH, "unsupported channel configuration");
     constexpr int RP = kRec;                        // 36: pitch/4 = 9 is odd
     constexpr int DS = (CH <= 4) ? 4 : ((CH <= 12) ? 12 : ((CH <= 20) ? 20 : 28));   // dL_dpixel row pitch, pitch/4 odd
@@ -306,6 +309,7 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
                 const bool hit = splat_hits<false>(p2, g1) && (p_hi - 1 - j) < last_contrib;
                 if (!__any_sync(kFull, hit)) continue;
                 float v[NV];
+                float u[8];   // MID: features 8..13 | RGB-pass pair
                 float n0, n1;
                 {
                     const float4 con = r[kRec / 4 - 1];
@@ -329,7 +333,10 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
                             if (ch >= 4) fdC = fmaf(fv[k], dv[k], fdC);
                             else if (ch == 3) fdB = fmaf(fv[k], dv[k], fdB);
                             else fdA = fmaf(fv[k], dv[k], fdA);
-                            if (ch < CG) v[8 + ch] = w * dv[k];
+                            if (ch < CG) {
+                                if (MID && ch >= 8) u[ch - 8] = w * dv[k];
+                                else v[8 + ch] = w * dv[k];
+                            }
                         }
                     }
                     const float nSA = last_alpha * lfA + om * SA;
@@ -341,7 +348,11 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
                     SA = hit ? nSA : SA; SB = hit ? nSB : SB; SC = hit ? nSC : SC;
                     lfA = hit ? fdA : lfA; lfB = hit ? fdB : lfB; lfC = hit ? fdC : lfC;
 #pragma unroll
-                    for (int q = 8 + CG; q < NV; ++q) v[q] = 0.f;
+                    for (int q = 8 + (MID ? 8 : CG); q < NV; ++q) v[q] = 0.f;
+                    if (MID) {
+#pragma unroll
+                        for (int q = CG - 8; q < 6; ++q) u[q] = 0.f;
+                    }
                     last_alpha = hit ? alpha : last_alpha;
                     const float dL_dG = g1.z * da_all;
                     const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
@@ -356,19 +367,29 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
                     v[2] = fabsf(n0); v[3] = fabsf(n1);
                 }
                 halving_reduce<NV, 0, NV>(v, lane);   // lane l (< NV) now holds the warp-wide sum of value l
-                // the two RGB-pass sums: one halving step (odd lanes take n1, even lanes n0), then 4 butterfly steps
-                const bool up = (lane & 1) != 0;
-                float e = (up ? n1 : n0) + __shfl_xor_sync(kFull, up ? n0 : n1, 1);
-#pragma unroll
-                for (int o = 2; o <= 16; o <<= 1) e += __shfl_xor_sync(kFull, e, o);
                 float *row = packed + (size_t)__float_as_int(g1.w) * kRowG;
-                if constexpr (NV == 16) {   // one RED: lanes 0..15 the network's sums, lanes 16,17 the RGB-pass pair
-                    const float val = lane < 16 ? v[0] : e;
-                    const int col = lane < 16 ? lane : 31 + (lane & 1);
-                    if (lane < 18 && val != 0.f) atomicAdd(row + col, val);
+                if constexpr (MID) {
+                    u[6] = n0; u[7] = n1;
+                    halving_reduce<8, 0, 8>(u, lane);     // lane l holds the sum of u[l % 8]
+                    const int t = lane - 16;              // one RED: lanes 0..15 <- v, lanes 16..23 <- u
+                    const float val = lane < 16 ? v[0] : u[0];
+                    const int col = lane < 16 ? lane : (t < 6 ? 16 + t : 31 + (t - 6));
+                    const bool live = lane < 16 || (lane < 24 && (t >= 6 || t < CG - 8));
+                    if (live && val != 0.f) atomicAdd(row + col, val);
                 } else {
-                    if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + lane, v[0]);
-                    if (lane < 2 && e != 0.f) atomicAdd(row + 31 + lane, e);
+                    // the two RGB-pass sums: one halving step (odd lanes take n1, even lanes n0), then 4 butterfly steps
+                    const bool up = (lane & 1) != 0;
+                    float e = (up ? n1 : n0) + __shfl_xor_sync(kFull, up ? n0 : n1, 1);
+#pragma unroll
+                    for (int o = 2; o <= 16; o <<= 1) e += __shfl_xor_sync(kFull, e, o);
+                    if constexpr (NV == 16) {   // one RED: lanes 0..15 the network's sums, lanes 16,17 the RGB-pass pair
+                        const float val = lane < 16 ? v[0] : e;
+                        const int col = lane < 16 ? lane : 31 + (lane & 1);
+                        if (lane < 18 && val != 0.f) atomicAdd(row + col, val);
+                    } else {
+                        if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + lane, v[0]);
+                        if (lane < 2 && e != 0.f) atomicAdd(row + 31 + lane, e);
+                    }
                 }
             }
         }
@@ -413,9 +434,10 @@ void launch_rec_bwd(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
 
 template <int CH>
 void dispatch_rec_bwd(const RecBwdArgs &a, int n_grad, int ntiles, cudaStream_t s) {
-    // feature-gradient channels reduced: 4 (rgb + depth only), 8, or all CH
+    // feature-gradient channels reduced: 4 (rgb + depth only), 8, 14, or all CH
     if (n_grad <= 4) launch_rec_bwd<CH, 4>(a, ntiles, s);
     else if (n_grad <= 8 && CH >= 8) launch_rec_bwd<CH, (CH >= 8 ? 8 : CH)>(a, ntiles, s);
+    else if (n_grad <= 14 && CH >= 16) launch_rec_bwd<CH, (CH >= 16 ? 14 : CH)>(a, ntiles, s);
     else launch_rec_bwd<CH, (CH > 23 ? 23 : CH)>(a, ntiles, s);
 }
 

@@ -40,6 +40,67 @@ deform_bwd_kernel(int P, int NI, const int *__restrict__ idx_dev, const float *_
     if (accumulate) { q[3 * s] += g; q[2 * s] += g * d; q[1 * s] += g * (d * d); q[0] += g * (d * d * d); }
     else { q[3 * s] = g; q[2 * s] = g * d; q[1 * s] = g * (d * d); q[0] = g * (d * d * d); }
 }
+// Two frame times in one pass (the trainer evaluates the model at ids1 and ids2 every step, trainer_fragGS.py:486-487: the
+// position of frame ids1 is rendered, the position of ids2 travels as the `track_gs` attribute, :506-508).  The two active
+// intervals are equal or adjacent for neighbouring frames, so the second evaluation re-uses the sectors of the first.
+__global__ void __launch_bounds__(kThreads)
+deform_fwd2_kernel(int P, int NI, const float *__restrict__ base, const float *__restrict__ coeff,
+                   const int *__restrict__ idx1_dev, const float *__restrict__ dist1_dev, const int *__restrict__ idx2_dev,
+                   const float *__restrict__ dist2_dev, float *__restrict__ pos1, float *__restrict__ pos2) {
+    const int k = blockIdx.x * kThreads + threadIdx.x;   // one thread per (Gaussian, xyz component)
+    if (k >= 3 * P) return;
+    const int i = k / 3, c = k % 3;
+    const int i1 = idx1_dev[0], i2 = idx2_dev[0];
+    const float d1 = dist1_dev[0], d2 = dist2_dev[0];
+    const size_t s = (size_t)NI * 3;
+    const float *row = coeff + (size_t)i * 4 * s + c;
+    const float *q = row + (size_t)i1 * 3;
+    const float a0 = q[0], a1 = q[s], a2 = q[2 * s], a3 = q[3 * s];
+    float b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+    if (i2 != i1) { const float *r = row + (size_t)i2 * 3; b0 = r[0]; b1 = r[s]; b2 = r[2 * s]; b3 = r[3 * s]; }
+    const float bs = base[k];
+    pos1[k] = (a3 + a2 * d1 + a1 * (d1 * d1) + a0 * (d1 * d1 * d1)) + bs;
+    pos2[k] = (b3 + b2 * d2 + b1 * (d2 * d2) + b0 * (d2 * d2 * d2)) + bs;
+}
+
+// Backward of the pair into a gradient SINK (e.g. the parameter's slice of a flat gradient buffer) that is kept clean
+// incrementally: `dirty` (device, [0] = count, [1..16] = interval indices) lists the intervals that hold non-zero gradient
+// from earlier calls / gradient exchanges; they are zeroed here unless re-written, instead of clearing all 4*NI*3 floats per
+// Gaussian every step (96 MB at 200 k Gaussians x 50 frames).  g2 may be NULL (ids2 position used without gradient).
+__global__ void __launch_bounds__(kThreads)
+deform_bwd2_kernel(int P, int NI, const int *__restrict__ idx1_dev, const float *__restrict__ dist1_dev,
+                   const int *__restrict__ idx2_dev, const float *__restrict__ dist2_dev, const float *__restrict__ g1,
+                   const float *__restrict__ g2, const int *__restrict__ dirty, float *__restrict__ dL_dcoeff) {
+    const int k = blockIdx.x * kThreads + threadIdx.x;
+    if (k >= 3 * P) return;
+    const int i = k / 3, c = k % 3;
+    const int i1 = idx1_dev[0], i2 = g2 ? idx2_dev[0] : i1;
+    const float d1 = dist1_dev[0], d2 = dist2_dev[0];
+    const size_t s = (size_t)NI * 3;
+    float *row = dL_dcoeff + (size_t)i * 4 * s + c;
+    const int nd = min(dirty[0], 16);
+    for (int t = 0; t < nd; ++t) {
+        const int z = dirty[1 + t];
+        if (z == i1 || z == i2 || z < 0 || z >= NI) continue;
+        float *q = row + (size_t)z * 3;
+        q[0] = 0.f; q[s] = 0.f; q[2 * s] = 0.f; q[3 * s] = 0.f;
+    }
+    const float ga = g1[k], gb = g2 ? g2[k] : 0.f;
+    float *q = row + (size_t)i1 * 3;
+    if (i2 == i1) {
+        q[3 * s] = ga + gb; q[2 * s] = ga * d1 + gb * d2; q[1 * s] = ga * (d1 * d1) + gb * (d2 * d2);
+        q[0] = ga * (d1 * d1 * d1) + gb * (d2 * d2 * d2);
+    } else {
+        q[3 * s] = ga; q[2 * s] = ga * d1; q[1 * s] = ga * (d1 * d1); q[0] = ga * (d1 * d1 * d1);
+        float *r = row + (size_t)i2 * 3;
+        r[3 * s] = gb; r[2 * s] = gb * d2; r[1 * s] = gb * (d2 * d2); r[0] = gb * (d2 * d2 * d2);
+    }
+}
+
+__global__ void deform_dirty_set_kernel(const int *__restrict__ idx1_dev, const int *__restrict__ idx2_dev, int *__restrict__ dirty) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { dirty[0] = 2; dirty[1] = idx1_dev[0]; dirty[2] = idx2_dev[0]; }
+}
+
 // Rotation of the active model at frame time t (dynamic_gaussian_with_base_point_cloud.py:184-198, get_rotation):
 //   q = rotation + sum_k rot_poly_feat[:,k,:] * t^k + sum_l rot_fourier_feat[:,l,:] * basis_l(t)   (both feature sums are
 //   .detach()ed there), returned through F.normalize.  basis = [t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] is read from
@@ -95,6 +156,27 @@ int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *d
     if (!accumulate) SPV_CUDA_TRY(cudaMemsetAsync(dL_dcoeff, 0, sizeof(float) * 12 * (size_t)NI * P, s), "spv_deform_spline_backward");
     deform_bwd_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, s>>>(P, NI, idx_dev, dist_dev, dL_dpos, dL_dcoeff, accumulate);
     return spv::check_launch("spv_deform_spline_backward");
+}
+
+int spv_deform_spline_forward2(int P, int NI, const float *base, const float *coeff, const int *idx1_dev, const float *dist1_dev,
+                               const int *idx2_dev, const float *dist2_dev, float *pos1, float *pos2, void *stream) {
+    if (P <= 0) return 0;
+    deform_fwd2_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, (cudaStream_t)stream>>>(P, NI, base, coeff, idx1_dev, dist1_dev,
+                                                                                           idx2_dev, dist2_dev, pos1, pos2);
+    return spv::check_launch("spv_deform_spline_forward2");
+}
+
+/* dL_dcoeff is a sink that this call keeps clean through `dirty` (int[17] on the device, zero-initialised by the caller
+ * together with the sink): intervals listed there are zeroed unless re-written, then the list becomes {idx1, idx2}. */
+int spv_deform_spline_backward2(int P, int NI, const int *idx1_dev, const float *dist1_dev, const int *idx2_dev,
+                                const float *dist2_dev, const float *dL_dpos1, const float *dL_dpos2 /*or NULL*/, int *dirty,
+                                float *dL_dcoeff, void *stream) {
+    if (P <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    deform_bwd2_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, s>>>(P, NI, idx1_dev, dist1_dev, idx2_dev, dist2_dev, dL_dpos1,
+                                                                        dL_dpos2, dirty, dL_dcoeff);
+    deform_dirty_set_kernel<<<1, 32, 0, s>>>(idx1_dev, dL_dpos2 ? idx2_dev : idx1_dev, dirty);
+    return spv::check_launch("spv_deform_spline_backward2", 2);
 }
 
 int spv_deform_rotation_forward(int P, const float *rotation, const float *rot_poly_feat, const float *rot_fourier_feat,

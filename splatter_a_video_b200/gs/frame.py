@@ -214,6 +214,58 @@ def deform_position(base: Tensor, pos_cubic_node: Tensor, idx_dev: Tensor, dist_
     return _DeformSpline.apply(base, pos_cubic_node, idx_dev, dist_dev, interval_num, grad_sink)
 
 
+class _DeformSplinePair(torch.autograd.Function):
+    """(pos at ids1, pos at ids2) in one kernel; backward writes both active intervals into a sink kept clean through a
+    device-side dirty list (no per-step clear of the whole [P, 4*NI*3] gradient), or into a fresh zero tensor."""
+
+    @staticmethod
+    def forward(ctx, base, coeff, idx1, dist1, idx2, dist2, NI, sink, dirty):
+        L.need_cuda(base, coeff, idx1, dist1, idx2, dist2)
+        b, c = L.f32c(base), L.f32c(coeff)
+        P = b.shape[0]
+        pos1 = torch.empty(P, 3, dtype=torch.float32, device=b.device)
+        pos2 = torch.empty(P, 3, dtype=torch.float32, device=b.device)
+        L.call("spv_deform_spline_forward2", P, int(NI), L.ptr(b), L.ptr(c), L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2),
+               L.ptr(pos1), L.ptr(pos2), L.stream())
+        ctx.meta = (P, int(NI), tuple(coeff.shape), base.requires_grad)
+        ctx.sink, ctx.dirty = sink, dirty
+        ctx.save_for_backward(idx1, dist1, idx2, dist2)
+        return pos1, pos2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        P, NI, shape, base_grad = ctx.meta
+        idx1, dist1, idx2, dist2 = ctx.saved_tensors
+        dev = idx1.device
+        if g1 is None:
+            g1 = torch.zeros(P, 3, dtype=torch.float32, device=dev)
+        g1 = L.f32c(g1)
+        g2 = None if g2 is None else L.f32c(g2)
+        if ctx.sink is not None:
+            g_coeff, dirty, ret = ctx.sink, ctx.dirty, None
+        else:
+            g_coeff = torch.zeros(shape, dtype=torch.float32, device=dev)
+            dirty, ret = torch.zeros(17, dtype=torch.int32, device=dev), g_coeff
+        L.call("spv_deform_spline_backward2", P, NI, L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2), L.ptr(g1), L.ptr(g2),
+               L.ptr(dirty), L.ptr(g_coeff), L.stream())
+        g_base = None
+        if base_grad:
+            g_base = g1 if g2 is None else g1 + g2
+        return g_base, ret, None, None, None, None, None, None, None
+
+
+def deform_position_pair(base: Tensor, pos_cubic_node: Tensor, idx1: Tensor, dist1: Tensor, idx2: Tensor, dist2: Tensor,
+                         interval_num: int, grad_sink: Optional[Tensor] = None, dirty: Optional[Tensor] = None):
+    """Positions at the two frame times of a training step (ids1 rendered; ids2 = the `track_gs` attribute,
+    src/trainer_fragGS.py:486-508) from ONE pass over the spline coefficients.  Both outputs are differentiable.
+    grad_sink + dirty: the coefficient gradient is WRITTEN into `grad_sink` ([P, 4*NI*3], zero-initialised once) and
+    `dirty` (int32[17] on the device, zero-initialised once) tracks which intervals hold gradient so only those are cleared on
+    the next call -- see FlatParams.grad_exchange for how exchanged intervals are added to the list."""
+    if (grad_sink is None) != (dirty is None):
+        raise ValueError("deform_position_pair: grad_sink and dirty go together")
+    return _DeformSplinePair.apply(base, pos_cubic_node, idx1, dist1, idx2, dist2, interval_num, grad_sink, dirty)
+
+
 def rotation_basis(time: float, start_frame_id: int, time_len: int) -> Tensor:
     """[t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] with t = (time - start)/time_len (get_rotation, :186-193)."""
     t = (time - start_frame_id) / time_len

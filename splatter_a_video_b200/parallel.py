@@ -72,82 +72,169 @@ class FlatParams:
     def floats_per_gaussian(self, P: int) -> float:
         return self.flat.numel() / max(P, 1)
 
-    def allreduce_grads(self, average: bool = True, sparse: Optional[dict] = None, subset: Optional[dict] = None):
-        """The step's gradient exchange over the flat gradient buffer; the result always equals the dense all-reduce sum.
-
-        Without hints: ONE all-reduce of the whole buffer.  Two exact volume reductions for this model:
-
-        sparse = {name: (view_shape, dim, index_tensor)}: the gradient is non-zero only in ONE slice along `dim`, a
-            different one per rank -- the cubic-spline coefficients: a frame touches the 12 coefficients of its own interval
-            out of 4*NI*3 (dynamic_gaussian_with_base_point_cloud.py:239-247).  The active slices travel through an
-            all-gather (N*P*12 floats instead of P*4*NI*3) and are scatter-added locally.
-        subset = {name: (view_shape, dim, index_tensor)}: the gradient is non-zero only in the SAME slices on every rank --
-            the SH coefficients under the renderer's constant view direction (0,0,1) (dptr_ortho_enhanced.py:270-271): only
-            bases 0, 2, 6, 12 have a non-zero basis value, 12 of 48 floats.  Only those slices are all-reduced.
-        Every other parameter is all-reduced in place, one collective per maximal contiguous run."""
+    def allreduce_grads(self, average: bool = True):
+        """ONE dense all-reduce of the whole flat gradient buffer (see GradExchange for the volume-reduced exact variant)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
-        world, rank = dist.get_world_size(), dist.get_rank()
-        sparse, subset = sparse or {}, subset or {}
-        if not sparse and not subset:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
-            if average:
-                self.flat_grad.div_(world)
-            return None
-        scale = 1.0 / world if average else 1.0
-        # ---- one packed all-reduce: [every dense parameter | the fixed slices of the `subset` parameters]
-        pieces, writeback, off = [], [], 0
-        gathers = []
-        for k, n in zip(self.names, self.sizes):
-            g = self.flat_grad[off:off + n]
-            if k in sparse:
-                shape, dim, index = sparse[k]
-                gathers.append((g.view(shape), dim, index))
-            elif k in subset:
-                shape, dim, index = subset[k]
-                gv = g.view(shape)
-                idx = index.to(torch.long)
-                pieces.append(gv.index_select(dim, idx).reshape(-1))
-                writeback.append(("subset", gv, dim, idx))
+        dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+        if average:
+            self.flat_grad.div_(dist.get_world_size())
+        return None
+
+
+class GradExchange:
+    """The step's gradient exchange over a FlatParams buffer: result == dense all-reduce (sum or mean) of the flat gradient.
+
+    dense parameters are all-reduced; `subset` parameters only in their fixed slices; the `sparse` parameter (at most one:
+    the spline coefficients) travels as each rank's <= 2 active slices through an all-gather and is added locally in rank order.
+
+        subset = {name: (view_shape, dim, [slice indices])}          e.g. {"shs": ((P,16,3), 1, [0,2,6,12])}
+        sparse = {name: (view_shape, dim, [idx_dev tensors (int32[1], <= 2)])}
+        dirty  = int32[17] device list shared with gs.frame.deform_position_pair: exchanged intervals are recorded there so
+                 the next backward clears them (CUDA path only).
+
+    CUDA tensors: two kernels of this library (`spv_exchange_pack/unpack`) around ONE all-reduce + ONE all-gather.  CPU tensors
+    (gloo tests): the same plan executed with torch indexing."""
+
+    def __init__(self, flat: FlatParams, P: int, subset: Optional[dict] = None, sparse: Optional[dict] = None,
+                 dirty: Optional[torch.Tensor] = None, skip: Sequence[str] = ()):
+        self.flat, self.P, self.dirty = flat, int(P), dirty
+        self.subset, self.sparse = dict(subset or {}), dict(sparse or {})
+        if len(self.sparse) > 1:
+            raise ValueError("GradExchange: at most one sparse parameter")
+        self.segs = []          # (name, flat_off, A, B, C, mode, sel)
+        off = 0
+        for k, n in zip(flat.names, flat.sizes):
+            w = n // self.P
+            if k in skip:
+                pass
+            elif k in self.sparse or k in self.subset:
+                shape, dim, sel = (self.sparse if k in self.sparse else self.subset)[k]
+                A = 1
+                for d in shape[1:dim]:
+                    A *= int(d)
+                B = int(shape[dim])
+                C = w // (A * B)
+                if k in self.sparse:
+                    if not (1 <= len(sel) <= 2):
+                        raise ValueError("GradExchange: 1 or 2 sparse slice indices")
+                    self.segs.append((k, off, A, B, C, 2, list(sel)))
+                else:
+                    self.segs.append((k, off, A, B, C, 1, [int(x) for x in sel]))
             else:
-                pieces.append(g)
-                writeback.append(("dense", g, None, None))
+                self.segs.append((k, off, 1, 1, w, 0, [0]))
             off += n
-        tail = self.flat_grad[off:]                       # float4 padding of the flat buffer
+        self._cuda = None
+
+    # ---- CUDA path -------------------------------------------------------------------------------------------------
+    def _setup_cuda(self):
+        import ctypes
+        from . import _lib as L
+
+        class Seg(ctypes.Structure):
+            _fields_ = [("flat_offset", ctypes.c_longlong), ("A", ctypes.c_int), ("B", ctypes.c_int), ("C", ctypes.c_int),
+                        ("mode", ctypes.c_int), ("nsel", ctypes.c_int), ("sel", ctypes.c_int * 16)]
+
+        arr = (Seg * len(self.segs))()
+        idx_ptrs = (ctypes.c_void_p * 16)()
+        for q, (k, off, A, B, C, mode, sel) in enumerate(self.segs):
+            arr[q].flat_offset, arr[q].A, arr[q].B, arr[q].C, arr[q].mode = off, A, B, C, mode
+            arr[q].nsel = B if mode == 0 else len(sel)
+            if mode == 1:
+                for t, v in enumerate(sel):
+                    arr[q].sel[t] = v
+            if mode == 2:
+                for t, v in enumerate(sel):
+                    idx_ptrs[t] = v.data_ptr()
+        n_ar, n_ag = ctypes.c_longlong(), ctypes.c_longlong()
+        L.call("spv_exchange_sizes", self.P, len(self.segs), ctypes.cast(arr, ctypes.c_void_p), ctypes.byref(n_ar), ctypes.byref(n_ag))
+        dev = self.flat.flat_grad.device
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        self._cuda = dict(arr=arr, idx=idx_ptrs, n_ar=n_ar.value, n_ag=n_ag.value,
+                          ar=torch.empty(max(n_ar.value, 1), dtype=torch.float32, device=dev),
+                          ag=torch.empty(max(n_ag.value, 1), dtype=torch.float32, device=dev),
+                          all=torch.empty(world, max(n_ag.value, 1), dtype=torch.float32, device=dev))
+
+    def pack(self, scale: float = 1.0):
+        import ctypes
+        from . import _lib as L
+        if self._cuda is None:
+            self._setup_cuda()
+        c = self._cuda
+        L.call("spv_exchange_pack", self.P, len(self.segs), ctypes.cast(c["arr"], ctypes.c_void_p), ctypes.cast(c["idx"], ctypes.c_void_p),
+               L.ptr(self.flat.flat_grad), float(scale), L.ptr(c["ar"]), L.ptr(c["ag"]), L.stream())
+        return c["ar"], c["ag"]
+
+    def unpack(self, reduced: torch.Tensor, gathered: torch.Tensor):
+        import ctypes
+        from . import _lib as L
+        c = self._cuda
+        L.call("spv_exchange_unpack", self.P, len(self.segs), ctypes.cast(c["arr"], ctypes.c_void_p), int(gathered.shape[0]),
+               L.ptr(reduced), L.ptr(gathered), L.ptr(self.flat.flat_grad), L.ptr(self.dirty), L.stream())
+
+    # ---- the exchange ----------------------------------------------------------------------------------------------
+    def run(self, average: bool = True):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        world = dist.get_world_size()
+        scale = 1.0 / world if average else 1.0
+        if self.flat.flat_grad.is_cuda:
+            ar, ag = self.pack(scale)
+            c = self._cuda
+            if c["n_ar"]:
+                dist.all_reduce(ar, op=dist.ReduceOp.SUM)
+            if c["n_ag"]:
+                dist.all_gather_into_tensor(c["all"], ag)
+            self.unpack(ar, c["all"])
+            return
+        self._run_torch(world, dist.get_rank(), scale)
+
+    def _views(self):
+        g, P = self.flat.flat_grad, self.P
+        for k, off, A, B, C, mode, sel in self.segs:
+            yield k, g[off:off + P * A * B * C].view(P, A, B, C), mode, sel
+
+    def _run_torch(self, world, rank, scale):
+        """Same plan with torch ops (CPU / gloo): the parity reference of the kernels."""
+        pieces, back = [], []
+        for k, v, mode, sel in self._views():
+            if mode == 2:
+                idx = [int(t.item()) for t in sel]
+                uniq = list(dict.fromkeys(idx))
+                mine = torch.zeros(v.shape[0], v.shape[1], 2, v.shape[3], dtype=v.dtype)
+                for t, b in enumerate(uniq):
+                    mine[:, :, t] = v[:, :, b] * scale
+                tail = torch.tensor(uniq + [-1] * (2 - len(uniq)), dtype=torch.float32)
+                payload = torch.cat([mine.reshape(-1), tail])
+                allp = [torch.empty_like(payload) for _ in range(world)]
+                dist.all_gather(allp, payload)
+                touched = sorted({int(b) for p_ in allp for b in p_[-2:].tolist() if b >= 0})
+                acc = {b: torch.zeros_like(v[:, :, 0]) for b in touched}
+                for p_ in allp:
+                    data = p_[:-2].view(mine.shape)
+                    for t, b in enumerate(p_[-2:].tolist()):
+                        if b >= 0:
+                            acc[int(b)] += data[:, :, t]
+                for b in touched:
+                    v[:, :, b] = acc[b]
+            else:
+                sl = v if mode == 0 else v[:, :, sel]
+                pieces.append((sl * scale).reshape(-1))
+                back.append((v, mode, sel, sl.shape))
         if pieces:
             comm = torch.cat(pieces)
-            if scale != 1.0:
-                comm.mul_(scale)
             dist.all_reduce(comm, op=dist.ReduceOp.SUM)
             o = 0
-            for (kind, gv, dim, idx), src in zip(writeback, pieces):
-                m = src.numel()
-                if kind == "dense":
-                    gv.copy_(comm[o:o + m])
+            for v, mode, sel, shape in back:
+                m = 1
+                for d in shape:
+                    m *= d
+                blk = comm[o:o + m].view(shape)
+                if mode == 0:
+                    v.copy_(blk)
                 else:
-                    sel_shape = list(gv.shape); sel_shape[dim] = idx.numel()
-                    gv.index_copy_(dim, idx, comm[o:o + m].view(sel_shape))
+                    v[:, :, sel] = blk
                 o += m
-        # ---- one all-gather per sparse parameter: [own active slice | its index]
-        for gv, dim, index in gathers:
-            idx = index.to(torch.long)
-            mine = gv.index_select(dim, idx)
-            if scale != 1.0:
-                mine = mine * scale
-                gv.index_copy_(dim, idx, mine)
-            payload = torch.cat([mine.reshape(-1), index.to(torch.float32).reshape(-1)])
-            allp = torch.empty(world, payload.numel(), dtype=torch.float32, device=payload.device)
-            if dist.get_backend() == "nccl":
-                dist.all_gather_into_tensor(allp, payload)
-            else:                                           # gloo (CPU tests) has no flat all-gather
-                dist.all_gather(list(allp.unbind(0)), payload)
-            nsl = mine.numel()
-            for r in range(world):
-                if r != rank:
-                    gv.index_add_(dim, allp[r, nsl:].to(torch.long), allp[r, :nsl].view(mine.shape))
-        if tail.numel():
-            tail.zero_()
-        return None
 
 
 class FlatAdam:

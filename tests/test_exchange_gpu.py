@@ -1,0 +1,82 @@
+"""-m gpu: the gradient-exchange pack / unpack kernels (`spv_exchange_*`) and the two-frame deformation op.  The collectives
+themselves are NCCL's; here W simulated ranks on one GPU are packed, reduced / gathered with torch, and unpacked -- the result
+must equal the dense sum of the ranks' flat gradient buffers (the property tests/test_parallel_cpu.py checks over gloo)."""
+import pytest
+import torch
+
+import helpers as Hh  # noqa: F401
+from splatter_a_video_b200.parallel import FlatParams, GradExchange
+
+pytestmark = pytest.mark.gpu
+
+
+def _rank_state(cuda, P, NI, rank, pair, seed):
+    g = torch.Generator().manual_seed(seed + rank)
+    flat = FlatParams({"node": torch.zeros(P, 4 * NI * 3, device=cuda), "scaling": torch.zeros(P, 3, device=cuda),
+                       "rotation": torch.zeros(P, 4, device=cuda), "shs": torch.zeros(P, 16, 3, device=cuda),
+                       "mask": torch.zeros(P, 1, device=cuda)})
+    i1, i2 = pair
+    gn = torch.zeros(P, 4, NI, 3)
+    for b in {i1, i2}:
+        gn[:, :, b] = torch.randn(P, 4, 3, generator=g)
+    gsh = torch.zeros(P, 16, 3); gsh[:, [0, 2, 6, 12]] = torch.randn(P, 4, 3, generator=g)
+    flat["node"].grad.copy_(gn.reshape(P, -1).to(cuda)); flat["shs"].grad.copy_(gsh.to(cuda))
+    for k, w in (("scaling", 3), ("rotation", 4), ("mask", 1)):
+        flat[k].grad.copy_(torch.randn(P, w, generator=g).to(cuda))
+    idx = [torch.tensor([i1], dtype=torch.int32, device=cuda), torch.tensor([i2], dtype=torch.int32, device=cuda)]
+    dirty = torch.zeros(17, dtype=torch.int32, device=cuda)
+    ex = GradExchange(flat, P, subset={"shs": ((P, 16, 3), 1, [0, 2, 6, 12])}, sparse={"node": ((P, 4, NI, 3), 2, idx)}, dirty=dirty)
+    return flat, ex, dirty
+
+
+@pytest.mark.parametrize("pairs", [[(2, 3), (5, 5)], [(1, 2), (2, 4), (0, 0), (9, 8)], [(0, 0)] * 8])
+def test_exchange_pack_unpack_equals_dense_sum(cuda, pairs):
+    P, NI, W = 3001, 10, len(pairs)
+    ranks = [_rank_state(cuda, P, NI, r, pairs[r], seed=7) for r in range(W)]
+    dense = sum(f.flat_grad.clone() for f, _, _ in ranks) / W
+    packed = [ex.pack(1.0 / W) for _, ex, _ in ranks]
+    reduced = sum(ar.clone() for ar, _ in packed)                       # what the all-reduce delivers
+    gathered = torch.stack([ag.clone() for _, ag in packed]).contiguous()   # what the all-gather delivers
+    assert reduced.numel() == P * (3 + 4 + 12 + 1) and gathered.shape[1] == P * 24 + 16
+    for r, (flat, ex, dirty) in enumerate(ranks):
+        ex.unpack(reduced, gathered)
+        torch.cuda.synchronize()
+        assert float((flat.flat_grad - dense).abs().max()) <= 1e-6 * float(dense.abs().max())
+        d = dirty.cpu().tolist()
+        assert d[0] == 2 * W and d[1:1 + 2 * W] == [b for p in pairs for b in p]
+    # bit-identical on every rank (same summation order)
+    for flat, _, _ in ranks[1:]:
+        assert torch.equal(flat.flat_grad, ranks[0][0].flat_grad)
+
+
+def test_deform_pair_matches_two_single_evaluations_and_keeps_the_sink_clean(cuda):
+    from splatter_a_video_b200.gs.frame import deform_position, deform_position_pair
+    P, NI = 5000, 10
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(P, 3, generator=g).to(cuda)
+    node = (0.1 * torch.randn(P, 4 * NI * 3, generator=g)).to(cuda)
+    sink = torch.zeros(P, 4 * NI * 3, device=cuda)
+    dirty = torch.zeros(17, dtype=torch.int32, device=cuda)
+    for (i1, d1, i2, d2) in [(2, 0.03, 2, 0.05), (2, 0.07, 3, 0.0), (7, 0.01, 1, 0.02), (4, 0.02, 4, 0.02)]:
+        t = lambda v, dt: torch.tensor([v], dtype=dt, device=cuda)
+        a1, b1, a2, b2 = t(i1, torch.int32), t(d1, torch.float32), t(i2, torch.int32), t(d2, torch.float32)
+        n_ref = node.clone().requires_grad_(True)
+        r1 = deform_position(base, n_ref, a1, b1, NI)
+        r2 = deform_position(base, n_ref, a2, b2, NI)
+        n_new = node.clone().requires_grad_(True)
+        p1, p2 = deform_position_pair(base, n_new, a1, b1, a2, b2, NI, sink, dirty)
+        assert torch.equal(p1, r1) and torch.equal(p2, r2)
+        g1, g2 = torch.randn(P, 3, generator=g).to(cuda), torch.randn(P, 3, generator=g).to(cuda)
+        torch.autograd.backward([r1, r2], [g1, g2])
+        torch.autograd.backward([p1, p2], [g1, g2])
+        assert n_new.grad is None                                   # written into the sink instead
+        # every interval touched by earlier iterations was cleared: the sink equals this step's gradient exactly
+        assert float((sink - n_ref.grad).abs().max()) <= 1e-6 * float(n_ref.grad.abs().max())
+        assert dirty.cpu().tolist()[:3] == [2, i1, i2]
+    # without a sink: a fresh gradient tensor through autograd; ids2 used without gradient
+    n3 = node.clone().requires_grad_(True)
+    p1, p2 = deform_position_pair(base, n3, a1, b1, a2, b2, NI)
+    p1.sum().backward()
+    n4 = node.clone().requires_grad_(True)
+    deform_position(base, n4, a1, b1, NI).sum().backward()
+    assert torch.equal(n3.grad, n4.grad)

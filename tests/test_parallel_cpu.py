@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 import helpers as Hh  # noqa: F401  (sys.path)
 from splatter_a_video_b200 import synth
-from splatter_a_video_b200.parallel import FlatParams, frame_for_step, reduce_densify_stats, shard_frames
+from splatter_a_video_b200.parallel import FlatParams, GradExchange, frame_for_step, reduce_densify_stats, shard_frames
 
 
 def _free_port():
@@ -56,25 +56,37 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _sparse_case(rank, case):
+    """Interval pairs (ids1, ids2) per rank: distinct, equal on one rank, and overlapping across ranks."""
+    return {0: [(2, 3), (5, 5)], 1: [(1, 2), (2, 4)], 2: [(0, 0), (0, 0)]}[case][rank]
+
+
 def _sparse_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     P, NI = 50, 6
-    g = torch.Generator().manual_seed(100 + rank)
-    flat = FlatParams({"node": torch.zeros(P, 4 * NI * 3), "other": torch.zeros(P, 7), "shs": torch.zeros(P, 16, 3),
-                       "tail": torch.zeros(P, 2)})
-    idx = torch.tensor([2 if rank == 0 else 5], dtype=torch.int32)       # each rank touched one interval
-    gn = torch.zeros(P, 4, NI, 3); gn[:, :, int(idx)] = torch.randn(P, 4, 3, generator=g)
-    go = torch.randn(P, 7, generator=g)
-    sh_idx = torch.tensor([0, 2, 6, 12])
-    gsh = torch.zeros(P, 16, 3); gsh[:, sh_idx] = torch.randn(P, 4, 3, generator=g)
-    flat["node"].grad.copy_(gn.reshape(P, -1)); flat["other"].grad.copy_(go); flat["shs"].grad.copy_(gsh)
-    flat["tail"].grad.copy_(torch.randn(P, 2, generator=g))
-    dense = flat.flat_grad.clone()
-    dist.all_reduce(dense)
-    flat.allreduce_grads(average=False, sparse={"node": ((P, 4, NI, 3), 2, idx)}, subset={"shs": ((P, 16, 3), 1, sh_idx)})
+    res = []
+    for case in range(3):
+        g = torch.Generator().manual_seed(100 + rank + 10 * case)
+        flat = FlatParams({"node": torch.zeros(P, 4 * NI * 3), "other": torch.zeros(P, 7), "shs": torch.zeros(P, 16, 3),
+                           "tail": torch.zeros(P, 2)})
+        i1, i2 = _sparse_case(rank, case)
+        idx = [torch.tensor([i1], dtype=torch.int32), torch.tensor([i2], dtype=torch.int32)]   # the rank's two frame times
+        gn = torch.zeros(P, 4, NI, 3)
+        for b in {i1, i2}:
+            gn[:, :, b] = torch.randn(P, 4, 3, generator=g)
+        go = torch.randn(P, 7, generator=g)
+        sh_idx = [0, 2, 6, 12]
+        gsh = torch.zeros(P, 16, 3); gsh[:, sh_idx] = torch.randn(P, 4, 3, generator=g)
+        flat["node"].grad.copy_(gn.reshape(P, -1)); flat["other"].grad.copy_(go); flat["shs"].grad.copy_(gsh)
+        flat["tail"].grad.copy_(torch.randn(P, 2, generator=g))
+        dense = flat.flat_grad.clone()
+        dist.all_reduce(dense)
+        ex = GradExchange(flat, P, subset={"shs": ((P, 16, 3), 1, sh_idx)}, sparse={"node": ((P, 4, NI, 3), 2, idx)})
+        ex.run(average=False)
+        res.append((flat.flat_grad.numpy().copy(), dense.numpy().copy()))
     if rank == 0:
-        q.put((flat.flat_grad.numpy().copy(), dense.numpy().copy()))
+        q.put(res)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -87,11 +99,12 @@ def test_sparse_interval_exchange_equals_dense_allreduce():
     procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got, want = q.get(timeout=200)
+    res = q.get(timeout=200)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+    for got, want in res:
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
 
 
 def test_shard_frames_partition():
