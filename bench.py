@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--staged", action="store_true", help="alias of --mode staged")
     ap.add_argument("--no-graph", action="store_true", help="frame mode without CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange-coefficients", action="store_true",
+                    help="N>1: exchange SH / spline COEFFICIENT gradients (24+24 floats/Gaussian) instead of deferring the linear tails")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="only warm-up + K train steps, no JSON (for ncu)")
     return ap.parse_args()
@@ -188,7 +190,16 @@ class Workload:
         self.sinks = self.flat.grad_sinks(self.sink_names) if self.sink_names else None
         self.node_sink = self.flat.params["pos_cubic_node"].grad if mode == "frame" else None
         self.node_dirty = torch.zeros(17, dtype=torch.int32, device=device) if mode == "frame" else None
+        self.node_defer = None
         self.autograd_names = [k for k in self.flat.names if k not in self.sink_names and not (mode == "frame" and k == "pos_cubic_node")]
+
+    def defer_linear_tails(self, exchange):
+        """Frame-parallel runs: the SH and spline backward run inside the gradient exchange on the reduced / gathered upstream
+        gradients (parallel.GradExchange, deferred mode) -- must be called before the first step (the buffers are captured)."""
+        assert self.mode == "frame" and not self.graphs
+        self.sinks = dict(self.flat.grad_sinks(["scaling", "rotation", "opacity"]))
+        self.sinks["shs_deferred"] = exchange.sh_sink()
+        self.node_defer = exchange.node_defer()
 
     # ---- per-step pieces -------------------------------------------------------------------------------------------
     def set_frame(self, frame):
@@ -203,7 +214,7 @@ class Workload:
             # frame mode: both frame times from one pass over the coefficients; `track_gs` = position at ids2 carries gradient
             # like the reference's render_dict2["position"] (trainer_fragGS.py:487,506)
             pos, track = deform_position_pair(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.idx2, self.dist2, self.NI,
-                                              self.node_sink, self.node_dirty)
+                                              self.node_sink, self.node_dirty, self.node_defer)
         else:
             pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI)
             track = deform_position(self.base, p["pos_cubic_node"], self.idx2, self.dist2, self.NI)
@@ -356,6 +367,50 @@ def live_kernel_times(wl, steps, warmup, flush_buf, frames_of):
     I = int(wl.renderer.last_status.cpu()[0])      # read before the graph (and its memory pool) goes away
     wl.graphs.pop("train", None)
     return {"fwd_ms": sum(fwd) / len(fwd), "bwd_ms": sum(bwd) / len(bwd), "step_ms": sum(step) / len(step), "I": I}
+
+
+def exchange_breakdown(exchange, world, reps=10):
+    """CUDA-event time of the four pieces of the gradient exchange, each bracketed by a barrier (all ranks run this)."""
+    import torch.distributed as dist
+    out = {"pack": [], "all_reduce": [], "all_gather": [], "unpack": []}
+    for it in range(reps + 2):
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        c = exchange._cuda
+        ev[0].record()
+        ar, ag = exchange.pack(1.0 if exchange.deferred else 1.0 / world)
+        ev[1].record()
+        if exchange.deferred:
+            if exchange._p2p_setup():
+                exchange._p2p_exchange(world, 1.0 / world)
+                ev[2].record(); ev[3].record()
+            else:
+                dist.all_gather_into_tensor(c["rows"], c["row"])
+                ev[2].record(); ev[3].record()
+                exchange._reduce_rows(world, 1.0 / world)
+            exchange.unpack(c["reduced"], c["all"])
+            exchange._finish_deferred(world, 1.0 / world)
+        else:
+            dist.all_reduce(ar)
+            ev[2].record()
+            dist.all_gather_into_tensor(c["all"], ag)
+            ev[3].record()
+            exchange.unpack(ar, c["all"])
+        ev[4].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            for k, (a, b) in zip(out, zip(ev[:-1], ev[1:])):
+                out[k].append(a.elapsed_time(b))
+    res = {k: float(np.median(v)) for k, v in out.items()}
+    if exchange.deferred:
+        res["collective"] = ("exchange path = " + exchange.exchange_path + "; the row exchange (+ the fused local reduction on the p2p "
+                             "path) is reported under all_reduce, all_gather = 0")
+        res["bytes_all_gather_per_rank"] = int(exchange._cuda["row"].numel()) * 4
+        res["unpack_includes"] = "local rank-order reduction + deferred SH + spline backward"
+    else:
+        res["bytes_all_reduce"] = int(exchange._cuda["ar"].numel()) * 4
+        res["bytes_all_gather_per_rank"] = int(exchange._cuda["ag"].numel()) * 4
+    return res
 
 
 def time_steps(fn, steps, warmup, flush_buf, world, rank, frames_of):
@@ -544,8 +599,16 @@ def run_ours(args):
     # gradient exchange: spline coefficients travel as each rank's two active intervals (all-gather), SH only in the 4 bases
     # that receive gradient under the renderer's constant view direction (0,0,1), everything else in one all-reduce
     from splatter_a_video_b200.parallel import GradExchange
-    exchange = GradExchange(wl.flat, wl.P, subset={"shs": ((wl.P, 16, 3), 1, [0, 2, 6, 12])},
-                            sparse={"pos_cubic_node": ((wl.P, 4, wl.NI, 3), 2, [wl.idx1, wl.idx2])}, dirty=wl.node_dirty)
+    if world > 1 and wl.mode == "frame" and not args.exchange_coefficients:
+        # default: the two linear tails of the backward (colour -> SH, position -> spline coefficients) are deferred behind
+        # the exchange: 12 dense + 3 colour floats/Gaussian all-reduced, 6 position-gradient floats/Gaussian all-gathered
+        exchange = GradExchange(wl.flat, wl.P, dirty=wl.node_dirty, deferred={"shs": "shs", "node": "pos_cubic_node", "NI": wl.NI})
+        wl.defer_linear_tails(exchange)
+        exchange_kind = "deferred SH/spline backward: ONE all-gather of 21 floats/Gaussian/rank (12 dense + 3 colour + 6 position gradients), summed locally in rank order"
+    else:
+        exchange = GradExchange(wl.flat, wl.P, subset={"shs": ((wl.P, 16, 3), 1, [0, 2, 6, 12])},
+                                sparse={"pos_cubic_node": ((wl.P, 4, wl.NI, 3), 2, [wl.idx1, wl.idx2])}, dirty=wl.node_dirty)
+        exchange_kind = "coefficient gradients: all-reduce of 24 floats/Gaussian + all-gather of 24 floats/Gaussian/rank"
 
     def train_step(frame):
         wl.step_resident(frame)
@@ -591,6 +654,7 @@ def run_ours(args):
     log(f"render: {fps_ms / args.steps:.3f} ms/frame, e2e {fps_e2e_ms / args.steps:.3f}")
     clocks = sampler.stop() if sampler else None
     live = live_kernel_times(wl, args.steps, args.warmup, flush, frames_of) if wl.mode == "frame" else None
+    exch = exchange_breakdown(exchange, world) if world > 1 else None
 
     if rank != 0:
         if world > 1:
@@ -624,7 +688,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: P={wl.P}, {wl.W}x{wl.H}, {wl.frames} frames, I={I} tile intersections/frame; one step = "
                                "render one frame (RGB K=20 + depth + 19 attribute channels) forward+backward through "
-                               f"{type(wl.renderer).__name__}.render_batch; frames sharded {world}-way, one packed gradient exchange/step (all-reduce of the dense rows + all-gather of the active spline slices)",
+                               f"{type(wl.renderer).__name__}.render_batch; frames sharded {world}-way, one gradient exchange/step ({exchange_kind})",
                    "renderer": type(wl.renderer).__name__, "mode": wl.mode, "cuda_graph": wl.use_graph,
                    "capacity_overflow": wl.overflowed(), "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
                    "grad_floats_per_gaussian": wl.flat.floats_per_gaussian(wl.P)},
@@ -648,6 +712,7 @@ def run_ours(args):
                      "limiter": "instruction issue (ncu: 62-77 % issue-active, DRAM 1-2 % of peak; profiles/README.md)"},
         "kernels_in_step_ms": live,
         "stages_ms": stages,
+        "exchange_ms": exch,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -89,7 +89,8 @@ SPV_API int spv_ewa_project_ortho_backward(int P, const float *cov3d, const floa
 /* ---- K7-K10: compute_sh(_free)_forward/backward (ext.cpp:23-24,29-30; src/compute_sh*.cu) --------- */
 /* shs is read with a per-point stride of (deg+1)^2 * 3 floats exactly like the reference
  * (compute_sh.cu:45); S_alloc = shs.size(1) only sizes the zero-filled dL_dshs[P,S_alloc,3].
- * visible == NULL means "every point visible" (what the renderers pass, dptr_ortho_enhanced.py:272).   */
+ * visible == NULL means "every point visible" (what the renderers pass, dptr_ortho_enhanced.py:272).
+ * dL_ddirs == NULL (backward): the direction gradient is not wanted -- the coefficients are then not read at all.   */
 SPV_API int spv_compute_sh_forward(int P, const float *shs, int deg, const float *dirs, const uint8_t *visible,
                            int free_variant, float *colors /*[P,3]*/, uint8_t *clamped /*[P,3], NULL if free*/,
                            void *stream);
@@ -178,6 +179,11 @@ SPV_API int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const in
                              const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
                              float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs /*[P,16,3]*/,
                              float *const *dL_dattr_ptrs, float *dL_dndc /*[P,2] or NULL*/, float *dL_dabs_ndc /*[P,2] or NULL*/,
+                             float *dL_drgb_out /*[P,3] or NULL.  Non-NULL defers the SH backward (frame-parallel training):
+                                                  the gradient of the SH-evaluated colours is written here, dL_dshs is not
+                                                  touched, and spv_compute_sh_backward is run by the caller on the
+                                                  all-reduced colour gradient*/,
+                             uint8_t *clamped_out /*[P,3] or NULL: the forward's clamp mask for that deferred call*/,
                              void *workspace, size_t ws_bytes, void *stream);
 /* Blend stage of the grouped backward with per-channel gradient planes; leaves 36-float packed rows in `packed`. */
 SPV_API int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, const float *uv, const float *conic,
@@ -204,6 +210,17 @@ SPV_API int spv_deform_spline_forward2(int P, int NI, const float *base, const f
 SPV_API int spv_deform_spline_backward2(int P, int NI, const int *idx1_dev, const float *dist1_dev, const int *idx2_dev,
                                 const float *dist2_dev, const float *dL_dpos1, const float *dL_dpos2 /*or NULL*/,
                                 int *dirty, float *dL_dcoeff /*[P,4,NI,3] sink*/, void *stream);
+
+/* Deferred spline backward for frame-parallel training: the coefficient gradient is linear in dL_dpos, so ranks exchange the
+ * 2 x 3 position-gradient floats per Gaussian (all-gather) instead of 2 x 12 coefficient-gradient floats and every rank
+ * rebuilds all ranks' interval gradients locally, summed per interval in (rank, slot) order (bit-identical everywhere).
+ * defer: payload = [dL_dpos1 (3P) | dL_dpos2 (3P, zeros if NULL) | idx1 bits, dist1, idx2 bits, dist2] (6P + 4 floats).
+ * gathered: `world` payloads, `stride` floats apart.  `dirty` as in spv_deform_spline_backward2. */
+SPV_API int spv_deform_defer(int P, const float *dL_dpos1, const float *dL_dpos2 /*or NULL*/, const int *idx1_dev,
+                     const float *dist1_dev, const int *idx2_dev, const float *dist2_dev, float *payload, void *stream);
+SPV_API int spv_deform_spline_backward_gathered(int P, int NI, int world, const float *gathered, long long stride,
+                                        float scale /*applied to every dL_dpos, e.g. 1/world*/, int *dirty,
+                                        float *dL_dcoeff /*[P,4,NI,3] sink*/, void *stream);
 
 /* Rotation at frame time t (get_rotation, :184-198): normalize(rotation + detached poly/Fourier offsets); basis_dev holds
  * [t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] on the device.  Backward: through the normalisation to `rotation`. */
@@ -242,6 +259,24 @@ SPV_API int spv_exchange_sizes(int P, int nseg, const spv_exchange_segment *segs
 SPV_API int spv_exchange_pack(int P, int nseg, const spv_exchange_segment *segs, const int *const *sparse_idx_dev /*host array of
                       nsel device pointers*/, const float *flat_grad, float scale, float *comm_allreduce,
                       float *comm_allgather, void *stream);
+/* Local reduction behind a single all-gather: out[0..n) = scale * sum over ranks (rank order) of gathered[r*stride + 0..n);
+ * n and stride multiples of 4 floats, buffers 16-byte aligned. */
+SPV_API int spv_exchange_reduce(long long n, int world, const float *gathered, long long stride, float scale, float *out,
+                        void *stream);
+/* The same through NVLink peer loads from symmetric buffers (no collective library on the data path): peer_rows = host array
+ * of `world` device pointers in rank order (own row included), each a row of n_row floats = [n_red floats that are summed |
+ * floats that are gathered]; the gathered tails are copied into rows[r*row_stride + n_red ..).  The caller synchronises the
+ * ranks before (all rows written) and must not let a row be overwritten before every rank ran this (double buffering). */
+SPV_API int spv_exchange_reduce_peers(long long n_red, long long n_row, int world, const float *const *peer_rows, float scale,
+                              float *reduced, float *rows, long long row_stride, void *stream);
+/* Two-phase form for larger groups (inbound volume 2(N-1)/N x the summed block instead of N-1 x): phase 1 sums this rank's
+ * 1/world slice of [0, n_red) over the peers' rows into red_pub (its symmetric area) and `reduced`, and copies the gathered
+ * tails into `rows`; the caller places a cross-rank barrier; phase 2 fetches the other slices from peer_red[owner]. */
+SPV_API int spv_exchange_reduce_scatter_peers(long long n_red, long long n_row, int rank, int world, const float *const *peer_rows,
+                                      float scale, float *red_pub, float *reduced, float *rows, long long row_stride,
+                                      void *stream);
+SPV_API int spv_exchange_fetch_reduced(long long n_red, int rank, int world, const float *const *peer_red, float *reduced,
+                               void *stream);
 SPV_API int spv_exchange_unpack(int P, int nseg, const spv_exchange_segment *segs, int world, const float *comm_allreduce,
                         const float *gathered /*[world, n_allgather]*/, float *flat_grad, int *dirty, void *stream);
 

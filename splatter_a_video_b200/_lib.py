@@ -56,18 +56,25 @@ _SIGS = {
     "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, c_int, c_int64, c_int, P_, P_, P_, P_, P_, P_, c_float,
                                         c_float, c_float, P_, P_, P_, P_, P_, c_size_t, P_]),
     "spv_frame_ortho_backward": (c_int, [c_int, c_int, c_int, c_int, P_, c_int, c_int64, P_, P_, P_, P_, P_, c_float, P_, P_, P_, P_,
-                                         P_, P_, P_, P_, P_, P_, c_size_t, P_]),
+                                         P_, P_, P_, P_, P_, P_, P_, P_, c_size_t, P_]),
     "spv_alpha_blend_groups_backward_packed": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float, c_float,
                                                        P_, P_, P_, c_int, P_, P_]),
     "spv_deform_spline_forward": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_]),
     "spv_deform_spline_backward": (c_int, [c_int, c_int, P_, P_, P_, P_, c_int, P_]),
     "spv_deform_spline_forward2": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
     "spv_deform_spline_backward2": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_defer": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_spline_backward_gathered": (c_int, [c_int, c_int, c_int, P_, ctypes.c_longlong, c_float, P_, P_, P_]),
     "spv_deform_rotation_forward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
     "spv_deform_rotation_backward": (c_int, [c_int, P_, P_, P_, P_, P_]),
     "spv_adam_step": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, c_int, P_]),
     "spv_exchange_sizes": (c_int, [c_int, c_int, P_, P_, P_]),
     "spv_exchange_pack": (c_int, [c_int, c_int, P_, P_, P_, c_float, P_, P_, P_]),
+    "spv_exchange_reduce": (c_int, [ctypes.c_longlong, c_int, P_, ctypes.c_longlong, c_float, P_, P_]),
+    "spv_exchange_reduce_peers": (c_int, [ctypes.c_longlong, ctypes.c_longlong, c_int, P_, c_float, P_, P_, ctypes.c_longlong, P_]),
+    "spv_exchange_reduce_scatter_peers": (c_int, [ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, P_, c_float, P_, P_, P_,
+                                                  ctypes.c_longlong, P_]),
+    "spv_exchange_fetch_reduced": (c_int, [ctypes.c_longlong, c_int, c_int, P_, P_, P_]),
     "spv_exchange_unpack": (c_int, [c_int, c_int, P_, c_int, P_, P_, P_, P_, P_]),
     "spv_loss_rgb_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "spv_loss_rgb": (c_int, [c_int, c_int, P_, P_, c_float, c_float, P_, P_, P_, ctypes.c_size_t, P_]),

@@ -101,6 +101,85 @@ __global__ void deform_dirty_set_kernel(const int *__restrict__ idx1_dev, const 
     if (threadIdx.x == 0 && blockIdx.x == 0) { dirty[0] = 2; dirty[1] = idx1_dev[0]; dirty[2] = idx2_dev[0]; }
 }
 
+__global__ void __launch_bounds__(kThreads)
+deform_defer_kernel(int P, const float *__restrict__ g1, const float *__restrict__ g2, const int *__restrict__ idx1_dev,
+                    const float *__restrict__ dist1_dev, const int *__restrict__ idx2_dev, const float *__restrict__ dist2_dev,
+                    float *__restrict__ payload) {
+    const int k = blockIdx.x * kThreads + threadIdx.x;
+    if (k < 3 * P) { payload[k] = g1[k]; payload[3 * P + k] = g2 ? g2[k] : 0.f; }
+    if (k == 0) {
+        float *tail = payload + 6 * (size_t)P;
+        tail[0] = __int_as_float(idx1_dev[0]); tail[1] = dist1_dev[0];
+        tail[2] = __int_as_float(idx2_dev[0]); tail[3] = dist2_dev[0];
+    }
+}
+
+// Entries e = 2*rank + slot (<= 16).  Thread 0 of every CTA groups them by interval once (shared memory); each thread then
+// owns one (Gaussian, xyz component): clears the dirty intervals nobody re-writes and accumulates g * {d^3, d^2, d, 1} per
+// distinct interval in entry order.
+__global__ void __launch_bounds__(kThreads)
+deform_bwd_gathered_kernel(int P, int NI, int world, const float *__restrict__ gathered, long long stride, float scale,
+                           int *__restrict__ dirty, float *__restrict__ dL_dcoeff) {
+    __shared__ int s_idx[16], s_uniq[16], s_nu, s_nd, s_dirty[16];
+    __shared__ unsigned s_members[16];
+    __shared__ float s_dist[16];
+    const int ne = 2 * world;
+    if (threadIdx.x == 0) {
+        int nu = 0;
+        for (int e = 0; e < ne; ++e) {
+            const float *tail = gathered + (e >> 1) * stride + 6 * (size_t)P + 2 * (e & 1);
+            const int b = __float_as_int(tail[0]);
+            s_idx[e] = b; s_dist[e] = tail[1];
+            if (b < 0 || b >= NI) continue;
+            int u = 0;
+            while (u < nu && s_uniq[u] != b) ++u;
+            if (u == nu) { s_uniq[nu] = b; s_members[nu] = 0u; ++nu; }
+            s_members[u] |= 1u << e;
+        }
+        s_nu = nu;
+        int nd = 0;
+        const int cnt = min(dirty[0], 16);
+        for (int t = 0; t < cnt; ++t) {
+            const int z = dirty[1 + t];
+            bool rewritten = z < 0 || z >= NI;
+            for (int u = 0; u < nu; ++u) rewritten |= s_uniq[u] == z;
+            if (!rewritten) s_dirty[nd++] = z;
+        }
+        s_nd = nd;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * kThreads + threadIdx.x;
+    if (k >= 3 * P) return;
+    const int i = k / 3, c = k % 3;
+    const size_t s = (size_t)NI * 3;
+    float *row = dL_dcoeff + (size_t)i * 4 * s + c;
+    for (int t = 0; t < s_nd; ++t) {
+        float *q = row + (size_t)s_dirty[t] * 3;
+        q[0] = 0.f; q[s] = 0.f; q[2 * s] = 0.f; q[3 * s] = 0.f;
+    }
+    for (int u = 0; u < s_nu; ++u) {
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        unsigned m = s_members[u];
+        while (m) {
+            const int e = __ffs(m) - 1;
+            m &= m - 1u;
+            const float g = gathered[(e >> 1) * stride + (size_t)(e & 1) * 3 * P + k] * scale, d = s_dist[e];
+            q3 += g; q2 += g * d; q1 += g * (d * d); q0 += g * (d * d * d);
+        }
+        float *q = row + (size_t)s_uniq[u] * 3;
+        q[3 * s] = q3; q[2 * s] = q2; q[1 * s] = q1; q[0] = q0;
+    }
+}
+
+__global__ void deform_dirty_gathered_kernel(int P, int world, const float *__restrict__ gathered, long long stride,
+                                             int *__restrict__ dirty) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int ne = 2 * world;
+        for (int e = 0; e < ne; ++e) dirty[1 + e] = __float_as_int(gathered[(e >> 1) * stride + 6 * (size_t)P + 2 * (e & 1)]);
+        dirty[0] = ne;
+    }
+}
+
 // Rotation of the active model at frame time t (dynamic_gaussian_with_base_point_cloud.py:184-198, get_rotation):
 //   q = rotation + sum_k rot_poly_feat[:,k,:] * t^k + sum_l rot_fourier_feat[:,l,:] * basis_l(t)   (both feature sums are
 //   .detach()ed there), returned through F.normalize.  basis = [t^0..t^3 | cos(t*pi*(1..4)) | sin(t*pi*(1..4))] is read from
@@ -177,6 +256,24 @@ int spv_deform_spline_backward2(int P, int NI, const int *idx1_dev, const float 
                                                                         dL_dpos2, dirty, dL_dcoeff);
     deform_dirty_set_kernel<<<1, 32, 0, s>>>(idx1_dev, dL_dpos2 ? idx2_dev : idx1_dev, dirty);
     return spv::check_launch("spv_deform_spline_backward2", 2);
+}
+
+int spv_deform_defer(int P, const float *dL_dpos1, const float *dL_dpos2, const int *idx1_dev, const float *dist1_dev,
+                     const int *idx2_dev, const float *dist2_dev, float *payload, void *stream) {
+    if (P <= 0) return 0;
+    deform_defer_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, (cudaStream_t)stream>>>(P, dL_dpos1, dL_dpos2, idx1_dev, dist1_dev,
+                                                                                            idx2_dev, dist2_dev, payload);
+    return spv::check_launch("spv_deform_defer");
+}
+
+int spv_deform_spline_backward_gathered(int P, int NI, int world, const float *gathered, long long stride, float scale,
+                                        int *dirty, float *dL_dcoeff, void *stream) {
+    if (P <= 0) return 0;
+    if (world < 1 || world > 8) { spv::set_error(cudaErrorInvalidValue, "spv_deform_spline_backward_gathered: 1..8 ranks"); return (int)cudaErrorInvalidValue; }
+    cudaStream_t s = (cudaStream_t)stream;
+    deform_bwd_gathered_kernel<<<spv::cdiv(3ll * P, kThreads), kThreads, 0, s>>>(P, NI, world, gathered, stride, scale, dirty, dL_dcoeff);
+    deform_dirty_gathered_kernel<<<1, 32, 0, s>>>(P, world, gathered, stride, dirty);
+    return spv::check_launch("spv_deform_spline_backward_gathered", 2);
 }
 
 int spv_deform_rotation_forward(int P, const float *rotation, const float *rot_poly_feat, const float *rot_fourier_feat,

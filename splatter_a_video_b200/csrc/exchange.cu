@@ -20,137 +20,218 @@ constexpr int kThreads = 256;
 constexpr int kMaxSeg = SPV_EXCHANGE_MAX_SEGMENTS;
 constexpr int kMaxSel = SPV_EXCHANGE_MAX_SELECT;
 
+constexpr int kMaxWidth = 48;   // floats per Gaussian a subset / sparse segment may contribute
+
 struct Seg {
     long long flat_off;   // first float of the parameter in the flat buffer
     long long comm_off;   // first float of its block in the all-reduce (dense / subset) or all-gather (sparse) buffer
     int A, B, Cn;         // the parameter's per-Gaussian row viewed as [A, B, Cn]; slices are taken along B
     int mode;             // 0 dense (all of B), 1 subset (sel[] host-known), 2 sparse (indices read from the device)
     int nsel;
-    int sel[kMaxSel];
+    int w;                // floats per Gaussian in the comm buffer = A * nsel * Cn
+    int cta0, ncta;       // this segment's CTAs inside the 1-D grid
+    short off[kMaxWidth];         // gather modes: comm column k -> offset inside the Gaussian's [A,B,Cn] row (sparse: slice 0)
+    unsigned char slot[kMaxWidth];   // sparse: which of the rank's slices column k belongs to
 };
 struct Plan {
     Seg seg[kMaxSeg];
-    int nseg;
-    const int *sparse_idx[kMaxSel];   // device scalars: this rank's active slices (sparse mode)
-    long long n_ar, n_ag;             // floats in the all-reduce part / the all-gather payload (without the index tail)
+    int nseg, ncta;
+    const int *sparse_idx[2];     // device scalars: this rank's active slices (sparse mode)
+    long long n_ar, n_ag;         // floats in the all-reduce part / the all-gather payload (without the index tail)
 };
 
-__device__ __forceinline__ int seg_width(const Seg &s) { return s.A * s.nsel * s.Cn; }
-
+// One 1-D grid; every CTA first finds its segment (uniform, <= 16 compares).  Dense segments are a scaled linear copy
+// (their comm block has the parameter's own layout); gather segments run 8 Gaussians per CTA with the lanes over the
+// Gaussian's comm columns and a host-built column -> row-offset table: no integer division anywhere.
 __global__ void __launch_bounds__(kThreads)
 exchange_pack_kernel(int P, Plan plan, const float *__restrict__ flat_grad, float scale, float *__restrict__ comm_ar,
                      float *__restrict__ comm_ag) {
-    const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const long long total = plan.n_ar + plan.n_ag;
-    if (e >= total + kMaxSel) return;
-    if (e >= total) {   // index tail of the all-gather payload (int bits)
-        const int t = (int)(e - total);
-        int v = -1;
-        for (int q = 0; q < plan.nseg; ++q)
-            if (plan.seg[q].mode == 2 && t < plan.seg[q].nsel) v = plan.sparse_idx[t][0];
-        reinterpret_cast<int *>(comm_ag)[plan.n_ag + t] = v;
+    int q = 0;
+    for (int t = 1; t < plan.nseg; ++t) if ((int)blockIdx.x >= plan.seg[t].cta0) q = t;
+    const Seg &s = plan.seg[q];
+    const int cta = blockIdx.x - s.cta0;
+    if (s.mode == 0) {
+        const long long r = (long long)cta * kThreads + threadIdx.x;
+        if (r < (long long)P * s.w) comm_ar[s.comm_off + r] = flat_grad[s.flat_off + r] * scale;
         return;
     }
-    const bool ag = e >= plan.n_ar;
-    const long long local = ag ? e - plan.n_ar : e;
-    int q = 0;
-#pragma unroll 1
-    for (int t = 0; t < plan.nseg; ++t) {
-        const Seg &s = plan.seg[t];
-        if ((s.mode == 2) == ag && local >= s.comm_off && local < s.comm_off + (long long)P * seg_width(s)) q = t;
+    const int lane = threadIdx.x & 31, i = cta * 8 + (threadIdx.x >> 5);
+    if (s.mode == 2 && cta == 0 && threadIdx.x < kMaxSel)   // index tail of the all-gather payload (int bits)
+        reinterpret_cast<int *>(comm_ag)[plan.n_ag + threadIdx.x] = (int)threadIdx.x < s.nsel ? plan.sparse_idx[threadIdx.x][0] : -1;
+    if (i >= P) return;
+    const float *row = flat_grad + s.flat_off + (long long)i * (s.A * s.B * s.Cn);
+    float *dst = (s.mode == 2 ? comm_ag : comm_ar) + s.comm_off + (long long)i * s.w;
+    int b0 = 0, b1 = 0;
+    if (s.mode == 2) { b0 = plan.sparse_idx[0][0]; b1 = s.nsel > 1 ? plan.sparse_idx[1][0] : b0; }
+    for (int k = lane; k < s.w; k += 32) {
+        float v;
+        if (s.mode == 2) {
+            const int sl = s.slot[k];
+            v = (sl == 1 && b1 == b0) ? 0.f : row[s.off[k] + (sl ? b1 : b0) * s.Cn] * scale;   // same interval twice: sent once
+        } else v = row[s.off[k]] * scale;
+        dst[k] = v;
     }
-    const Seg &s = plan.seg[q];
-    const int w = seg_width(s);
-    const long long r = local - s.comm_off;
-    const int i = (int)(r / w), k = (int)(r % w);
-    const int a = k / (s.nsel * s.Cn), si = (k / s.Cn) % s.nsel, c = k % s.Cn;
-    int b;
-    bool dup = false;
-    if (s.mode == 2) {
-        b = plan.sparse_idx[si][0];
-        for (int t = 0; t < si; ++t) dup |= plan.sparse_idx[t][0] == b;   // the same interval twice: sent once
-    } else b = s.sel[si];
-    const float v = flat_grad[s.flat_off + (long long)i * s.A * s.B * s.Cn + ((long long)a * s.B + b) * s.Cn + c];
-    (ag ? comm_ag : comm_ar)[local] = dup ? 0.f : v * scale;
 }
 
 __global__ void __launch_bounds__(kThreads)
 exchange_unpack_kernel(int P, Plan plan, int world, const float *__restrict__ comm_ar, const float *__restrict__ gathered,
                        long long ag_stride, float *__restrict__ flat_grad, int *__restrict__ dirty) {
-    const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
-    // the sparse part is walked once per (Gaussian, a, c): n_ag / nsel work items
-    int sq = -1;
-    for (int t = 0; t < plan.nseg; ++t) if (plan.seg[t].mode == 2) sq = t;
-    const int nsel = sq >= 0 ? plan.seg[sq].nsel : 1;
-    const long long n_sp = plan.n_ag / nsel;
-    if (e == 0 && dirty && sq >= 0) {
-        int n = 0;
-        for (int r = 0; r < world; ++r)
-            for (int t = 0; t < nsel; ++t)
-                if (n < 16) dirty[1 + n++] = reinterpret_cast<const int *>(gathered + r * ag_stride)[plan.n_ag + t];
-        dirty[0] = n;
-    }
-    if (e < plan.n_ar) {
-        int q = 0;
-#pragma unroll 1
-        for (int t = 0; t < plan.nseg; ++t) {
-            const Seg &s = plan.seg[t];
-            if (s.mode != 2 && e >= s.comm_off && e < s.comm_off + (long long)P * seg_width(s)) q = t;
-        }
-        const Seg &s = plan.seg[q];
-        const int w = seg_width(s);
-        const long long r = e - s.comm_off;
-        const int i = (int)(r / w), k = (int)(r % w);
-        const int a = k / (s.nsel * s.Cn), si = (k / s.Cn) % s.nsel, c = k % s.Cn;
-        flat_grad[s.flat_off + (long long)i * s.A * s.B * s.Cn + ((long long)a * s.B + s.sel[si]) * s.Cn + c] = comm_ar[e];
+    int q = 0;
+    for (int t = 1; t < plan.nseg; ++t) if ((int)blockIdx.x >= plan.seg[t].cta0) q = t;
+    const Seg &s = plan.seg[q];
+    const int cta = blockIdx.x - s.cta0;
+    if (s.mode == 0) {
+        const long long r = (long long)cta * kThreads + threadIdx.x;
+        if (r < (long long)P * s.w) flat_grad[s.flat_off + r] = comm_ar[s.comm_off + r];
         return;
     }
-    const long long u = e - plan.n_ar;
-    if (u >= n_sp || sq < 0) return;
-    const Seg &s = plan.seg[sq];
-    const int per = s.A * s.Cn;                       // work items per Gaussian
-    const int i = (int)(u / per), k = (int)(u % per);
-    const int a = k / s.Cn, c = k % s.Cn;
-    float *row = flat_grad + s.flat_off + (long long)i * s.A * s.B * s.Cn + (long long)a * s.B * s.Cn + c;
-    const int pairs = world * nsel;                   // <= 16 (rank, slot) contributions, summed per interval in rank order
-    for (int j = 0; j < pairs; ++j) {
-        const int rj = j / nsel, tj = j % nsel;
-        const int bj = reinterpret_cast<const int *>(gathered + rj * ag_stride)[plan.n_ag + tj];
-        bool first = true;
-        for (int j2 = 0; j2 < j; ++j2)
-            first &= reinterpret_cast<const int *>(gathered + (j2 / nsel) * ag_stride)[plan.n_ag + (j2 % nsel)] != bj;
-        if (!first || bj < 0 || bj >= s.B) continue;
-        float sum = 0.f;
-        for (int j2 = j; j2 < pairs; ++j2) {
-            const int r2 = j2 / nsel, t2 = j2 % nsel;
-            if (reinterpret_cast<const int *>(gathered + r2 * ag_stride)[plan.n_ag + t2] != bj) continue;
-            sum += gathered[r2 * ag_stride + s.comm_off + ((long long)i * s.A * nsel + (long long)a * nsel + t2) * s.Cn + c];
-        }
-        row[(long long)bj * s.Cn] = sum;
+    const int lane = threadIdx.x & 31, i = cta * 8 + (threadIdx.x >> 5);
+    if (s.mode == 1) {
+        if (i >= P) return;
+        float *row = flat_grad + s.flat_off + (long long)i * (s.A * s.B * s.Cn);
+        const float *src = comm_ar + s.comm_off + (long long)i * s.w;
+        for (int k = lane; k < s.w; k += 32) row[s.off[k]] = src[k];
+        return;
     }
+    // sparse: every rank's slices are summed per interval in (rank, slot) order -- bit-identical on every rank
+    const int nsel = s.nsel, pairs = world * nsel;   // <= 16 contributions
+    int idx[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        idx[j] = j < pairs ? reinterpret_cast<const int *>(gathered + (j / nsel) * ag_stride)[plan.n_ag + (j % nsel)] : -1;
+    if (cta == 0 && threadIdx.x == 0 && dirty) {
+        for (int j = 0; j < 16; ++j) if (j < pairs) dirty[1 + j] = idx[j];
+        dirty[0] = pairs;
+    }
+    if (i >= P) return;
+    float *row = flat_grad + s.flat_off + (long long)i * (s.A * s.B * s.Cn);
+    const float *src = gathered + s.comm_off + (long long)i * s.w;
+    for (int k = lane; k < s.w; k += 32) {
+        if (s.slot[k] != 0) continue;                 // one lane per (a, c): the columns of slot 0
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j >= pairs) break;
+            const int bj = idx[j];
+            bool first = bj >= 0 && bj < s.B;
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2) if (j2 < j) first &= idx[j2] != bj;
+            if (!first) continue;
+            float sum = 0.f;
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2)
+                if (j2 >= j && j2 < pairs && idx[j2] == bj) sum += src[(j2 / nsel) * ag_stride + k + (j2 % nsel) * s.Cn];
+            row[s.off[k] + bj * s.Cn] = sum;
+        }
+    }
+}
+
+// out[e] = scale * sum over ranks (in rank order: bit-identical on every rank) of gathered[r * stride + e]
+__global__ void __launch_bounds__(kThreads)
+exchange_reduce_kernel(long long n4, int world, const float4 *__restrict__ gathered, long long stride4, float scale,
+                       float4 *__restrict__ out) {
+    const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= n4) return;
+    float4 acc = gathered[e];
+    for (int r = 1; r < world; ++r) {
+        const float4 v = gathered[r * stride4 + e];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[e] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+}
+
+// The same reduction straight out of the peers' memory (NVLink P2P loads from symmetric buffers; no NCCL collective):
+// [0, n_red) is summed over ranks in rank order, [n_red, n_row) is copied rank by rank into the local `rows` (the gathered
+// position gradients + frame scalars the deferred spline backward reads).  One pass: every remote byte crosses NVLink once.
+struct PeerPtrs { const float4 *p[8]; };
+__global__ void __launch_bounds__(kThreads)
+exchange_reduce_peers_kernel(long long n_red4, long long n_row4, int world, PeerPtrs peers, float scale, float4 *__restrict__ reduced,
+                             float4 *__restrict__ rows, long long row_stride4) {
+    const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= n_row4) return;
+    if (e < n_red4) {
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < world) v[r] = peers.p[r][e];   // all loads in flight before the adds
+        float4 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        reduced[e] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = peers.p[r][e];
+    }
+}
+
+// Two-phase variant for larger groups (inbound volume 2(N-1)/N instead of N-1 times the summed block): phase 1 -- every
+// rank sums ITS 1/N slice of the block over all peers and publishes it in its symmetric `red` area (and copies the gathered
+// tails); a barrier; phase 2 -- every rank fetches the other slices from their owners.  Same rank-order sums, so the result is
+// still bit-identical on every rank.
+__global__ void __launch_bounds__(kThreads)
+exchange_reduce_scatter_kernel(long long n_red4, long long n_row4, long long chunk4, int rank, int world, PeerPtrs peers, float scale,
+                               float4 *__restrict__ red_pub, float4 *__restrict__ reduced, float4 *__restrict__ rows,
+                               long long row_stride4) {
+    const long long lo = (long long)rank * chunk4, hi = min(n_red4, lo + chunk4), mine = max(hi - lo, 0ll);
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (t < mine) {
+        const long long e = lo + t;
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < world) v[r] = peers.p[r][e];
+        float4 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        acc = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+        red_pub[e] = acc;
+        reduced[e] = acc;
+    } else {
+        const long long e = n_red4 + (t - mine);
+        if (e >= n_row4) return;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = peers.p[r][e];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+exchange_fetch_reduced_kernel(long long n_red4, long long chunk4, int rank, PeerPtrs red_peers, float4 *__restrict__ reduced) {
+    const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= n_red4) return;
+    const int owner = (int)(e / chunk4);
+    if (owner != rank) reduced[e] = red_peers.p[owner][e];
 }
 
 int build_plan(Plan &plan, int P, int nseg, const spv_exchange_segment *segs, const int *const *sparse_idx_dev, const char *where) {
     if (nseg < 1 || nseg > kMaxSeg) { spv::set_error(cudaErrorInvalidValue, where); return (int)cudaErrorInvalidValue; }
     plan.nseg = nseg;
     long long ar = 0, ag = 0;
-    int n_sparse = 0;
-    for (int t = 0; t < kMaxSel; ++t) plan.sparse_idx[t] = nullptr;
+    int n_sparse = 0, cta = 0;
+    plan.sparse_idx[0] = plan.sparse_idx[1] = nullptr;
     for (int q = 0; q < nseg; ++q) {
         const spv_exchange_segment &in = segs[q];
         Seg &s = plan.seg[q];
         s.flat_off = in.flat_offset; s.A = in.A; s.B = in.B; s.Cn = in.C; s.mode = in.mode;
         s.nsel = in.mode == 0 ? in.B : in.nsel;
-        if (in.A < 1 || in.B < 1 || in.C < 1 || in.mode < 0 || in.mode > 2 || s.nsel < 1 || s.nsel > kMaxSel ||
-            (in.mode == 2 && (s.nsel > 2 || ++n_sparse > 1 || !sparse_idx_dev))) {
-            spv::set_error(cudaErrorInvalidValue, where);
-            return (int)cudaErrorInvalidValue;
-        }
-        for (int t = 0; t < kMaxSel; ++t) s.sel[t] = in.mode == 0 ? t : (t < s.nsel && in.mode == 1 ? in.sel[t] : 0);
-        const long long n = (long long)P * s.A * s.nsel * s.Cn;
+        bool bad = in.A < 1 || in.B < 1 || in.C < 1 || in.mode < 0 || in.mode > 2 || s.nsel < 1 || s.nsel > kMaxSel;
+        s.w = bad ? 0 : s.A * s.nsel * s.Cn;
+        bad = bad || (in.mode != 0 && (s.w > kMaxWidth || (long long)s.A * s.B * s.Cn > 32767)) ||
+              (in.mode == 2 && (s.nsel > 2 || ++n_sparse > 1 || !sparse_idx_dev));
+        if (bad) { spv::set_error(cudaErrorInvalidValue, where); return (int)cudaErrorInvalidValue; }
+        for (int k = 0; k < kMaxWidth; ++k) { s.off[k] = 0; s.slot[k] = 0; }
+        if (in.mode != 0)
+            for (int k = 0; k < s.w; ++k) {   // comm column k = (a, si, c)
+                const int a = k / (s.nsel * s.Cn), si = (k / s.Cn) % s.nsel, c = k % s.Cn;
+                const int b = in.mode == 1 ? in.sel[si] : 0;
+                if (b < 0 || b >= in.B) { spv::set_error(cudaErrorInvalidValue, where); return (int)cudaErrorInvalidValue; }
+                s.off[k] = (short)((a * s.B + b) * s.Cn + c);
+                s.slot[k] = (unsigned char)si;
+            }
+        const long long n = (long long)P * s.w;
+        const long long nc = in.mode == 0 ? (n + kThreads - 1) / kThreads : ((long long)P + 7) / 8;
+        if (cta + nc >= (1ll << 31)) { spv::set_error(cudaErrorInvalidValue, where); return (int)cudaErrorInvalidValue; }
+        s.cta0 = cta; s.ncta = (int)nc; cta += (int)nc;
         if (in.mode == 2) { s.comm_off = ag; ag += n; for (int t = 0; t < s.nsel; ++t) plan.sparse_idx[t] = sparse_idx_dev[t]; }
         else { s.comm_off = ar; ar += n; }
     }
+    plan.ncta = cta;
     plan.n_ar = ar; plan.n_ag = ag;
     return 0;
 }
@@ -174,9 +255,7 @@ int spv_exchange_pack(int P, int nseg, const spv_exchange_segment *segs, const i
     Plan plan;
     int rc = build_plan(plan, P, nseg, segs, sparse_idx_dev, "spv_exchange_pack: bad segment table");
     if (rc) return rc;
-    const long long total = plan.n_ar + plan.n_ag + (plan.n_ag ? kMaxSel : 0);
-    exchange_pack_kernel<<<spv::cdiv(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(P, plan, flat_grad, scale, comm_allreduce,
-                                                                                           comm_allgather);
+    exchange_pack_kernel<<<plan.ncta, kThreads, 0, (cudaStream_t)stream>>>(P, plan, flat_grad, scale, comm_allreduce, comm_allgather);
     return spv::check_launch("spv_exchange_pack");
 }
 
@@ -188,13 +267,70 @@ int spv_exchange_unpack(int P, int nseg, const spv_exchange_segment *segs, int w
     static const int *dummy[kMaxSel] = {nullptr};
     int rc = build_plan(plan, P, nseg, segs, dummy, "spv_exchange_unpack: bad segment table");
     if (rc) return rc;
-    int nsel = 1;
-    for (int q = 0; q < nseg; ++q) if (plan.seg[q].mode == 2) nsel = plan.seg[q].nsel;
-    const long long total = plan.n_ar + plan.n_ag / nsel;
     const long long stride = plan.n_ag + (plan.n_ag ? kMaxSel : 0);
-    exchange_unpack_kernel<<<spv::cdiv(total > 0 ? total : 1, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        P, plan, world, comm_allreduce, gathered, stride, flat_grad, dirty);
+    exchange_unpack_kernel<<<plan.ncta, kThreads, 0, (cudaStream_t)stream>>>(P, plan, world, comm_allreduce, gathered, stride, flat_grad,
+                                                                             dirty);
     return spv::check_launch("spv_exchange_unpack");
+}
+
+/* out[0..n) = scale * sum_r gathered[r*stride + 0..n): the local reduction behind a single all-gather (n and stride multiples
+ * of 4, 16-byte aligned buffers). */
+int spv_exchange_reduce(long long n, int world, const float *gathered, long long stride, float scale, float *out, void *stream) {
+    if (n <= 0) return 0;
+    if ((n & 3) || (stride & 3) || world < 1) { spv::set_error(cudaErrorInvalidValue, "spv_exchange_reduce: n and stride must be multiples of 4"); return (int)cudaErrorInvalidValue; }
+    exchange_reduce_kernel<<<spv::cdiv(n / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(n / 4, world, (const float4 *)gathered,
+                                                                                             stride / 4, scale, (float4 *)out);
+    return spv::check_launch("spv_exchange_reduce");
+}
+
+/* peer_rows: host array of `world` device pointers (this rank's own row included, in rank order) to rows of n_row floats laid
+ * out as [n_red summed floats | gathered floats]; the caller has synchronised the ranks (all rows written) before this launch. */
+int spv_exchange_reduce_peers(long long n_red, long long n_row, int world, const float *const *peer_rows, float scale, float *reduced,
+                              float *rows, long long row_stride, void *stream) {
+    if (n_row <= 0) return 0;
+    if ((n_red & 3) || (n_row & 3) || (row_stride & 3) || world < 1 || world > 8 || n_red > n_row) {
+        spv::set_error(cudaErrorInvalidValue, "spv_exchange_reduce_peers: sizes must be multiples of 4, 1..8 ranks");
+        return (int)cudaErrorInvalidValue;
+    }
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
+    exchange_reduce_peers_kernel<<<spv::cdiv(n_row / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n_red / 4, n_row / 4, world, pp, scale, (float4 *)reduced, (float4 *)rows, row_stride / 4);
+    return spv::check_launch("spv_exchange_reduce_peers");
+}
+
+/* Two-phase form (world >= 4): phase 1 sums this rank's 1/world slice of [0, n_red) over the peers' rows into red_pub (this
+ * rank's symmetric area, read by the peers in phase 2) and `reduced`, and copies the gathered tails; the caller places a
+ * cross-rank barrier; phase 2 fetches the other slices from peer_red[owner]. */
+int spv_exchange_reduce_scatter_peers(long long n_red, long long n_row, int rank, int world, const float *const *peer_rows, float scale,
+                                      float *red_pub, float *reduced, float *rows, long long row_stride, void *stream) {
+    if (n_row <= 0) return 0;
+    if ((n_red & 3) || (n_row & 3) || (row_stride & 3) || world < 1 || world > 8 || n_red > n_row || rank < 0 || rank >= world) {
+        spv::set_error(cudaErrorInvalidValue, "spv_exchange_reduce_scatter_peers: sizes must be multiples of 4, 1..8 ranks");
+        return (int)cudaErrorInvalidValue;
+    }
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
+    const long long n_red4 = n_red / 4, n_row4 = n_row / 4, chunk4 = (n_red4 + world - 1) / world;
+    const long long lo = (long long)rank * chunk4, hi = lo + chunk4 < n_red4 ? lo + chunk4 : n_red4;
+    const long long work = (hi > lo ? hi - lo : 0) + (n_row4 - n_red4);
+    exchange_reduce_scatter_kernel<<<spv::cdiv(work > 0 ? work : 1, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n_red4, n_row4, chunk4 > 0 ? chunk4 : 1, rank, world, pp, scale, (float4 *)red_pub, (float4 *)reduced, (float4 *)rows, row_stride / 4);
+    return spv::check_launch("spv_exchange_reduce_scatter_peers");
+}
+
+int spv_exchange_fetch_reduced(long long n_red, int rank, int world, const float *const *peer_red, float *reduced, void *stream) {
+    if (n_red <= 0) return 0;
+    if ((n_red & 3) || world < 1 || world > 8 || rank < 0 || rank >= world) {
+        spv::set_error(cudaErrorInvalidValue, "spv_exchange_fetch_reduced: n_red must be a multiple of 4, 1..8 ranks");
+        return (int)cudaErrorInvalidValue;
+    }
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_red[r < world ? r : 0];
+    const long long n_red4 = n_red / 4, chunk4 = (n_red4 + world - 1) / world;
+    exchange_fetch_reduced_kernel<<<spv::cdiv(n_red4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(n_red4, chunk4 > 0 ? chunk4 : 1, rank, pp,
+                                                                                                  (float4 *)reduced);
+    return spv::check_launch("spv_exchange_fetch_reduced");
 }
 
 }  // extern "C"

@@ -196,8 +196,8 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
                              const float *scaling, const float *rotation, const float *opacity, const float *shs,
                              const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
                              float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs,
-                             float *const *dL_dattr_ptrs, float *dL_dndc, float *dL_dabs_ndc, void *workspace,
-                             size_t ws_bytes, void *stream) {
+                             float *const *dL_dattr_ptrs, float *dL_dndc, float *dL_dabs_ndc, float *dL_drgb_out,
+                             uint8_t *clamped_out, void *workspace, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0 || W <= 0 || H <= 0) return 0;
     AttrGroups gr;
@@ -209,7 +209,11 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     float *packed = (float *)f.blend_ws;
     SPV_TRY_RC(spv::blend_records_backward(P, C, W, H, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, f.final_T,
                                            f.ncontrib, dL_dimage_planes, n_grad_channels, packed, stream));
-    unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, (float2 *)f.g_uv, f.g_conic, dL_dopacity, f.g_rgb, f.g_depth, gr,
+    // deferred SH backward (frame-parallel training): the colour gradient and the clamp mask leave through the caller's
+    // buffers, the SH coefficients' gradient is produced after the gradient exchange from the REDUCED colour gradient
+    const bool defer_sh = dL_drgb_out != nullptr;
+    float *g_rgb = defer_sh ? dL_drgb_out : f.g_rgb;
+    unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, (float2 *)f.g_uv, f.g_conic, dL_dopacity, g_rgb, f.g_depth, gr,
                                                (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));
     // colours -> SH coefficients (view direction is a constant: its gradient is discarded) on the side stream, next to
@@ -218,7 +222,11 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     if (!lane) { spv::set_error(cudaGetLastError(), "spv_frame_ortho_backward: side stream"); return (int)cudaErrorUnknown; }
     SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_backward/fork");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_backward/fork");
-    SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, nullptr, f.clamped, f.g_rgb, 16, dL_dshs, f.g_dirs, (void *)lane->stream));
+    if (defer_sh) {
+        if (clamped_out) SPV_CUDA_TRY(cudaMemcpyAsync(clamped_out, f.clamped, (size_t)P * 3, cudaMemcpyDeviceToDevice, lane->stream), "spv_frame_ortho_backward");
+    } else {
+        SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, nullptr, f.clamped, f.g_rgb, 16, dL_dshs, /*dL_ddirs=*/nullptr, (void *)lane->stream));   // constant view direction: its gradient is discarded
+    }
     SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_backward/join");
     SPV_TRY_RC(spv_project_point_ortho_backward(P, extr, W, H, f.depth, f.g_uv, f.g_depth, dL_dposition, stream));
     SPV_TRY_RC(spv_ewa_project_ortho_backward(P, f.cov3d, extr, W, H, f.radius, f.g_conic, f.g_cov3d, stream));

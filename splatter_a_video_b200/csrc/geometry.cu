@@ -607,19 +607,23 @@ sh_fwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
     if (clamped) { clamped[3 * i] = cl[0]; clamped[3 * i + 1] = cl[1]; clamped[3 * i + 2] = cl[2]; }
 }
 
-template <int DEG>
+// DIRS = false (dL_ddirs == NULL, e.g. the renderers' constant view direction): the SH coefficients are not even read --
+// the gradient of the coefficients only needs the direction's basis values and the (clamp-masked) colour gradient.
+template <int DEG, bool DIRS>
 __global__ void __launch_bounds__(kShBwdThreads)
 sh_bwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ dirs,
               const uint8_t *__restrict__ visible, const uint8_t *__restrict__ clamped,
               const float *__restrict__ dL_dcolors, float *__restrict__ dL_dshs, float *__restrict__ dL_ddirs) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     constexpr int ROW = NB * 3;
-    __shared__ float s_sh[kShBwdThreads * (ROW + 1)];
+    __shared__ float s_sh[DIRS ? kShBwdThreads * (ROW + 1) : 1];
     __shared__ float s_g[kShBwdThreads * (ROW + 1)];
     const int base = blockIdx.x * kShBwdThreads;
     const int rows = min(kShBwdThreads, P - base);
-    sh_slab_load<ROW, kShBwdThreads>(shs + (size_t)base * ROW, s_sh, rows);
-    __syncthreads();
+    if (DIRS) {
+        sh_slab_load<ROW, kShBwdThreads>(shs + (size_t)base * ROW, s_sh, rows);
+        __syncthreads();
+    }
     const int i = base + threadIdx.x;
     float gdir[3] = {0.f, 0.f, 0.f};
     if (i < P) {
@@ -627,13 +631,13 @@ sh_bwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
 #pragma unroll
         for (int k = 0; k < ROW; ++k) dsh[k] = 0.f;     // invisible rows stay zero (torch::zeros in the reference)
         if (visible == nullptr || visible[i]) {   // NULL mask = every point visible
-            const float *sh = s_sh + threadIdx.x * (ROW + 1);
+            const float *sh = s_sh + (DIRS ? threadIdx.x * (ROW + 1) : 0);
             const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 float g = dL_dcolors[3 * i + ch];
                 if (clamped) g *= clamped[3 * i + ch] ? 0.0f : 1.0f;
-#define S(k) sh[(k) * 3 + ch]
+#define S(k) (DIRS ? sh[(k) * 3 + ch] : 0.f)
 #define DS(k) dsh[(k) * 3 + ch]
                 float dx = 0, dy = 0, dz = 0;
                 DS(0) = SH_C0 * g;
@@ -672,7 +676,7 @@ sh_bwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
                 gdir[0] += dx * g; gdir[1] += dy * g; gdir[2] += dz * g;
             }
         }
-        dL_ddirs[3 * i] = gdir[0]; dL_ddirs[3 * i + 1] = gdir[1]; dL_ddirs[3 * i + 2] = gdir[2];
+        if (DIRS) { dL_ddirs[3 * i] = gdir[0]; dL_ddirs[3 * i + 1] = gdir[1]; dL_ddirs[3 * i + 2] = gdir[2]; }
     }
     __syncthreads();
     sh_slab_store<ROW, kShBwdThreads>(dL_dshs + (size_t)base * ROW, s_g, rows);
@@ -807,10 +811,14 @@ int spv_compute_sh_backward(int P, const float *shs, int deg, const float *dirs,
                      "spv_compute_sh_backward");
     dim3 g(spv::cdiv(P, kShBwdThreads));
     switch (deg) {
-        case 0: sh_bwd_kernel<0><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
-        case 1: sh_bwd_kernel<1><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
-        case 2: sh_bwd_kernel<2><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
-        default: sh_bwd_kernel<3><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs); break;
+#define SPV_SH_BWD(D)                                                                                                            \
+    if (dL_ddirs) sh_bwd_kernel<D, true><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, dL_ddirs);  \
+    else sh_bwd_kernel<D, false><<<g, kShBwdThreads, 0, s>>>(P, shs, dirs, visible, clamped, dL_dcolors, dL_dshs, nullptr)
+        case 0: SPV_SH_BWD(0); break;
+        case 1: SPV_SH_BWD(1); break;
+        case 2: SPV_SH_BWD(2); break;
+        default: SPV_SH_BWD(3); break;
+#undef SPV_SH_BWD
     }
     return spv::check_launch("spv_compute_sh_backward");
 }

@@ -132,7 +132,11 @@ class _FrameOrtho(torch.autograd.Function):
         g_sc, r_sc = out("scaling", P, 3)
         g_rot, r_rot = out("rotation", P, 4)
         g_op, r_op = out("opacity", P, 1)
-        g_sh, r_sh = out("shs", P, 16, 3)
+        defer = sinks.get("shs_deferred")          # (dL_drgb[P,3], clamped[P,3] uint8): SH backward runs after the exchange
+        if defer is not None:
+            g_sh, r_sh = None, None
+        else:
+            g_sh, r_sh = out("shs", P, 16, 3)
         g_attr = [torch.empty(P, n, dtype=torch.float32, device=dev) if need else None for n, need in zip(chans, ctx.attr_needs)]
         g_ndc = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_ndc else None
         g_abs = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_abs else None
@@ -140,7 +144,8 @@ class _FrameOrtho(torch.autograd.Function):
         L.call("spv_frame_ortho_backward", P, W, H, ng, ctypes.cast(ch_arr, ctypes.c_void_p), n_grad_channels, I_cap, L.ptr(sc), L.ptr(rot), L.ptr(op),
                L.ptr(sh), L.ptr(ex), bg_rgb, ctypes.cast(_ptr_array(planes), ctypes.c_void_p), L.ptr(g_pos), L.ptr(g_sc), L.ptr(g_rot),
                L.ptr(g_op), L.ptr(g_sh), ctypes.cast(_ptr_array([None if t is None else t.data_ptr() for t in g_attr]), ctypes.c_void_p),
-               L.ptr(g_ndc), L.ptr(g_abs), L.ptr(ws), ws.numel(), L.stream())
+               L.ptr(g_ndc), L.ptr(g_abs), L.ptr(defer[0]) if defer is not None else None,
+               L.ptr(defer[1]) if defer is not None else None, L.ptr(ws), ws.numel(), L.stream())
         g_user = [None] * ng
         for slot, t in zip(ctx.order, g_attr):
             g_user[slot] = t
@@ -219,8 +224,9 @@ class _DeformSplinePair(torch.autograd.Function):
     device-side dirty list (no per-step clear of the whole [P, 4*NI*3] gradient), or into a fresh zero tensor."""
 
     @staticmethod
-    def forward(ctx, base, coeff, idx1, dist1, idx2, dist2, NI, sink, dirty):
+    def forward(ctx, base, coeff, idx1, dist1, idx2, dist2, NI, sink, dirty, defer):
         L.need_cuda(base, coeff, idx1, dist1, idx2, dist2)
+        ctx.defer = defer
         b, c = L.f32c(base), L.f32c(coeff)
         P = b.shape[0]
         pos1 = torch.empty(P, 3, dtype=torch.float32, device=b.device)
@@ -241,6 +247,10 @@ class _DeformSplinePair(torch.autograd.Function):
             g1 = torch.zeros(P, 3, dtype=torch.float32, device=dev)
         g1 = L.f32c(g1)
         g2 = None if g2 is None else L.f32c(g2)
+        if ctx.defer is not None:      # frame-parallel: only stage the position gradients; GradExchange finishes the backward
+            L.call("spv_deform_defer", P, L.ptr(g1), L.ptr(g2), L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2), L.ptr(ctx.defer),
+                   L.stream())
+            return (g1 if g2 is None else g1 + g2) if base_grad else None, None, None, None, None, None, None, None, None, None
         if ctx.sink is not None:
             g_coeff, dirty, ret = ctx.sink, ctx.dirty, None
         else:
@@ -251,19 +261,23 @@ class _DeformSplinePair(torch.autograd.Function):
         g_base = None
         if base_grad:
             g_base = g1 if g2 is None else g1 + g2
-        return g_base, ret, None, None, None, None, None, None, None
+        return g_base, ret, None, None, None, None, None, None, None, None
 
 
 def deform_position_pair(base: Tensor, pos_cubic_node: Tensor, idx1: Tensor, dist1: Tensor, idx2: Tensor, dist2: Tensor,
-                         interval_num: int, grad_sink: Optional[Tensor] = None, dirty: Optional[Tensor] = None):
+                         interval_num: int, grad_sink: Optional[Tensor] = None, dirty: Optional[Tensor] = None,
+                         defer: Optional[Tensor] = None):
     """Positions at the two frame times of a training step (ids1 rendered; ids2 = the `track_gs` attribute,
     src/trainer_fragGS.py:486-508) from ONE pass over the spline coefficients.  Both outputs are differentiable.
     grad_sink + dirty: the coefficient gradient is WRITTEN into `grad_sink` ([P, 4*NI*3], zero-initialised once) and
     `dirty` (int32[17] on the device, zero-initialised once) tracks which intervals hold gradient so only those are cleared on
-    the next call -- see FlatParams.grad_exchange for how exchanged intervals are added to the list."""
+    the next call.
+    defer (frame-parallel training): float32[6P + 4] staging buffer of parallel.GradExchange -- the backward only stores the two
+    position gradients there; the coefficient gradient of EVERY rank's frames is rebuilt after the all-gather
+    (`spv_deform_spline_backward_gathered`), which is 4x less traffic than exchanging coefficient gradients."""
     if (grad_sink is None) != (dirty is None):
         raise ValueError("deform_position_pair: grad_sink and dirty go together")
-    return _DeformSplinePair.apply(base, pos_cubic_node, idx1, dist1, idx2, dist2, interval_num, grad_sink, dirty)
+    return _DeformSplinePair.apply(base, pos_cubic_node, idx1, dist1, idx2, dist2, interval_num, grad_sink, dirty, defer)
 
 
 def rotation_basis(time: float, start_frame_id: int, time_len: int) -> Tensor:

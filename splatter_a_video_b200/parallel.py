@@ -97,8 +97,16 @@ class GradExchange:
     (gloo tests): the same plan executed with torch indexing."""
 
     def __init__(self, flat: FlatParams, P: int, subset: Optional[dict] = None, sparse: Optional[dict] = None,
-                 dirty: Optional[torch.Tensor] = None, skip: Sequence[str] = ()):
+                 dirty: Optional[torch.Tensor] = None, skip: Sequence[str] = (), deferred: Optional[dict] = None):
         self.flat, self.P, self.dirty = flat, int(P), dirty
+        self.exchange_path = "nccl"
+        # deferred = {"shs": name of the SH parameter, "node": name of the spline parameter, "NI": interval count}: the two
+        # LINEAR tails of the backward pass (colour -> SH coefficients, position -> spline coefficients) run AFTER the
+        # exchange on the reduced / gathered upstream gradients -- 3 + 6 floats per Gaussian on the wire instead of 12 + 24.
+        self.deferred = dict(deferred) if deferred else None
+        if self.deferred:
+            skip = tuple(skip) + (self.deferred["shs"], self.deferred["node"])
+            subset, sparse = None, None
         self.subset, self.sparse = dict(subset or {}), dict(sparse or {})
         if len(self.sparse) > 1:
             raise ValueError("GradExchange: at most one sparse parameter")
@@ -151,9 +159,110 @@ class GradExchange:
         dev = self.flat.flat_grad.device
         world = dist.get_world_size() if dist.is_initialized() else 1
         self._cuda = dict(arr=arr, idx=idx_ptrs, n_ar=n_ar.value, n_ag=n_ag.value,
-                          ar=torch.empty(max(n_ar.value, 1), dtype=torch.float32, device=dev),
+                          ar=torch.zeros(max(n_ar.value, 1), dtype=torch.float32, device=dev),
                           ag=torch.empty(max(n_ag.value, 1), dtype=torch.float32, device=dev),
                           all=torch.empty(world, max(n_ag.value, 1), dtype=torch.float32, device=dev))
+        if self.deferred:
+            # ONE staging row per rank: [packed dense parameters | colour gradient 3P | position gradients 6P | 4 frame scalars]
+            c, P = self._cuda, self.P
+            nd = (n_ar.value + 3) // 4 * 4                       # keep every block 16-byte aligned
+            n_red = nd + (3 * P + 3) // 4 * 4                    # floats that are SUMMED over ranks (dense + colour)
+            row = n_red + (6 * P + 4 + 3) // 4 * 4
+            c["row"] = torch.zeros(row, dtype=torch.float32, device=dev)
+            c["rows"] = torch.zeros(world, row, dtype=torch.float32, device=dev)
+            c["reduced"] = torch.zeros(n_red, dtype=torch.float32, device=dev)
+            c["n_red"], c["n_dense"] = n_red, nd
+            c["ar"] = c["row"][:max(n_ar.value, 1)]              # pack writes the dense parameters straight into the row
+            c["g_rgb"] = c["row"][nd:nd + 3 * P].view(P, 3)
+            c["payload"] = c["row"][n_red:n_red + 6 * P + 4]
+            c["gathered"] = c["rows"][:, n_red:]                 # per-rank [6P + 4 (+pad)] views, stride = row
+            c["g_rgb_red"] = c["reduced"][nd:nd + 3 * P].view(P, 3)
+            c["clamped"] = torch.zeros(P, 3, dtype=torch.uint8, device=dev)
+            c["dirs"] = torch.zeros(P, 3, dtype=torch.float32, device=dev); c["dirs"][:, 2] = 1     # the renderer's constant view direction
+
+    # ---- deferred linear tails (CUDA only) ------------------------------------------------------------------------
+    def sh_sink(self):
+        """(dL_drgb[P,3], clamped[P,3]) for render_ortho_frame(grad_sinks={"shs_deferred": ...}): the frame backward leaves the
+        colour gradient in the all-reduce buffer instead of running the SH backward."""
+        if self._cuda is None:
+            self._setup_cuda()
+        return self._cuda["g_rgb"], self._cuda["clamped"]
+
+    def node_defer(self):
+        """Staging buffer for gs.frame.deform_position_pair(defer=...)."""
+        if self._cuda is None:
+            self._setup_cuda()
+        return self._cuda["payload"]
+
+    def _p2p_setup(self) -> bool:
+        """Symmetric (peer-mapped) double buffer for the staging rows via torch.distributed._symmetric_memory.  Disabled with
+        SPV_EXCHANGE=nccl; falls back to the NCCL all-gather if the rendezvous is not possible on this system."""
+        c = self._cuda
+        if "p2p" in c:
+            return c["p2p"] is not None
+        c["p2p"] = None
+        import os
+        if os.environ.get("SPV_EXCHANGE", "p2p") != "p2p":
+            return False
+        try:
+            import ctypes
+            import torch.distributed._symmetric_memory as symm
+            row, n_red = c["row"].numel(), int(c["n_red"])
+            span = row + n_red                       # per half: [staging row | this rank's published slice of the reduced block]
+            buf = symm.empty(2 * span, dtype=torch.float32, device=c["row"].device)
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            arrs, reds = [], []
+            for half in range(2):
+                a, b = (ctypes.c_void_p * 8)(), (ctypes.c_void_p * 8)()
+                for r in range(len(ptrs)):
+                    a[r] = ptrs[r] + half * span * 4
+                    b[r] = ptrs[r] + (half * span + row) * 4
+                arrs.append(a); reds.append(b)
+            two_phase = os.environ.get("SPV_EXCHANGE_PHASES", "auto")
+            two_phase = (dist.get_world_size() >= 4) if two_phase == "auto" else two_phase == "2"
+            c["p2p"] = dict(buf=buf, hdl=hdl, arrs=arrs, reds=reds, span=span, step=0, two_phase=two_phase)
+            self.exchange_path = "p2p two-phase" if two_phase else "p2p one-shot"
+        except Exception as e:   # noqa: BLE001 -- any failure here means: no peer mapping on this system
+            self.exchange_path = f"nccl ({type(e).__name__}: {str(e)[:80]})"
+        return c["p2p"] is not None
+
+    def _p2p_exchange(self, world: int, scale: float):
+        import ctypes
+        from . import _lib as L
+        c = self._cuda
+        p = c["p2p"]
+        half, row, span = p["step"] & 1, c["row"].numel(), p["span"]
+        p["step"] += 1
+        p["buf"][half * span:half * span + row].copy_(c["row"])
+        p["hdl"].barrier(channel=0)
+        if not p["two_phase"]:
+            L.call("spv_exchange_reduce_peers", int(c["n_red"]), row, world, ctypes.cast(p["arrs"][half], ctypes.c_void_p), float(scale),
+                   L.ptr(c["reduced"]), L.ptr(c["rows"]), c["rows"].stride(0), L.stream())
+            return
+        rank = dist.get_rank()
+        red_pub = p["buf"][half * span + row:(half + 1) * span]
+        L.call("spv_exchange_reduce_scatter_peers", int(c["n_red"]), row, rank, world, ctypes.cast(p["arrs"][half], ctypes.c_void_p),
+               float(scale), L.ptr(red_pub), L.ptr(c["reduced"]), L.ptr(c["rows"]), c["rows"].stride(0), L.stream())
+        p["hdl"].barrier(channel=1)
+        L.call("spv_exchange_fetch_reduced", int(c["n_red"]), rank, world, ctypes.cast(p["reds"][half], ctypes.c_void_p), L.ptr(c["reduced"]),
+               L.stream())
+
+    def _reduce_rows(self, world: int, scale: float):
+        from . import _lib as L
+        c = self._cuda
+        L.call("spv_exchange_reduce", int(c["n_red"]), world, L.ptr(c["rows"]), c["rows"].stride(0), float(scale), L.ptr(c["reduced"]),
+               L.stream())
+
+    def _finish_deferred(self, world: int, scale: float):
+        from . import _lib as L
+        c, P, d = self._cuda, self.P, self.deferred
+        shs = self.flat.params[d["shs"]]
+        L.call("spv_compute_sh_backward", P, L.ptr(shs), 3, L.ptr(c["dirs"]), None, L.ptr(c["clamped"]), L.ptr(c["g_rgb_red"]), 16,
+               L.ptr(shs.grad), None, L.stream())
+        node = self.flat.params[d["node"]]
+        L.call("spv_deform_spline_backward_gathered", P, int(d["NI"]), world, c["gathered"].data_ptr(), c["gathered"].stride(0), float(scale),
+               L.ptr(self.dirty), L.ptr(node.grad), L.stream())
 
     def pack(self, scale: float = 1.0):
         import ctypes
@@ -175,12 +284,33 @@ class GradExchange:
     # ---- the exchange ----------------------------------------------------------------------------------------------
     def run(self, average: bool = True):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            if self.deferred:                      # single process: no collective, but the deferred tails still have to run
+                if self._cuda is None:
+                    self._setup_cuda()
+                self.pack(1.0)
+                self._cuda["rows"][0].copy_(self._cuda["row"])
+                self._reduce_rows(1, 1.0)
+                self.unpack(self._cuda["reduced"], self._cuda["all"])
+                self._finish_deferred(1, 1.0)
             return
         world = dist.get_world_size()
         scale = 1.0 / world if average else 1.0
         if self.flat.flat_grad.is_cuda:
-            ar, ag = self.pack(scale)
+            ar, ag = self.pack(1.0 if self.deferred else scale)      # deferred: the scale is applied by the local reduction
             c = self._cuda
+            if self.deferred:
+                if self._p2p_setup():
+                    # symmetric-memory path: publish the row, one device-side barrier, then every rank pulls its peers' rows
+                    # over NVLink inside the reduction kernel (double-buffered: the barrier of step k+1 also proves that
+                    # every rank finished reading the buffer of step k)
+                    self._p2p_exchange(world, scale)
+                else:
+                    # ONE NCCL all-gather of the staging rows; dense parameters and colour gradient are summed locally
+                    dist.all_gather_into_tensor(c["rows"], c["row"])
+                    self._reduce_rows(world, scale)
+                self.unpack(c["reduced"], c["all"])
+                self._finish_deferred(world, scale)
+                return
             if c["n_ar"]:
                 dist.all_reduce(ar, op=dist.ReduceOp.SUM)
             if c["n_ag"]:

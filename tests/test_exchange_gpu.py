@@ -80,3 +80,70 @@ def test_deform_pair_matches_two_single_evaluations_and_keeps_the_sink_clean(cud
     n4 = node.clone().requires_grad_(True)
     deform_position(base, n4, a1, b1, NI).sum().backward()
     assert torch.equal(n3.grad, n4.grad)
+
+
+def test_deferred_tails_equal_direct_backward_single_rank(cuda):
+    """GradExchange(deferred=...) at world size 1: the frame backward leaves dL_drgb / dL_dpos, run() finishes the SH and
+    spline backward -- every gradient must equal the direct (non-deferred) backward."""
+    from splatter_a_video_b200 import synth
+    from splatter_a_video_b200.gs.frame import deform_position_pair, render_ortho_frame
+    sc = synth.make_scene(20_000, 50, 200, 150, seed=5)
+    P, NI, W, H = sc.P, 10, sc.W, sc.H
+    g = torch.Generator().manual_seed(2)
+    node0 = (0.02 * torch.randn(P, 4 * NI * 3, generator=g)).to(cuda)
+    gimg = [torch.randn(c, H, W, generator=g).to(cuda) for c in (3, 1, 3, 1)]
+    t = lambda v, dt: torch.tensor([v], dtype=dt, device=cuda)
+    i1, d1, i2, d2 = t(3, torch.int32), t(0.04, torch.float32), t(4, torch.int32), t(0.0, torch.float32)
+
+    def run(deferred):
+        flat = FlatParams({"pos_cubic_node": node0.clone(), "scaling": sc.scaling.to(cuda), "rotation": sc.rotation.to(cuda),
+                           "opacity": sc.opacity.to(cuda), "shs": sc.shs.to(cuda), "mask_attribute": sc.attrs["mask_attribute"].to(cuda)})
+        dirty = torch.zeros(17, dtype=torch.int32, device=cuda)
+        sinks = dict(flat.grad_sinks(["scaling", "rotation", "opacity"]))
+        ex = None
+        if deferred:
+            ex = GradExchange(flat, P, dirty=dirty, deferred={"shs": "shs", "node": "pos_cubic_node", "NI": NI})
+            sinks["shs_deferred"] = ex.sh_sink()
+        else:
+            sinks["shs"] = flat["shs"].grad
+        pos, track = deform_position_pair(sc.position.to(cuda), flat["pos_cubic_node"], i1, d1, i2, d2, NI, flat["pos_cubic_node"].grad,
+                                          dirty, ex.node_defer() if deferred else None)
+        imgs, _, _, status = render_ortho_frame(pos, flat["scaling"], flat["rotation"], flat["opacity"], flat["shs"],
+                                                [track, flat["mask_attribute"]], sc.extr.to(cuda), W, H, 20, 0.0, 8 * P, grad_sinks=sinks)
+        assert int(status.cpu()[1]) == 0
+        torch.autograd.backward(imgs, gimg)
+        if deferred:
+            ex.run()
+        torch.cuda.synchronize()
+        return flat
+
+    a, b = run(False), run(True)
+    for k in a.names:
+        ga, gb = a[k].grad, b[k].grad
+        assert float(ga.abs().max()) > 0, k
+        assert float((ga - gb).abs().max()) <= 2e-5 * float(ga.abs().max()) + 1e-7, k
+
+
+def test_spline_backward_gathered_sums_ranks_in_order(cuda):
+    from splatter_a_video_b200 import _lib as L
+    P, NI, W = 4001, 10, 3
+    g = torch.Generator().manual_seed(9)
+    frames = [(2, 0.01, 3, 0.0), (3, 0.02, 3, 0.04), (9, 0.0, 2, 0.05)]
+    gathered = torch.zeros(W, 6 * P + 4, device=cuda)
+    want = torch.zeros(P, 4, NI, 3, dtype=torch.float64)
+    for r, (i1, d1, i2, d2) in enumerate(frames):
+        g1, g2 = torch.randn(P, 3, generator=g), torch.randn(P, 3, generator=g)
+        gathered[r, :3 * P] = g1.reshape(-1).to(cuda); gathered[r, 3 * P:6 * P] = g2.reshape(-1).to(cuda)
+        tail = torch.tensor([i1, i2], dtype=torch.int32).view(torch.float32)
+        gathered[r, 6 * P:] = torch.tensor([float(tail[0]), d1, float(tail[1]), d2]).to(cuda)
+        for gg, ii, dd in ((g1, i1, d1), (g2, i2, d2)):
+            for a_, pw in enumerate((3, 2, 1, 0)):
+                want[:, a_, ii] += 0.5 * gg.double() * dd ** pw
+    sink = torch.full((P, 4 * NI * 3), 7.0, device=cuda)            # stale content in the listed dirty intervals only
+    sink.view(P, 4, NI, 3)[:, :, [0, 1, 4, 6, 7, 8]] = 0            # 5 is dirty but not re-written: must be cleared
+    dirty = torch.tensor([4, 2, 3, 9, 5] + [0] * 12, dtype=torch.int32, device=cuda)
+    L.call("spv_deform_spline_backward_gathered", P, NI, W, L.ptr(gathered), gathered.stride(0), 0.5, L.ptr(dirty), L.ptr(sink), L.stream())
+    torch.cuda.synchronize()
+    got = sink.view(P, 4, NI, 3).cpu().double()
+    assert float((got - want).abs().max()) <= 1e-5
+    assert dirty.cpu().tolist()[:7] == [6, 2, 3, 3, 3, 9, 2]
