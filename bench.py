@@ -61,6 +61,7 @@ def parse():
                     help="N>1: exchange SH / spline COEFFICIENT gradients (24+24 floats/Gaussian) instead of deferring the linear tails")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="only warm-up + K train steps, no JSON (for ncu)")
+    ap.add_argument("--trace", default="", help="write a torch.profiler (CUPTI) per-kernel summary of K train steps (rank 0) to this file and exit")
     return ap.parse_args()
 
 
@@ -381,15 +382,10 @@ def exchange_breakdown(exchange, world, reps=10):
         ar, ag = exchange.pack(1.0 if exchange.deferred else 1.0 / world)
         ev[1].record()
         if exchange.deferred:
-            if exchange._p2p_setup():
-                exchange._p2p_exchange(world, 1.0 / world)
-                ev[2].record(); ev[3].record()
-            else:
-                dist.all_gather_into_tensor(c["rows"], c["row"])
-                ev[2].record(); ev[3].record()
-                exchange._reduce_rows(world, 1.0 / world)
-            exchange.unpack(c["reduced"], c["all"])
-            exchange._finish_deferred(world, 1.0 / world)
+            reduced = exchange._exchange_rows(world, 1.0 / world)
+            ev[2].record(); ev[3].record()
+            exchange.unpack(reduced, c["all"])
+            exchange._finish_deferred(world, 1.0 / world, reduced)
         else:
             dist.all_reduce(ar)
             ev[2].record()
@@ -621,6 +617,33 @@ def run_ours(args):
     if args.profile_mode:
         time_steps(train_step, args.steps, args.warmup, None, world, rank, frames_of)
         return
+    if args.trace:
+        # device durations of every kernel INSIDE the real step (graph replay + gradient exchange), all ranks stepping together
+        from torch.profiler import ProfilerActivity, profile as tprofile
+        for i in range(args.warmup):
+            train_step(frames_of(i))
+        torch.cuda.synchronize()
+        with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(args.steps):
+                flush.zero_()
+                train_step(frames_of(args.warmup + i))
+            torch.cuda.synchronize()
+        if rank == 0:
+            rows, t_min, t_max = {}, None, None
+            for ev in prof.events():
+                if ev.device_type is None or "cuda" not in str(ev.device_type).lower():
+                    continue
+                r = rows.setdefault(ev.name, [0, 0.0])
+                r[0] += 1; r[1] += float(ev.device_time if hasattr(ev, "device_time") else ev.cuda_time)
+            out = [{"kernel": k, "launches_per_step": n / args.steps, "us_per_step": t / args.steps} for k, (n, t) in rows.items()]
+            out.sort(key=lambda r: -r["us_per_step"])
+            with open(args.trace, "w") as f:
+                json.dump({"n_gpus": world, "steps": args.steps, "sum_us_per_step": sum(r["us_per_step"] for r in out), "kernels": out}, f, indent=1)
+            for r in out[:45]:
+                log(f"{r['us_per_step']:9.1f} us x{r['launches_per_step']:5.1f}  {r['kernel'][:100]}")
+        if world > 1:
+            dist.destroy_process_group()
+        return
     log(f"workload ready: P={wl.P} {wl.W}x{wl.H}, renderer={type(wl.renderer).__name__}")
     # kernels of this library per step, counted on one eager step (graph replays do not pass through the host counter)
     wl.set_frame(0)
@@ -688,7 +711,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: P={wl.P}, {wl.W}x{wl.H}, {wl.frames} frames, I={I} tile intersections/frame; one step = "
                                "render one frame (RGB K=20 + depth + 19 attribute channels) forward+backward through "
-                               f"{type(wl.renderer).__name__}.render_batch; frames sharded {world}-way, one gradient exchange/step ({exchange_kind})",
+                               f"{type(wl.renderer).__name__}.render_batch; frames dealt to the {world} ranks in DistributedSampler order (rank r renders frame step*N + r), one gradient exchange/step ({exchange_kind})",
                    "renderer": type(wl.renderer).__name__, "mode": wl.mode, "cuda_graph": wl.use_graph,
                    "capacity_overflow": wl.overflowed(), "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
                    "grad_floats_per_gaussian": wl.flat.floats_per_gaussian(wl.P)},

@@ -269,12 +269,22 @@ SPV_API int spv_exchange_reduce(long long n, int world, const float *gathered, l
  * ranks before (all rows written) and must not let a row be overwritten before every rank ran this (double buffering). */
 SPV_API int spv_exchange_reduce_peers(long long n_red, long long n_row, int world, const float *const *peer_rows, float scale,
                               float *reduced, float *rows, long long row_stride, void *stream);
+/* The gather part alone: rows[r*row_stride + e] = peer_rows[r][e] for e in [n_red, n_row).  The three reduction entry points
+ * skip their gather part when called with rows == NULL, so the gather (and the deferred spline backward behind it) can run on
+ * a second stream next to the reduction. */
+SPV_API int spv_exchange_gather_peers(long long n_red, long long n_row, int world, const float *const *peer_rows, float *rows,
+                              long long row_stride, void *stream);
 /* Two-phase form for larger groups (inbound volume 2(N-1)/N x the summed block instead of N-1 x): phase 1 sums this rank's
  * 1/world slice of [0, n_red) over the peers' rows into red_pub (its symmetric area) and `reduced`, and copies the gathered
  * tails into `rows`; the caller places a cross-rank barrier; phase 2 fetches the other slices from peer_red[owner]. */
 SPV_API int spv_exchange_reduce_scatter_peers(long long n_red, long long n_row, int rank, int world, const float *const *peer_rows,
                                       float scale, float *red_pub, float *reduced, float *rows, long long row_stride,
                                       void *stream);
+/* NVLS form: the NVSwitch sums.  mc_row / mc_red are the MULTICAST addresses of the symmetric row / red areas: this rank
+ * multimem.ld_reduce's its 1/world slice (fp32 add in the switch), scales it and multimem.st's it into every rank's red area;
+ * after the caller's second barrier each rank finds the whole summed block in its own red area. */
+SPV_API int spv_exchange_nvls(long long n_red, long long n_row, int rank, int world, const float *mc_row, float *mc_red,
+                      const float *const *peer_rows, float scale, float *rows, long long row_stride, void *stream);
 SPV_API int spv_exchange_fetch_reduced(long long n_red, int rank, int world, const float *const *peer_red, float *reduced,
                                void *stream);
 SPV_API int spv_exchange_unpack(int P, int nseg, const spv_exchange_segment *segs, int world, const float *comm_allreduce,

@@ -81,7 +81,9 @@ deform_bwd2_kernel(int P, int NI, const int *__restrict__ idx1_dev, const float 
     const int nd = min(dirty[0], 16);
     for (int t = 0; t < nd; ++t) {
         const int z = dirty[1 + t];
-        if (z == i1 || z == i2 || z < 0 || z >= NI) continue;
+        bool skip = z == i1 || z == i2 || z < 0 || z >= NI;
+        for (int t2 = 0; t2 < t; ++t2) skip |= dirty[1 + t2] == z;       // listed twice: cleared once
+        if (skip) continue;
         float *q = row + (size_t)z * 3;
         q[0] = 0.f; q[s] = 0.f; q[2 * s] = 0.f; q[3 * s] = 0.f;
     }
@@ -98,7 +100,10 @@ deform_bwd2_kernel(int P, int NI, const int *__restrict__ idx1_dev, const float 
 }
 
 __global__ void deform_dirty_set_kernel(const int *__restrict__ idx1_dev, const int *__restrict__ idx2_dev, int *__restrict__ dirty) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { dirty[0] = 2; dirty[1] = idx1_dev[0]; dirty[2] = idx2_dev[0]; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int a = idx1_dev[0], b = idx2_dev[0];
+        dirty[0] = a == b ? 1 : 2; dirty[1] = a; dirty[2] = b;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -124,12 +129,18 @@ deform_bwd_gathered_kernel(int P, int NI, int world, const float *__restrict__ g
     __shared__ unsigned s_members[16];
     __shared__ float s_dist[16];
     const int ne = 2 * world;
-    if (threadIdx.x == 0) {
+    __shared__ int s_draw[17];
+    // the <= 16 frame scalars and the dirty list are fetched by 33 threads in parallel (one global round trip), ...
+    if ((int)threadIdx.x < ne) {
+        const int e = threadIdx.x;
+        const float *tail = gathered + (e >> 1) * stride + 6 * (size_t)P + 2 * (e & 1);
+        s_idx[e] = __float_as_int(tail[0]); s_dist[e] = tail[1];
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + 17) s_draw[threadIdx.x - 32] = dirty[threadIdx.x - 32];
+    __syncthreads();
+    if (threadIdx.x == 0) {   // ... grouped by interval from shared memory
         int nu = 0;
         for (int e = 0; e < ne; ++e) {
-            const float *tail = gathered + (e >> 1) * stride + 6 * (size_t)P + 2 * (e & 1);
-            const int b = __float_as_int(tail[0]);
-            s_idx[e] = b; s_dist[e] = tail[1];
+            const int b = s_idx[e];
             if (b < 0 || b >= NI) continue;
             int u = 0;
             while (u < nu && s_uniq[u] != b) ++u;
@@ -138,12 +149,13 @@ deform_bwd_gathered_kernel(int P, int NI, int world, const float *__restrict__ g
         }
         s_nu = nu;
         int nd = 0;
-        const int cnt = min(dirty[0], 16);
+        const int cnt = min(s_draw[0], 16);
         for (int t = 0; t < cnt; ++t) {
-            const int z = dirty[1 + t];
-            bool rewritten = z < 0 || z >= NI;
-            for (int u = 0; u < nu; ++u) rewritten |= s_uniq[u] == z;
-            if (!rewritten) s_dirty[nd++] = z;
+            const int z = s_draw[1 + t];
+            bool skip = z < 0 || z >= NI;                                 // invalid, re-written below, or already listed
+            for (int u = 0; u < nu; ++u) skip |= s_uniq[u] == z;
+            for (int u = 0; u < nd; ++u) skip |= s_dirty[u] == z;
+            if (!skip) s_dirty[nd++] = z;
         }
         s_nd = nd;
     }
@@ -175,8 +187,14 @@ __global__ void deform_dirty_gathered_kernel(int P, int world, const float *__re
                                              int *__restrict__ dirty) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int ne = 2 * world;
-        for (int e = 0; e < ne; ++e) dirty[1 + e] = __float_as_int(gathered[(e >> 1) * stride + 6 * (size_t)P + 2 * (e & 1)]);
-        dirty[0] = ne;
+        int n = 0;
+        for (int e = 0; e < ne; ++e) {
+            const int b = __float_as_int(gathered[(e >> 1) * stride + 6 * (size_t)P + 2 * (e & 1)]);
+            bool seen = false;
+            for (int t = 0; t < n; ++t) seen |= dirty[1 + t] == b;
+            if (!seen) dirty[1 + n++] = b;
+        }
+        dirty[0] = n;
     }
 }
 

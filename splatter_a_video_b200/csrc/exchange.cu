@@ -156,10 +156,24 @@ exchange_reduce_peers_kernel(long long n_red4, long long n_row4, int world, Peer
 #pragma unroll
         for (int r = 1; r < 8; ++r) if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
         reduced[e] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
-    } else {
+    } else if (rows) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = peers.p[r][e];
     }
+}
+
+// The gathered tails alone ([n_red, n_row) of every rank's row -> local `rows`): lets the caller run the gather and what
+// depends on it (the deferred spline backward) on a second stream next to the reduction.
+__global__ void __launch_bounds__(kThreads)
+exchange_gather_peers_kernel(long long n_red4, long long n_row4, int world, PeerPtrs peers, float4 *__restrict__ rows,
+                             long long row_stride4) {
+    const long long e = n_red4 + (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= n_row4) return;
+    float4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (r < world) v[r] = peers.p[r][e];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = v[r];
 }
 
 // Two-phase variant for larger groups (inbound volume 2(N-1)/N instead of N-1 times the summed block): phase 1 -- every
@@ -185,7 +199,7 @@ exchange_reduce_scatter_kernel(long long n_red4, long long n_row4, long long chu
         reduced[e] = acc;
     } else {
         const long long e = n_red4 + (t - mine);
-        if (e >= n_row4) return;
+        if (e >= n_row4 || !rows) return;
 #pragma unroll
         for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = peers.p[r][e];
     }
@@ -197,6 +211,37 @@ exchange_fetch_reduced_kernel(long long n_red4, long long chunk4, int rank, Peer
     if (e >= n_red4) return;
     const int owner = (int)(e / chunk4);
     if (owner != rank) reduced[e] = red_peers.p[owner][e];
+}
+
+// NVLS form: the NVSwitch does the sum.  Every rank reads ITS 1/N slice of the block through the MULTICAST address with
+// multimem.ld_reduce (the switch returns the fp32 sum over all ranks' buffers: one inbound copy instead of N-1), scales it and
+// multimem.st's it to the `red` area of EVERY rank at once.  Per rank the summed block costs ~1x its size on the wire for any
+// N, and every rank receives the very same bits.  The gathered tails still travel as peer loads.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4 *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float4 *mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+exchange_nvls_kernel(long long n_red4, long long n_row4, long long chunk4, int rank, int world, const float4 *__restrict__ mc_row,
+                     float4 *__restrict__ mc_red, PeerPtrs peers, float scale, float4 *__restrict__ rows, long long row_stride4) {
+    const long long lo = (long long)rank * chunk4, hi = min(n_red4, lo + chunk4), mine = max(hi - lo, 0ll);
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (t < mine) {
+        const long long e = lo + t;
+        float4 v = multimem_ld_reduce_add(mc_row + e);
+        multimem_st(mc_red + e, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
+    } else {
+        const long long e = n_red4 + (t - mine);
+        if (e >= n_row4 || !rows) return;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = peers.p[r][e];
+    }
 }
 
 int build_plan(Plan &plan, int P, int nseg, const spv_exchange_segment *segs, const int *const *sparse_idx_dev, const char *where) {
@@ -294,7 +339,7 @@ int spv_exchange_reduce_peers(long long n_red, long long n_row, int world, const
     }
     PeerPtrs pp;
     for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
-    exchange_reduce_peers_kernel<<<spv::cdiv(n_row / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+    exchange_reduce_peers_kernel<<<spv::cdiv((rows ? n_row : (n_red > 0 ? n_red : 4)) / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         n_red / 4, n_row / 4, world, pp, scale, (float4 *)reduced, (float4 *)rows, row_stride / 4);
     return spv::check_launch("spv_exchange_reduce_peers");
 }
@@ -313,10 +358,46 @@ int spv_exchange_reduce_scatter_peers(long long n_red, long long n_row, int rank
     for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
     const long long n_red4 = n_red / 4, n_row4 = n_row / 4, chunk4 = (n_red4 + world - 1) / world;
     const long long lo = (long long)rank * chunk4, hi = lo + chunk4 < n_red4 ? lo + chunk4 : n_red4;
-    const long long work = (hi > lo ? hi - lo : 0) + (n_row4 - n_red4);
+    const long long work = (hi > lo ? hi - lo : 0) + (rows ? n_row4 - n_red4 : 0);
     exchange_reduce_scatter_kernel<<<spv::cdiv(work > 0 ? work : 1, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         n_red4, n_row4, chunk4 > 0 ? chunk4 : 1, rank, world, pp, scale, (float4 *)red_pub, (float4 *)reduced, (float4 *)rows, row_stride / 4);
     return spv::check_launch("spv_exchange_reduce_scatter_peers");
+}
+
+/* rows[r*row_stride + e] = peer_rows[r][e] for e in [n_red, n_row): the gather part alone (the reduction entry points skip it
+ * when called with rows == NULL). */
+int spv_exchange_gather_peers(long long n_red, long long n_row, int world, const float *const *peer_rows, float *rows,
+                              long long row_stride, void *stream) {
+    if (n_row <= n_red) return 0;
+    if ((n_red & 3) || (n_row & 3) || (row_stride & 3) || world < 1 || world > 8) {
+        spv::set_error(cudaErrorInvalidValue, "spv_exchange_gather_peers: sizes must be multiples of 4, 1..8 ranks");
+        return (int)cudaErrorInvalidValue;
+    }
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
+    exchange_gather_peers_kernel<<<spv::cdiv((n_row - n_red) / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n_red / 4, n_row / 4, world, pp, (float4 *)rows, row_stride / 4);
+    return spv::check_launch("spv_exchange_gather_peers");
+}
+
+/* NVLS form: mc_row / mc_red = MULTICAST addresses of the symmetric row / red areas; after the caller's second barrier the
+ * summed block (scaled) is in every rank's own red area. */
+int spv_exchange_nvls(long long n_red, long long n_row, int rank, int world, const float *mc_row, float *mc_red,
+                      const float *const *peer_rows, float scale, float *rows, long long row_stride, void *stream) {
+    if (n_row <= 0) return 0;
+    if ((n_red & 3) || (n_row & 3) || (row_stride & 3) || world < 1 || world > 8 || n_red > n_row || rank < 0 || rank >= world || !mc_row || !mc_red) {
+        spv::set_error(cudaErrorInvalidValue, "spv_exchange_nvls: sizes must be multiples of 4, 1..8 ranks, multicast pointers set");
+        return (int)cudaErrorInvalidValue;
+    }
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
+    const long long n_red4 = n_red / 4, n_row4 = n_row / 4, chunk4 = (n_red4 + world - 1) / world;
+    const long long lo = (long long)rank * chunk4, hi = lo + chunk4 < n_red4 ? lo + chunk4 : n_red4;
+    const long long work = (hi > lo ? hi - lo : 0) + (rows ? n_row4 - n_red4 : 0);
+    exchange_nvls_kernel<<<spv::cdiv(work > 0 ? work : 1, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n_red4, n_row4, chunk4 > 0 ? chunk4 : 1, rank, world, (const float4 *)mc_row, (float4 *)mc_red, pp, scale, (float4 *)rows,
+        row_stride / 4);
+    return spv::check_launch("spv_exchange_nvls");
 }
 
 int spv_exchange_fetch_reduced(long long n_red, int rank, int world, const float *const *peer_red, float *reduced, void *stream) {

@@ -21,8 +21,16 @@ def shard_frames(num_frames: int, rank: int, world: int) -> range:
     return range(lo, min(lo + per, num_frames))
 
 
-def frame_for_step(step: int, rank: int, world: int, num_frames: int) -> int:
-    """Frame rendered by `rank` at global step `step`: rank r walks its own contiguous shard."""
+def frame_for_step(step: int, rank: int, world: int, num_frames: int, policy: str = "interleaved") -> int:
+    """Frame rendered by `rank` at global step `step`.
+
+    "interleaved" (default): frame (step*world + rank) mod F -- the index stream a non-shuffling DistributedSampler deals out
+    (indices[rank::world]; the reference swaps one in under --distributed, src/loaders/create_training_dataset.py:168,186).  The
+    `world` frames of one step are consecutive, so they fall into one or two spline intervals (a node every 5 frames) and
+    have similar tile lists: the exchanged interval gradients stay as compact as on one GPU and the ranks finish together.
+    "blocks": rank r walks its own contiguous shard of the clip (keeps a rank's ground-truth frames local)."""
+    if policy == "interleaved":
+        return (step * world + rank) % max(num_frames, 1)
     shard = shard_frames(num_frames, rank, world)
     if len(shard) == 0:
         return (step * world + rank) % max(num_frames, 1)
@@ -176,7 +184,6 @@ class GradExchange:
             c["g_rgb"] = c["row"][nd:nd + 3 * P].view(P, 3)
             c["payload"] = c["row"][n_red:n_red + 6 * P + 4]
             c["gathered"] = c["rows"][:, n_red:]                 # per-rank [6P + 4 (+pad)] views, stride = row
-            c["g_rgb_red"] = c["reduced"][nd:nd + 3 * P].view(P, 3)
             c["clamped"] = torch.zeros(P, 3, dtype=torch.uint8, device=dev)
             c["dirs"] = torch.zeros(P, 3, dtype=torch.float32, device=dev); c["dirs"][:, 2] = 1     # the renderer's constant view direction
 
@@ -203,6 +210,7 @@ class GradExchange:
         c["p2p"] = None
         import os
         if os.environ.get("SPV_EXCHANGE", "p2p") != "p2p":
+            self.exchange_path = "nccl all-gather"
             return False
         try:
             import ctypes
@@ -219,34 +227,70 @@ class GradExchange:
                     a[r] = ptrs[r] + half * span * 4
                     b[r] = ptrs[r] + (half * span + row) * 4
                 arrs.append(a); reds.append(b)
-            two_phase = os.environ.get("SPV_EXCHANGE_PHASES", "auto")
-            two_phase = (dist.get_world_size() >= 4) if two_phase == "auto" else two_phase == "2"
-            c["p2p"] = dict(buf=buf, hdl=hdl, arrs=arrs, reds=reds, span=span, step=0, two_phase=two_phase)
-            self.exchange_path = "p2p two-phase" if two_phase else "p2p one-shot"
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            want = os.environ.get("SPV_EXCHANGE_MODE", "auto")       # auto | oneshot | twophase | nvls
+            if want == "auto":
+                want = "nvls" if (mc and dist.get_world_size() >= 4) else "oneshot"
+            if want == "nvls" and not mc:
+                want = "oneshot"
+            c["p2p"] = dict(buf=buf, hdl=hdl, arrs=arrs, reds=reds, span=span, step=0, mode=want, mc=mc)
+            self.exchange_path = {"oneshot": "p2p one-shot (peer loads)", "twophase": "p2p two-phase (peer loads)",
+                                  "nvls": "nvls (multimem.ld_reduce / multimem.st through the NVSwitch)"}[want]
         except Exception as e:   # noqa: BLE001 -- any failure here means: no peer mapping on this system
             self.exchange_path = f"nccl ({type(e).__name__}: {str(e)[:80]})"
         return c["p2p"] is not None
 
-    def _p2p_exchange(self, world: int, scale: float):
+    def _p2p_exchange(self, world: int, scale: float) -> torch.Tensor:
+        """Publishes the staging row in the symmetric buffer and returns the tensor holding the summed (scaled) block.
+        The gathered tails and the spline backward that consumes them run on a second stream next to the reduction
+        (joined by `_finish_deferred`)."""
         import ctypes
         from . import _lib as L
         c = self._cuda
         p = c["p2p"]
-        half, row, span = p["step"] & 1, c["row"].numel(), p["span"]
+        half, row, span, n_red = p["step"] & 1, c["row"].numel(), p["span"], int(c["n_red"])
         p["step"] += 1
         p["buf"][half * span:half * span + row].copy_(c["row"])
         p["hdl"].barrier(channel=0)
-        if not p["two_phase"]:
-            L.call("spv_exchange_reduce_peers", int(c["n_red"]), row, world, ctypes.cast(p["arrs"][half], ctypes.c_void_p), float(scale),
-                   L.ptr(c["reduced"]), L.ptr(c["rows"]), c["rows"].stride(0), L.stream())
-            return
+        rows_ptr = ctypes.cast(p["arrs"][half], ctypes.c_void_p)
+        # ---- side stream: gather every rank's position gradients + frame scalars, rebuild the spline-coefficient gradient
+        main = torch.cuda.current_stream()
+        side = p.setdefault("side", torch.cuda.Stream())
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            L.call("spv_exchange_gather_peers", n_red, row, world, rows_ptr, L.ptr(c["rows"]), c["rows"].stride(0), L.stream())
+            self._spline_tail(world, scale)
+        p["side_pending"] = True
+        # ---- main stream: the summed block
+        if p["mode"] == "oneshot":
+            L.call("spv_exchange_reduce_peers", n_red, row, world, rows_ptr, float(scale), L.ptr(c["reduced"]), None, c["rows"].stride(0),
+                   L.stream())
+            return c["reduced"]
         rank = dist.get_rank()
         red_pub = p["buf"][half * span + row:(half + 1) * span]
-        L.call("spv_exchange_reduce_scatter_peers", int(c["n_red"]), row, rank, world, ctypes.cast(p["arrs"][half], ctypes.c_void_p),
-               float(scale), L.ptr(red_pub), L.ptr(c["reduced"]), L.ptr(c["rows"]), c["rows"].stride(0), L.stream())
+        if p["mode"] == "nvls":
+            mc_row = p["mc"] + half * span * 4
+            L.call("spv_exchange_nvls", n_red, row, rank, world, mc_row, mc_row + row * 4, rows_ptr, float(scale), None,
+                   c["rows"].stride(0), L.stream())
+            p["hdl"].barrier(channel=1)
+            return red_pub                      # every rank's own red area now holds the whole block (written by its owners)
+        L.call("spv_exchange_reduce_scatter_peers", n_red, row, rank, world, rows_ptr, float(scale), L.ptr(red_pub), L.ptr(c["reduced"]),
+               None, c["rows"].stride(0), L.stream())
         p["hdl"].barrier(channel=1)
-        L.call("spv_exchange_fetch_reduced", int(c["n_red"]), rank, world, ctypes.cast(p["reds"][half], ctypes.c_void_p), L.ptr(c["reduced"]),
+        L.call("spv_exchange_fetch_reduced", n_red, rank, world, ctypes.cast(p["reds"][half], ctypes.c_void_p), L.ptr(c["reduced"]),
                L.stream())
+        return c["reduced"]
+
+    def _exchange_rows(self, world: int, scale: float) -> torch.Tensor:
+        c = self._cuda
+        if self._p2p_setup():
+            # symmetric-memory path: publish the row, one device-side barrier, then the reduction kernel pulls the peers' rows
+            # over NVLink (double-buffered: the barrier of step k+1 also proves every rank finished reading step k's buffer)
+            return self._p2p_exchange(world, scale)
+        # ONE NCCL all-gather of the staging rows; dense parameters and colour gradient are summed locally in rank order
+        dist.all_gather_into_tensor(c["rows"], c["row"])
+        self._reduce_rows(world, scale)
+        return c["reduced"]
 
     def _reduce_rows(self, world: int, scale: float):
         from . import _lib as L
@@ -254,15 +298,26 @@ class GradExchange:
         L.call("spv_exchange_reduce", int(c["n_red"]), world, L.ptr(c["rows"]), c["rows"].stride(0), float(scale), L.ptr(c["reduced"]),
                L.stream())
 
-    def _finish_deferred(self, world: int, scale: float):
+    def _spline_tail(self, world: int, scale: float):
+        from . import _lib as L
+        c, d = self._cuda, self.deferred
+        node = self.flat.params[d["node"]]
+        L.call("spv_deform_spline_backward_gathered", self.P, int(d["NI"]), world, c["gathered"].data_ptr(), c["gathered"].stride(0),
+               float(scale), L.ptr(self.dirty), L.ptr(node.grad), L.stream())
+
+    def _finish_deferred(self, world: int, scale: float, reduced: torch.Tensor):
         from . import _lib as L
         c, P, d = self._cuda, self.P, self.deferred
+        g_rgb_red = reduced[c["n_dense"]:c["n_dense"] + 3 * P]
         shs = self.flat.params[d["shs"]]
-        L.call("spv_compute_sh_backward", P, L.ptr(shs), 3, L.ptr(c["dirs"]), None, L.ptr(c["clamped"]), L.ptr(c["g_rgb_red"]), 16,
+        L.call("spv_compute_sh_backward", P, L.ptr(shs), 3, L.ptr(c["dirs"]), None, L.ptr(c["clamped"]), L.ptr(g_rgb_red), 16,
                L.ptr(shs.grad), None, L.stream())
-        node = self.flat.params[d["node"]]
-        L.call("spv_deform_spline_backward_gathered", P, int(d["NI"]), world, c["gathered"].data_ptr(), c["gathered"].stride(0), float(scale),
-               L.ptr(self.dirty), L.ptr(node.grad), L.stream())
+        p = c.get("p2p")
+        if p and p.get("side_pending"):          # the spline tail already runs on the side stream: join it
+            torch.cuda.current_stream().wait_stream(p["side"])
+            p["side_pending"] = False
+        else:
+            self._spline_tail(world, scale)
 
     def pack(self, scale: float = 1.0):
         import ctypes
@@ -291,7 +346,7 @@ class GradExchange:
                 self._cuda["rows"][0].copy_(self._cuda["row"])
                 self._reduce_rows(1, 1.0)
                 self.unpack(self._cuda["reduced"], self._cuda["all"])
-                self._finish_deferred(1, 1.0)
+                self._finish_deferred(1, 1.0, self._cuda["reduced"])
             return
         world = dist.get_world_size()
         scale = 1.0 / world if average else 1.0
@@ -299,17 +354,9 @@ class GradExchange:
             ar, ag = self.pack(1.0 if self.deferred else scale)      # deferred: the scale is applied by the local reduction
             c = self._cuda
             if self.deferred:
-                if self._p2p_setup():
-                    # symmetric-memory path: publish the row, one device-side barrier, then every rank pulls its peers' rows
-                    # over NVLink inside the reduction kernel (double-buffered: the barrier of step k+1 also proves that
-                    # every rank finished reading the buffer of step k)
-                    self._p2p_exchange(world, scale)
-                else:
-                    # ONE NCCL all-gather of the staging rows; dense parameters and colour gradient are summed locally
-                    dist.all_gather_into_tensor(c["rows"], c["row"])
-                    self._reduce_rows(world, scale)
-                self.unpack(c["reduced"], c["all"])
-                self._finish_deferred(world, scale)
+                reduced = self._exchange_rows(world, scale)
+                self.unpack(reduced, c["all"])
+                self._finish_deferred(world, scale, reduced)
                 return
             if c["n_ar"]:
                 dist.all_reduce(ar, op=dist.ReduceOp.SUM)

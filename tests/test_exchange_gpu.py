@@ -72,7 +72,7 @@ def test_deform_pair_matches_two_single_evaluations_and_keeps_the_sink_clean(cud
         assert n_new.grad is None                                   # written into the sink instead
         # every interval touched by earlier iterations was cleared: the sink equals this step's gradient exactly
         assert float((sink - n_ref.grad).abs().max()) <= 1e-6 * float(n_ref.grad.abs().max())
-        assert dirty.cpu().tolist()[:3] == [2, i1, i2]
+        assert dirty.cpu().tolist()[:3] == ([1, i1, i1] if i1 == i2 else [2, i1, i2])
     # without a sink: a fresh gradient tensor through autograd; ids2 used without gradient
     n3 = node.clone().requires_grad_(True)
     p1, p2 = deform_position_pair(base, n3, a1, b1, a2, b2, NI)
@@ -146,4 +146,4 @@ def test_spline_backward_gathered_sums_ranks_in_order(cuda):
     torch.cuda.synchronize()
     got = sink.view(P, 4, NI, 3).cpu().double()
     assert float((got - want).abs().max()) <= 1e-5
-    assert dirty.cpu().tolist()[:7] == [6, 2, 3, 3, 3, 9, 2]
+    assert dirty.cpu().tolist()[:4] == [3, 2, 3, 9]

@@ -113,7 +113,10 @@ def test_shard_frames_partition():
         for r in range(w):
             seen += list(shard_frames(n, r, w))
         assert seen == list(range(n))
-    assert frame_for_step(0, 1, 2, 50) == 25 and frame_for_step(26, 1, 2, 50) == 26
+    assert frame_for_step(0, 1, 2, 50, policy="blocks") == 25 and frame_for_step(26, 1, 2, 50, policy="blocks") == 26
+    # default = DistributedSampler order: the ranks of one step render consecutive frames, every frame once per epoch
+    assert [frame_for_step(3, r, 4, 50) for r in range(4)] == [12, 13, 14, 15]
+    assert sorted(frame_for_step(s_, r, 2, 50) for s_ in range(25) for r in range(2)) == list(range(50))
 
 
 def test_flat_params_views_and_grads():
