@@ -157,7 +157,7 @@ SPV_API int spv_bin_capacity(int P, int64_t I_cap, const float *uv, const float 
                      void *workspace, size_t ws_bytes, void *stream);
 /* spv_bin_tiles: same contract and bit-identical results, without the global radix sort: per-tile histogram in the count
  * pass, one-CTA scan over the tiles, scatter of (depth bits << 32 | id) keys into per-tile segments, per-tile bitonic sort in
- * shared memory (segments above 4096 / 25600 keys: 200 KB dynamic shared memory / in place in global memory). */
+ * shared memory (segments above 1024 / 25600 keys: 1024-thread CTAs with 200 KB dynamic shared memory / in place in global memory). */
 SPV_API size_t spv_bin_tiles_workspace_bytes(int P, int64_t I_cap, int W, int H);
 SPV_API int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
                   const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,

@@ -52,7 +52,9 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
 // pixel centres [x0,x1] x [y0,y1]?  q is a convex quadratic: zero if the centre is inside, else its minimum is on an edge.
 __device__ __forceinline__ float quad_min_on_segment(float A, float B, float C0, float lo, float hi) {
     // min over t in [lo,hi] of A t^2 + B t + C0, A >= 0
-    float t = (A > 0.f) ? fminf(fmaxf(-B / (2.f * A), lo), hi) : ((B > 0.f) ? lo : hi);
+    // fast division: any t in [lo,hi] gives a value >= the true minimum, and a 2-ulp error of the minimiser moves the value by
+    // O(1e-13) of it -- far inside the safety margin of tile_may_hit
+    float t = (A > 0.f) ? fminf(fmaxf(__fdividef(-B, 2.f * A), lo), hi) : ((B > 0.f) ? lo : hi);
     return (A * t + B) * t + C0;
 }
 

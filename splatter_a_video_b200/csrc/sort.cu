@@ -110,12 +110,15 @@ cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__rest
     int rounds = any ? (area + kLanesPerSplat - 1) / kLanesPerSplat : 0;
     rounds = __reduce_max_sync(0xffffffffu, rounds);
     const int w = max(x1 - x0, 1);
+    const float w_inv = __fdividef(1.f, (float)w);   // k / w through a float reciprocal: exact for k < 2^20 ((k + 0.5) / w is never
+                                                     // within 0.5 / w of an integer, the reciprocal is good to 2^-21)
     for (int it = 0; it < rounds; ++it) {
         const int k = it * kLanesPerSplat + sub;
         bool keep = any && k < area;
         int x = 0, y = 0;
         if (keep) {
-            y = y0 + k / w; x = x0 + k % w;
+            const int q = __float2int_rz(((float)k + 0.5f) * w_inv);
+            y = y0 + q; x = x0 + (k - q * w);
             if (EMIT && cull && !retest) keep = (m >> k) & 1ull;
             else if (retest) {
                 const float px0 = (float)(x * 16), py0 = (float)(y * 16);
@@ -175,7 +178,8 @@ tile_range_dev_kernel(long long cap, const int *__restrict__ status, const unsig
 // shared memory (bitonic network over 64-bit keys; ids are unique, so the result is the unique (depth, id) order -- exactly
 // what the stable radix sort over emission order yields).  12 B/intersection of global traffic instead of 6 radix passes.
 constexpr int kScanThreads = 1024;
-constexpr int kSortSmall = 4096;          // keys a 256-thread CTA sorts in static shared memory (32 KB)
+constexpr int kSortSmall = 1024;          // keys a 256-thread CTA sorts in static shared memory (8 KB); the heavy tail of the
+                                          // tile-list distribution goes to the 1024-thread CTAs of tile_sort_big_kernel
 constexpr int kSortBig = 25600;           // keys a 1024-thread CTA sorts in 200 KB of dynamic shared memory
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -227,21 +231,23 @@ tile_scan_kernel(int T, long long cap, int *__restrict__ tile_count, int2 *__res
 // behave as +inf padding without being stored.  keys: shared or global memory.
 template <int THREADS>
 __device__ __forceinline__ void bitonic_sort_u64(unsigned long long *keys, int n) {
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int i = threadIdx.x; i < np2 / 2; i += THREADS) {   // flip step: partner = mirror inside the k-block
-            const int h = k >> 1, blk = i / h, off = i % h;
-            const int a = blk * k + off, b = blk * k + (k - 1 - off);
+    int lg = 0;                                   // np2 = 1 << lg = next power of two >= n
+    while ((1 << lg) < n) ++lg;
+    const int half = (1 << lg) >> 1;
+    for (int lk = 1; lk <= lg; ++lk) {            // k = 1 << lk
+        const int k = 1 << lk, lh = lk - 1;
+        for (int i = threadIdx.x; i < half; i += THREADS) {   // flip step: partner = mirror inside the k-block
+            const int off = i & ((1 << lh) - 1), base = (i >> lh) << lk;
+            const int a = base + off, b = base + (k - 1 - off);
             if (b < n) {
                 const unsigned long long x = keys[a], y = keys[b];
                 if (x > y) { keys[a] = y; keys[b] = x; }
             }
         }
         __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np2 / 2; i += THREADS) {
-                const int a = (i / j) * 2 * j + (i % j), b = a + j;
+        for (int lj = lk - 2; lj >= 0; --lj) {    // j = 1 << lj
+            for (int i = threadIdx.x; i < half; i += THREADS) {
+                const int a = ((i >> lj) << (lj + 1)) + (i & ((1 << lj) - 1)), b = a + (1 << lj);
                 if (b < n) {
                     const unsigned long long x = keys[a], y = keys[b];
                     if (x > y) { keys[a] = y; keys[b] = x; }
@@ -265,8 +271,8 @@ tile_sort_small_kernel(const int2 *__restrict__ tile_range, const unsigned long 
     for (int i = threadIdx.x; i < n; i += kThreads) idx_sorted[r.x + i] = (int)(unsigned)(s_keys[i] & 0xffffffffull);
 }
 
-// Persistent CTAs over the queue of segments with more than kSortSmall keys (none on the DAVIS-shaped workload; every tile
-// at 5 M Gaussians x 480p).  Up to kSortBig keys in shared memory, beyond that in place in global memory (L2).
+// Persistent CTAs over the queue of segments with more than kSortSmall keys (a few dozen heavy tiles on the DAVIS-shaped
+// workload -- they would otherwise set the duration of the whole sort; every tile at 5 M Gaussians x 480p).  Up to kSortBig keys in shared memory, beyond that in place in global memory (L2).
 __global__ void __launch_bounds__(kScanThreads)
 tile_sort_big_kernel(const int2 *__restrict__ tile_range, unsigned long long *__restrict__ keys, int *__restrict__ idx_sorted,
                      int *__restrict__ big_queue) {

@@ -300,7 +300,7 @@ def _bin(name, uv, depth, radius, conic, opacity, cull, W, H, I_cap):
     return idx, tr, st.cpu()
 
 
-# (P, W, H, scale multiplier): the last two make every tile segment exceed 4096 keys (200 KB shared-memory sort) and
+# (P, W, H, scale multiplier): the last two make every tile segment exceed the small-sort limit (200 KB shared-memory sort) and
 # 25600 keys (in-place global sort) respectively
 @pytest.mark.parametrize("P,W,H,big", [(3000, 96, 80, 1.0), (60_000, 333, 250, 1.0), (12_000, 48, 32, 6.0), (150_000, 32, 32, 8.0)])
 @pytest.mark.parametrize("cull", [0, 1])
