@@ -694,6 +694,7 @@ def run_ours(args):
     abytes = info[pname]["bwd_bytes" if "bwd" in dom else "fwd_bytes"]
     ach = abytes / (stages[dom] * 1e-3) / 1e9
     dom_ms, dom_label, share = stages[dom], f"spv_alpha_blend_{'backward' if 'bwd' in dom else 'forward'} ({pname} pass, C={info[pname]['C']})", None
+    traffic_key = ("blend_groups_" if "fused" in dom else "blend_") + ("backward" if "bwd" in dom else "forward")
     if live is not None:
         # the dominant kernel timed INSIDE the real (graph-replayed) step: the culled intersection list is what it traverses
         dom_is_bwd = live["bwd_ms"] >= live["fwd_ms"]
@@ -703,14 +704,16 @@ def run_ours(args):
         ach = abytes / (dom_ms * 1e-3) / 1e9
         share = dom_ms / live["step_ms"]
         dom = "blend_bwd_fused23" if dom_is_bwd else "blend_fwd_fused23"
-        dom_label = (f"blend_{'bwd' if dom_is_bwd else 'fwd'}_kernel inside spv_frame_ortho_{'backward' if dom_is_bwd else 'forward'} "
-                     f"(grouped pass, C=23, I={live['I']} after tile culling)")
+        dom_label = (f"blend_rec_{'bwd' if dom_is_bwd else 'fwd'}_kernel inside spv_frame_ortho_{'backward' if dom_is_bwd else 'forward'} "
+                     f"(record-staged grouped pass, C=23, I={live['I']} after tile culling)")
+        traffic_key = "blend_records_" + ("backward" if dom_is_bwd else "forward")
     line = {
         "metric": "train_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: P={wl.P}, {wl.W}x{wl.H}, {wl.frames} frames, I={I} tile intersections/frame; one step = "
-                               "render one frame (RGB K=20 + depth + 19 attribute channels) forward+backward through "
+                               "both frame times of the step from the spline coefficients, render one frame (RGB K=20 + depth + 19 attribute "
+                               "channels; gradients to spline coefficients, scaling, rotation, opacity, SH, track/mask/dino attributes) forward+backward through "
                                f"{type(wl.renderer).__name__}.render_batch; frames dealt to the {world} ranks in DistributedSampler order (rank r renders frame step*N + r), one gradient exchange/step ({exchange_kind})",
                    "renderer": type(wl.renderer).__name__, "mode": wl.mode, "cuda_graph": wl.use_graph,
                    "capacity_overflow": wl.overflowed(), "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
@@ -727,12 +730,12 @@ def run_ours(args):
                            "pipeline": "double-buffered D2H: frame i-1 downloads on a second stream while frame i renders"},
         "roofline": {"bound": "hbm", "kernel": dom_label,
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": ncu_traffic(("blend_groups_" if "fused" in dom else "blend_") + ("backward" if "bwd" in dom else "forward")),
+                     "traffic": ncu_traffic(traffic_key),
                      "peak_source": peak_src,
                      "algorithmic_bytes": abytes, "ms": dom_ms, "share_of_step": share,
                      "timed": ("CUDA events around the kernel inside the graph-replayed step (spv_kernel_timer_*), L2 flushed between steps"
                                if live is not None else "CUDA events around the standalone C-ABI stage, L2 flushed before it"),
-                     "limiter": "instruction issue (ncu: 62-77 % issue-active, DRAM 1-2 % of peak; profiles/README.md)"},
+                     "limiter": "instruction issue (ncu: 74-77 % issue-active, DRAM 1-2 % of peak; profiles/README.md)"},
         "kernels_in_step_ms": live,
         "stages_ms": stages,
         "exchange_ms": exch,
