@@ -85,6 +85,14 @@ int blend_groups_forward(int P, int C, int W, int H, int K, const float *uv, con
 //   0,1 dL_duv(all)  2,3 |RGB-pass dL_duv|  4,5,6 dL_dconic  7 dL_dopacity  8..8+C-1 dL_dfeature  31,32 RGB-pass dL_duv
 constexpr int kPackedRowGroups = 36;
 
+// geometry.cu: the per-Gaussian geometry of one orthographic frame in one pass each way (frame.cu)
+int frame_geometry_forward(int P, const float *xyz, const float *scales, const float *uquats, const float *extr, int W, int H,
+                           float nearest, float extent, float *uv, float *depth, uint8_t *vis, float *cov3d, float *conic, int *radius,
+                           int *tiles, int *radii_out, void *stream);
+int frame_geometry_backward(int P, const float *packed, const float *scales, const float *uquats, const float *extr, int W, int H,
+                            const float *depth, const uint8_t *vis, const float *cov3d, const int *radius, float *dL_dxyz,
+                            float *dL_dscales, float *dL_duquats, void *stream);
+
 // blend_rec.cu: record-staged blending of the fused frame path.  One record of kRecordFloats floats per Gaussian:
 //   [x y a2 b2 | c2 log2(o) o id | feature[0..23] = rgb(3) depth(1) attributes, zero padded | a b c 0]
 constexpr int kRecordFloats = 36;

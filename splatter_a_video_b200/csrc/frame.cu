@@ -60,12 +60,6 @@ frame_prep_kernel(int P, float *__restrict__ dirs) {
     dirs[3 * i] = 0.f; dirs[3 * i + 1] = 0.f; dirs[3 * i + 2] = 1.f;   // constant view direction (0,0,1), :270-271
 }
 
-__global__ void __launch_bounds__(kThreads)
-visible_kernel(int P, const float *__restrict__ depth, uint8_t *__restrict__ vis) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i < P) vis[i] = depth[i] != 0.f;
-}
-
 // Attribute groups: the renderer receives the attribute stack as separately named per-Gaussian tensors
 // (render_attributes_list, trainer_fragGS.py:510-512); they are consumed / differentiated in place, no torch.cat.
 constexpr int kMaxGroups = 8;
@@ -87,11 +81,13 @@ unpack_frame_kernel(int P, int A, const float *__restrict__ packed, float2 *__re
         const float4 q = row[k];
         r[4 * k] = q.x; r[4 * k + 1] = q.y; r[4 * k + 2] = q.z; r[4 * k + 3] = q.w;
     }
-    g_uv[i] = make_float2(r[0], r[1]);
-    g_conic[3 * i] = r[4]; g_conic[3 * i + 1] = r[5]; g_conic[3 * i + 2] = r[6];
+    if (g_uv) {   // NULL: the fused geometry backward reads uv / conic / depth gradients straight from the packed rows
+        g_uv[i] = make_float2(r[0], r[1]);
+        g_conic[3 * i] = r[4]; g_conic[3 * i + 1] = r[5]; g_conic[3 * i + 2] = r[6];
+        g_depth[i] = r[11];
+    }
     g_op[i] = r[7];
     g_rgb[3 * i] = r[8]; g_rgb[3 * i + 1] = r[9]; g_rgb[3 * i + 2] = r[10];
-    g_depth[i] = r[11];
 #pragma unroll
     for (int q = 0; q < kMaxGroups; ++q) {
         if (q < gr.n && gr.grad[q]) {
@@ -160,9 +156,7 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     if (ws_bytes < f.total) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: workspace too small"); return (int)cudaErrorInvalidValue; }
     const unsigned g = spv::cdiv(P, kThreads);
     frame_prep_kernel<<<g, kThreads, 0, s>>>(P, f.dirs);
-    SPV_TRY_RC(spv_project_point_ortho_forward(P, position, extr, W, H, nearest, extent, f.uv, f.depth, stream));
-    visible_kernel<<<g, kThreads, 0, s>>>(P, f.depth, f.vis);
-    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep", 2));
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep"));
     const int C = 4 + A;
     // ---- side branch: SH colours (evaluated for every point: the renderer passes no visibility mask, :272), then -- once
     //      the main branch has the conics -- the per-Gaussian blend records and the -1 fill of the id image
@@ -172,15 +166,15 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_forward/fork");
     SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
     SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, lane->stream), "spv_frame_ortho_forward");
-    // ---- main branch: covariance, conic / radius / tile rectangle, culled binning + sort
-    SPV_TRY_RC(spv_compute_cov3d_forward(P, scaling, rotation, f.vis, f.cov3d, stream));
-    SPV_TRY_RC(spv_ewa_project_ortho_forward(P, f.cov3d, extr, f.uv, W, H, f.vis, f.conic, f.radius, f.tiles, stream));
+    // ---- main branch: projection, visibility, covariance, conic / radius / tile rectangle in ONE pass (geometry.cu: the staged
+    //      kernels' bodies back to back, bit-identical results), then culled binning + tile sort
+    SPV_TRY_RC(spv::frame_geometry_forward(P, position, scaling, rotation, extr, W, H, nearest, extent, f.uv, f.depth, f.vis, f.cov3d,
+                                           f.conic, f.radius, f.tiles, radii, stream));
     SPV_CUDA_TRY(cudaEventRecord(lane->mid, s), "spv_frame_ortho_forward/mid");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->mid, 0), "spv_frame_ortho_forward/mid");
     SPV_TRY_RC(spv::pack_records(P, A, f.uv, f.conic, opacity, f.radius, f.rgb, f.depth, n_groups, attr_ptrs, attr_channels,
                                  f.feature, (void *)lane->stream));
     SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_forward/join");
-    SPV_CUDA_TRY(cudaMemcpyAsync(radii, f.radius, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, s), "spv_frame_ortho_forward");
     // binning: per-tile segments + shared-memory tile sort (SPV_BIN_RADIX=1 selects the global radix sort for A/B runs)
     static const bool radix = [] { const char *e = getenv("SPV_BIN_RADIX"); return e && e[0] == '1'; }();
     if (radix) SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
@@ -213,7 +207,7 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     // buffers, the SH coefficients' gradient is produced after the gradient exchange from the REDUCED colour gradient
     const bool defer_sh = dL_drgb_out != nullptr;
     float *g_rgb = defer_sh ? dL_drgb_out : f.g_rgb;
-    unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, (float2 *)f.g_uv, f.g_conic, dL_dopacity, g_rgb, f.g_depth, gr,
+    unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, nullptr, nullptr, dL_dopacity, g_rgb, nullptr, gr,
                                                (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));
     // colours -> SH coefficients (view direction is a constant: its gradient is discarded) on the side stream, next to
@@ -228,9 +222,8 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
         SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, nullptr, f.clamped, f.g_rgb, 16, dL_dshs, /*dL_ddirs=*/nullptr, (void *)lane->stream));   // constant view direction: its gradient is discarded
     }
     SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_backward/join");
-    SPV_TRY_RC(spv_project_point_ortho_backward(P, extr, W, H, f.depth, f.g_uv, f.g_depth, dL_dposition, stream));
-    SPV_TRY_RC(spv_ewa_project_ortho_backward(P, f.cov3d, extr, W, H, f.radius, f.g_conic, f.g_cov3d, stream));
-    SPV_TRY_RC(spv_compute_cov3d_backward(P, scaling, rotation, f.vis, f.g_cov3d, dL_dscaling, dL_drotation, stream));
+    SPV_TRY_RC(spv::frame_geometry_backward(P, packed, scaling, rotation, extr, W, H, f.depth, f.vis, f.cov3d, f.radius, dL_dposition,
+                                            dL_dscaling, dL_drotation, stream));
     SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0), "spv_frame_ortho_backward/join");
     return 0;
 }

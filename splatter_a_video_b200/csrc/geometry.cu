@@ -149,14 +149,12 @@ project_point_bwd_kernel(int P, const float *__restrict__ xyz, const float *__re
     }
 }
 
-// Orthographic projection: pointrix/renderer/dptr_ortho_enhanced.py:177-202.
-__global__ void __launch_bounds__(kThreads)
-project_point_ortho_fwd_kernel(int P, const float *__restrict__ xyz, const float *__restrict__ extr, int W, int H,
-                               float nearest, float xmin, float xmax, float ymin, float ymax,
-                               float2 *__restrict__ uv, float *__restrict__ depth) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P) return;
-    const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+// Orthographic projection: pointrix/renderer/dptr_ortho_enhanced.py:177-202.  The bodies are device functions so the fused
+// per-frame kernels at the end of this file execute exactly the same operations as the staged kernels.
+struct OrthoBounds { float nearest, xmin, xmax, ymin, ymax; };
+
+__device__ __forceinline__ void project_ortho_body(float px, float py, float pz, const float *__restrict__ extr, int W, int H,
+                                                   const OrthoBounds &bd, float2 &uv, float &depth) {
     const float cx = extr[0] * px + extr[1] * py + extr[2] * pz + extr[3];
     const float cy = extr[4] * px + extr[5] * py + extr[6] * pz + extr[7];
     const float cz = extr[8] * px + extr[9] * py + extr[10] * pz + extr[11];
@@ -165,9 +163,34 @@ project_point_ortho_fwd_kernel(int P, const float *__restrict__ xyz, const float
     float d = cz;
     if (isnan(d)) d = 0.0f;                                              // nan_to_num
     else if (isinf(d)) d = d > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-    const bool mask = (d <= nearest) || (u < xmin) || (u > xmax) || (v < ymin) || (v > ymax);
-    uv[i] = mask ? make_float2(0.f, 0.f) : make_float2(u, v);
-    depth[i] = mask ? 0.f : d;
+    const bool mask = (d <= bd.nearest) || (u < bd.xmin) || (u > bd.xmax) || (v < bd.ymin) || (v > bd.ymax);
+    uv = mask ? make_float2(0.f, 0.f) : make_float2(u, v);
+    depth = mask ? 0.f : d;
+}
+
+__device__ __forceinline__ void project_ortho_bwd_body(const float *__restrict__ extr, float hw, float hh, float depth, float2 guv,
+                                                       float gdepth, float &gx, float &gy, float &gz) {
+    gx = 0.f; gy = 0.f; gz = 0.f;
+    if (depth != 0.f) {  // masked rows were overwritten with 0 in the forward: no gradient
+        const float a = guv.x * hw, b = guv.y * hh, c = gdepth;
+        gx = extr[0] * a + extr[4] * b + extr[8] * c;
+        gy = extr[1] * a + extr[5] * b + extr[9] * c;
+        gz = extr[2] * a + extr[6] * b + extr[10] * c;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+project_point_ortho_fwd_kernel(int P, const float *__restrict__ xyz, const float *__restrict__ extr, int W, int H,
+                               float nearest, float xmin, float xmax, float ymin, float ymax,
+                               float2 *__restrict__ uv, float *__restrict__ depth) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const OrthoBounds bd{nearest, xmin, xmax, ymin, ymax};
+    float2 o;
+    float d;
+    project_ortho_body(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], extr, W, H, bd, o, d);
+    uv[i] = o;
+    depth[i] = d;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -176,44 +199,26 @@ project_point_ortho_bwd_kernel(int P, const float *__restrict__ extr, float hw, 
                                const float *__restrict__ dL_ddepth, float *__restrict__ dL_dxyz) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= P) return;
-    float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (depth[i] != 0.f) {  // masked rows were overwritten with 0 in the forward: no gradient
-        const float a = dL_duv[i].x * hw, b = dL_duv[i].y * hh, c = dL_ddepth[i];
-        gx = extr[0] * a + extr[4] * b + extr[8] * c;
-        gy = extr[1] * a + extr[5] * b + extr[9] * c;
-        gz = extr[2] * a + extr[6] * b + extr[10] * c;
-    }
+    float gx, gy, gz;
+    project_ortho_bwd_body(extr, hw, hh, depth[i], dL_duv[i], dL_ddepth[i], gx, gy, gz);
     dL_dxyz[3 * i] = gx; dL_dxyz[3 * i + 1] = gy; dL_dxyz[3 * i + 2] = gz;
 }
 
 // ------------------------------------------------------------------------------------------------ K3/K4
-__global__ void __launch_bounds__(kThreads)
-cov3d_fwd_kernel(int P, const float *__restrict__ scales, const float4 *__restrict__ uquats,
-                 const uint8_t *__restrict__ visible, float *__restrict__ cov3d) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P) return;
-    float c[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (visible[i]) {
-        const M3 M = mul(scale_to_S(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]), quat_to_R(uquats[i]));
+__device__ __forceinline__ void cov3d_body(float sx, float sy, float sz, float4 q, bool visible, float (&c)[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c[k] = 0.f;
+    if (visible) {
+        const M3 M = mul(scale_to_S(sx, sy, sz), quat_to_R(q));
         const M3 Sg = mul(transpose(M), M);
         c[0] = Sg.m[0][0]; c[1] = Sg.m[0][1]; c[2] = Sg.m[0][2]; c[3] = Sg.m[1][1]; c[4] = Sg.m[1][2]; c[5] = Sg.m[2][2];
     }
-    float2 *o = reinterpret_cast<float2 *>(cov3d + 6 * (size_t)i);
-    o[0] = make_float2(c[0], c[1]); o[1] = make_float2(c[2], c[3]); o[2] = make_float2(c[4], c[5]);
 }
 
-__global__ void __launch_bounds__(kThreads)
-cov3d_bwd_kernel(int P, const float *__restrict__ scales, const float4 *__restrict__ uquats,
-                 const uint8_t *__restrict__ visible, const float *__restrict__ dL_dcov3d,
-                 float *__restrict__ dL_dscales, float4 *__restrict__ dL_duquats) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P) return;
-    float gs[3] = {0.f, 0.f, 0.f};
-    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (visible[i]) {
-        const float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
-        const float4 q = uquats[i];
-        const float *g = dL_dcov3d + 6 * (size_t)i;
+__device__ __forceinline__ void cov3d_bwd_body(const float (&s)[3], float4 q, bool visible, const float *g, float (&gs)[3], float4 &gq) {
+    gs[0] = gs[1] = gs[2] = 0.f;
+    gq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (visible) {
         const M3 R = quat_to_R(q);
         const M3 M = mul(scale_to_S(s[0], s[1], s[2]), R);
         M3 dS;  // compute_cov3d.cu:69-77
@@ -246,6 +251,29 @@ cov3d_bwd_kernel(int P, const float *__restrict__ scales, const float4 *__restri
                4 * z * (D(1, 1) + D(0, 0));
 #undef D
     }
+}
+
+__global__ void __launch_bounds__(kThreads)
+cov3d_fwd_kernel(int P, const float *__restrict__ scales, const float4 *__restrict__ uquats,
+                 const uint8_t *__restrict__ visible, float *__restrict__ cov3d) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    float c[6];
+    cov3d_body(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2], uquats[i], visible[i] != 0, c);
+    float2 *o = reinterpret_cast<float2 *>(cov3d + 6 * (size_t)i);
+    o[0] = make_float2(c[0], c[1]); o[1] = make_float2(c[2], c[3]); o[2] = make_float2(c[4], c[5]);
+}
+
+__global__ void __launch_bounds__(kThreads)
+cov3d_bwd_kernel(int P, const float *__restrict__ scales, const float4 *__restrict__ uquats,
+                 const uint8_t *__restrict__ visible, const float *__restrict__ dL_dcov3d,
+                 float *__restrict__ dL_dscales, float4 *__restrict__ dL_duquats) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+    float gs[3];
+    float4 gq;
+    cov3d_bwd_body(s, uquats[i], visible[i] != 0, dL_dcov3d + 6 * (size_t)i, gs, gq);
     dL_dscales[3 * i] = gs[0]; dL_dscales[3 * i + 1] = gs[1]; dL_dscales[3 * i + 2] = gs[2];
     dL_duquats[i] = gq;
 }
@@ -442,15 +470,11 @@ __device__ __forceinline__ void ortho_cov2d(const OrthoT &T, const float *c, flo
     c11 = (M[1][0] * T.t[1][0] + M[1][1] * T.t[1][1] + M[1][2] * T.t[1][2]) + 0.3f;
 }
 
-__global__ void __launch_bounds__(kThreads)
-ewa_ortho_fwd_kernel(int P, const float *__restrict__ cov3d, const float *__restrict__ extr, float jx, float jy,
-                     const float2 *__restrict__ uv, int gx, int gy, const uint8_t *__restrict__ visible,
-                     float *__restrict__ conic, int *__restrict__ radius, int *__restrict__ tiles) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P) return;
+__device__ __forceinline__ void ewa_ortho_body(const float *c6, const float *__restrict__ extr, float jx, float jy, float2 c, int gx,
+                                               int gy, bool visible, float (&conic)[3], int &radius, int &tiles) {
     const OrthoT T = ortho_T(extr, jx, jy);
     float c00, c01, c11;
-    ortho_cov2d(T, cov3d + 6 * (size_t)i, c00, c01, c11);
+    ortho_cov2d(T, c6, c00, c01, c11);
     const float det = c00 * c11 - c01 * c01;
     const float k0 = c11 / det, k1 = -c01 / det, k2 = c00 / det;
     const float b = (c00 + c11) / 2.0f;
@@ -458,7 +482,6 @@ ewa_ortho_fwd_kernel(int P, const float *__restrict__ cov3d, const float *__rest
     if (disc < 0.1f) disc = 0.1f;
     const float v1 = b + sqrtf(disc), v2 = b - sqrtf(disc);
     const float rad = ceilf(3.0f * sqrtf(v1 > v2 ? v1 : v2));
-    const float2 c = uv[i];
     const float f0 = (c.x - rad) / 16.0f, f1 = (c.y - rad) / 16.0f;
     const float f2 = (c.x + rad + 16.0f - 1.0f) / 16.0f, f3 = (c.y + rad + 16.0f - 1.0f) / 16.0f;
     const bool finite = isfinite(f0) && isfinite(f1) && isfinite(f2) && isfinite(f3) && isfinite(k0) && isfinite(k1) &&
@@ -470,28 +493,25 @@ ewa_ortho_fwd_kernel(int P, const float *__restrict__ cov3d, const float *__rest
         const int x1 = min(max((int)f2, 0), gx), y1 = min(max((int)f3, 0), gy);
         nt = (x1 - x0) * (y1 - y0);
     }
-    const bool mask = finite && nt != 0 && det != 0.0f && visible[i];
-    conic[3 * i] = mask ? k0 : 0.f; conic[3 * i + 1] = mask ? k1 : 0.f; conic[3 * i + 2] = mask ? k2 : 0.f;
-    radius[i] = mask ? (int)rad : 0;
-    tiles[i] = mask ? nt : 0;
+    const bool mask = finite && nt != 0 && det != 0.0f && visible;
+    conic[0] = mask ? k0 : 0.f; conic[1] = mask ? k1 : 0.f; conic[2] = mask ? k2 : 0.f;
+    radius = mask ? (int)rad : 0;
+    tiles = mask ? nt : 0;
 }
 
 // Gradient of the ortho EWA w.r.t. cov3d only (J is constant, so xyz receives nothing): what torch autograd
 // produces for dptr_ortho_enhanced.py:42-63,107.
-__global__ void __launch_bounds__(kThreads)
-ewa_ortho_bwd_kernel(int P, const float *__restrict__ cov3d, const float *__restrict__ extr, float jx, float jy,
-                     const int *__restrict__ radius, const float *__restrict__ dL_dconic,
-                     float *__restrict__ dL_dcov3d) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P) return;
-    float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (radius[i] > 0) {
+__device__ __forceinline__ void ewa_ortho_bwd_body(const float *c6, const float *__restrict__ extr, float jx, float jy, int radius,
+                                                   const float *g_conic, float (&o)[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = 0.f;
+    if (radius > 0) {
         const OrthoT T = ortho_T(extr, jx, jy);
         float c00, c01, c11;
-        ortho_cov2d(T, cov3d + 6 * (size_t)i, c00, c01, c11);
+        ortho_cov2d(T, c6, c00, c01, c11);
         const float det = c00 * c11 - c01 * c01;
         float d00, d01, d11;
-        conic_grad_to_cov2d(c00, c01, c11, det, dL_dconic + 3 * (size_t)i, d00, d01, d11);
+        conic_grad_to_cov2d(c00, c01, c11, det, g_conic, d00, d01, d11);
         // dL/dS_jk = d00 T0j T0k + d01 T0j T1k + d11 T1j T1k ; symmetric entries of the 6-vector add up.
 #define A(j) T.t[0][j]
 #define B(j) T.t[1][j]
@@ -504,8 +524,84 @@ ewa_ortho_bwd_kernel(int P, const float *__restrict__ cov3d, const float *__rest
 #undef A
 #undef B
     }
+}
+
+__global__ void __launch_bounds__(kThreads)
+ewa_ortho_fwd_kernel(int P, const float *__restrict__ cov3d, const float *__restrict__ extr, float jx, float jy,
+                     const float2 *__restrict__ uv, int gx, int gy, const uint8_t *__restrict__ visible,
+                     float *__restrict__ conic, int *__restrict__ radius, int *__restrict__ tiles) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    float k[3];
+    int rad, nt;
+    ewa_ortho_body(cov3d + 6 * (size_t)i, extr, jx, jy, uv[i], gx, gy, visible[i] != 0, k, rad, nt);
+    conic[3 * i] = k[0]; conic[3 * i + 1] = k[1]; conic[3 * i + 2] = k[2];
+    radius[i] = rad;
+    tiles[i] = nt;
+}
+
+__global__ void __launch_bounds__(kThreads)
+ewa_ortho_bwd_kernel(int P, const float *__restrict__ cov3d, const float *__restrict__ extr, float jx, float jy,
+                     const int *__restrict__ radius, const float *__restrict__ dL_dconic,
+                     float *__restrict__ dL_dcov3d) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    float o[6];
+    ewa_ortho_bwd_body(cov3d + 6 * (size_t)i, extr, jx, jy, radius[i], dL_dconic + 3 * (size_t)i, o);
 #pragma unroll
     for (int k = 0; k < 6; ++k) dL_dcov3d[6 * (size_t)i + k] = o[k];
+}
+
+// ---- fused per-frame geometry (spv_frame_ortho_forward/backward): the same bodies back to back in one pass -------------
+// forward: projection -> visibility -> covariance -> EWA; one launch and one read of the inputs instead of four launches with
+// uv / depth / vis / cov3d round trips.  radii_out = the caller-facing copy of `radius`; dirs = the renderer's constant view
+// direction (0,0,1) for the SH kernels.
+__global__ void __launch_bounds__(kThreads)
+frame_geometry_fwd_kernel(int P, const float *__restrict__ xyz, const float *__restrict__ scales, const float4 *__restrict__ uquats,
+                          const float *__restrict__ extr, int W, int H, OrthoBounds bd, float jx, float jy, int gx, int gy,
+                          float2 *__restrict__ uv, float *__restrict__ depth, uint8_t *__restrict__ vis, float *__restrict__ cov3d,
+                          float *__restrict__ conic, int *__restrict__ radius, int *__restrict__ tiles, int *__restrict__ radii_out) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    float2 o;
+    float d;
+    project_ortho_body(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], extr, W, H, bd, o, d);
+    const bool visible = d != 0.f;                                   // dptr_ortho_enhanced.py:295
+    float c[6];
+    cov3d_body(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2], uquats[i], visible, c);
+    float k[3];
+    int rad, nt;
+    ewa_ortho_body(c, extr, jx, jy, o, gx, gy, visible, k, rad, nt);
+    uv[i] = o; depth[i] = d; vis[i] = visible;
+    float2 *oc = reinterpret_cast<float2 *>(cov3d + 6 * (size_t)i);
+    oc[0] = make_float2(c[0], c[1]); oc[1] = make_float2(c[2], c[3]); oc[2] = make_float2(c[4], c[5]);
+    conic[3 * i] = k[0]; conic[3 * i + 1] = k[1]; conic[3 * i + 2] = k[2];
+    radius[i] = rad; tiles[i] = nt; radii_out[i] = rad;
+}
+
+// backward: (dL_duv, dL_ddepth) -> position ; dL_dconic -> cov3d -> scaling, rotation, with the gradients read straight from
+// the packed rows of the blend backward (row layout: spv::kPackedRowGroups).
+__global__ void __launch_bounds__(kThreads)
+frame_geometry_bwd_kernel(int P, const float *__restrict__ packed, const float *__restrict__ scales, const float4 *__restrict__ uquats,
+                          const float *__restrict__ extr, float jx, float jy, const float *__restrict__ depth,
+                          const uint8_t *__restrict__ vis, const float *__restrict__ cov3d, const int *__restrict__ radius,
+                          float *__restrict__ dL_dxyz, float *__restrict__ dL_dscales, float4 *__restrict__ dL_duquats) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const float4 *row = reinterpret_cast<const float4 *>(packed + (size_t)i * spv::kPackedRowGroups);
+    const float4 r0 = row[0], r1 = row[1], r2 = row[2];   // 0,1 dL_duv | 4,5,6 dL_dconic | 11 dL_ddepth
+    float gx, gy, gz;
+    project_ortho_bwd_body(extr, jx, jy, depth[i], make_float2(r0.x, r0.y), r2.w, gx, gy, gz);
+    dL_dxyz[3 * i] = gx; dL_dxyz[3 * i + 1] = gy; dL_dxyz[3 * i + 2] = gz;
+    const float gcon[3] = {r1.x, r1.y, r1.z};
+    float gcov[6];
+    ewa_ortho_bwd_body(cov3d + 6 * (size_t)i, extr, jx, jy, radius[i], gcon, gcov);
+    const float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+    float gs[3];
+    float4 gq;
+    cov3d_bwd_body(s, uquats[i], vis[i] != 0, gcov, gs, gq);
+    dL_dscales[3 * i] = gs[0]; dL_dscales[3 * i + 1] = gs[1]; dL_dscales[3 * i + 2] = gs[2];
+    dL_duquats[i] = gq;
 }
 
 // ------------------------------------------------------------------------------------------------ K7-K10
@@ -685,6 +781,33 @@ sh_bwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
 inline dim3 grid_for(int P) { return dim3(spv::cdiv(P, kThreads)); }
 
 }  // namespace
+
+// ---- internal entry points of the fused frame path (frame.cu) ----------------------------------------------------------------
+namespace spv {
+int frame_geometry_forward(int P, const float *xyz, const float *scales, const float *uquats, const float *extr, int W, int H,
+                           float nearest, float extent, float *uv, float *depth, uint8_t *vis, float *cov3d, float *conic, int *radius,
+                           int *tiles, int *radii_out, void *stream) {
+    if (P <= 0) return 0;
+    OrthoBounds bd;
+    bd.nearest = nearest;   // same narrowing as spv_project_point_ortho_forward
+    bd.xmin = (float)((1.0 - (double)extent) * W * 0.5); bd.xmax = (float)((1.0 + (double)extent) * W * 0.5);
+    bd.ymin = (float)((1.0 - (double)extent) * H * 0.5); bd.ymax = (float)((1.0 + (double)extent) * H * 0.5);
+    frame_geometry_fwd_kernel<<<grid_for(P), kThreads, 0, (cudaStream_t)stream>>>(
+        P, xyz, scales, (const float4 *)uquats, extr, W, H, bd, (float)((double)W / 2.0), (float)((double)H / 2.0), spv::tiles_x(W),
+        spv::tiles_y(H), (float2 *)uv, depth, vis, cov3d, conic, radius, tiles, radii_out);
+    return spv::check_launch("spv_frame_ortho_forward/geometry");
+}
+
+int frame_geometry_backward(int P, const float *packed, const float *scales, const float *uquats, const float *extr, int W, int H,
+                            const float *depth, const uint8_t *vis, const float *cov3d, const int *radius, float *dL_dxyz,
+                            float *dL_dscales, float *dL_duquats, void *stream) {
+    if (P <= 0) return 0;
+    frame_geometry_bwd_kernel<<<grid_for(P), kThreads, 0, (cudaStream_t)stream>>>(
+        P, packed, scales, (const float4 *)uquats, extr, (float)((double)W / 2.0), (float)((double)H / 2.0), depth, vis, cov3d, radius,
+        dL_dxyz, dL_dscales, (float4 *)dL_duquats);
+    return spv::check_launch("spv_frame_ortho_backward/geometry");
+}
+}  // namespace spv
 
 // ================================================================================================ C ABI
 extern "C" {
