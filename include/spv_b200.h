@@ -184,6 +184,8 @@ SPV_API int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const in
                                                   touched, and spv_compute_sh_backward is run by the caller on the
                                                   all-reduced colour gradient*/,
                              uint8_t *clamped_out /*[P,3] or NULL: the forward's clamp mask for that deferred call*/,
+                             int first_backward /*1: first backward over this workspace (the forward call left the packed
+                                                  gradient rows cleared, off the critical path); 0: clear them again*/,
                              void *workspace, size_t ws_bytes, void *stream);
 /* Blend stage of the grouped backward with per-channel gradient planes; leaves 36-float packed rows in `packed`. */
 SPV_API int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, const float *uv, const float *conic,

@@ -56,7 +56,7 @@ _SIGS = {
     "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, c_int, c_int64, c_int, P_, P_, P_, P_, P_, P_, c_float,
                                         c_float, c_float, P_, P_, P_, P_, P_, c_size_t, P_]),
     "spv_frame_ortho_backward": (c_int, [c_int, c_int, c_int, c_int, P_, c_int, c_int64, P_, P_, P_, P_, P_, c_float, P_, P_, P_, P_,
-                                         P_, P_, P_, P_, P_, P_, P_, P_, c_size_t, P_]),
+                                         P_, P_, P_, P_, P_, P_, P_, c_int, P_, c_size_t, P_]),
     "spv_alpha_blend_groups_backward_packed": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float, c_float,
                                                        P_, P_, P_, c_int, P_, P_]),
     "spv_deform_spline_forward": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_]),

@@ -485,13 +485,19 @@ int blend_records_forward(int C, int W, int H, int K, const float *rec, const in
 
 int blend_records_backward(int P, int C, int W, int H, const float *rec, const int *idx_sorted, const int *tile_range,
                            float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
-                           const float *const *planes_host, int n_grad_channels, float *packed, void *stream) {
+                           const float *const *planes_host, int n_grad_channels, float *packed, bool packed_is_zero, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0) return 0;
     if (C < 4 || C > 23) { spv::set_error(cudaErrorInvalidValue, "blend_records_backward: need 4 <= C <= 23"); return (int)cudaErrorInvalidValue; }
     const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
-    SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)kRowG * P, s), "blend_records_backward");
+    if (!packed_is_zero) SPV_CUDA_TRY(cudaMemsetAsync(packed, 0, sizeof(float) * (size_t)kRowG * P, s), "blend_records_backward");
     if (W <= 0 || H <= 0) return 0;
+    // Trailing image channels without an upstream gradient (e.g. the trainer renders mask / dino / pos_poly_feat images it puts
+    // no loss on, trainer_fragGS.py:600-640) contribute exact zeros to every sum: they are not traversed at all.
+    int C_live = 4;
+    for (int c = 4; c < C; ++c) if (planes_host[c]) C_live = c + 1;
+    if (n_grad_channels > C_live) n_grad_channels = C_live;   // their feature gradients are exact zeros (the rows were cleared)
+    C = C_live;
     RecBwdArgs a;
     a.C = C; a.W = W; a.H = H; a.gx = gx; a.rec = rec; a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range;
     a.bgA = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.final_T = final_T; a.ncontrib = ncontrib; a.packed = packed;

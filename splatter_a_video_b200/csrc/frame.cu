@@ -166,6 +166,8 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_forward/fork");
     SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
     SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, lane->stream), "spv_frame_ortho_forward");
+    // the backward's packed gradient rows are cleared here, off the critical path (the workspace belongs to this frame)
+    SPV_CUDA_TRY(cudaMemsetAsync(f.blend_ws, 0, sizeof(float) * (size_t)spv::kPackedRowGroups * P, lane->stream), "spv_frame_ortho_forward");
     // ---- main branch: projection, visibility, covariance, conic / radius / tile rectangle in ONE pass (geometry.cu: the staged
     //      kernels' bodies back to back, bit-identical results), then culled binning + tile sort
     SPV_TRY_RC(spv::frame_geometry_forward(P, position, scaling, rotation, extr, W, H, nearest, extent, f.uv, f.depth, f.vis, f.cov3d,
@@ -191,7 +193,7 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
                              const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
                              float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs,
                              float *const *dL_dattr_ptrs, float *dL_dndc, float *dL_dabs_ndc, float *dL_drgb_out,
-                             uint8_t *clamped_out, void *workspace, size_t ws_bytes, void *stream) {
+                             uint8_t *clamped_out, int first_backward, void *workspace, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0 || W <= 0 || H <= 0) return 0;
     AttrGroups gr;
@@ -202,7 +204,7 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     const unsigned g = spv::cdiv(P, kThreads);
     float *packed = (float *)f.blend_ws;
     SPV_TRY_RC(spv::blend_records_backward(P, C, W, H, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, f.final_T,
-                                           f.ncontrib, dL_dimage_planes, n_grad_channels, packed, stream));
+                                           f.ncontrib, dL_dimage_planes, n_grad_channels, packed, /*packed_is_zero=*/first_backward != 0, stream));
     // deferred SH backward (frame-parallel training): the colour gradient and the clamp mask leave through the caller's
     // buffers, the SH coefficients' gradient is produced after the gradient exchange from the REDUCED colour gradient
     const bool defer_sh = dL_drgb_out != nullptr;

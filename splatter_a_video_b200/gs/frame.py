@@ -107,6 +107,8 @@ class _FrameOrtho(torch.autograd.Function):
         import ctypes
         P, W, H, chans, I_cap, bg_rgb, has_ndc, has_abs = ctx.meta
         sc, rot, op, sh, ex, ws = ctx.saved_tensors
+        first = not getattr(ctx, "backward_ran", False)     # a second backward over the same graph must clear the packed rows itself
+        ctx.backward_ran = True
         dev = sc.device
         sinks = ctx.sinks
         ng = len(chans)
@@ -145,7 +147,7 @@ class _FrameOrtho(torch.autograd.Function):
                L.ptr(sh), L.ptr(ex), bg_rgb, ctypes.cast(_ptr_array(planes), ctypes.c_void_p), L.ptr(g_pos), L.ptr(g_sc), L.ptr(g_rot),
                L.ptr(g_op), L.ptr(g_sh), ctypes.cast(_ptr_array([None if t is None else t.data_ptr() for t in g_attr]), ctypes.c_void_p),
                L.ptr(g_ndc), L.ptr(g_abs), L.ptr(defer[0]) if defer is not None else None,
-               L.ptr(defer[1]) if defer is not None else None, L.ptr(ws), ws.numel(), L.stream())
+               L.ptr(defer[1]) if defer is not None else None, int(first), L.ptr(ws), ws.numel(), L.stream())
         g_user = [None] * ng
         for slot, t in zip(ctx.order, g_attr):
             g_user[slot] = t

@@ -74,3 +74,15 @@ def test_ops_fail_loudly_without_cuda():
     with pytest.raises(RuntimeError):
         gs.alpha_blending(torch.zeros(1, 2), torch.zeros(1, 3), torch.zeros(1, 1), torch.zeros(1, 3),
                           torch.zeros(1, dtype=torch.int32), torch.zeros(1, 2, dtype=torch.int32), 0.0, 16, 16)
+
+
+def test_ctypes_signatures_have_the_header_arity():
+    """Every ctypes argtypes list must have as many entries as the header's parameter list (a mismatch only shows on the GPU)."""
+    from splatter_a_video_b200 import _lib
+    hdr = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+    for name, (_, args) in _lib._SIGS.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", hdr, flags=re.S)
+        assert m, f"{name} is bound but not declared"
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(args), f"{name}: header declares {n} parameters, ctypes binds {len(args)}"

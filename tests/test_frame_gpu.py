@@ -335,3 +335,50 @@ def test_tile_segment_binning_equals_radix_binning(cuda, P, W, H, big, cull):
     small = max(I // 3, 1)
     c_idx, c_tr, c_st = _bin("spv_bin_tiles", uv, depth, radius, conic, opacity, cull, W, H, small)
     assert int(c_st[1]) == 1 and int(c_st[0]) == small and int(c_tr.max()) <= small
+
+
+def test_frame_backward_twice_and_gradient_free_images(cuda):
+    """(a) a second backward over the same graph (retain_graph) must reproduce the first -- the packed gradient rows are cleared
+    by the forward call for the first backward only; (b) rendered images that receive NO upstream gradient (the trainer puts no
+    loss on its mask / dino / pos_poly_feat images) are pruned from the backward traversal: same gradients as explicit zeros."""
+    from splatter_a_video_b200.gs.frame import render_ortho_frame
+    sc = synth.make_scene(20_000, 4, 256, 192, seed=21)
+    W, H, P = sc.W, sc.H, sc.P
+    g = torch.Generator().manual_seed(4)
+    g_rgb, g_depth, g_track = (torch.randn(c, H, W, generator=g).to(cuda) for c in (3, 1, 3))
+
+    def leaves():
+        d = {"position": sc.frame_position(0), "scaling": sc.scaling, "rotation": sc.rotation, "opacity": sc.opacity, "shs": sc.shs,
+             "track": sc.frame_position(1), "mask": sc.attrs["mask_attribute"], "poly": sc.attrs["pos_poly_feat"]}
+        return {k: v.to(cuda).clone().requires_grad_(k != "poly") for k, v in d.items()}
+
+    def render(L_):
+        imgs, _, _, status = render_ortho_frame(L_["position"], L_["scaling"], L_["rotation"], L_["opacity"], L_["shs"],
+                                                [L_["track"], L_["mask"], L_["poly"]], sc.extr.to(cuda), W, H, 20, 0.0, 8 * P)
+        assert int(status.cpu()[1]) == 0
+        return imgs      # [rgb, depth, track, mask, poly]
+
+    # (a)
+    A_ = leaves()
+    imgs = render(A_)
+    outs, grads = [imgs[0], imgs[1], imgs[2]], [g_rgb, g_depth, g_track]
+    first = torch.autograd.grad(outs, [A_[k] for k in ("position", "opacity", "shs", "track")], grads, retain_graph=True)
+    second = torch.autograd.grad(outs, [A_[k] for k in ("position", "opacity", "shs", "track")], grads)
+    for a, b in zip(first, second):
+        Hh.assert_grad_close(n(b), n(a), "second backward", norm_tol=2e-6)
+    # (b) no gradient on the mask / poly images  ==  explicit zero gradients on them
+    B_ = leaves()
+    imgs = render(B_)
+    zeros = [torch.zeros_like(imgs[3]), torch.zeros_like(imgs[4])]
+    ref = torch.autograd.grad(imgs, [B_[k] for k in ("position", "scaling", "opacity", "shs", "track", "mask")], grads + zeros)
+    C_ = leaves()
+    imgs = render(C_)
+    got = torch.autograd.grad([imgs[0], imgs[1], imgs[2]], [C_[k] for k in ("position", "scaling", "opacity", "shs", "track", "mask")],
+                              grads, allow_unused=True)
+    for name, a, b in zip(("position", "scaling", "opacity", "shs", "track", "mask"), ref, got):
+        if b is None:
+            assert float(a.abs().max()) == 0.0, name
+        elif name == "mask":
+            assert float(b.abs().max()) == 0.0 and float(a.abs().max()) == 0.0
+        else:
+            Hh.assert_grad_close(n(b), n(a), f"pruned d/d{name}", norm_tol=2e-6)
