@@ -237,6 +237,34 @@ SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *e
                   const long long *seg_end_host, const float *seg_lr_host, float beta1, float beta2, float eps, int step,
                   void *stream);
 
+/* ---- Densification on the flat SoA (next row f-3, structure half) -------------------------------------------------
+ * Role of AtlasGaussianSplattingOptimizer.update_structure / densification / prune / reset_opacity
+ * (src/pointrix/optimizer/atlas_gs_optimizer.py:93-379) and PointCloud.extand_points / remove_points with their
+ * optimizer-state surgery (src/pointrix/point_cloud/points.py:281-365).
+ * stats: for visible points (visible == NULL: radii > 0) max_radii = max(., radii), grad_accum += |ndc_grad|, denom += 1.
+ * flags: bit 0 clone, bit 1 split, bit 2 prune from grads = grad_accum / denom (NaN -> 0), max(scaling), opacity, max_radii;
+ *        scaling / opacity are the STORED parameters (scaling_is_log / opacity_is_logit select exp / sigmoid activation);
+ *        size_threshold <= 0 disables the two size tests like the reference's `if size_threshold:`.
+ * flat_regather: every [P_old, width] block of `old_flat` moves to its [P_new, width] place in `new_flat`:
+ *        new_row[j] = old_row[src[j]], zeros where src[j] < 0 (fresh Adam moments of new points).  One launch for all blocks.
+ * split_children: for new rows with child_index[j] >= 0 (index into `samples`, the torch.normal draw of new_pos_scale):
+ *        position = R(rotation[src]) @ sample + position[src]; scaling = inverse_activation(scaling[src] / div).
+ * reset_opacity: opacity = inverse_sigmoid(min(sigmoid(opacity), cap)) and cleared moments (replace_optimizer). */
+SPV_API int spv_densify_stats(int P, const float *ndc_grad /*[P,2]*/, const int *radii, const uint8_t *visible, float *grad_accum,
+                      float *denom, float *max_radii, void *stream);
+SPV_API int spv_densify_flags(int P, const float *grad_accum, const float *denom, const float *scaling /*[P,3]*/,
+                      const float *opacity /*[P]*/, const float *max_radii, int scaling_is_log, int opacity_is_logit,
+                      float grad_threshold, float dense_extent, float min_opacity, float size_threshold, float big_extent,
+                      uint8_t *flags, void *stream);
+SPV_API int spv_flat_regather(int n_blocks /*<= 32*/, const int *widths_host, const long long *old_offsets_host,
+                      const long long *new_offsets_host, int P_new, const int *src /*[P_new] device*/, const float *old_flat,
+                      float *new_flat, void *stream);
+SPV_API int spv_split_children(int P_new, const int *src, const int *child_index, const float *samples /*[n_children,3]*/,
+                       const float *old_position, const float *old_scaling, const float *old_rotation, int scaling_is_log,
+                       float div, float *new_position, float *new_scaling, void *stream);
+SPV_API int spv_reset_opacity(int P, float cap, int opacity_is_logit, float *opacity, float *exp_avg /*or NULL*/,
+                      float *exp_avg_sq /*or NULL*/, void *stream);
+
 /* ---- Gradient exchange packing for frame-parallel training (the reference has no gradient collective,
  * src/train.py:19-31,210-213) ----
  * The flat gradient buffer is described by a table of per-parameter segments; each parameter's per-Gaussian row is viewed as

@@ -68,6 +68,11 @@ _SIGS = {
     "spv_deform_rotation_forward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
     "spv_deform_rotation_backward": (c_int, [c_int, P_, P_, P_, P_, P_]),
     "spv_adam_step": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, c_int, P_]),
+    "spv_densify_stats": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_densify_flags": (c_int, [c_int, P_, P_, P_, P_, P_, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P_, P_]),
+    "spv_flat_regather": (c_int, [c_int, P_, P_, P_, c_int, P_, P_, P_, P_]),
+    "spv_split_children": (c_int, [c_int, P_, P_, P_, P_, P_, P_, c_int, c_float, P_, P_, P_]),
+    "spv_reset_opacity": (c_int, [c_int, c_float, c_int, P_, P_, P_, P_]),
     "spv_exchange_sizes": (c_int, [c_int, c_int, P_, P_, P_]),
     "spv_exchange_pack": (c_int, [c_int, c_int, P_, P_, P_, c_float, P_, P_, P_]),
     "spv_exchange_reduce": (c_int, [ctypes.c_longlong, c_int, P_, ctypes.c_longlong, c_float, P_, P_]),

@@ -61,6 +61,27 @@ class FlatParams:
             self.params[k] = p
             off += n
 
+    @classmethod
+    def empty_like(cls, other: "FlatParams", P_old: int, P_new: int) -> "FlatParams":
+        """Same named parameters for a population of P_new points (uninitialised values, zero gradients): used when the
+        structure changes (densification) so no per-parameter temporaries are needed."""
+        self = cls.__new__(cls)
+        self.names = list(other.names)
+        self.shapes = {k: (P_new,) + tuple(other.shapes[k][1:]) for k in self.names}
+        self.sizes = [n // max(P_old, 1) * P_new for n in other.sizes]
+        total = (sum(self.sizes) + 3) // 4 * 4
+        dev = other.flat.device
+        self.flat = torch.zeros(max(total, 4), dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(max(total, 4), dtype=torch.float32, device=dev)
+        self.params = {}
+        off = 0
+        for k, n in zip(self.names, self.sizes):
+            p = self.flat[off:off + n].view(self.shapes[k]).requires_grad_(True)
+            p.grad = self.flat_grad[off:off + n].view(self.shapes[k])
+            self.params[k] = p
+            off += n
+        return self
+
     def __getitem__(self, k: str) -> torch.Tensor:
         return self.params[k]
 
