@@ -28,9 +28,9 @@ ref)
 ncu)
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_${TAG}.csv \
       python bench.py --steps 2 --warmup 1 --profile-mode > gpurun_out/ncu_launches_${TAG}.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_bwd -s 2 -c 2 -f -o gpurun_out/prof_bwd_${TAG} \
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_rec_bwd -s 2 -c 2 -f -o gpurun_out/prof_bwd_${TAG} \
       python bench.py --steps 2 --warmup 1 --profile-mode > gpurun_out/ncu_bwd_${TAG}.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_fwd -s 2 -c 2 -f -o gpurun_out/prof_fwd_${TAG} \
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_rec_fwd -s 2 -c 2 -f -o gpurun_out/prof_fwd_${TAG} \
       python bench.py --steps 2 --warmup 1 --profile-mode > gpurun_out/ncu_fwd_${TAG}.log 2>&1
   tail -3 gpurun_out/ncu_bwd_${TAG}.log ;;
 esac
