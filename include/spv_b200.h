@@ -46,6 +46,9 @@ SPV_API long long spv_launch_count(void);
 /* Measurement hook (no reference counterpart): when enabled, every blend kernel launch is bracketed by a pair of CUDA events
  * on its own stream (slot 0 = forward kernel, 1 = backward kernel; also inside a captured graph).  `read` waits for the
  * slot's closing event and returns the device time of the most recent launch.  Disabled (default): no cost. */
+/* Runtime switch of an experimental kernel variant (0 = the validated default).  "bwd_wide" = 2 | 4: pixels per lane of the
+ * frame path's backward blend kernel (also read once from the environment variable SPV_BWD_WIDE). */
+SPV_API int spv_set_option(const char *name, int value);
 SPV_API int spv_kernel_timer_enable(int on);
 SPV_API int spv_kernel_timer_read(int slot, float *ms);
 

@@ -20,6 +20,7 @@ _SIGS = {
     "spv_abi_version": (c_int, []),
     "spv_last_error": (ctypes.c_char_p, []),
     "spv_launch_count": (ctypes.c_longlong, []),
+    "spv_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "spv_kernel_timer_enable": (c_int, [c_int]),
     "spv_kernel_timer_read": (c_int, [c_int, P_]),
     "spv_project_point_forward": (c_int, [c_int, P_, P_, P_, c_int, c_int, c_float, c_float, P_, P_, P_]),
@@ -128,6 +129,11 @@ def call(name: str, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed: {lib.spv_last_error().decode()}")
+
+
+def set_option(name: str, value: int):
+    """Runtime switch of an experimental kernel variant (include/spv_b200.h: spv_set_option); 0 restores the validated default."""
+    call("spv_set_option", name.encode(), int(value))
 
 
 def query(name: str, *args) -> int:

@@ -397,6 +397,210 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
     }
 }
 
+// ---- backward, wide warp footprints (EXPERIMENTAL, opt-in: SPV_BWD_WIDE=2|4 or spv_set_option("bwd_wide", 2|4)) ----------------
+// 41 % of blend_rec_bwd_kernel's instructions are its per-(warp, entry) shuffle reductions (profiles/r01_ncu_blend_rec_bwd_lines.txt),
+// one per ACTIVE (8x4-pixel block, entry) pair: 1.283 M on the config-A frame.  With R pixels per lane a warp covers R of those blocks
+// (R = 2: 16x4, R = 4: 16x8 pixels), accumulates the partials of its R sub-blocks in registers and reduces ONCE per entry:
+// 0.890 M / 0.605 M reductions (scripts/hit_stats.py).  CTA = 256 / R threads per tile; the per-pixel constants (T_final, <bg, dL_dpixel>)
+// move into the spare slots of the pixel's dL_dpixel row in shared memory; chunks shrink to 32 entries so 5 tiles stay resident per SM.
+// Same arithmetic per (pixel, entry) as blend_rec_bwd_kernel; only the association of the per-Gaussian sums changes.
+// NOT YET VALIDATED ON A GPU (written after the round's GPU budget was spent): default off, tests opt-in (SPV_TEST_EXPERIMENTAL=1).
+constexpr int kChunkW = 32;
+
+template <int CH, int CG, int R>
+__global__ void __launch_bounds__(kBlock / R)
+blend_rec_bwd_wide_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
+                          const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
+                          const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
+                          float *__restrict__ packed) {
+    constexpr int NV = (CG <= 14) ? 16 : 32;
+    constexpr bool MID = CG > 8 && CG <= 14;
+    static_assert(R == 2 || R == 4, "R pixels per lane");
+    static_assert(CH % 4 == 0 && CH >= 4 && CH <= 24 && 8 + CG <= 32 && CG <= CH, "unsupported channel configuration");
+    constexpr int RP = kRec;
+    // dL_dpixel row: CH gradients + [bgdA bgdB bgdC T_final], pitch/4 odd
+    constexpr int DS = ((CH + 4) / 4) % 2 ? CH + 4 : CH + 8;
+    constexpr int kThreadsW = kBlock / R;
+    extern __shared__ __align__(128) float s_dyn[];
+    float *s_rec0 = s_dyn;                            // [2][kChunkW][RP]
+    float *s_dq = s_dyn + 2 * kChunkW * RP;           // [256 pixels][DS]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_max;
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // sub-block sb = warp*R + r is the 8x4 block at (8*(sb&1), 4*(sb>>1)) of the tile: R = 2 -> 16x4 per warp, R = 4 -> 16x8
+    const int px0 = tile_x * SPV_TILE + (lane & 7), py0 = tile_y * SPV_TILE + (lane >> 3) + 4 * ((warp * R) >> 1);
+    const float wx0 = (float)(tile_x * SPV_TILE), wy0 = (float)(tile_y * SPV_TILE + 4 * ((warp * R) >> 1));
+    const float wx1 = wx0 + 15.f, wy1 = wy0 + (float)(2 * R - 1);     // pixel-centre rectangle of the warp's footprint
+
+    const int2 range = tile_range[tile];
+    float T[R], last_alpha[R], lfA[R], lfB[R], lfC[R], SA[R], SB[R], SC[R];
+    int last_contrib[R];
+    int wmax = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int px = px0 + 8 * (r & 1), py = py0 + 4 * (r >> 1);
+        const bool inside = px < W && py < H;
+        const size_t pix = (size_t)W * py + px;
+        const float Tf = inside ? final_T[pix] : 0.f;
+        T[r] = Tf;
+        last_contrib[r] = inside ? ncontrib[pix] : 0;
+        wmax = max(wmax, last_contrib[r]);
+        last_alpha[r] = lfA[r] = lfB[r] = lfC[r] = SA[r] = SB[r] = SC[r] = 0.f;
+        float *dq = s_dq + ((warp * R + r) * 32 + lane) * DS;
+        float bA = 0.f, bB = 0.f, bC = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float dv = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
+            dq[c] = dv;
+            if (c >= 4) bC += dv;
+            else if (c == 3) bB += dv;
+            else bA += dv;
+        }
+        dq[CH] = bA * bgA; dq[CH + 1] = bB * bgB; dq[CH + 2] = bC * bgC; dq[CH + 3] = Tf;
+    }
+    if (threadIdx.x == 0) {
+        s_max = 0;
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    wmax = __reduce_max_sync(kFull, wmax);          // positions >= wmax were applied by no pixel of this warp
+    if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int n_eff = min(range.y - range.x, s_max);
+    const int nchunks = (n_eff + kChunkW - 1) / kChunkW;
+
+    auto issue = [&](int c) {
+        const int b = c & 1, p_hi = n_eff - c * kChunkW, m = min(kChunkW, p_hi);
+        if (threadIdx.x == 0) mbar_expect_tx(&s_bar[b], (uint32_t)(m * kRec * 4));
+        if ((int)threadIdx.x < m) {
+            const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];
+            bulk_g2s(s_rec0 + (b * kChunkW + threadIdx.x) * RP, rec + (size_t)id * kRec, kRec * 4, &s_bar[b]);
+        }
+    };
+    if (nchunks > 0) issue(0);
+
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) issue(c + 1);
+        mbar_wait(&s_bar[c & 1], (c >> 1) & 1);
+        const float *sr = s_rec0 + (c & 1) * kChunkW * RP;
+        const int p_hi = n_eff - c * kChunkW, m = min(kChunkW, p_hi);
+        // stage 1: one chunk entry per lane (kChunkW == 32) -- can the warp's footprint have taken it at all?
+        bool maybe = false;
+        if (lane < m && p_hi - 1 - lane < wmax) {
+            const float4 *q = reinterpret_cast<const float4 *>(sr + lane * RP);
+            const float4 g0 = q[0], g1 = q[1];
+            const float tau2 = g1.y - kLog2AlphaMin;
+            maybe = (tau2 >= 0.f) && spv::tile_may_hit(g0.x, g0.y, -2.f * g0.z, -g0.w, -2.f * g1.x, tau2, wx0, wy0, wx1, wy1);
+        }
+        unsigned todo = __ballot_sync(kFull, maybe);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const float4 *q = reinterpret_cast<const float4 *>(sr + j * RP);
+            const float4 g0 = q[0], g1 = q[1];
+            const float4 con = q[kRec / 4 - 1];
+            const int pos = p_hi - 1 - j;
+            float v[NV];
+            float u[8];
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = 0.f;
+            bool any_hit = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float pxf = (float)(px0 + 8 * (r & 1)), pyf = (float)(py0 + 4 * (r >> 1));
+                float dx, dy;
+                float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                const bool hit = splat_hits<false>(p2, g1) && pos < last_contrib[r];
+                if (!__any_sync(kFull, hit)) continue;                 // warp-uniform: this 8x4 sub-block did not take it
+                any_hit = true;
+                const float *dq = s_dq + ((warp * R + r) * 32 + lane) * DS;
+                const float4 cst = *reinterpret_cast<const float4 *>(dq + CH);   // bgdA bgdB bgdC T_final
+                float Gv;
+                p2 = hit ? p2 : -INFINITY;
+                const float alpha = splat_alpha<false>(p2, g1, Gv);
+                const float rinv = __fdividef(1.f, 1.f - alpha);
+                T[r] = T[r] * rinv;
+                const float w = alpha * T[r];
+                const float tb = -cst.w * rinv;
+                const float om = 1.f - last_alpha[r];
+                float fdA = 0.f, fdB = 0.f, fdC = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < CH / 4; ++c4) {
+                    const float4 ff = q[2 + c4];
+                    const float4 dd = *reinterpret_cast<const float4 *>(dq + 4 * c4);
+                    const float fv[4] = {ff.x, ff.y, ff.z, ff.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int ch = 4 * c4 + k;
+                        if (ch >= 4) fdC = fmaf(fv[k], dv[k], fdC);
+                        else if (ch == 3) fdB = fmaf(fv[k], dv[k], fdB);
+                        else fdA = fmaf(fv[k], dv[k], fdA);
+                        if (ch < CG) {
+                            if (MID && ch >= 8) u[ch - 8] = fmaf(w, dv[k], u[ch - 8]);
+                            else v[8 + ch] = fmaf(w, dv[k], v[8 + ch]);
+                        }
+                    }
+                }
+                const float nSA = last_alpha[r] * lfA[r] + om * SA[r];
+                const float nSB = last_alpha[r] * lfB[r] + om * SB[r];
+                const float nSC = last_alpha[r] * lfC[r] + om * SC[r];
+                const float da_ndc = (fdA - nSA) * T[r] + tb * cst.x;
+                const float da_op = da_ndc + ((fdB - nSB) * T[r] + tb * cst.y);
+                const float da_all = da_op + ((fdC - nSC) * T[r] + tb * cst.z);
+                SA[r] = hit ? nSA : SA[r]; SB[r] = hit ? nSB : SB[r]; SC[r] = hit ? nSC : SC[r];
+                lfA[r] = hit ? fdA : lfA[r]; lfB[r] = hit ? fdB : lfB[r]; lfC[r] = hit ? fdC : lfC[r];
+                last_alpha[r] = hit ? alpha : last_alpha[r];
+                const float dL_dG = g1.z * da_all;
+                const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
+                const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
+                v[0] += dL_dG * dGx; v[1] += dL_dG * dGy;
+                v[4] += -0.5f * Gv * dx * dx * dL_dG;
+                v[5] += -Gv * dx * dy * dL_dG;
+                v[6] += -0.5f * Gv * dy * dy * dL_dG;
+                v[7] += Gv * da_op;
+                const float dL_dG_ndc = g1.z * da_ndc;
+                const float n0 = dL_dG_ndc * dGx, n1 = dL_dG_ndc * dGy;
+                e0 += n0; e1 += n1;
+                v[2] += fabsf(n0); v[3] += fabsf(n1);
+            }
+            if (!any_hit) continue;
+            halving_reduce<NV, 0, NV>(v, lane);
+            float *row = packed + (size_t)__float_as_int(g1.w) * kRowG;
+            if constexpr (MID) {
+                u[6] = e0; u[7] = e1;
+                halving_reduce<8, 0, 8>(u, lane);
+                const int t = lane - 16;
+                const float val = lane < 16 ? v[0] : u[0];
+                const int col = lane < 16 ? lane : (t < 6 ? 16 + t : 31 + (t - 6));
+                const bool live = lane < 16 || (lane < 24 && (t >= 6 || t < CG - 8));
+                if (live && val != 0.f) atomicAdd(row + col, val);
+            } else {
+                const bool up = (lane & 1) != 0;
+                float e = (up ? e1 : e0) + __shfl_xor_sync(kFull, up ? e0 : e1, 1);
+#pragma unroll
+                for (int o = 2; o <= 16; o <<= 1) e += __shfl_xor_sync(kFull, e, o);
+                if constexpr (NV == 16) {
+                    const float val = lane < 16 ? v[0] : e;
+                    const int col = lane < 16 ? lane : 31 + (lane & 1);
+                    if (lane < 18 && val != 0.f) atomicAdd(row + col, val);
+                } else {
+                    if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + lane, v[0]);
+                    if (lane < 2 && e != 0.f) atomicAdd(row + 31 + lane, e);
+                }
+            }
+        }
+        __syncthreads();   // every warp is done with buffer c&1
+    }
+}
+
 struct RecFwdArgs {
     int C, W, H, gx, K;
     const float *rec; const int *idx_sorted; const int2 *tile_range; float bgA, bgB, bgC;
@@ -432,8 +636,31 @@ void launch_rec_bwd(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
     spv::timer_mark(1, 1, s);
 }
 
+template <int CH, int CG, int R>
+void launch_rec_bwd_wide(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
+    constexpr int DS = ((CH + 4) / 4) % 2 ? CH + 4 : CH + 8;
+    constexpr size_t dyn = sizeof(float) * (2 * kChunkW * kRec + kBlock * DS);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(blend_rec_bwd_wide_kernel<CH, CG, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        configured = true;
+    }
+    spv::timer_mark(1, 0, s);
+    blend_rec_bwd_wide_kernel<CH, CG, R><<<ntiles, kBlock / R, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA,
+                                                                         a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
+    spv::timer_mark(1, 1, s);
+}
+
 template <int CH>
 void dispatch_rec_bwd(const RecBwdArgs &a, int n_grad, int ntiles, cudaStream_t s) {
+    // experimental wide footprints: only the two configurations of the video trainer's frame (CH = 24, 8 or 14 gradient channels)
+    if constexpr (CH == 24) {
+        const int wide = spv::get_option("bwd_wide");
+        if (wide == 2 || wide == 4) {
+            if (n_grad > 4 && n_grad <= 8) { if (wide == 2) launch_rec_bwd_wide<24, 8, 2>(a, ntiles, s); else launch_rec_bwd_wide<24, 8, 4>(a, ntiles, s); return; }
+            if (n_grad > 8 && n_grad <= 14) { if (wide == 2) launch_rec_bwd_wide<24, 14, 2>(a, ntiles, s); else launch_rec_bwd_wide<24, 14, 4>(a, ntiles, s); return; }
+        }
+    }
     // feature-gradient channels reduced: 4 (rgb + depth only), 8, 14, or all CH
     if (n_grad <= 4) launch_rec_bwd<CH, 4>(a, ntiles, s);
     else if (n_grad <= 8 && CH >= 8) launch_rec_bwd<CH, (CH >= 8 ? 8 : CH)>(a, ntiles, s);

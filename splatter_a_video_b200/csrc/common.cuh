@@ -12,6 +12,7 @@ namespace spv {
 // Error plumbing: every extern "C" entry returns this after its launches.
 void set_error(cudaError_t e, const char *where);
 void timer_mark(int slot, int edge, cudaStream_t s);  // no-op unless spv_kernel_timer_enable(1)
+int get_option(const char *name);  // runtime switches of experimental kernel variants (runtime.cu); 0 = validated default
 void count_launches(int n);  // bookkeeping for spv_launch_count(): kernels this library has launched
 inline int check_launch(const char *where, int launches = 1) {
     count_launches(launches);

@@ -3,6 +3,8 @@
 #include "../../include/spv_b200.h"
 
 #include <atomic>
+#include <stdlib.h>
+#include <string.h>
 
 namespace spv {
 static thread_local char g_err[512] = "";
@@ -24,9 +26,33 @@ void timer_mark(int slot, int edge, cudaStream_t s) {
     cudaEventRecordWithFlags(g_timer_ev[slot][edge], s,
                              st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
+
+// Small runtime switches for experimental kernel variants (default 0 = the validated path).  First read falls back to the
+// environment variable SPV_<NAME> so a run can be switched without code changes.
+static std::atomic<int> g_opt_bwd_wide{-1};
+int get_option(const char *name) {
+    if (strcmp(name, "bwd_wide") == 0) {
+        int v = g_opt_bwd_wide.load(std::memory_order_relaxed);
+        if (v < 0) {
+            const char *e = getenv("SPV_BWD_WIDE");
+            v = e ? atoi(e) : 0;
+            g_opt_bwd_wide.store(v, std::memory_order_relaxed);
+        }
+        return v;
+    }
+    return 0;
+}
+int set_option(const char *name, int value) {
+    if (strcmp(name, "bwd_wide") == 0) { g_opt_bwd_wide.store(value, std::memory_order_relaxed); return 0; }
+    return 1;
+}
 }  // namespace spv
 
 extern "C" {
+int spv_set_option(const char *name, int value) {
+    if (!name || spv::set_option(name, value)) { spv::set_error(cudaErrorInvalidValue, "spv_set_option: unknown option"); return (int)cudaErrorInvalidValue; }
+    return 0;
+}
 int spv_kernel_timer_enable(int on) {
     if (on && !spv::g_timer_made) {
         for (int i = 0; i < 2; ++i)

@@ -382,3 +382,41 @@ def test_frame_backward_twice_and_gradient_free_images(cuda):
             assert float(b.abs().max()) == 0.0 and float(a.abs().max()) == 0.0
         else:
             Hh.assert_grad_close(n(b), n(a), f"pruned d/d{name}", norm_tol=2e-6)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SPV_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental kernel variant, not yet validated on a GPU: opt in with SPV_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("wide", [2, 4])
+@pytest.mark.parametrize("track_grad", [False, True])          # 8 / 11 feature-gradient channels: the 16 and 16+8 networks
+def test_experimental_wide_backward_equals_default(cuda, wide, track_grad):
+    """spv_set_option("bwd_wide", 2|4): R pixels per lane in the frame path's backward blend kernel (blend_rec_bwd_wide_kernel).
+    Same gradients as the default kernel up to the association of the per-Gaussian sums."""
+    from splatter_a_video_b200 import _lib as L
+    from splatter_a_video_b200.gs.frame import render_ortho_frame
+    sc = synth.make_scene(40_000, 4, 333, 250, seed=12)
+    W, H, P = sc.W, sc.H, sc.P
+    g = torch.Generator().manual_seed(6)
+    gimg = [torch.randn(c, H, W, generator=g).to(cuda) for c in (3, 1, 3, 1, 12, 3)]
+    names = ("position", "scaling", "rotation", "opacity", "shs", "track", "mask", "dino")
+
+    def run():
+        d = {"position": sc.frame_position(0), "scaling": sc.scaling, "rotation": sc.rotation, "opacity": sc.opacity, "shs": sc.shs,
+             "track": sc.frame_position(1), "mask": sc.attrs["mask_attribute"], "poly": sc.attrs["pos_poly_feat"],
+             "dino": sc.attrs["dino_attribute"]}
+        L_ = {k: v.to(cuda).clone().requires_grad_(k != "poly" and (k != "track" or track_grad)) for k, v in d.items()}
+        imgs, _, _, status = render_ortho_frame(L_["position"], L_["scaling"], L_["rotation"], L_["opacity"], L_["shs"],
+                                                [L_["track"], L_["mask"], L_["poly"], L_["dino"]], sc.extr.to(cuda), W, H, 20, 0.0, 8 * P,
+                                                ndc=torch.zeros(P, 2, device=cuda, requires_grad=True),
+                                                abs_ndc=torch.zeros(P, 2, device=cuda, requires_grad=True))
+        assert int(status.cpu()[1]) == 0
+        torch.autograd.backward(imgs, gimg)
+        return {k: L_[k].grad for k in names if L_[k].requires_grad}
+
+    ref = run()
+    try:
+        L.set_option("bwd_wide", wide)
+        got = run()
+    finally:
+        L.set_option("bwd_wide", 0)
+    for k in ref:
+        Hh.assert_grad_close(n(got[k]), n(ref[k]), f"bwd_wide={wide} d/d{k}", norm_tol=2e-5)
