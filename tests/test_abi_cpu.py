@@ -86,3 +86,11 @@ def test_ctypes_signatures_have_the_header_arity():
         params = m.group(1).strip()
         n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
         assert n == len(args), f"{name}: header declares {n} parameters, ctypes binds {len(args)}"
+
+
+def test_runtime_options_default_to_the_validated_kernels(lib_path):
+    """spv_set_option is host-only state: known names are accepted, unknown ones rejected with an error message."""
+    from splatter_a_video_b200 import _lib
+    lib = _lib.load()
+    assert lib.spv_set_option(b"bwd_wide", 0) == 0
+    assert lib.spv_set_option(b"no_such_option", 1) != 0 and b"unknown option" in lib.spv_last_error()
