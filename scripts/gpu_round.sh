@@ -2,7 +2,7 @@
 # One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list + full captures of the blend kernels.
 # Every step has its own timeout so one stall cannot eat the visit.  Usage: bash scripts/gpu_round.sh [tag] [what...]
 TAG=${1:-r01}; shift
-WHAT=${@:-tests smoke bench ncu ref}
+WHAT=${@:-tests smoke bench ncu ref}   # also: benchstaged benchfull trace experimental multi2 multi4 multi8
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > gpurun_out/gpu_${TAG}.txt
 echo "host cores: $(nproc)" >> gpurun_out/gpu_${TAG}.txt
@@ -33,6 +33,21 @@ ncu)
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_rec_fwd -s 2 -c 2 -f -o gpurun_out/prof_fwd_${TAG} \
       python bench.py --steps 2 --warmup 1 --profile-mode > gpurun_out/ncu_fwd_${TAG}.log 2>&1
   tail -3 gpurun_out/ncu_bwd_${TAG}.log ;;
+multi[248])
+  N=${w#multi}   # needs gpurun --gpus N
+  T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port"
+  timeout 200 $T 29533 scripts/check_exchange_multi.py 2>&1 | grep -E "step|ok|rror" | tail -5
+  timeout 300 $T 29517 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${N}gpu_${TAG}.json 2> gpurun_out/bench_${N}gpu_${TAG}.err
+  grep "train (res" gpurun_out/bench_${N}gpu_${TAG}.err | tail -1
+  timeout 300 $T 29518 bench.py --gpus $N --steps 10 --warmup 3 --trace gpurun_out/trace_${N}gpu_${TAG}.json 2>&1 | grep "us x" | head -14 ;;
+experimental)
+  # default-off kernel variants: parity first, then the in-step backward time with each variant
+  SPV_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_frame_gpu.py -m gpu -q -p no:cacheprovider -k wide --tb=short 2>&1 | tail -5
+  for v in 0 2 4; do
+    SPV_BWD_WIDE=$v timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_wide${v}_${TAG}.err | python -c "import sys, json; d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bwd_wide=$v', round(d['value'], 1), 'it/s', d['kernels_in_step_ms'])"
+  done ;;
+trace)
+  timeout 200 python bench.py --steps 10 --warmup 3 --trace gpurun_out/trace_1gpu_${TAG}.json 2>&1 | grep "us x" | head -30 ;;
 esac
 done
 ls -la gpurun_out | tail -25
