@@ -231,3 +231,49 @@ def test_loss_oracle_track_matches_reference_golden():
     ref = G["track_grad"]
     assert np.abs(grad.numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
     assert np.count_nonzero(grad.numpy()[2]) == 0                  # the track's depth channel is not part of the loss
+
+
+# ---- densification oracle pinned to the reference's own code (tests/golden/make_densify_golden.py) -------------------------
+def _densify_golden():
+    import numpy as np
+    return np.load(os.path.join(Hh.GOLDEN, "golden_densify.npz"))
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_densify_oracle_matches_reference_golden(case):
+    """oracle/densify_ref.py against outputs of the reference's update_structure / densification / prune code, executed on the
+    CPU with a real torch.optim.Adam (golden_densify.npz): population order, parameters, both Adam moments, statistics."""
+    from oracle import densify_ref as R
+    G = _densify_golden()
+    pre = f"c{case}_"
+    duplicate, prune = (bool(x) for x in G[pre + "flags"])
+    names = ["position", "node", "scaling", "rotation", "opacity", "shs"]
+    attrs = {k: torch.from_numpy(G[pre + "in_" + k]) for k in names}
+    moments = {k: (torch.from_numpy(G[pre + "in_m_" + k]), torch.from_numpy(G[pre + "in_v_" + k])) for k in names}
+    P = attrs["position"].shape[0]
+    state = {"grad_accum": torch.zeros(P), "denom": torch.zeros(P), "max_radii": torch.zeros(P)}
+    for i in range(3):
+        R.update_stats(state, torch.from_numpy(G[pre + f"vg{i}"]), torch.from_numpy(G[pre + f"radii{i}"]), torch.from_numpy(G[pre + f"vis{i}"]))
+    assert torch.allclose(state["grad_accum"], torch.from_numpy(G[pre + "state_accum"]).reshape(-1), rtol=1e-6, atol=0)
+    assert torch.equal(state["denom"], torch.from_numpy(G[pre + "state_denom"]).reshape(-1))
+    assert torch.equal(state["max_radii"], torch.from_numpy(G[pre + "state_maxr"]))
+    cfg = dict(split_num=2, grad_threshold=0.0002, percent_dense=0.01, extent=1.0, min_opacity=0.005, size_threshold=20.0)
+    samples = torch.from_numpy(G[pre + "samples"]) if G[pre + "samples"].shape[0] else None
+    a, m, s = R.densification(attrs, moments, state, cfg, duplicate, prune, samples)
+    for k in names:
+        want = torch.from_numpy(G[pre + "out_" + k])
+        assert a[k].shape == want.shape, k
+        assert torch.allclose(a[k], want, rtol=1e-6, atol=1e-7), k
+        assert torch.equal(m[k][0], torch.from_numpy(G[pre + "out_m_" + k])) and torch.equal(m[k][1], torch.from_numpy(G[pre + "out_v_" + k])), k
+    assert torch.allclose(s["grad_accum"], torch.from_numpy(G[pre + "out_accum"]).reshape(-1), rtol=1e-6, atol=0)
+    assert torch.equal(s["denom"], torch.from_numpy(G[pre + "out_denom"]).reshape(-1))
+    assert torch.equal(s["max_radii"], torch.from_numpy(G[pre + "out_maxr"]))
+
+
+def test_reset_opacity_oracle_matches_reference_golden():
+    from oracle import densify_ref as R
+    G = _densify_golden()
+    op = torch.from_numpy(G["ro_in_opacity"])
+    a, m = R.reset_opacity({"opacity": op.clone()}, {"opacity": (torch.ones_like(op), torch.ones_like(op))})
+    assert torch.allclose(a["opacity"], torch.from_numpy(G["ro_out_opacity"]), rtol=1e-6, atol=1e-7)
+    assert float(m["opacity"][0].abs().max()) == 0 and float(G["ro_out_m"].__abs__().max()) == 0 and float(G["ro_out_v"].__abs__().max()) == 0
