@@ -277,3 +277,31 @@ def test_reset_opacity_oracle_matches_reference_golden():
     a, m = R.reset_opacity({"opacity": op.clone()}, {"opacity": (torch.ones_like(op), torch.ones_like(op))})
     assert torch.allclose(a["opacity"], torch.from_numpy(G["ro_out_opacity"]), rtol=1e-6, atol=1e-7)
     assert float(m["opacity"][0].abs().max()) == 0 and float(G["ro_out_m"].__abs__().max()) == 0 and float(G["ro_out_v"].__abs__().max()) == 0
+
+
+# ---- ortho geometry oracle pinned to the reference's own torch code (tests/golden/make_ortho_golden.py) --------------------
+@pytest.mark.parametrize("case", ["identity", "rotated"])
+def test_ortho_geometry_oracle_matches_reference_golden(case):
+    """C oracle project_point_ortho / ewa_project_ortho against outputs of DPTROrthoEnhancedRender.project_point and
+    ewa_project_torch_impl (dptr_ortho_enhanced.py:17-111,145-202) executed on the CPU (golden_ortho.npz).  "identity" is the
+    trainer's fixed camera: everything bit-exact.  "rotated": the reference multiplies by the extrinsics with a BLAS matmul, so
+    continuous outputs agree to rounding and the discrete ones may flip only where a value sits on a boundary."""
+    G = np.load(os.path.join(Hh.GOLDEN, "golden_ortho.npz"))
+    xyz, extr, cov3d = G[f"{case}_xyz"], G[f"{case}_extr"], G[f"{case}_cov3d"]
+    W, H = (int(v) for v in G[f"{case}_WH"])
+    uv, depth = O.project_point_ortho(xyz, extr, W, H, nearest=0.01)
+    g_uv, g_depth = G[f"{case}_uv"], G[f"{case}_depth"]
+    culled = g_depth.reshape(-1) == 0
+    assert np.array_equal(depth.reshape(-1) == 0, culled)                 # same points culled (near plane, extent)
+    assert culled.sum() > 0
+    vis = ~culled
+    conic, radius, tiles = O.ewa_project_ortho(cov3d, extr, uv, W, H, vis)
+    if case == "identity":
+        assert np.array_equal(uv, g_uv) and np.array_equal(depth, g_depth)
+        assert np.array_equal(radius, G[f"{case}_radius"]) and np.array_equal(tiles, G[f"{case}_tiles"])
+        np.testing.assert_allclose(conic, G[f"{case}_conic"], rtol=2e-6, atol=0)
+    else:
+        np.testing.assert_allclose(uv, g_uv, rtol=0, atol=2e-4)
+        np.testing.assert_allclose(depth, g_depth, rtol=2e-6, atol=0)
+        np.testing.assert_allclose(conic, G[f"{case}_conic"], rtol=1e-4, atol=1e-7)
+        assert (radius != G[f"{case}_radius"]).mean() <= 2e-3 and (tiles != G[f"{case}_tiles"]).mean() <= 2e-3
