@@ -305,3 +305,30 @@ def test_ortho_geometry_oracle_matches_reference_golden(case):
         np.testing.assert_allclose(depth, g_depth, rtol=2e-6, atol=0)
         np.testing.assert_allclose(conic, G[f"{case}_conic"], rtol=1e-4, atol=1e-7)
         assert (radius != G[f"{case}_radius"]).mean() <= 2e-3 and (tiles != G[f"{case}_tiles"]).mean() <= 2e-3
+
+
+# ---- deformation host logic + evaluation formulas pinned to the reference's own code (tests/golden/make_deform_golden.py) --
+@pytest.mark.parametrize("F", [50, 80, 7])
+def test_deformation_host_logic_matches_reference_golden(F):
+    """gs.frame.spline_interval (the interval index / in-interval distance the CUDA op receives as device scalars) and
+    gs.frame.rotation_basis, combined with the evaluation formulas tests/test_frame_gpu.py holds the kernels to, must
+    reproduce get_position(t) / get_rotation(t) of dynamic_gaussian_with_base_point_cloud.py for EVERY frame of the clip
+    (golden_deform.npz, produced by executing the reference's own method bodies)."""
+    import math
+    from splatter_a_video_b200.gs.frame import rotation_basis, spline_interval
+    G = np.load(os.path.join(Hh.GOLDEN, "golden_deform.npz"))
+    pre = f"F{F}_"
+    NI = math.ceil(F / 5)
+    base, node = torch.from_numpy(G[pre + "position"]), torch.from_numpy(G[pre + "node"])
+    coeff = node.reshape(-1, 4, NI, 3)
+    rot, poly, four = (torch.from_numpy(G[pre + k]) for k in ("rotation", "rot_poly", "rot_fourier"))
+    for t in range(F):
+        idx, dist = spline_interval(t, F, NI)
+        assert 0 <= idx < NI
+        d = torch.tensor(dist, dtype=torch.float32)
+        pos = coeff[:, 3, idx] + coeff[:, 2, idx] * d + coeff[:, 1, idx] * d ** 2 + coeff[:, 0, idx] * d ** 3 + base
+        np.testing.assert_allclose(pos.numpy(), G[pre + "pos_t"][t], rtol=0, atol=2e-6, err_msg=f"frame {t}")
+        b = rotation_basis(t, 0, F - 1)
+        q = rot + (poly * b[None, :4, None]).sum(1) + (four * b[None, 4:, None]).sum(1)
+        q = q / q.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        np.testing.assert_allclose(q.numpy(), G[pre + "rot_t"][t], rtol=0, atol=2e-6, err_msg=f"frame {t}")
