@@ -10,6 +10,7 @@ import torch
 import helpers as Hh
 from helpers import O
 from oracle import torch_ref as TR
+from splatter_a_video_b200 import synth
 
 
 @pytest.fixture(scope="module")
@@ -332,3 +333,28 @@ def test_deformation_host_logic_matches_reference_golden(F):
         q = rot + (poly * b[None, :4, None]).sum(1) + (four * b[None, 4:, None]).sum(1)
         q = q / q.norm(dim=1, keepdim=True).clamp_min(1e-12)
         np.testing.assert_allclose(q.numpy(), G[pre + "rot_t"][t], rtol=0, atol=2e-6, err_msg=f"frame {t}")
+
+
+# ---- renderer orchestration pinned to the reference's own render_batch (tests/golden/make_render_golden.py) -----------------
+def test_renderer_orchestration_matches_reference_golden():
+    """oracle/torch_ref.render_ortho_frame -- the restatement tests/test_renderer_gpu.py holds the renderer plugin to -- against
+    the output dict of the reference's own DPTROrthoEnhancedRender.render_batch executed on the CPU (golden_render.npz): same
+    images for rgb (bg 0), depth (bg 1) and every attribute in RenderFeatures order (bg 0), same first-K ids, radii, visibility,
+    same dict layout ([1,C,H,W], [1,H,W,K], one viewspace tensor of [P,2])."""
+    G = np.load(os.path.join(Hh.GOLDEN, "golden_render.npz"))
+    sc = synth.make_config("cfg1_tiny")
+    W, H = sc.W, sc.H
+    attrs = torch.cat([sc.frame_position(1), sc.attrs["mask_attribute"], sc.attrs["pos_poly_feat"], sc.attrs["dino_attribute"]], 1)
+    with torch.no_grad():
+        r = TR.render_ortho_frame(sc.frame_position(0), sc.scaling, sc.rotation, sc.opacity, sc.shs, attrs, sc.extr, W, H, K=20)
+    f = O.alpha_blending_forward(r["uv"].numpy(), r["conic"].numpy(), sc.opacity.numpy(), r["colors"].numpy(), r["idx_sorted"].numpy(),
+                                 r["tile_range"].numpy(), 0.0, W, H, K=20, frag_eps=Hh.FRAG_EPS)
+    frag = f["fragile"]
+    assert G["rgb"].shape == (1, 3, H, W) and G["gs_idx"].shape == (1, H, W, 20) and int(G["n_viewspace"]) == 1
+    assert tuple(G["viewspace_shape"]) == (sc.P, 2)
+    Hh.assert_pixels_close(r["rgb"].numpy(), G["rgb"][0], frag, "rgb")
+    Hh.assert_pixels_close(r["depth"].numpy(), G["depth"][0], frag, "depth")
+    want_attr = np.concatenate([G[k][0] for k in ("track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute")], 0)
+    Hh.assert_pixels_close(r["attrs"].numpy(), want_attr, frag, "attrs")
+    assert np.array_equal(r["gs_idx"].numpy()[~frag], G["gs_idx"][0][~frag])
+    assert np.array_equal(r["radius"].numpy(), G["radii"]) and np.array_equal((r["radius"] > 0).numpy(), G["visibility"])
