@@ -401,7 +401,7 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
 // 41 % of blend_rec_bwd_kernel's instructions are its per-(warp, entry) shuffle reductions (profiles/r01_ncu_blend_rec_bwd_lines.txt),
 // one per ACTIVE (8x4-pixel block, entry) pair: 1.283 M on the config-A frame.  With R pixels per lane a warp covers R of those blocks
 // (R = 2: 16x4, R = 4: 16x8 pixels), accumulates the partials of its R sub-blocks in registers and reduces ONCE per entry:
-// 0.890 M / 0.605 M reductions (scripts/hit_stats.py).  CTA = 256 / R threads per tile; the per-pixel constants (T_final, <bg, dL_dpixel>)
+// 0.890 M / 0.605 M reductions (tests/hit_stats.py).  CTA = 256 / R threads per tile; the per-pixel constants (T_final, <bg, dL_dpixel>)
 // move into the spare slots of the pixel's dL_dpixel row in shared memory; chunks shrink to 32 entries so 5 tiles stay resident per SM.
 // Same arithmetic per (pixel, entry) as blend_rec_bwd_kernel; only the association of the per-Gaussian sums changes.
 // NOT YET VALIDATED ON A GPU (written after the round's GPU budget was spent): default off, tests opt-in (SPV_TEST_EXPERIMENTAL=1).

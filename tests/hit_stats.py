@@ -1,6 +1,6 @@
 """Applied (pixel, Gaussian) pairs and active (pixel-block, entry) pairs per warp footprint for one frame of config A, counted on
 the CPU from the oracle's tile lists (numpy; ~10 s).  Used for the instruction budgets in DESIGN.md sections 3 and 8.
-    python scripts/hit_stats.py"""
+    python tests/hit_stats.py      (lives under tests/ because it uses the oracle, which only test infrastructure may import)"""
 import os
 import sys
 import time
