@@ -1,7 +1,8 @@
 """CPU: the reference's on-disk formats -- `model_*.pth` checkpoint layout and PLY attribute naming -- through
 splatter_a_video_b200.formats.  The expected layouts are written out literally here from the reference sources
 (trainer_fragGS.py:927-950, frag_model.py:345-353, base_model.py:178-188, points.py:397-465); the reference's Python stack
-(omegaconf, plyfile) is not installable in this environment, so these are layout tests, not cross-reads ("parity unpinned")."""
+(omegaconf, plyfile) is not installable in this environment, so the checkpoint tests are layout tests ("parity unpinned"); the PLY
+property naming / ordering / flattening is pinned to the reference's own save_ply / load_ply code (golden_ply.npz)."""
 import os
 import struct
 
@@ -133,3 +134,25 @@ def test_state_from_scene_inverts_the_activations():
     rd = st.render_dict(0, 10, fused=False)
     assert torch.allclose(rd["scaling"], scaling, rtol=1e-5) and torch.allclose(rd["opacity"], opacity, atol=1e-6) and torch.allclose(rd["shs"], shs)
     assert torch.allclose(rd["rotation"], rot, atol=1e-6) and rd["track_like"].shape == (n, 2) and st.interval_num == 2
+
+
+def test_ply_matches_what_the_reference_code_writes_and_reads(tmp_path):
+    """tests/golden/golden_ply.npz holds (a) the structured vertex array the reference's own save_ply / list_of_attributes
+    (points.py:397-435) hand to plyfile for a population, (b) what the reference's own load_ply (:437-465) reconstructed from a file
+    written by formats.save_ply (tests/golden/make_ply_golden.py executes those method bodies).  The product must write exactly
+    (a) -- names, order, values -- and (b) must be the population itself."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ply.npz"))
+    names = [str(x) for x in G["names"]]
+    attr = [k[3:] for k in G.files if k.startswith("in_") and k != "in_position"]
+    tensors = {"position": torch.from_numpy(G["in_position"])}
+    tensors.update({k: torch.from_numpy(G["in_" + k]) for k in attr})
+    st = F.AtlasState(tensors, attr)
+    assert F.ply_property_names(st) == names
+    path = str(tmp_path / "pc.ply")
+    F.save_ply(path, st)
+    cols = F.read_ply_vertices(path)
+    assert list(cols) == names
+    got = np.stack([cols[n] for n in names], 1)
+    assert got.dtype == np.float32 and np.array_equal(got, G["table"])
+    for k in ["position"] + attr:
+        assert np.array_equal(G["loaded_" + k], G["in_" + k]), k
