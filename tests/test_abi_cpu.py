@@ -94,3 +94,44 @@ def test_runtime_options_default_to_the_validated_kernels(lib_path):
     lib = _lib.load()
     assert lib.spv_set_option(b"bwd_wide", 0) == 0
     assert lib.spv_set_option(b"no_such_option", 1) != 0 and b"unknown option" in lib.spv_last_error()
+
+
+def test_operator_surface_has_the_reference_signatures():
+    """Boundary B1: `import dptr.gs as gs` must offer the reference's functions with the same positional parameters (count and
+    order; a reference keyword name must be accepted too) and the same defaults -- tests/golden/golden_gs_signatures.json is read
+    from the reference's sources (src/submodules/dptr/dptr/gs/*.py) by tests/golden/make_signature_golden.py."""
+    import inspect
+    import json
+    import dptr.gs as gs
+    G = json.load(open(os.path.join(Hh.ROOT, "tests", "golden", "golden_gs_signatures.json")))
+    for name, ref in G["gs"].items():
+        fn = getattr(gs, name, None)
+        assert callable(fn), f"dptr.gs.{name} is missing ({ref['file']}:{ref['line']})"
+        params = [p for p in inspect.signature(fn).parameters.values() if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+        assert len(params) >= len(ref["params"]), f"{name}: takes {len(params)} positional parameters, the reference {len(ref['params'])}"
+        for i, (rname, rdef, has) in enumerate(zip(ref["params"], ref["defaults"], ref["has_default"])):
+            p = params[i]
+            assert p.name == rname, f"{name}: parameter {i} is `{p.name}`, the reference calls it `{rname}`"
+            if has:
+                assert p.default is not inspect.Parameter.empty and p.default == rdef, f"{name}.{rname}: default {p.default!r} != {rdef!r}"
+            else:
+                assert p.default is inspect.Parameter.empty, f"{name}.{rname} is required in the reference"
+        for p in params[len(ref["params"]):]:
+            assert p.default is not inspect.Parameter.empty, f"{name}: extra parameter `{p.name}` must be optional"
+
+
+def test_renderer_plugin_has_the_reference_methods():
+    import inspect
+    import json
+    from splatter_a_video_b200.renderer import DPTROrthoEnhancedRender
+    G = json.load(open(os.path.join(Hh.ROOT, "tests", "golden", "golden_gs_signatures.json")))
+    for name, ref in G["renderer"].items():
+        fn = getattr(DPTROrthoEnhancedRender, name, None)
+        assert callable(fn), f"DPTROrthoEnhancedRender.{name} is missing (dptr_ortho_enhanced.py:{ref['line']})"
+        params = list(inspect.signature(fn).parameters.values())
+        names = [p.name for p in params if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+        if name == "render_iter":            # called as render_iter(**batch): every reference keyword must be accepted
+            accepts_kw = any(p.kind == p.VAR_KEYWORD for p in params)
+            assert all(r in names or accepts_kw for r in ref["params"]), (names, ref["params"])
+        else:
+            assert names[:len(ref["params"])] == ref["params"], f"{name}: {names} vs reference {ref['params']}"
