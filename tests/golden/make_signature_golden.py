@@ -26,7 +26,7 @@ def sig(fn):
 
 
 def main():
-    out = {"gs": {}, "renderer": {}}
+    out = {"gs": {}, "renderer": {}, "b2": {}}
     for path in sorted(glob.glob(os.path.join(GS, "*.py"))):
         for node in ast.parse(open(path).read()).body:
             if isinstance(node, ast.FunctionDef) and node.name in PUBLIC:
@@ -38,6 +38,17 @@ def main():
         if isinstance(fn, ast.FunctionDef) and fn.name in ("project_point", "render_iter", "render_batch", "update_sh_degree", "load_state_dict",
                                                            "state_dict"):
             out["renderer"][fn.name] = dict(sig(fn), line=fn.lineno)
+    # boundary B2: the keywords the one call site passes (src/pointrix/renderer/base_splatting.py:122-174)
+    b2 = {}
+    for node in ast.walk(ast.parse(open("/root/reference/src/pointrix/renderer/base_splatting.py").read())):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name):
+            if node.func.id == "GaussianRasterizationSettings":
+                b2["settings_kwargs"], b2["settings_line"] = [k.arg for k in node.keywords], node.lineno
+            elif node.func.id == "GaussianRasterizer":
+                b2["rasterizer_ctor_kwargs"] = [k.arg for k in node.keywords]
+            elif node.func.id == "rasterizer":
+                b2["call_kwargs"], b2["call_line"] = [k.arg for k in node.keywords], node.lineno
+    out["b2"] = b2
     json.dump(out, open(os.path.join(HERE, "golden_gs_signatures.json"), "w"), indent=1)
     for k, v in out["gs"].items():
         print(k, v["params"], [d for d, h in zip(v["defaults"], v["has_default"]) if h])

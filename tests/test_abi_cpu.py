@@ -135,3 +135,15 @@ def test_renderer_plugin_has_the_reference_methods():
             assert all(r in names or accepts_kw for r in ref["params"]), (names, ref["params"])
         else:
             assert names[:len(ref["params"])] == ref["params"], f"{name}: {names} vs reference {ref['params']}"
+
+
+def test_b2_shim_accepts_the_reference_call_site_keywords():
+    """Boundary B2: every keyword src/pointrix/renderer/base_splatting.py:122-174 passes to GaussianRasterizationSettings,
+    GaussianRasterizer and the rasterizer call must be accepted by the shim (golden_gs_signatures.json["b2"])."""
+    import inspect
+    import json
+    import diff_gaussian_rasterization as D
+    b2 = json.load(open(os.path.join(Hh.ROOT, "tests", "golden", "golden_gs_signatures.json")))["b2"]
+    assert set(b2["settings_kwargs"]) <= set(D.GaussianRasterizationSettings._fields)
+    assert set(b2["rasterizer_ctor_kwargs"]) <= set(inspect.signature(D.GaussianRasterizer.__init__).parameters)
+    assert set(b2["call_kwargs"]) <= set(inspect.signature(D.GaussianRasterizer.forward).parameters)
