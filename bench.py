@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--staged", action="store_true", help="alias of --mode staged")
     ap.add_argument("--no-graph", action="store_true", help="frame mode without CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="development: only the resident train step + in-step blend kernel times (not a bench line)")
     ap.add_argument("--exchange-coefficients", action="store_true",
                     help="N>1: exchange SH / spline COEFFICIENT gradients (24+24 floats/Gaussian) instead of deferring the linear tails")
     ap.add_argument("--no-flush", action="store_true")
@@ -654,6 +655,16 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms, per_step = time_steps(train_step, args.steps, args.warmup, flush, world, rank, frames_of)
     log(f"train (resident): {total_ms / args.steps:.3f} ms/step (per step min {min(per_step):.3f} / median {float(np.median(per_step)):.3f} / max {max(per_step):.3f})")
+    if args.quick:
+        live = live_kernel_times(wl, args.steps, args.warmup, flush, frames_of) if wl.mode == "frame" else None
+        if sampler:
+            sampler.stop()
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": world * args.steps / (total_ms * 1e-3), "ms_per_step": total_ms / args.steps,
+                              "median_ms": float(np.median(per_step)), "kernels_in_step_ms": live, "capacity_overflow": wl.overflowed()}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_ms, _ = time_steps(train_step_e2e, args.steps, args.warmup, flush, world, rank, frames_of)
     log(f"train (e2e): {e2e_ms / args.steps:.3f} ms/step")
     # the same step followed by the fused Adam update of every trainable tensor ("full train loop" of BASELINE configs[1])

@@ -142,9 +142,21 @@ def query(name: str, *args) -> int:
 
 def need_cuda(*tensors):
     """Same contract as the reference's CHECK_INPUT (include/utils.h:9-10): inputs must be CUDA tensors."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("splatter_a_video_b200: all tensors must be CUDA tensors (no CPU path)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"splatter_a_video_b200: tensors on different devices ({dev} and {t.device})")
+    # the library launches on the CURRENT device and torch's current stream: refuse a mismatch loudly instead of launching
+    # kernels of cuda:0 on pointers of cuda:1
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(f"splatter_a_video_b200: tensors live on {dev} but the current device is cuda:{torch.cuda.current_device()}; "
+                           f"wrap the call in `with torch.cuda.device({dev.index}):`")
 
 
 def f32c(t):

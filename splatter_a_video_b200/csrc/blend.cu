@@ -141,24 +141,6 @@ blend_fwd_kernel(int C, int Cstride, int c0, int W, int H, int gx, int K, int tr
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// ---- 3xTF32 tensor-core helper (mma.sync m16n8k8): fp32-accurate small GEMM for the feature gradients ----------
-// dL_dfeature[j][c] = sum_px w[j][px] * dL_dpixel[px][c] is a genuine contraction (32 Gaussians x 32 pixels x CH
-// channels per warp and chunk).  Each operand is split x = hi + lo with hi, lo representable in TF32 and the product is
-// accumulated as hi*hi + lo*hi + hi*lo in fp32, which keeps ~21 mantissa bits (plain TF32 would not meet the 1e-3
-// gradient tolerance).  Fragment layouts follow the PTX ISA for mma.m16n8k8 .tf32 (g = lane>>2, t = lane&3):
-//   A[16x8] row: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);  B[8x8] col: b0=(k=t,n=g) b1=(k=t+4,n=g);
-//   C[16x8]: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1).
-__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
 // Packed gradient row layouts.
 //  plain / bias (row = NV floats): 0,1 dL_duv  2,3 dL_dabs_uv  4,5,6 dL_dconic  7 dL_dopacity  8.. dL_dfeature  NV-1 dL_dbias
 //    NV = 16 (C <= 8), 32 (C <= 24) or 64 (C <= 32).  One launch covers up to 32 channels -- the reference's channel
@@ -434,263 +416,6 @@ blend_bwd_kernel(int C, int Cstride, int c0, int W, int H, int gx,
     }
 }
 
-// ------------------------------------------------------------------------------------------------ backward, 9..24 channels
-// Same traversal as blend_bwd_kernel, but the C feature-gradient sums no longer go through the shuffle network:
-// each lane parks its blend weight w = alpha*T in a per-warp [32 Gaussians x 32 pixels] shared tile and, once per chunk,
-// the warp multiplies that tile with its [32 pixels x CH] dL_dpixel tile on the tensor cores (3xTF32).  Only the 8-10
-// geometric sums (uv, |uv|, conic, opacity[, bias | RGB-pass uv]) still use the 16-wide halving network.
-// Per-warp parking row: [0,16) geometric sums, [16,16+CH) feature sums.
-template <int CH, int MODE>
-__global__ void __launch_bounds__(kBlock, 2)
-blend_bwd_mma_kernel(int C, int Cstride, int c0, int W, int H, int gx,
-                     const float2 *__restrict__ uv, const float *__restrict__ conic, const float *__restrict__ opacity,
-                     const float *__restrict__ feature, const float *__restrict__ bias,
-                     const int *__restrict__ idx_sorted, const int2 *__restrict__ tile_range, float bg, float bgB,
-                     float bgC, const float *__restrict__ final_T, const int *__restrict__ ncontrib,
-                     const spv::ChanPlanes planes, float *__restrict__ packed) {
-    constexpr bool HAS_BIAS = MODE == kBias;
-    constexpr bool GROUPS = MODE == kGroups;
-    static_assert(CH % 8 == 0 && CH <= 24, "MMA backward handles 8/16/24 padded channels");
-    constexpr int kG = 32;
-    constexpr int kRow = GROUPS ? kRowG : 32;   // packed row stride in global memory
-    constexpr int kSP = 16 + CH;                // parking row
-    constexpr int kWS = 36;                     // row stride of the weight tile (conflict-free A-fragment loads)
-    constexpr int NT = CH / 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *s_g0 = reinterpret_cast<float4 *>(smem_raw);
-    float4 *s_g1 = s_g0 + kG;
-    float4 *s_con = s_g1 + kG;
-    float *s_feat = reinterpret_cast<float *>(s_con + kG);      // [kG][CH]
-    float *s_part = s_feat + kG * CH;                            // [8][kG][kSP]
-    float *s_w = s_part + 8 * kG * kSP;                          // [8][kG][kWS]
-    float *s_d = s_w + 8 * kG * kWS;                             // [8][32 px][CH]
-    int *s_id = reinterpret_cast<int *>(s_d + 8 * 32 * CH);      // [kG]
-    int *s_maxp = s_id + kG;
-
-    const int tile = blockIdx.x;
-    const int tile_x = tile % gx, tile_y = tile / gx;
-    int px, py;
-    thread_pixel(tile_x, tile_y, px, py);
-    const bool inside = px < W && py < H;
-    const size_t pix = (size_t)W * py + px;
-    const float pxf = (float)px, pyf = (float)py;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g8 = lane >> 2, t4 = lane & 3;
-    float *my_part = s_part + warp * kG * kSP;
-    float *my_w = s_w + warp * kG * kWS;
-    float *my_d = s_d + warp * 32 * CH;
-
-    const int2 range = tile_range[tile];
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    const int last_contrib = inside ? ncontrib[pix] : 0;
-
-    float d[CH];
-    const size_t HW = (size_t)H * W;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        d[c] = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
-        my_d[lane * CH + c] = d[c];
-    }
-    float bgdA = 0.f, bgdB = 0.f, bgdC = 0.f;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        if (GROUPS && c >= 4) bgdC += d[c];
-        else if (GROUPS && c == 3) bgdB += d[c];
-        else bgdA += d[c];
-    }
-    bgdA *= bg; bgdB *= bgB; bgdC *= bgC;
-
-    if (threadIdx.x == 0) *s_maxp = 0;
-    __syncthreads();
-    const int wmax = __reduce_max_sync(kFull, last_contrib);
-    if (lane == 0 && wmax > 0) atomicMax(s_maxp, wmax);
-    __syncthreads();
-    const int n_eff = min(range.y - range.x, *s_maxp);
-
-    float last_alpha = 0.f, lfA = 0.f, lfB = 0.f, lfC = 0.f, SA = 0.f, SB = 0.f, SC = 0.f;
-
-    for (int p_hi = n_eff; p_hi > 0; p_hi -= kG) {
-        const int m = min(kG, p_hi);
-        __syncthreads();
-        if ((int)threadIdx.x < m) {
-            const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];
-            s_id[threadIdx.x] = id;
-            const float a = conic[3 * id], b = conic[3 * id + 1], c = conic[3 * id + 2];
-            float4 g0, g1;
-            stage_splat(uv[id], a, b, c, opacity[id], HAS_BIAS ? bias[id] : 0.f, g0, g1);
-            s_g0[threadIdx.x] = g0;
-            s_g1[threadIdx.x] = g1;
-            s_con[threadIdx.x] = make_float4(a, b, c, 0.f);
-        }
-        __syncthreads();
-        if (lane < CH) {  // padding channels (C <= c < CH) are zero-filled: they meet d[c] == 0 but must stay finite
-#pragma unroll
-            for (int jj = 0; jj < kG / 8; ++jj) {
-                const int j = warp * (kG / 8) + jj;
-                if (j < m) s_feat[j * CH + lane] = lane < C ? feature[(size_t)s_id[j] * Cstride + c0 + lane] : 0.f;
-            }
-        }
-        __syncthreads();
-
-        unsigned mask = 0;
-#pragma unroll 8
-        for (int j = 0; j < kG; ++j) {
-            const float4 g0 = s_g0[j];
-            const float4 g1 = s_g1[j];
-            float dx, dy;
-            const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-            const bool hit = splat_hits<HAS_BIAS>(p2, g1) && (p_hi - 1 - j) < last_contrib;
-            mask |= (hit ? 1u : 0u) << j;
-        }
-        if (m < 32) mask &= (1u << m) - 1u;
-        const unsigned wmask = __reduce_or_sync(kFull, mask);
-
-        for (int j = 0; j < kG; ++j) {          // all 32 rows of the weight tile are (re)written every chunk
-            if (!((wmask >> j) & 1u)) {
-                my_w[j * kWS + lane] = 0.f;
-                if (lane < 16) my_part[j * kSP + lane] = 0.f;
-                continue;
-            }
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-            float w = 0.f;
-            if ((mask >> j) & 1u) {
-                const float4 g0 = s_g0[j];
-                const float4 g1 = s_g1[j];
-                const float4 con = s_con[j];
-                float dx, dy, Gv;
-                const float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-                const float alpha = splat_alpha<HAS_BIAS>(p2, g1, Gv);
-                const float rinv = __fdividef(1.f, 1.f - alpha);
-                T = T * rinv;
-                w = alpha * T;
-                const float *fr = s_feat + j * CH;
-                const float tb = -T_final * rinv;
-                const float om = 1.f - last_alpha;
-                float da_all, da_op, da_ndc;
-                if (GROUPS) {
-                    float fdA = 0.f, fdC = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) fdA = fmaf(fr[c], d[c], fdA);
-                    const float fdB = fr[3] * d[3];
-#pragma unroll
-                    for (int c = 4; c < CH; ++c) fdC = fmaf(fr[c], d[c], fdC);
-                    SA = last_alpha * lfA + om * SA;
-                    SB = last_alpha * lfB + om * SB;
-                    SC = last_alpha * lfC + om * SC;
-                    lfA = fdA; lfB = fdB; lfC = fdC;
-                    da_ndc = (fdA - SA) * T + tb * bgdA;
-                    da_op = da_ndc + ((fdB - SB) * T + tb * bgdB);
-                    da_all = da_op + ((fdC - SC) * T + tb * bgdC);
-                } else {
-                    float fd = 0.f;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) fd = fmaf(fr[c], d[c], fd);
-                    SA = last_alpha * lfA + om * SA;
-                    lfA = fd;
-                    da_all = da_op = da_ndc = (fd - SA) * T + tb * bgdA;
-                }
-                last_alpha = alpha;
-                const float dL_dG = g1.z * da_all;
-                const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
-                const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
-                const float g0x = dL_dG * dGx, g0y = dL_dG * dGy;
-                v[0] = g0x; v[1] = g0y;
-                v[4] = -0.5f * Gv * dx * dx * dL_dG;
-                v[5] = -Gv * dx * dy * dL_dG;
-                v[6] = -0.5f * Gv * dy * dy * dL_dG;
-                v[7] = Gv * da_op;
-                if (GROUPS) {
-                    const float dL_dG_ndc = g1.z * da_ndc;
-                    const float n0 = dL_dG_ndc * dGx, n1 = dL_dG_ndc * dGy;
-                    v[2] = fabsf(n0); v[3] = fabsf(n1);
-                    v[8] = n0; v[9] = n1;
-                } else {
-                    v[2] = fabsf(g0x); v[3] = fabsf(g0y);
-                    if (HAS_BIAS) v[8] = da_all;
-                }
-            }
-            my_w[j * kWS + lane] = w;
-            halving_reduce<16, 0, 16>(v, lane);
-            if (lane < 16) my_part[j * kSP + lane] = v[0];
-        }
-        __syncwarp();
-        // feature gradients of this warp's 32 pixels: [32 x 32] weights x [32 x CH] dL_dpixel on the tensor cores
-        {
-            float acc[2][NT][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const float *wr = my_w + (mt * 16 + g8) * kWS + ks * 8 + t4;
-                    split_tf32(wr[0], ahi[mt][0], alo[mt][0]);
-                    split_tf32(wr[8 * kWS], ahi[mt][1], alo[mt][1]);
-                    split_tf32(wr[4], ahi[mt][2], alo[mt][2]);
-                    split_tf32(wr[8 * kWS + 4], ahi[mt][3], alo[mt][3]);
-                }
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    uint32_t bhi[2], blo[2];
-                    split_tf32(my_d[(ks * 8 + t4) * CH + nt * 8 + g8], bhi[0], blo[0]);
-                    split_tf32(my_d[(ks * 8 + t4 + 4) * CH + nt * 8 + g8], bhi[1], blo[1]);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        mma_tf32(acc[mt][nt], alo[mt], bhi);
-                        mma_tf32(acc[mt][nt], ahi[mt], blo);
-                        mma_tf32(acc[mt][nt], ahi[mt], bhi);
-                    }
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    float *r0 = my_part + (mt * 16 + g8) * kSP + 16 + nt * 8 + 2 * t4;
-                    r0[0] = acc[mt][nt][0]; r0[1] = acc[mt][nt][1];
-                    r0[8 * kSP] = acc[mt][nt][2]; r0[8 * kSP + 1] = acc[mt][nt][3];
-                }
-        }
-        __syncthreads();
-        // fold the 8 warps and push one packed row per (tile, Gaussian); packed column -> parking column
-#pragma unroll
-        for (int jj = 0; jj < kG / 8; ++jj) {
-            const int j = warp * (kG / 8) + jj;
-            if (j < m) {
-                float *row = packed + (size_t)s_id[j] * kRow;
-#pragma unroll
-                for (int half = 0; half < (kRow + 31) / 32; ++half) {
-                    const int col = half * 32 + lane;
-                    int src = -1;
-                    if (col < 8) src = col;
-                    else if (GROUPS) src = col < 31 ? (col - 8 < CH ? 16 + col - 8 : -1) : (col < 33 ? 8 + (col - 31) : -1);
-                    else if (HAS_BIAS && col == 31) src = 8;
-                    else if (col < 32) src = col - 8 < CH ? 16 + col - 8 : -1;
-                    if (src >= 0) {
-                        float sum = 0.f;
-#pragma unroll
-                        for (int w8 = 0; w8 < 8; ++w8) sum += s_part[(w8 * kG + j) * kSP + src];
-                        if (sum != 0.f) atomicAdd(row + col, sum);
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <int CH, int MODE>
-constexpr size_t bwd_mma_smem_bytes() {
-    return sizeof(float4) * 3 * 32 + sizeof(float) * (32 * CH + 8 * 32 * (16 + CH) + 8 * 32 * 36 + 8 * 32 * CH) + sizeof(int) * (32 + 4);
-}
-
 // packed [P,NV] -> the reference's separate gradient tensors.  accumulate: later channel chunks add their share
 // of the channel-summed gradients (uv, conic, opacity), exactly like the reference's per-chunk launches do.
 template <int NV>
@@ -800,40 +525,14 @@ template <int NV, int CH, int MODE, int CG = CH>
 void launch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
     constexpr int FS = (CH + 3) & ~3;
     constexpr size_t dyn = (CH > 8 && NV <= 32) ? sizeof(float) * kBlock * ((FS <= 20) ? 20 : 28) : 0;
-    static bool configured = false;   // static (<= 38 KB) + dynamic (<= 28 KB) shared memory exceeds the 48 KB default
-    if (dyn && !configured) {
-        cudaFuncSetAttribute(blend_bwd_kernel<NV, CH, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};   // static (<= 38 KB) + dynamic (<= 28 KB) shared memory exceeds the 48 KB default
+    if (dyn) spv::opt_in_dynamic_smem(blend_bwd_kernel<NV, CH, MODE, CG>, dyn, configured);
     spv::timer_mark(1, 0, s);
     blend_bwd_kernel<NV, CH, MODE, CG><<<ntiles, kBlock, dyn, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
                                                             a.opacity, a.feature, a.bias, a.idx_sorted, a.tile_range,
                                                             a.bg, a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes,
                                                             a.packed);
     spv::timer_mark(1, 1, s);
-}
-
-template <int CH, int MODE>
-void launch_bwd_mma(const BwdArgs &a, int ntiles, cudaStream_t s) {
-    constexpr size_t bytes = bwd_mma_smem_bytes<CH, MODE>();
-    static bool configured = false;  // one-time opt-in to > 48 KB dynamic shared memory for this instantiation
-    if (!configured) {
-        cudaFuncSetAttribute(blend_bwd_mma_kernel<CH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        configured = true;
-    }
-    blend_bwd_mma_kernel<CH, MODE><<<ntiles, kBlock, bytes, s>>>(a.C, a.Cstride, a.c0, a.W, a.H, a.gx, a.uv, a.conic,
-                                                                 a.opacity, a.feature, a.bias, a.idx_sorted,
-                                                                 a.tile_range, a.bg, a.bgB, a.bgC, a.final_T,
-                                                                 a.ncontrib, a.planes, a.packed);
-}
-
-// The tensor-core variant is numerically correct (it passes the same parity tests) but MEASURED SLOWER on the
-// DAVIS-shaped workload (C=19 pass: 1.08 ms vs 0.82 ms; only ~24 % of the (warp, Gaussian) pairs of a chunk are active, so
-// the dense per-chunk fragment building costs more than the shuffle network it replaces).  Kept selectable for
-// experiments with SPV_BWD_MMA=1; the default is the halving-shuffle kernel.
-inline bool use_mma_backward() {
-    static const bool on = [] { const char *e = getenv("SPV_BWD_MMA"); return e && e[0] == '1'; }();
-    return on;
 }
 
 inline int bwd_nv(int C, bool bias) { return C <= (bias ? 7 : 8) ? 16 : (C <= (bias ? 23 : 24) ? 32 : 64); }
@@ -849,10 +548,7 @@ void dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
         else if (C <= 4) launch_bwd<16, 4, MODE>(a, ntiles, s);
         else launch_bwd<16, cap16, MODE>(a, ntiles, s);
     } else if (C <= cap32) {
-        if (use_mma_backward()) {
-            if (C <= 16) launch_bwd_mma<16, MODE>(a, ntiles, s);
-            else launch_bwd_mma<24, MODE>(a, ntiles, s);
-        } else if (C <= 12) launch_bwd<32, 12, MODE>(a, ntiles, s);
+        if (C <= 12) launch_bwd<32, 12, MODE>(a, ntiles, s);
         else if (C <= 16) launch_bwd<32, 16, MODE>(a, ntiles, s);
         else if (C <= 20) launch_bwd<32, 20, MODE>(a, ntiles, s);
         else launch_bwd<32, cap32, MODE>(a, ntiles, s);
@@ -864,12 +560,6 @@ void dispatch_bwd(const BwdArgs &a, int ntiles, cudaStream_t s) {
 
 void dispatch_bwd_groups(const BwdArgs &a, int ntiles, cudaStream_t s) {
     const int C = a.C;
-    if (use_mma_backward()) {
-        if (C <= 8) launch_bwd_mma<8, kGroups>(a, ntiles, s);
-        else if (C <= 16) launch_bwd_mma<16, kGroups>(a, ntiles, s);
-        else launch_bwd_mma<24, kGroups>(a, ntiles, s);
-        return;
-    }
     if (a.n_grad_channels <= 8) {   // <= 8 feature-gradient channels: 16-wide network + the two RGB-pass butterflies
         if (C <= 4) launch_bwd<16, 4, kGroups, 4>(a, ntiles, s);
         else if (C <= 8) launch_bwd<16, 8, kGroups, 8>(a, ntiles, s);

@@ -397,6 +397,231 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
     }
 }
 
+// ---- backward, ring-staged (default) ---------------------------------------------------------------------------------------
+// blend_rec_bwd_kernel above synchronises its 8 warps at every chunk: ncu (profiles/r01_ncu_blend_rec_bwd.csv) shows the CTA
+// barrier as its top stall reason (2.2 warps per issue slot) -- the 8x4-pixel blocks of a tile take a different number of list
+// entries, and every chunk ends when the slowest block is done.  Here the warps of a tile are decoupled:
+//   * the list is staged into a ring of kRing buffers of kRingChunk entries (same 36 KB as the two 128-entry buffers), all of
+//     them requested up front -- tile lists average ~290 entries, so most tiles never wait again;
+//   * a warp that finishes a chunk bumps that buffer's counter; the LAST warp to do so (by definition nobody is left reading
+//     it) re-arms the buffer's mbarrier and issues the bulk copies of the chunk kRing further down the list.  Nobody ever
+//     waits for a slower warp, only for data;
+//   * the per-pixel recurrences run on R = sum over the Gaussians behind of <f, dL_dpixel> alpha T (one FMA per group and
+//     entry, no state selects: a lane that did not take the Gaussian has w = 0) instead of the normalised accum_rec form:
+//         dL_dalpha = T <f, d> - (R + T_final <bg, d>) / (1 - alpha)         (alpha_blending.cu:180-246, same sum)
+// Reduction networks and packed-row layout are those of blend_rec_bwd_kernel.
+constexpr int kRing = 4, kRingChunk = 64;
+
+__device__ __forceinline__ int atom_add_acq_rel_shared(int *addr, int v) {
+    int old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+    return old;
+}
+
+template <int CH, int CG>
+__global__ void __launch_bounds__(kBlock, 3)
+blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
+                          const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
+                          const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
+                          float *__restrict__ packed) {
+    constexpr int NV = (CG <= 14) ? 16 : 32;
+    constexpr bool MID = CG > 8 && CG <= 14;
+    static_assert(CH % 4 == 0 && CH >= 4 && CH <= 24 && 8 + CG <= 32 && CG <= CH, "unsupported channel configuration");
+    static_assert(kRing * kRingChunk == kBlock, "one bulk copy per thread fills the whole ring");
+    constexpr int RP = kRec;                        // 36: pitch/4 = 9 is odd
+    constexpr int DS = rec_pitch(CH);               // dL_dpixel row pitch, pitch/4 odd
+    extern __shared__ __align__(128) float s_dyn[];
+    float *s_rec0 = s_dyn;                                       // [kRing][kRingChunk][RP]
+    float *dq = s_dyn + kRing * kRingChunk * RP + threadIdx.x * DS;   // this pixel's dL_dpixel row
+    __shared__ __align__(8) uint64_t s_full[kRing];
+    __shared__ int s_done[kRing];
+    __shared__ int s_max;
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    int px, py;
+    thread_pixel(tile_x, tile_y, px, py);
+    const bool inside = px < W && py < H;
+    const size_t pix = (size_t)W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float bx0 = (float)(tile_x * SPV_TILE + ((warp & 1) << 3)), by0 = (float)(tile_y * SPV_TILE + ((warp >> 1) << 2));
+
+    const int2 range = tile_range[tile];
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    const int last_contrib = inside ? ncontrib[pix] : 0;
+
+    if (threadIdx.x == 0) {
+        s_max = 0;
+#pragma unroll
+        for (int b = 0; b < kRing; ++b) { mbar_init(&s_full[b], 1); s_done[b] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int wmax = __reduce_max_sync(kFull, last_contrib);   // positions >= wmax were applied by no pixel of this warp
+    if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int n_eff = min(range.y - range.x, s_max);   // ... and positions >= s_max by no pixel of the tile: never staged
+    const int nchunks = (n_eff + kRingChunk - 1) / kRingChunk;
+
+    // chunk c covers list positions [p_hi - m, p_hi), p_hi = n_eff - c*kRingChunk; slot t holds position p_hi - 1 - t
+    {   // the first kRing chunks: one bulk copy per thread
+        const int c = threadIdx.x / kRingChunk, t = threadIdx.x % kRingChunk;
+        if (c < nchunks) {
+            const int p_hi = n_eff - c * kRingChunk, m = min(kRingChunk, p_hi);
+            if (t == 0) mbar_expect_tx(&s_full[c], (uint32_t)(m * kRec * 4));
+            if (t < m) {
+                const int id = idx_sorted[range.x + p_hi - 1 - t];
+                bulk_g2s(s_rec0 + (c * kRingChunk + t) * RP, rec + (size_t)id * kRec, kRec * 4, &s_full[c]);
+            }
+        }
+    }
+
+    // <bg, dL_dpixel> per gradient group, pre-multiplied by T_final
+    float tfA = 0.f, tfB = 0.f, tfC = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const float dv = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
+        dq[c] = dv;
+        if (c >= 4) tfC += dv;
+        else if (c == 3) tfB += dv;
+        else tfA += dv;
+    }
+    tfA *= bgA * T_final; tfB *= bgB * T_final; tfC *= bgC * T_final;
+
+    float RA = 0.f, RB = 0.f, RC = 0.f;
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c % kRing;
+        mbar_wait(&s_full[b], (c / kRing) & 1);   // every warp waits for every chunk, also one it will skip: a refill is only
+                                                  // ever issued into a buffer whose previous copies have landed
+        const float *sr = s_rec0 + b * kRingChunk * RP;
+        const int p_hi = n_eff - c * kRingChunk, m = min(kRingChunk, p_hi);
+        for (int j0 = 0; j0 < m; j0 += 32) {
+            if (p_hi - 1 - (j0 + 31) >= wmax) continue;   // the whole sub-batch lies behind this warp's last contributor
+            // stage 1: one chunk entry per lane -- can the warp's 8x4 pixel block have taken it at all?
+            bool maybe = false;
+            if (j0 + lane < m && p_hi - 1 - (j0 + lane) < wmax) {
+                const float4 *r = reinterpret_cast<const float4 *>(sr + (j0 + lane) * RP);
+                maybe = block_may_hit<false>(r[0], r[1], bx0, by0);
+            }
+            unsigned todo = __ballot_sync(kFull, maybe);
+            // stage 2 (chunk order = back to front).  Branch-free body: a lane that did not take the Gaussian runs it with
+            // p2 = -inf, i.e. G = alpha = w = 0 and 1/(1-alpha) = 1 -- every partial sum it contributes is an exact zero and
+            // its T / R state does not move.
+            while (todo) {
+                const int j = j0 + __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const float4 *r = reinterpret_cast<const float4 *>(sr + j * RP);
+                float dx = 0.f, dy = 0.f;
+                const float4 g0 = r[0], g1 = r[1];
+                float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
+                // did this pixel apply the Gaussian in the forward pass?  (same test, and before its last contributor)
+                const bool hit = splat_hits<false>(p2, g1) && (p_hi - 1 - j) < last_contrib;
+                if (!__any_sync(kFull, hit)) continue;
+                float v[NV];
+                float u[8];   // MID: features 8..13 | RGB-pass pair
+                float n0, n1;
+                {
+                    const float4 con = r[kRec / 4 - 1];
+                    float Gv;
+                    p2 = hit ? p2 : -INFINITY;
+                    const float alpha = splat_alpha<false>(p2, g1, Gv);
+                    const float rinv = __fdividef(1.f, 1.f - alpha);
+                    T = T * rinv;  // transmittance in front of this Gaussian (unchanged when alpha == 0)
+                    const float w = alpha * T;
+                    float fdA = 0.f, fdB = 0.f, fdC = 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < CH / 4; ++c4) {
+                        const float4 ff = r[2 + c4];
+                        const float4 dd = *reinterpret_cast<const float4 *>(dq + 4 * c4);
+                        const float fv[4] = {ff.x, ff.y, ff.z, ff.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int ch = 4 * c4 + k;
+                            if (ch >= 4) fdC = fmaf(fv[k], dv[k], fdC);
+                            else if (ch == 3) fdB = fmaf(fv[k], dv[k], fdB);
+                            else fdA = fmaf(fv[k], dv[k], fdA);
+                            if (ch < CG) {
+                                if (MID && ch >= 8) u[ch - 8] = w * dv[k];
+                                else v[8 + ch] = w * dv[k];
+                            }
+                        }
+                    }
+                    const float da_ndc = fmaf(T, fdA, -rinv * (RA + tfA));
+                    const float da_op = da_ndc + fmaf(T, fdB, -rinv * (RB + tfB));
+                    const float da_all = da_op + fmaf(T, fdC, -rinv * (RC + tfC));
+                    RA = fmaf(fdA, w, RA); RB = fmaf(fdB, w, RB); RC = fmaf(fdC, w, RC);
+#pragma unroll
+                    for (int q = 8 + (MID ? 8 : CG); q < NV; ++q) v[q] = 0.f;
+                    if (MID) {
+#pragma unroll
+                        for (int q = CG - 8; q < 6; ++q) u[q] = 0.f;
+                    }
+                    const float dL_dG = g1.z * da_all;
+                    const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
+                    const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
+                    v[0] = dL_dG * dGx; v[1] = dL_dG * dGy;
+                    v[4] = -0.5f * Gv * dx * dx * dL_dG;
+                    v[5] = -Gv * dx * dy * dL_dG;
+                    v[6] = -0.5f * Gv * dy * dy * dL_dG;
+                    v[7] = Gv * da_op;
+                    const float dL_dG_ndc = g1.z * da_ndc;
+                    n0 = dL_dG_ndc * dGx; n1 = dL_dG_ndc * dGy;
+                    v[2] = fabsf(n0); v[3] = fabsf(n1);
+                }
+                halving_reduce<NV, 0, NV>(v, lane);   // lane l (< NV) now holds the warp-wide sum of value l
+                float *row = packed + (size_t)__float_as_int(g1.w) * kRowG;
+                if constexpr (MID) {
+                    u[6] = n0; u[7] = n1;
+                    halving_reduce<8, 0, 8>(u, lane);     // lane l holds the sum of u[l % 8]
+                    const int t = lane - 16;              // one RED: lanes 0..15 <- v, lanes 16..23 <- u
+                    const float val = lane < 16 ? v[0] : u[0];
+                    const int col = lane < 16 ? lane : (t < 6 ? 16 + t : 31 + (t - 6));
+                    const bool live = lane < 16 || (lane < 24 && (t >= 6 || t < CG - 8));
+                    if (live && val != 0.f) atomicAdd(row + col, val);
+                } else {
+                    const bool up = (lane & 1) != 0;
+                    float e = (up ? n1 : n0) + __shfl_xor_sync(kFull, up ? n0 : n1, 1);
+#pragma unroll
+                    for (int o = 2; o <= 16; o <<= 1) e += __shfl_xor_sync(kFull, e, o);
+                    if constexpr (NV == 16) {
+                        const float val = lane < 16 ? v[0] : e;
+                        const int col = lane < 16 ? lane : 31 + (lane & 1);
+                        if (lane < 18 && val != 0.f) atomicAdd(row + col, val);
+                    } else {
+                        if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + lane, v[0]);
+                        if (lane < 2 && e != 0.f) atomicAdd(row + 31 + lane, e);
+                    }
+                }
+            }
+        }
+        // release buffer b; the last of the 8 warps to get here refills it with chunk c + kRing
+        if (c + kRing < nchunks) {      // (uniform over the CTA: buffers that will not be refilled need no bookkeeping)
+            __syncwarp();
+            int old = 0;
+            if (lane == 0) old = atom_add_acq_rel_shared(&s_done[b], 1);
+            old = __shfl_sync(kFull, old, 0);
+            if (old == kBlock / 32 - 1) {
+                const int cn = c + kRing, q_hi = n_eff - cn * kRingChunk, mn = min(kRingChunk, q_hi);
+                if (lane == 0) {
+                    s_done[b] = 0;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warps' reads of the buffer before the async writes
+                    mbar_expect_tx(&s_full[b], (uint32_t)(mn * kRec * 4));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = lane; t < kRingChunk; t += 32)
+                    if (t < mn) {
+                        const int id = idx_sorted[range.x + q_hi - 1 - t];
+                        bulk_g2s(s_rec0 + (b * kRingChunk + t) * RP, rec + (size_t)id * kRec, kRec * 4, &s_full[b]);
+                    }
+            }
+        }
+    }
+}
+
 // ---- backward, wide warp footprints (EXPERIMENTAL, opt-in: SPV_BWD_WIDE=2|4 or spv_set_option("bwd_wide", 2|4)) ----------------
 // 41 % of blend_rec_bwd_kernel's instructions are its per-(warp, entry) shuffle reductions (profiles/r01_ncu_blend_rec_bwd_lines.txt),
 // one per ACTIVE (8x4-pixel block, entry) pair: 1.283 M on the config-A frame.  With R pixels per lane a warp covers R of those blocks
@@ -625,14 +850,22 @@ template <int CH, int CG>
 void launch_rec_bwd(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
     constexpr int DS = (CH <= 4) ? 4 : ((CH <= 12) ? 12 : ((CH <= 20) ? 20 : 28));
     constexpr size_t dyn = sizeof(float) * (2 * kChunk * kRec + kBlock * DS);
-    static bool configured = false;   // up to 64.5 KB of dynamic shared memory: above the 48 KB default
-    if (!configured) {
-        cudaFuncSetAttribute(blend_rec_bwd_kernel<CH, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};   // up to 64.5 KB of dynamic shared memory: above the 48 KB default
+    spv::opt_in_dynamic_smem(blend_rec_bwd_kernel<CH, CG>, dyn, configured);
     spv::timer_mark(1, 0, s);
     blend_rec_bwd_kernel<CH, CG><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA, a.bgB,
                                                             a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
+    spv::timer_mark(1, 1, s);
+}
+
+template <int CH, int CG>
+void launch_rec_bwd_ring(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
+    constexpr size_t dyn = sizeof(float) * (kRing * kRingChunk * kRec + kBlock * rec_pitch(CH));
+    static std::atomic<unsigned long long> configured{0};   // up to 64.5 KB of dynamic shared memory: above the 48 KB default
+    spv::opt_in_dynamic_smem(blend_rec_bwd_ring_kernel<CH, CG>, dyn, configured);
+    spv::timer_mark(1, 0, s);
+    blend_rec_bwd_ring_kernel<CH, CG><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA,
+                                                                 a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
     spv::timer_mark(1, 1, s);
 }
 
@@ -640,11 +873,8 @@ template <int CH, int CG, int R>
 void launch_rec_bwd_wide(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
     constexpr int DS = ((CH + 4) / 4) % 2 ? CH + 4 : CH + 8;
     constexpr size_t dyn = sizeof(float) * (2 * kChunkW * kRec + kBlock * DS);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(blend_rec_bwd_wide_kernel<CH, CG, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    spv::opt_in_dynamic_smem(blend_rec_bwd_wide_kernel<CH, CG, R>, dyn, configured);
     spv::timer_mark(1, 0, s);
     blend_rec_bwd_wide_kernel<CH, CG, R><<<ntiles, kBlock / R, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA,
                                                                          a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
@@ -662,6 +892,13 @@ void dispatch_rec_bwd(const RecBwdArgs &a, int n_grad, int ntiles, cudaStream_t 
         }
     }
     // feature-gradient channels reduced: 4 (rgb + depth only), 8, 14, or all CH
+    if (spv::get_option("bwd_variant") != 1) {   // default: ring-staged, warps decoupled
+        if (n_grad <= 4) launch_rec_bwd_ring<CH, 4>(a, ntiles, s);
+        else if (n_grad <= 8 && CH >= 8) launch_rec_bwd_ring<CH, (CH >= 8 ? 8 : CH)>(a, ntiles, s);
+        else if (n_grad <= 14 && CH >= 16) launch_rec_bwd_ring<CH, (CH >= 16 ? 14 : CH)>(a, ntiles, s);
+        else launch_rec_bwd_ring<CH, (CH > 23 ? 23 : CH)>(a, ntiles, s);
+        return;
+    }
     if (n_grad <= 4) launch_rec_bwd<CH, 4>(a, ntiles, s);
     else if (n_grad <= 8 && CH >= 8) launch_rec_bwd<CH, (CH >= 8 ? 8 : CH)>(a, ntiles, s);
     else if (n_grad <= 14 && CH >= 16) launch_rec_bwd<CH, (CH >= 16 ? 14 : CH)>(a, ntiles, s);

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #define SPV_TILE 16
 #define SPV_TILE_PIX 256
 
@@ -32,6 +34,24 @@ inline int check_launch(const char *where, int launches = 1) {
             return (int)_e;                       \
         }                                         \
     } while (0)
+
+// cudaFuncSetAttribute applies to the CURRENT device only: opt-ins to more than 48 KB of dynamic shared memory are made once
+// per (kernel, device).  `done` is a per-call-site bit mask over device ordinals (devices >= 64 simply repeat the cheap call).
+template <typename Kernel>
+inline void opt_in_dynamic_smem(Kernel kernel, size_t bytes, std::atomic<unsigned long long> &done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = dev < 64 ? (1ull << dev) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bit) done.fetch_or(bit, std::memory_order_release);
+}
+inline int sm_count() {   // of the current device (the runtime caches device attributes: this is a table lookup)
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
 
 inline int tiles_x(int W) { return (W + SPV_TILE - 1) / SPV_TILE; }
 inline int tiles_y(int H) { return (H + SPV_TILE - 1) / SPV_TILE; }

@@ -121,16 +121,21 @@ inline int make_groups(AttrGroups &g, int n, const float *const *in, float *cons
 // gradient next to the covariance chain).  Forked from and joined back into the caller's stream with events, so the caller
 // still sees one in-order stream -- and a stream capture records the branches as parallel graph nodes.
 struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, mid = nullptr, join = nullptr; bool ok = false; };
-static thread_local SideLane g_side;
+// one lane per (host thread, device): streams and events belong to the device that was current when they were created
+constexpr int kMaxDevices = 64;
+static thread_local SideLane g_side[kMaxDevices];
 SideLane *side_lane() {
-    if (!g_side.ok) {
-        if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&g_side.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        g_side.ok = true;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    SideLane &l = g_side[dev];
+    if (!l.ok) {
+        if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        l.ok = true;
     }
-    return &g_side;
+    return &l;
 }
 
 }  // namespace

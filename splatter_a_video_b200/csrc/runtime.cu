@@ -27,23 +27,29 @@ void timer_mark(int slot, int edge, cudaStream_t s) {
                              st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
-// Small runtime switches for experimental kernel variants (default 0 = the validated path).  First read falls back to the
-// environment variable SPV_<NAME> so a run can be switched without code changes.
-static std::atomic<int> g_opt_bwd_wide{-1};
+// Small runtime switches for kernel variants (default 0).  First read falls back to the environment variable SPV_<NAME>
+// (upper case) so a run can be switched without code changes.
+//   bwd_wide    2 | 4: pixels per lane of the experimental wide-footprint backward blend kernel
+//   bwd_variant 1: the round-1 backward blend kernel (CTA barrier per chunk) instead of the ring-staged default
+struct Option { const char *name; const char *env; std::atomic<int> value; };
+static Option g_options[] = {{"bwd_wide", "SPV_BWD_WIDE", {-1}}, {"bwd_variant", "SPV_BWD_VARIANT", {-1}}};
 int get_option(const char *name) {
-    if (strcmp(name, "bwd_wide") == 0) {
-        int v = g_opt_bwd_wide.load(std::memory_order_relaxed);
+    for (Option &o : g_options) {
+        if (strcmp(name, o.name) != 0) continue;
+        int v = o.value.load(std::memory_order_relaxed);
         if (v < 0) {
-            const char *e = getenv("SPV_BWD_WIDE");
+            const char *e = getenv(o.env);
             v = e ? atoi(e) : 0;
-            g_opt_bwd_wide.store(v, std::memory_order_relaxed);
+            if (v < 0) v = 0;
+            o.value.store(v, std::memory_order_relaxed);
         }
         return v;
     }
     return 0;
 }
 int set_option(const char *name, int value) {
-    if (strcmp(name, "bwd_wide") == 0) { g_opt_bwd_wide.store(value, std::memory_order_relaxed); return 0; }
+    for (Option &o : g_options)
+        if (strcmp(name, o.name) == 0) { o.value.store(value < 0 ? 0 : value, std::memory_order_relaxed); return 0; }
     return 1;
 }
 }  // namespace spv

@@ -131,8 +131,13 @@ cull_count_emit_kernel(int P, const float2 *__restrict__ uv, const float *__rest
         if (EMIT && TILES) {
             if (keep) {   // slot order inside a tile's segment is arbitrary: the tile sort orders by (depth, id)
                 const int tl = y * gx + x;
-                const long long pos = (long long)tile_seg[tl].x + atomicAdd(&tile_count[tl], 1);
-                if (pos < cap) keys[pos] = (dbits << 32) | (unsigned long long)(unsigned)i;
+                const int2 seg = tile_seg[tl];
+                // capacity overflow: the scan clipped this tile's segment (possibly to (0,0)) -- entries beyond it are dropped
+                // here instead of spilling into the neighbouring (or, for an empty range, the first) tiles' slots
+                if (seg.y > seg.x) {
+                    const int pos = seg.x + atomicAdd(&tile_count[tl], 1);
+                    if (pos < seg.y) keys[pos] = (dbits << 32) | (unsigned long long)(unsigned)i;
+                }
             }
         } else if (EMIT) {
             if (keep) {
@@ -458,17 +463,9 @@ int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *depth, con
     int rc = spv::check_launch("spv_bin_tiles/emit", 3);
     if (rc) return rc;
     tile_sort_small_kernel<<<T, kThreads, 0, s>>>((const int2 *)tile_range, keys, idx_sorted);
-    static bool configured = false;
-    static int n_sms = 0;
-    if (!configured) {
-        cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortBig * 8);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sms <= 0) n_sms = 148;
-        configured = true;
-    }
-    tile_sort_big_kernel<<<n_sms, kScanThreads, kSortBig * 8, s>>>((const int2 *)tile_range, keys, idx_sorted, big_queue);
+    static std::atomic<unsigned long long> configured{0};
+    spv::opt_in_dynamic_smem(tile_sort_big_kernel, kSortBig * 8, configured);
+    tile_sort_big_kernel<<<spv::sm_count(), kScanThreads, kSortBig * 8, s>>>((const int2 *)tile_range, keys, idx_sorted, big_queue);
     return spv::check_launch("spv_bin_tiles/sort", 2);
 }
 

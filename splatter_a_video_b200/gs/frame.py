@@ -18,36 +18,94 @@ from torch import Tensor
 from .. import _lib as L
 
 
+class CapacityOverflow(RuntimeError):
+    """A frame that was already handed to the caller turned out to have been rendered from a truncated tile list."""
+
+
 class Capacity:
     """Intersection-capacity policy of the sync-free path.  The count of tile intersections never leaves the device on the
-    hot path; it is copied to pinned host memory asynchronously and inspected one call later.  On overflow the affected
-    frame was rendered from a truncated list, so `check()` raises and the caller re-renders with the grown capacity."""
+    hot path: every frame's (count, overflow) status is copied to its own pinned host slot asynchronously, and EVERY status is
+    eventually inspected -- the previous frame's before the next one is queued (by then its forward has long finished, so the
+    wait is free), the current one on demand (`check(wait=True)`).  Overflow is sticky until reported:
 
-    def __init__(self, initial: int = 0, growth: float = 1.5, slack: float = 1.25):
+      * found for the frame being rendered (`wait=True`): `check()` grows the capacity and returns False, the renderer renders
+        the frame again;
+      * found LATE (an earlier frame whose images / gradients were already used): the capacity is grown, `late_overflows` is
+        counted and `check()` raises CapacityOverflow once, so the training step that consumed the truncated frame is known.
+
+    Head-room is kept proactively (grow at `refill` of the capacity in use, rescale when the Gaussian count changes), so with
+    a slowly growing scene the late case needs a > 1/refill jump of the intersection count between two frames."""
+
+    def __init__(self, initial: int = 0, growth: float = 1.5, slack: float = 1.25, refill: float = 0.85):
         self.I_cap = int(initial)
-        self.growth, self.slack = growth, slack
-        self._host = torch.zeros(2, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(2, dtype=torch.int32)
-        self._event = None
+        self.growth, self.slack, self.refill = growth, slack, refill
+        self._pending = []          # [(event, pinned host int32[2], capacity the frame was rendered with)]
+        self._free = []
         self.last_I = 0
+        self.P = None
+        self.late_overflows = 0
+        self._late = False
+
+    def _slot(self):
+        if self._free:
+            return self._free.pop()
+        t = torch.zeros(2, dtype=torch.int32)
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+    def set_population(self, P: int):
+        """Rescale the capacity when the number of Gaussians changes (densification / pruning)."""
+        if self.P is not None and P != self.P and self.P > 0 and self.I_cap > 0:
+            self.I_cap = max(self.I_cap, int(self.I_cap * (P / self.P) * 1.05) + 1024)
+        self.P = P
+
+    def _fold(self, wait: bool, current: bool):
+        """Read every finished status (all of them when `wait`).  `current`: the newest pending status belongs to the frame
+        being rendered right now (it can still be rendered again); every other overflow is a late one.  Returns True if the
+        current frame overflowed."""
+        current_overflowed = False
+        while self._pending:
+            ev, host, cap = self._pending[0]
+            if not wait and not ev.query():
+                break
+            ev.synchronize()
+            self._pending.pop(0)
+            self.last_I = int(host[0])
+            over = int(host[1]) != 0
+            self._free.append(host)
+            if over:
+                if cap >= self.I_cap:                      # not already grown past the capacity that overflowed
+                    self.I_cap = int(self.I_cap * self.growth) + 1024
+                if current and wait and not self._pending:
+                    current_overflowed = True
+                else:
+                    self._late = True
+                    self.late_overflows += 1
+            elif self.last_I > self.refill * cap and cap >= self.I_cap:
+                self.I_cap = int(self.I_cap * self.growth) + 1024      # proactive head-room
+        return current_overflowed
 
     def observe(self, status: Tensor):
-        self._host.copy_(status, non_blocking=True)
-        self._event = torch.cuda.Event()
-        self._event.record()
+        """Queue the status of the frame just enqueued; first settles every EARLIER frame (their kernels ran long ago)."""
+        self._fold(wait=True, current=False)
+        host = self._slot()
+        host.copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((ev, host, self.I_cap))
 
     def check(self, wait: bool = False) -> bool:
-        """True if the last observed frame fitted.  Grows the capacity when it did not."""
-        if self._event is None:
-            return True
-        if not wait and not self._event.query():
-            return True
-        self._event.synchronize()
-        self._event = None
-        self.last_I = int(self._host[0])
-        if int(self._host[1]) != 0:
-            self.I_cap = int(self.I_cap * self.growth) + 1024
-            return False
-        return True
+        """True if the frame observed last can be used (wait=False: as far as is known without blocking).  False: it
+        overflowed and the capacity has grown -- render it again.  Raises CapacityOverflow once for an overflow found late."""
+        newest = self._fold(wait=wait, current=True)
+        if self._late:
+            self._late = False
+            raise CapacityOverflow(f"an earlier frame overflowed the tile-intersection capacity (now grown to {self.I_cap}); "
+                                   "its images and gradients were computed from truncated tile lists")
+        return not newest
+
+    def drain(self) -> bool:
+        """Block until every observed frame has been inspected (end of an epoch / before a checkpoint); same result as check."""
+        return self.check(wait=True)
 
 
 def _ptr_array(ptrs):

@@ -241,6 +241,8 @@ class GradExchange:
             buf = symm.empty(2 * span, dtype=torch.float32, device=c["row"].device)
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) > 8:
+                raise ValueError("the peer-pointer tables of the exchange kernels hold 8 ranks (one NVSwitch domain)")
             arrs, reds = [], []
             for half in range(2):
                 a, b = (ctypes.c_void_p * 8)(), (ctypes.c_void_p * 8)()
@@ -259,6 +261,8 @@ class GradExchange:
                                   "nvls": "nvls (multimem.ld_reduce / multimem.st through the NVSwitch)"}[want]
         except Exception as e:   # noqa: BLE001 -- any failure here means: no peer mapping on this system
             self.exchange_path = f"nccl ({type(e).__name__}: {str(e)[:80]})"
+            import warnings
+            warnings.warn(f"GradExchange: symmetric-memory rendezvous failed, falling back to the NCCL all-gather: {e!r}", RuntimeWarning)
         return c["p2p"] is not None
 
     def _p2p_exchange(self, world: int, scale: float) -> torch.Tensor:
@@ -276,7 +280,9 @@ class GradExchange:
         rows_ptr = ctypes.cast(p["arrs"][half], ctypes.c_void_p)
         # ---- side stream: gather every rank's position gradients + frame scalars, rebuild the spline-coefficient gradient
         main = torch.cuda.current_stream()
-        side = p.setdefault("side", torch.cuda.Stream())
+        if "side" not in p:
+            p["side"] = torch.cuda.Stream()
+        side = p["side"]
         side.wait_stream(main)
         with torch.cuda.stream(side):
             L.call("spv_exchange_gather_peers", n_red, row, world, rows_ptr, L.ptr(c["rows"]), c["rows"].stride(0), L.stream())

@@ -210,6 +210,7 @@ class DPTROrthoEnhancedRender(_BaseRender):
         if self.capacity is None:
             self.capacity = _frame.Capacity(initial=8 * P)
         cap = self.capacity
+        cap.set_population(P)          # densification / pruning changed P: rescale the intersection capacity
         first = cap.last_I == 0 and self.observe_capacity
         if self._ndc_zero is None or self._ndc_zero.shape[0] != P or self._ndc_zero.device != position.device:
             self._ndc_zero = torch.zeros(P, 2, device=position.device)

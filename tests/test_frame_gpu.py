@@ -384,13 +384,12 @@ def test_frame_backward_twice_and_gradient_free_images(cuda):
             Hh.assert_grad_close(n(b), n(a), f"pruned d/d{name}", norm_tol=2e-6)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SPV_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental kernel variant, not yet validated on a GPU: opt in with SPV_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("wide", [2, 4])
+@pytest.mark.parametrize("option,value", [("bwd_variant", 1), ("bwd_wide", 2), ("bwd_wide", 4)])
 @pytest.mark.parametrize("track_grad", [False, True])          # 8 / 11 feature-gradient channels: the 16 and 16+8 networks
-def test_experimental_wide_backward_equals_default(cuda, wide, track_grad):
-    """spv_set_option("bwd_wide", 2|4): R pixels per lane in the frame path's backward blend kernel (blend_rec_bwd_wide_kernel).
-    Same gradients as the default kernel up to the association of the per-Gaussian sums."""
+def test_backward_kernel_variants_equal_default(cuda, option, value, track_grad):
+    """The selectable variants of the frame path's backward blend kernel -- spv_set_option("bwd_variant", 1): the chunk-barrier
+    kernel of round 1; ("bwd_wide", 2|4): R pixels per lane -- against the ring-staged default.  Same gradients up to the
+    association of the per-Gaussian sums."""
     from splatter_a_video_b200 import _lib as L
     from splatter_a_video_b200.gs.frame import render_ortho_frame
     sc = synth.make_scene(40_000, 4, 333, 250, seed=12)
@@ -414,9 +413,52 @@ def test_experimental_wide_backward_equals_default(cuda, wide, track_grad):
 
     ref = run()
     try:
-        L.set_option("bwd_wide", wide)
+        L.set_option(option, value)
         got = run()
     finally:
-        L.set_option("bwd_wide", 0)
+        L.set_option(option, 0)
     for k in ref:
-        Hh.assert_grad_close(n(got[k]), n(ref[k]), f"bwd_wide={wide} d/d{k}", norm_tol=2e-5)
+        Hh.assert_grad_close(n(got[k]), n(ref[k]), f"{option}={value} d/d{k}", norm_tol=2e-5)
+
+
+def test_capacity_overflow_after_the_first_frame_is_reported(cuda):
+    """An overflow on a LATER frame (the capacity was settled on an easier one) must not pass silently: the frame that follows
+    raises CapacityOverflow, the capacity has grown, and the overflowing frame rendered again matches the staged ops.  The
+    truncated launch itself must not write outside its clipped tile segments (sort.cu emit pass)."""
+    from splatter_a_video_b200.gs.frame import CapacityOverflow
+    from splatter_a_video_b200.renderer import parse_renderer
+    sc = synth.make_scene(20_000, 4, 256, 192, seed=33)
+    ref = parse_renderer({"name": "DPTROrthoEnhancedRender"}, white_bg=False, device=cuda)
+    rnd = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+    easy = {k: v.detach() for k, v in _rd(sc, cuda).items()}
+    hard = dict(easy); hard["scaling"] = easy["scaling"] * 3.0          # ~9x the tile intersections
+    rnd.render_batch(dict(easy), [_batch(sc, cuda)])                    # settles the capacity (waits once)
+    cap0 = rnd.capacity.I_cap
+    o_trunc = rnd.render_batch(dict(hard), [_batch(sc, cuda)])          # overflows; not known yet (no host wait)
+    torch.cuda.synchronize()
+    assert int(rnd.last_status.cpu()[1]) == 1
+    assert torch.isfinite(o_trunc["rgb"]).all()
+    with pytest.raises(CapacityOverflow):
+        rnd.render_batch(dict(easy), [_batch(sc, cuda)])                # the earlier frame's status is inspected here
+    assert rnd.capacity.I_cap > cap0 and rnd.capacity.late_overflows == 1
+    for _ in range(16):                                                 # grown (x1.5 per report) until the hard frame fits
+        o2 = rnd.render_batch(dict(hard), [_batch(sc, cuda)])
+        if rnd.capacity.drain():                                        # False: this frame overflowed, capacity grown
+            break
+    o1 = ref.render_batch(dict(hard), [_batch(sc, cuda)])
+    assert int(rnd.last_status.cpu()[1]) == 0
+    assert float((o1["rgb"] - o2["rgb"]).abs().max()) <= 1e-6 and torch.equal(o1["gs_idx"], o2["gs_idx"])
+
+
+def test_capacity_follows_the_population(cuda):
+    """P changes after densification: the capacity is rescaled instead of staying at the first frame's value."""
+    from splatter_a_video_b200.renderer import parse_renderer
+    rnd = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+    small = synth.make_scene(5_000, 4, 128, 96, seed=9)
+    big = synth.make_scene(15_000, 4, 128, 96, seed=9)
+    rnd.render_batch({k: v.detach() for k, v in _rd(small, cuda).items()}, [_batch(small, cuda)])
+    cap0 = rnd.capacity.I_cap
+    out = rnd.render_batch({k: v.detach() for k, v in _rd(big, cuda).items()}, [_batch(big, cuda)])
+    assert rnd.capacity.I_cap >= 3 * (cap0 - 4096)
+    rnd.capacity.drain()
+    assert int(rnd.last_status.cpu()[1]) == 0 and torch.isfinite(out["rgb"]).all()

@@ -164,3 +164,142 @@ def test_diff_gaussian_rasterization_shim(cuda):
     img.sum().backward()
     assert means2D.grad is not None and float(means2D.grad[:, :2].abs().sum()) > 0 and float(means2D.grad[:, 2].abs().sum()) == 0
     assert torch.isfinite(means3D.grad).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The path bench.py actually times -- DPTROrthoEnhancedRenderB200 in frame mode, tile culling on, record-staged kernels --
+# held DIRECTLY against the oracle at full size (forward images / ids / radii and the whole backward chain to every leaf).
+def _oracle_frame_backward(s, oo, grads, W, H, K=20):
+    """C-oracle blend backward of the three passes (dptr_ortho_enhanced.py:342-376: RGB bg 0, depth bg 1, attributes bg 0 with
+    opacity.detach()), then the per-Gaussian chain (uv, depth, conic, rgb) -> (position, scaling, rotation, shs) through the
+    differentiable torch restatement on the CPU (itself pinned bit-exactly to the reference's own ortho functions)."""
+    P = s["P"]
+    uv, conic, op, idx, tr = oo["uv"], oo["conic"], s["opacity"], oo["idx_sorted"], oo["tile_range"]
+    passes = {"rgb": (oo["rgb"], 0.0), "depth": (oo["depth"], 1.0), "attrs": (s["attrs"], 0.0)}
+    fwd, bwd = {}, {}
+    fragile = np.zeros((H, W), bool)
+    for name, (feat, bg) in passes.items():
+        fwd[name] = O.alpha_blending_forward(uv, conic, op, feat, idx, tr, bg, W, H, K=(K if name == "rgb" else 0), frag_eps=Hh.FRAG_EPS)
+        fragile |= fwd[name]["fragile"]
+    for name, (feat, bg) in passes.items():
+        g = grads[name].copy()
+        g[:, fragile] = 0
+        bwd[name] = O.alpha_blending_backward(uv, conic, op, feat, idx, tr, bg, W, H, fwd[name]["final_T"], fwd[name]["ncontrib"], g)
+    g_uv = bwd["rgb"]["dL_duv"] + bwd["depth"]["dL_duv"] + bwd["attrs"]["dL_duv"]
+    g_conic = bwd["rgb"]["dL_dconic"] + bwd["depth"]["dL_dconic"] + bwd["attrs"]["dL_dconic"]
+    out = {"opacity": bwd["rgb"]["dL_dopacity"] + bwd["depth"]["dL_dopacity"], "attrs": bwd["attrs"]["dL_dfeature"],
+           "ndc": bwd["rgb"]["dL_duv"] * np.array([0.5 * W, 0.5 * H], np.float32)}
+    leaves = {k: torch.from_numpy(s[k]).clone().requires_grad_(True) for k in ("xyz", "scaling", "rotation", "shs")}
+    dirs = torch.zeros(P, 3); dirs[:, 2] = 1.0
+    rgb = TR.compute_sh(leaves["shs"], 3, dirs)
+    uv_t, depth_t = TR.project_point_ortho(leaves["xyz"], torch.from_numpy(s["extr"]), W, H, nearest=0.01)
+    vis = depth_t.detach() != 0
+    cov3d = TR.compute_cov3d(leaves["scaling"], leaves["rotation"], vis)
+    conic_t, radius_t, _ = TR.ewa_project_ortho(cov3d, torch.from_numpy(s["extr"]), uv_t, W, H, vis.reshape(-1))
+    assert np.array_equal(radius_t.numpy(), oo["radius"])
+    torch.autograd.backward([uv_t, depth_t, conic_t, rgb],
+                            [torch.from_numpy(g_uv), torch.from_numpy(bwd["depth"]["dL_dfeature"]), torch.from_numpy(g_conic),
+                             torch.from_numpy(bwd["rgb"]["dL_dfeature"])])
+    out.update(position=leaves["xyz"].grad.numpy(), scaling=leaves["scaling"].grad.numpy(), rotation=leaves["rotation"].grad.numpy(),
+               shs=leaves["shs"].grad.numpy())
+    return fwd, out, fragile
+
+
+@pytest.mark.parametrize("P,W,H,track_grad", [(200_000, 854, 480, True), (200_000, 854, 480, False), (600_000, 1920, 1080, True)],
+                         ids=["cfg2-bwd24x14", "cfg2-bwd24x8", "1080p-600k"])
+def test_benched_frame_path_against_oracle_full_size(cuda, P, W, H, track_grad):
+    """`track_grad` selects the backward dispatch: with a gradient on track_gs 11 feature channels are reduced
+    (blend_rec_bwd<24,14>), without it 8 (blend_rec_bwd<24,8>).  The 1080p case covers 8160-tile grids and > 2 M keys."""
+    from splatter_a_video_b200.renderer import parse_renderer
+    s = Hh.scene_np(P, W, H, seed=1234, frames=50)
+    oo = Hh.oracle_ortho(s, K=20)
+    rng = np.random.default_rng(11)
+    grads = {"rgb": rng.standard_normal((3, H, W)).astype(np.float32), "depth": rng.standard_normal((1, H, W)).astype(np.float32),
+             "attrs": rng.standard_normal((19, H, W)).astype(np.float32)}
+    fwd, want, fragile = _oracle_frame_backward(s, oo, grads, W, H)
+    for g in grads.values():
+        g[:, fragile] = 0
+
+    a = s["attrs"]
+    rd = {"position": s["xyz"], "opacity": s["opacity"], "scaling": s["scaling"], "rotation": s["rotation"], "shs": s["shs"],
+          "track_gs": a[:, 0:3], "mask_attribute": a[:, 3:4], "pos_poly_feat": a[:, 4:16], "dino_attribute": a[:, 16:19]}
+    rd = {k: t(v, cuda).clone().requires_grad_(track_grad or k != "track_gs") for k, v in rd.items()}
+    rnd = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+    assert rnd.frame and rnd.cull
+    batch = {"height": H, "width": W, "extrinsic_matrix": t(s["extr"], cuda), "intrinsic_matrix": t(s["intr"], cuda),
+             "camera_center": torch.zeros(3, device=cuda), "render_attributes_list": list(ATTRS), "num_idx": 20}
+    out = rnd.render_batch(rd, [batch])
+    assert int(rnd.last_status.cpu()[1]) == 0
+    I_culled, I_ref = int(rnd.last_status.cpu()[0]), int(oo["idx_sorted"].size)
+    assert 0 < I_culled < I_ref                         # culling shortened the lists ...
+    if W >= 1920:
+        assert I_ref > 2_000_000 and ((W + 15) // 16) * ((H + 15) // 16) == 8160
+    # ... without moving a pixel: images, first-K ids, radii against the oracle's UN-culled traversal
+    ok = ~fragile
+    Hh.assert_pixels_close(n(out["rgb"][0]), fwd["rgb"]["rendered"], fragile, "rgb")
+    Hh.assert_pixels_close(n(out["depth"][0]), fwd["depth"]["rendered"], fragile, "depth")
+    got_attr = torch.cat([out[k][0] for k in ATTRS], 0)
+    Hh.assert_pixels_close(n(got_attr), fwd["attrs"]["rendered"], fragile, "attrs")
+    assert np.array_equal(n(out["gs_idx"][0])[ok], fwd["rgb"]["gs_idx"][ok])
+    assert np.array_equal(n(out["radii"]), oo["radius"]) and np.array_equal(n(out["visibility"]), oo["radius"] > 0)
+    torch.autograd.backward([out["rgb"][0], out["depth"][0], got_attr], [t(grads["rgb"], cuda), t(grads["depth"], cuda), t(grads["attrs"], cuda)])
+    for k in ("position", "scaling", "rotation", "opacity", "shs"):
+        Hh.assert_grad_close(n(rd[k].grad), want[k], f"d/d{k}", norm_tol=1e-4)
+    ga = want["attrs"]
+    for k, sl in (("track_gs", slice(0, 3)), ("mask_attribute", slice(3, 4)), ("pos_poly_feat", slice(4, 16)), ("dino_attribute", slice(16, 19))):
+        if rd[k].requires_grad:
+            Hh.assert_grad_close(n(rd[k].grad), ga[:, sl], f"d/d{k}", norm_tol=1e-4)
+        else:
+            assert rd[k].grad is None
+    Hh.assert_grad_close(n(out["viewspace_points"][0].grad), want["ndc"], "ndc.grad", norm_tol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The other two renderer mirrors (boundary B0): DPTRRender (perspective, src/pointrix/renderer/dptr.py:42-169) and
+# DPTROrthoRender (src/pointrix/renderer/dptr_ortho.py): view-dependent SH, ONE blend of cat(rgb, depth[, pixel_flow]).
+@pytest.mark.parametrize("name", ["DPTRRender", "DPTROrthoRender"])
+def test_single_blend_renderer_mirrors_match_torch_restatement(cuda, name):
+    from splatter_a_video_b200.renderer import parse_renderer
+    sc = synth.make_config("cfg1_tiny")
+    W, H, P = sc.W, sc.H, sc.P
+    persp = name == "DPTRRender"
+    g = torch.Generator().manual_seed(5)
+    flow = torch.rand(P, 2, generator=g)
+    campos = torch.tensor([0.05, -0.02, -0.3])
+    src = {"position": sc.frame_position(0), "opacity": sc.opacity, "scaling": sc.scaling * (2.0 if persp else 1.0), "rotation": sc.rotation,
+           "shs": sc.shs, "pixel_flow": flow}
+    rd = {k: v.to(cuda).clone().requires_grad_(True) for k, v in src.items()}
+    rnd = parse_renderer({"name": name}, white_bg=True, device=cuda)
+    batch = {"height": H, "width": W, "extrinsic_matrix": sc.extr.to(cuda), "intrinsic_matrix": sc.intr.to(cuda), "camera_center": campos.to(cuda)}
+    out = rnd.render_batch(rd, [batch])
+    assert out["rgb"].shape == (1, 3, H, W) and out["depth"].shape == (1, 1, H, W) and out["pixel_flow"].shape == (1, 2, H, W)
+    assert out["radii"].dtype == torch.int32 and out["visibility"].dtype == torch.bool and len(out["viewspace_points"]) == 1
+
+    cpu = {k: v.clone().requires_grad_(True) for k, v in src.items()}
+    d = cpu["position"] - campos.reshape(1, 3)
+    d = d / d.norm(dim=1, keepdim=True)
+    rgb = TR.compute_sh(cpu["shs"], 3, d)
+    if persp:
+        uv, depth = TR.project_point(cpu["position"], sc.intr, sc.extr, W, H, nearest=0.01)
+    else:
+        uv, depth = TR.project_point_ortho(cpu["position"], sc.extr, W, H, nearest=0.01)
+    vis = depth.detach() != 0
+    cov3d = TR.compute_cov3d(cpu["scaling"], cpu["rotation"], vis)
+    if persp:
+        conic, radius, tiles = TR.ewa_project(cpu["position"], cov3d, sc.intr, sc.extr, uv, W, H, vis)
+    else:
+        conic, radius, tiles = TR.ewa_project_ortho(cov3d, sc.extr, uv, W, H, vis.reshape(-1))
+    idx, tr = TR.sort_gaussian(uv.detach(), depth.detach(), W, H, radius, tiles)
+    feat = torch.cat([rgb, depth, cpu["pixel_flow"]], 1)
+    img, _, _, _ = TR.alpha_blending(uv, conic, cpu["opacity"], feat, idx, tr, 1.0, W, H)
+    f = O.alpha_blending_forward(uv.detach().numpy(), conic.detach().numpy(), sc.opacity.numpy(), feat.detach().numpy(), idx.numpy(), tr.numpy(),
+                                 1.0, W, H, frag_eps=Hh.FRAG_EPS)
+    frag = f["fragile"]
+    assert np.array_equal(n(out["radii"]), radius.numpy()) and np.array_equal(n(out["visibility"]), (radius > 0).numpy())
+    got = torch.cat([out["rgb"][0], out["depth"][0], out["pixel_flow"][0]], 0)
+    Hh.assert_pixels_close(n(got), img.detach().numpy(), frag, name)
+    gimg = torch.randn(6, H, W, generator=g)
+    gimg[:, torch.from_numpy(frag)] = 0
+    got.backward(gimg.to(cuda)); img.backward(gimg)
+    for k in src:
+        Hh.assert_grad_close(n(rd[k].grad), cpu[k].grad.numpy(), f"{name} d/d{k}", norm_tol=2e-4)
