@@ -46,8 +46,8 @@ SPV_API long long spv_launch_count(void);
 /* Measurement hook (no reference counterpart): when enabled, every blend kernel launch is bracketed by a pair of CUDA events
  * on its own stream (slot 0 = forward kernel, 1 = backward kernel; also inside a captured graph).  `read` waits for the
  * slot's closing event and returns the device time of the most recent launch.  Disabled (default): no cost. */
-/* Runtime switch of an experimental kernel variant (0 = the validated default).  "bwd_wide" = 2 | 4: pixels per lane of the
- * frame path's backward blend kernel (also read once from the environment variable SPV_BWD_WIDE). */
+/* Runtime switch of a kernel variant (0 = the default).  "bwd_variant" = 1: the chunk-barrier backward blend kernel of round 1
+ * instead of the ring-staged one (also read once from the environment variable SPV_BWD_VARIANT). */
 SPV_API int spv_set_option(const char *name, int value);
 SPV_API int spv_kernel_timer_enable(int on);
 SPV_API int spv_kernel_timer_read(int slot, float *ms);
@@ -239,6 +239,11 @@ SPV_API int spv_deform_rotation_backward(int P, const float *out, const float *i
 SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,
                   const long long *seg_end_host, const float *seg_lr_host, float beta1, float beta2, float eps, int step,
                   void *stream);
+/* Same update with the optimizer clock and the learning rates in device memory (CUDA-graph capturable: every replay advances
+ * the bias corrections).  state_dev = float[4] {step, 1-b1^step, sqrt(1-b2^step), -}, zero-initialised once; lr_dev = float[nseg]. */
+SPV_API int spv_adam_step_device(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,
+                         const long long *seg_end_host, const float *lr_dev, float beta1, float beta2, float eps,
+                         float *state_dev, void *stream);
 
 /* ---- Densification on the flat SoA (next row f-3, structure half) -------------------------------------------------
  * Role of AtlasGaussianSplattingOptimizer.update_structure / densification / prune / reset_opacity

@@ -41,8 +41,9 @@ multi[248])
   grep "train (res" gpurun_out/bench_${N}gpu_${TAG}.err | tail -1
   timeout 300 $T 29518 bench.py --gpus $N --steps 10 --warmup 3 --trace gpurun_out/trace_${N}gpu_${TAG}.json 2>&1 | grep "us x" | head -14 ;;
 experimental)
-  # kernel variants of the backward blend: in-step time of each (parity: tests/test_frame_gpu.py::test_backward_kernel_variants_equal_default)
-  for v in "SPV_BWD_VARIANT=0" "SPV_BWD_VARIANT=1" "SPV_BWD_VARIANT=1 SPV_BWD_WIDE=2" "SPV_BWD_VARIANT=1 SPV_BWD_WIDE=4"; do
+  # kernel variants of the backward blend: parity, then the in-step time of each
+  timeout 300 python -m pytest tests/test_frame_gpu.py -m gpu -q -p no:cacheprovider -k "variants or loss" --tb=short 2>&1 | tail -5
+  for v in ${VARIANTS:-"SPV_BWD_VARIANT=0" "SPV_BWD_VARIANT=1"}; do
     env $v timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --quick 2> gpurun_out/bench_variant_${TAG}.err | python -c "import sys, json; d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v', round(d['value'], 1), 'it/s', d['kernels_in_step_ms'])"
   done ;;
 ncubwd)

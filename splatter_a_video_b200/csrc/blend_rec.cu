@@ -211,196 +211,10 @@ blend_rec_fwd_kernel(int C, int W, int H, int gx, int K, const float *__restrict
 // 8.. dL_dfeature  31,32 RGB-pass dL_duv.  CG = leading feature channels whose gradient is wanted.  Reduction networks:
 // CG <= 8: 16-wide (8 geometric sums + 8 features) + the RGB-pass pair on a 2-wide one (21 shuffles);
 // CG <= 14: 16-wide + an 8-wide one carrying features 8..13 and the RGB-pass pair (25 shuffles); else 32-wide + the pair (36).
-template <int CH, int CG>
-__global__ void __launch_bounds__(kBlock, 3)
-blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
-                     const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
-                     const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
-                     float *__restrict__ packed) {
-    constexpr int NV = (CG <= 14) ? 16 : 32;
-    constexpr bool MID = CG > 8 && CG <= 14;
-    static_assert(CH % 4 == 0 && CH >= 4 && CH <= 24 && 8 + CG <= 32 && CG <= CH, "unsupported channel configuration");
-    constexpr int RP = kRec;                        // 36: pitch/4 = 9 is odd
-    constexpr int DS = (CH <= 4) ? 4 : ((CH <= 12) ? 12 : ((CH <= 20) ? 20 : 28));   // dL_dpixel row pitch, pitch/4 odd
-    extern __shared__ __align__(128) float s_dyn[];
-    float *s_rec0 = s_dyn;                           // [2][kChunk][RP]
-    float *dq = s_dyn + 2 * kChunk * RP + threadIdx.x * DS;   // this pixel's dL_dpixel row
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ int s_max;
-
-    const int tile = blockIdx.x;
-    const int tile_x = tile % gx, tile_y = tile / gx;
-    int px, py;
-    thread_pixel(tile_x, tile_y, px, py);
-    const bool inside = px < W && py < H;
-    const size_t pix = (size_t)W * py + px;
-    const float pxf = (float)px, pyf = (float)py;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float bx0 = (float)(tile_x * SPV_TILE + ((warp & 1) << 3)), by0 = (float)(tile_y * SPV_TILE + ((warp >> 1) << 2));
-
-    const int2 range = tile_range[tile];
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    const int last_contrib = inside ? ncontrib[pix] : 0;
-
-    if (threadIdx.x == 0) {
-        s_max = 0;
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int wmax = __reduce_max_sync(kFull, last_contrib);   // positions >= wmax were applied by no pixel of this warp
-    if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
-    __syncthreads();
-    const int n_eff = min(range.y - range.x, s_max);   // ... and positions >= s_max by no pixel of the tile: never staged
-    const int nchunks = (n_eff + kChunk - 1) / kChunk;
-
-    // chunk c covers list positions [p_hi - m, p_hi), p_hi = n_eff - c*kChunk; slot t holds position p_hi - 1 - t
-    auto issue = [&](int c) {
-        const int b = c & 1, p_hi = n_eff - c * kChunk, m = min(kChunk, p_hi);
-        if (threadIdx.x == 0) mbar_expect_tx(&s_bar[b], (uint32_t)(m * kRec * 4));
-        if ((int)threadIdx.x < m) {
-            const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];
-            bulk_g2s(s_rec0 + (b * kChunk + threadIdx.x) * RP, rec + (size_t)id * kRec, kRec * 4, &s_bar[b]);
-        }
-    };
-    if (nchunks > 0) issue(0);
-
-    // <bg, dL_dpixel> per gradient group
-    float bgdA = 0.f, bgdB = 0.f, bgdC = 0.f;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        const float dv = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
-        dq[c] = dv;
-        if (c >= 4) bgdC += dv;
-        else if (c == 3) bgdB += dv;
-        else bgdA += dv;
-    }
-    bgdA *= bgA; bgdB *= bgB; bgdC *= bgC;
-
-    float last_alpha = 0.f, lfA = 0.f, lfB = 0.f, lfC = 0.f, SA = 0.f, SB = 0.f, SC = 0.f;
-
-    for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) issue(c + 1);
-        mbar_wait(&s_bar[c & 1], (c >> 1) & 1);
-        const float *sr = s_rec0 + (c & 1) * kChunk * RP;
-        const int p_hi = n_eff - c * kChunk, m = min(kChunk, p_hi);
-        for (int j0 = 0; j0 < m; j0 += 32) {
-            if (p_hi - 1 - (j0 + 31) >= wmax) continue;   // the whole sub-batch lies behind this warp's last contributor
-            // stage 1: one chunk entry per lane -- can the warp's 8x4 pixel block have taken it at all?
-            bool maybe = false;
-            if (j0 + lane < m && p_hi - 1 - (j0 + lane) < wmax) {
-                const float4 *r = reinterpret_cast<const float4 *>(sr + (j0 + lane) * RP);
-                maybe = block_may_hit<false>(r[0], r[1], bx0, by0);
-            }
-            unsigned todo = __ballot_sync(kFull, maybe);
-            // stage 2 (chunk order = back to front, which the recurrences need).  The body is branch-free: a lane that did
-            // not take the Gaussian runs it with p2 = -inf, i.e. G = alpha = w = 0, so every partial sum it contributes is
-            // an exact zero and only the recurrence state needs selects.
-            while (todo) {
-                const int j = j0 + __ffs(todo) - 1;
-                todo &= todo - 1u;
-                const float4 *r = reinterpret_cast<const float4 *>(sr + j * RP);
-                float dx = 0.f, dy = 0.f;
-                const float4 g0 = r[0], g1 = r[1];
-                float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-                // did this pixel apply the Gaussian in the forward pass?  (same test, and before its last contributor)
-                const bool hit = splat_hits<false>(p2, g1) && (p_hi - 1 - j) < last_contrib;
-                if (!__any_sync(kFull, hit)) continue;
-                float v[NV];
-                float u[8];   // MID: features 8..13 | RGB-pass pair
-                float n0, n1;
-                {
-                    const float4 con = r[kRec / 4 - 1];
-                    float Gv;
-                    p2 = hit ? p2 : -INFINITY;
-                    const float alpha = splat_alpha<false>(p2, g1, Gv);
-                    const float rinv = __fdividef(1.f, 1.f - alpha);
-                    T = T * rinv;  // transmittance in front of this Gaussian (unchanged when alpha == 0)
-                    const float w = alpha * T;
-                    const float tb = -T_final * rinv;
-                    const float om = 1.f - last_alpha;
-                    float fdA = 0.f, fdB = 0.f, fdC = 0.f;
-#pragma unroll
-                    for (int c4 = 0; c4 < CH / 4; ++c4) {
-                        const float4 ff = r[2 + c4];
-                        const float4 dd = *reinterpret_cast<const float4 *>(dq + 4 * c4);
-                        const float fv[4] = {ff.x, ff.y, ff.z, ff.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int ch = 4 * c4 + k;
-                            if (ch >= 4) fdC = fmaf(fv[k], dv[k], fdC);
-                            else if (ch == 3) fdB = fmaf(fv[k], dv[k], fdB);
-                            else fdA = fmaf(fv[k], dv[k], fdA);
-                            if (ch < CG) {
-                                if (MID && ch >= 8) u[ch - 8] = w * dv[k];
-                                else v[8 + ch] = w * dv[k];
-                            }
-                        }
-                    }
-                    const float nSA = last_alpha * lfA + om * SA;
-                    const float nSB = last_alpha * lfB + om * SB;
-                    const float nSC = last_alpha * lfC + om * SC;
-                    const float da_ndc = (fdA - nSA) * T + tb * bgdA;
-                    const float da_op = da_ndc + ((fdB - nSB) * T + tb * bgdB);
-                    const float da_all = da_op + ((fdC - nSC) * T + tb * bgdC);
-                    SA = hit ? nSA : SA; SB = hit ? nSB : SB; SC = hit ? nSC : SC;
-                    lfA = hit ? fdA : lfA; lfB = hit ? fdB : lfB; lfC = hit ? fdC : lfC;
-#pragma unroll
-                    for (int q = 8 + (MID ? 8 : CG); q < NV; ++q) v[q] = 0.f;
-                    if (MID) {
-#pragma unroll
-                        for (int q = CG - 8; q < 6; ++q) u[q] = 0.f;
-                    }
-                    last_alpha = hit ? alpha : last_alpha;
-                    const float dL_dG = g1.z * da_all;
-                    const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
-                    const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
-                    v[0] = dL_dG * dGx; v[1] = dL_dG * dGy;
-                    v[4] = -0.5f * Gv * dx * dx * dL_dG;
-                    v[5] = -Gv * dx * dy * dL_dG;
-                    v[6] = -0.5f * Gv * dy * dy * dL_dG;
-                    v[7] = Gv * da_op;
-                    const float dL_dG_ndc = g1.z * da_ndc;
-                    n0 = dL_dG_ndc * dGx; n1 = dL_dG_ndc * dGy;
-                    v[2] = fabsf(n0); v[3] = fabsf(n1);
-                }
-                halving_reduce<NV, 0, NV>(v, lane);   // lane l (< NV) now holds the warp-wide sum of value l
-                float *row = packed + (size_t)__float_as_int(g1.w) * kRowG;
-                if constexpr (MID) {
-                    u[6] = n0; u[7] = n1;
-                    halving_reduce<8, 0, 8>(u, lane);     // lane l holds the sum of u[l % 8]
-                    const int t = lane - 16;              // one RED: lanes 0..15 <- v, lanes 16..23 <- u
-                    const float val = lane < 16 ? v[0] : u[0];
-                    const int col = lane < 16 ? lane : (t < 6 ? 16 + t : 31 + (t - 6));
-                    const bool live = lane < 16 || (lane < 24 && (t >= 6 || t < CG - 8));
-                    if (live && val != 0.f) atomicAdd(row + col, val);
-                } else {
-                    // the two RGB-pass sums: one halving step (odd lanes take n1, even lanes n0), then 4 butterfly steps
-                    const bool up = (lane & 1) != 0;
-                    float e = (up ? n1 : n0) + __shfl_xor_sync(kFull, up ? n0 : n1, 1);
-#pragma unroll
-                    for (int o = 2; o <= 16; o <<= 1) e += __shfl_xor_sync(kFull, e, o);
-                    if constexpr (NV == 16) {   // one RED: lanes 0..15 the network's sums, lanes 16,17 the RGB-pass pair
-                        const float val = lane < 16 ? v[0] : e;
-                        const int col = lane < 16 ? lane : 31 + (lane & 1);
-                        if (lane < 18 && val != 0.f) atomicAdd(row + col, val);
-                    } else {
-                        if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + lane, v[0]);
-                        if (lane < 2 && e != 0.f) atomicAdd(row + 31 + lane, e);
-                    }
-                }
-            }
-        }
-        __syncthreads();   // every warp is done with buffer c&1: chunk c+2 may land in it
-    }
-}
-
-// ---- backward, ring-staged (default) ---------------------------------------------------------------------------------------
-// blend_rec_bwd_kernel above synchronises its 8 warps at every chunk: ncu (profiles/r01_ncu_blend_rec_bwd.csv) shows the CTA
-// barrier as its top stall reason (2.2 warps per issue slot) -- the 8x4-pixel blocks of a tile take a different number of list
-// entries, and every chunk ends when the slowest block is done.  Here the warps of a tile are decoupled:
+// Ring staging.  Round 1's kernel synchronised its 8 warps at every 128-entry chunk; ncu (profiles/r01_ncu_blend_rec_bwd.csv)
+// showed the CTA barrier as its top stall reason (2.2 warps per issue slot) -- the 8x4-pixel blocks of a tile take a different
+// number of list entries, and every chunk ended when the slowest block was done.  Here the warps of a tile are decoupled
+// (measured: -2.4 %, profiles/r02_bwd_variants.txt -- the barrier was where warps waited, not what bounds the kernel):
 //   * the list is staged into a ring of kRing buffers of kRingChunk entries (same 36 KB as the two 128-entry buffers), all of
 //     them requested up front -- tile lists average ~290 entries, so most tiles never wait again;
 //   * a warp that finishes a chunk bumps that buffer's counter; the LAST warp to do so (by definition nobody is left reading
@@ -409,7 +223,6 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
 //   * the per-pixel recurrences run on R = sum over the Gaussians behind of <f, dL_dpixel> alpha T (one FMA per group and
 //     entry, no state selects: a lane that did not take the Gaussian has w = 0) instead of the normalised accum_rec form:
 //         dL_dalpha = T <f, d> - (R + T_final <bg, d>) / (1 - alpha)         (alpha_blending.cu:180-246, same sum)
-// Reduction networks and packed-row layout are those of blend_rec_bwd_kernel.
 constexpr int kRing = 4, kRingChunk = 64;
 
 __device__ __forceinline__ int atom_add_acq_rel_shared(int *addr, int v) {
@@ -418,20 +231,28 @@ __device__ __forceinline__ int atom_add_acq_rel_shared(int *addr, int v) {
     return old;
 }
 
-template <int CH, int CG>
+// ABS: the |RGB-pass dL_duv| pair (packed columns 2,3) is wanted.  The renderer only reads it under densify_abs_grad_enable
+// (dptr_ortho_enhanced.py:378-383 returns ONE of ndc / abs_ndc as viewspace_points); without it the RGB-pass pair takes its two
+// slots in the 16-wide network and the extra network shrinks or disappears:
+//                    ABS                                          !ABS
+//   CG <= 8          16-wide + pair butterfly       21 shuffles   16-wide                        16
+//   CG <= 12         16-wide + 8-wide (feat + pair) 25            16-wide + 4-wide (feat 8..11)  22
+//   CG <= 14         16-wide + 8-wide               25            16-wide + 8-wide (feat 8..13)  25
+//   else             32-wide + pair butterfly       36            32-wide                        31
+template <int CH, int CG, bool ABS>
 __global__ void __launch_bounds__(kBlock, 3)
-blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
-                          const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
-                          const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
-                          float *__restrict__ packed) {
+blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
+                     const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
+                     const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
+                     float *__restrict__ packed) {
     constexpr int NV = (CG <= 14) ? 16 : 32;
-    constexpr bool MID = CG > 8 && CG <= 14;
+    constexpr int NU = (CG <= 8 || NV == 32) ? 0 : ((!ABS && CG <= 12) ? 4 : 8);   // second network: features 8.. (+ the pair if ABS)
     static_assert(CH % 4 == 0 && CH >= 4 && CH <= 24 && 8 + CG <= 32 && CG <= CH, "unsupported channel configuration");
     static_assert(kRing * kRingChunk == kBlock, "one bulk copy per thread fills the whole ring");
     constexpr int RP = kRec;                        // 36: pitch/4 = 9 is odd
     constexpr int DS = rec_pitch(CH);               // dL_dpixel row pitch, pitch/4 odd
     extern __shared__ __align__(128) float s_dyn[];
-    float *s_rec0 = s_dyn;                                       // [kRing][kRingChunk][RP]
+    float *s_rec0 = s_dyn;                                            // [kRing][kRingChunk][RP]
     float *dq = s_dyn + kRing * kRingChunk * RP + threadIdx.x * DS;   // this pixel's dL_dpixel row
     __shared__ __align__(8) uint64_t s_full[kRing];
     __shared__ int s_done[kRing];
@@ -521,7 +342,7 @@ blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__
                 const bool hit = splat_hits<false>(p2, g1) && (p_hi - 1 - j) < last_contrib;
                 if (!__any_sync(kFull, hit)) continue;
                 float v[NV];
-                float u[8];   // MID: features 8..13 | RGB-pass pair
+                float u[NU > 0 ? NU : 1];   // second network: features 8.. (| RGB-pass pair when ABS)
                 float n0, n1;
                 {
                     const float4 con = r[kRec / 4 - 1];
@@ -544,7 +365,7 @@ blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__
                             else if (ch == 3) fdB = fmaf(fv[k], dv[k], fdB);
                             else fdA = fmaf(fv[k], dv[k], fdA);
                             if (ch < CG) {
-                                if (MID && ch >= 8) u[ch - 8] = w * dv[k];
+                                if (NU > 0 && ch >= 8) u[ch - 8] = w * dv[k];
                                 else v[8 + ch] = w * dv[k];
                             }
                         }
@@ -554,11 +375,9 @@ blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__
                     const float da_all = da_op + fmaf(T, fdC, -rinv * (RC + tfC));
                     RA = fmaf(fdA, w, RA); RB = fmaf(fdB, w, RB); RC = fmaf(fdC, w, RC);
 #pragma unroll
-                    for (int q = 8 + (MID ? 8 : CG); q < NV; ++q) v[q] = 0.f;
-                    if (MID) {
+                    for (int q = 8 + (NU > 0 ? 8 : CG); q < NV; ++q) v[q] = 0.f;
 #pragma unroll
-                        for (int q = CG - 8; q < 6; ++q) u[q] = 0.f;
-                    }
+                    for (int q = CG - 8; q < NU - (ABS ? 2 : 0); ++q) u[q] = 0.f;
                     const float dL_dG = g1.z * da_all;
                     const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
                     const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
@@ -569,24 +388,29 @@ blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__
                     v[7] = Gv * da_op;
                     const float dL_dG_ndc = g1.z * da_ndc;
                     n0 = dL_dG_ndc * dGx; n1 = dL_dG_ndc * dGy;
-                    v[2] = fabsf(n0); v[3] = fabsf(n1);
+                    if constexpr (ABS) { v[2] = fabsf(n0); v[3] = fabsf(n1); }
+                    else { v[2] = n0; v[3] = n1; }        // the RGB-pass pair rides in the |.| slots
                 }
                 halving_reduce<NV, 0, NV>(v, lane);   // lane l (< NV) now holds the warp-wide sum of value l
                 float *row = packed + (size_t)__float_as_int(g1.w) * kRowG;
-                if constexpr (MID) {
-                    u[6] = n0; u[7] = n1;
-                    halving_reduce<8, 0, 8>(u, lane);     // lane l holds the sum of u[l % 8]
-                    const int t = lane - 16;              // one RED: lanes 0..15 <- v, lanes 16..23 <- u
+                // network slot -> packed column: 2,3 hold the RGB-pass pair (columns 31,32) when !ABS
+                const int vcol = (!ABS && (lane == 2 || lane == 3)) ? 29 + lane : lane;
+                if constexpr (NU > 0) {
+                    if constexpr (ABS) { u[NU - 2] = n0; u[NU - 1] = n1; }
+                    halving_reduce<NU, 0, NU>(u, lane);     // lane l holds the sum of u[l % NU]
+                    const int t = lane - 16;                // one RED: lanes 0..15 <- v, lanes 16..16+NU-1 <- u
                     const float val = lane < 16 ? v[0] : u[0];
-                    const int col = lane < 16 ? lane : (t < 6 ? 16 + t : 31 + (t - 6));
-                    const bool live = lane < 16 || (lane < 24 && (t >= 6 || t < CG - 8));
+                    const int nf = ABS ? NU - 2 : NU;       // feature slots of the second network
+                    const int col = lane < 16 ? vcol : (t < nf ? 16 + t : 31 + (t - nf));
+                    const bool live = lane < 16 || (lane < 16 + NU && (t >= nf || t < CG - 8));
                     if (live && val != 0.f) atomicAdd(row + col, val);
-                } else {
+                } else if constexpr (ABS) {
+                    // the two RGB-pass sums: one halving step (odd lanes take n1, even lanes n0), then 4 butterfly steps
                     const bool up = (lane & 1) != 0;
                     float e = (up ? n1 : n0) + __shfl_xor_sync(kFull, up ? n0 : n1, 1);
 #pragma unroll
                     for (int o = 2; o <= 16; o <<= 1) e += __shfl_xor_sync(kFull, e, o);
-                    if constexpr (NV == 16) {
+                    if constexpr (NV == 16) {   // one RED: lanes 0..15 the network's sums, lanes 16,17 the RGB-pass pair
                         const float val = lane < 16 ? v[0] : e;
                         const int col = lane < 16 ? lane : 31 + (lane & 1);
                         if (lane < 18 && val != 0.f) atomicAdd(row + col, val);
@@ -594,6 +418,8 @@ blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__
                         if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + lane, v[0]);
                         if (lane < 2 && e != 0.f) atomicAdd(row + 31 + lane, e);
                     }
+                } else {
+                    if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + vcol, v[0]);
                 }
             }
         }
@@ -622,210 +448,6 @@ blend_rec_bwd_ring_kernel(int C, int W, int H, int gx, const float *__restrict__
     }
 }
 
-// ---- backward, wide warp footprints (EXPERIMENTAL, opt-in: SPV_BWD_WIDE=2|4 or spv_set_option("bwd_wide", 2|4)) ----------------
-// 41 % of blend_rec_bwd_kernel's instructions are its per-(warp, entry) shuffle reductions (profiles/r01_ncu_blend_rec_bwd_lines.txt),
-// one per ACTIVE (8x4-pixel block, entry) pair: 1.283 M on the config-A frame.  With R pixels per lane a warp covers R of those blocks
-// (R = 2: 16x4, R = 4: 16x8 pixels), accumulates the partials of its R sub-blocks in registers and reduces ONCE per entry:
-// 0.890 M / 0.605 M reductions (tests/hit_stats.py).  CTA = 256 / R threads per tile; the per-pixel constants (T_final, <bg, dL_dpixel>)
-// move into the spare slots of the pixel's dL_dpixel row in shared memory; chunks shrink to 32 entries so 5 tiles stay resident per SM.
-// Same arithmetic per (pixel, entry) as blend_rec_bwd_kernel; only the association of the per-Gaussian sums changes.
-// NOT YET VALIDATED ON A GPU (written after the round's GPU budget was spent): default off, tests opt-in (SPV_TEST_EXPERIMENTAL=1).
-constexpr int kChunkW = 32;
-
-template <int CH, int CG, int R>
-__global__ void __launch_bounds__(kBlock / R)
-blend_rec_bwd_wide_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
-                          const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
-                          const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
-                          float *__restrict__ packed) {
-    constexpr int NV = (CG <= 14) ? 16 : 32;
-    constexpr bool MID = CG > 8 && CG <= 14;
-    static_assert(R == 2 || R == 4, "R pixels per lane");
-    static_assert(CH % 4 == 0 && CH >= 4 && CH <= 24 && 8 + CG <= 32 && CG <= CH, "unsupported channel configuration");
-    constexpr int RP = kRec;
-    // dL_dpixel row: CH gradients + [bgdA bgdB bgdC T_final], pitch/4 odd
-    constexpr int DS = ((CH + 4) / 4) % 2 ? CH + 4 : CH + 8;
-    constexpr int kThreadsW = kBlock / R;
-    extern __shared__ __align__(128) float s_dyn[];
-    float *s_rec0 = s_dyn;                            // [2][kChunkW][RP]
-    float *s_dq = s_dyn + 2 * kChunkW * RP;           // [256 pixels][DS]
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ int s_max;
-
-    const int tile = blockIdx.x;
-    const int tile_x = tile % gx, tile_y = tile / gx;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // sub-block sb = warp*R + r is the 8x4 block at (8*(sb&1), 4*(sb>>1)) of the tile: R = 2 -> 16x4 per warp, R = 4 -> 16x8
-    const int px0 = tile_x * SPV_TILE + (lane & 7), py0 = tile_y * SPV_TILE + (lane >> 3) + 4 * ((warp * R) >> 1);
-    const float wx0 = (float)(tile_x * SPV_TILE), wy0 = (float)(tile_y * SPV_TILE + 4 * ((warp * R) >> 1));
-    const float wx1 = wx0 + 15.f, wy1 = wy0 + (float)(2 * R - 1);     // pixel-centre rectangle of the warp's footprint
-
-    const int2 range = tile_range[tile];
-    float T[R], last_alpha[R], lfA[R], lfB[R], lfC[R], SA[R], SB[R], SC[R];
-    int last_contrib[R];
-    int wmax = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int px = px0 + 8 * (r & 1), py = py0 + 4 * (r >> 1);
-        const bool inside = px < W && py < H;
-        const size_t pix = (size_t)W * py + px;
-        const float Tf = inside ? final_T[pix] : 0.f;
-        T[r] = Tf;
-        last_contrib[r] = inside ? ncontrib[pix] : 0;
-        wmax = max(wmax, last_contrib[r]);
-        last_alpha[r] = lfA[r] = lfB[r] = lfC[r] = SA[r] = SB[r] = SC[r] = 0.f;
-        float *dq = s_dq + ((warp * R + r) * 32 + lane) * DS;
-        float bA = 0.f, bB = 0.f, bC = 0.f;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const float dv = (inside && c < C && planes.p[c]) ? planes.p[c][pix] : 0.f;
-            dq[c] = dv;
-            if (c >= 4) bC += dv;
-            else if (c == 3) bB += dv;
-            else bA += dv;
-        }
-        dq[CH] = bA * bgA; dq[CH + 1] = bB * bgB; dq[CH + 2] = bC * bgC; dq[CH + 3] = Tf;
-    }
-    if (threadIdx.x == 0) {
-        s_max = 0;
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    wmax = __reduce_max_sync(kFull, wmax);          // positions >= wmax were applied by no pixel of this warp
-    if (lane == 0 && wmax > 0) atomicMax(&s_max, wmax);
-    __syncthreads();
-    const int n_eff = min(range.y - range.x, s_max);
-    const int nchunks = (n_eff + kChunkW - 1) / kChunkW;
-
-    auto issue = [&](int c) {
-        const int b = c & 1, p_hi = n_eff - c * kChunkW, m = min(kChunkW, p_hi);
-        if (threadIdx.x == 0) mbar_expect_tx(&s_bar[b], (uint32_t)(m * kRec * 4));
-        if ((int)threadIdx.x < m) {
-            const int id = idx_sorted[range.x + p_hi - 1 - threadIdx.x];
-            bulk_g2s(s_rec0 + (b * kChunkW + threadIdx.x) * RP, rec + (size_t)id * kRec, kRec * 4, &s_bar[b]);
-        }
-    };
-    if (nchunks > 0) issue(0);
-
-    for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) issue(c + 1);
-        mbar_wait(&s_bar[c & 1], (c >> 1) & 1);
-        const float *sr = s_rec0 + (c & 1) * kChunkW * RP;
-        const int p_hi = n_eff - c * kChunkW, m = min(kChunkW, p_hi);
-        // stage 1: one chunk entry per lane (kChunkW == 32) -- can the warp's footprint have taken it at all?
-        bool maybe = false;
-        if (lane < m && p_hi - 1 - lane < wmax) {
-            const float4 *q = reinterpret_cast<const float4 *>(sr + lane * RP);
-            const float4 g0 = q[0], g1 = q[1];
-            const float tau2 = g1.y - kLog2AlphaMin;
-            maybe = (tau2 >= 0.f) && spv::tile_may_hit(g0.x, g0.y, -2.f * g0.z, -g0.w, -2.f * g1.x, tau2, wx0, wy0, wx1, wy1);
-        }
-        unsigned todo = __ballot_sync(kFull, maybe);
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const float4 *q = reinterpret_cast<const float4 *>(sr + j * RP);
-            const float4 g0 = q[0], g1 = q[1];
-            const float4 con = q[kRec / 4 - 1];
-            const int pos = p_hi - 1 - j;
-            float v[NV];
-            float u[8];
-            float e0 = 0.f, e1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) u[k] = 0.f;
-            bool any_hit = false;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float pxf = (float)(px0 + 8 * (r & 1)), pyf = (float)(py0 + 4 * (r >> 1));
-                float dx, dy;
-                float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
-                const bool hit = splat_hits<false>(p2, g1) && pos < last_contrib[r];
-                if (!__any_sync(kFull, hit)) continue;                 // warp-uniform: this 8x4 sub-block did not take it
-                any_hit = true;
-                const float *dq = s_dq + ((warp * R + r) * 32 + lane) * DS;
-                const float4 cst = *reinterpret_cast<const float4 *>(dq + CH);   // bgdA bgdB bgdC T_final
-                float Gv;
-                p2 = hit ? p2 : -INFINITY;
-                const float alpha = splat_alpha<false>(p2, g1, Gv);
-                const float rinv = __fdividef(1.f, 1.f - alpha);
-                T[r] = T[r] * rinv;
-                const float w = alpha * T[r];
-                const float tb = -cst.w * rinv;
-                const float om = 1.f - last_alpha[r];
-                float fdA = 0.f, fdB = 0.f, fdC = 0.f;
-#pragma unroll
-                for (int c4 = 0; c4 < CH / 4; ++c4) {
-                    const float4 ff = q[2 + c4];
-                    const float4 dd = *reinterpret_cast<const float4 *>(dq + 4 * c4);
-                    const float fv[4] = {ff.x, ff.y, ff.z, ff.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int ch = 4 * c4 + k;
-                        if (ch >= 4) fdC = fmaf(fv[k], dv[k], fdC);
-                        else if (ch == 3) fdB = fmaf(fv[k], dv[k], fdB);
-                        else fdA = fmaf(fv[k], dv[k], fdA);
-                        if (ch < CG) {
-                            if (MID && ch >= 8) u[ch - 8] = fmaf(w, dv[k], u[ch - 8]);
-                            else v[8 + ch] = fmaf(w, dv[k], v[8 + ch]);
-                        }
-                    }
-                }
-                const float nSA = last_alpha[r] * lfA[r] + om * SA[r];
-                const float nSB = last_alpha[r] * lfB[r] + om * SB[r];
-                const float nSC = last_alpha[r] * lfC[r] + om * SC[r];
-                const float da_ndc = (fdA - nSA) * T[r] + tb * cst.x;
-                const float da_op = da_ndc + ((fdB - nSB) * T[r] + tb * cst.y);
-                const float da_all = da_op + ((fdC - nSC) * T[r] + tb * cst.z);
-                SA[r] = hit ? nSA : SA[r]; SB[r] = hit ? nSB : SB[r]; SC[r] = hit ? nSC : SC[r];
-                lfA[r] = hit ? fdA : lfA[r]; lfB[r] = hit ? fdB : lfB[r]; lfC[r] = hit ? fdC : lfC[r];
-                last_alpha[r] = hit ? alpha : last_alpha[r];
-                const float dL_dG = g1.z * da_all;
-                const float dGx = -Gv * dx * con.x - Gv * dy * con.y;
-                const float dGy = -Gv * dy * con.z - Gv * dx * con.y;
-                v[0] += dL_dG * dGx; v[1] += dL_dG * dGy;
-                v[4] += -0.5f * Gv * dx * dx * dL_dG;
-                v[5] += -Gv * dx * dy * dL_dG;
-                v[6] += -0.5f * Gv * dy * dy * dL_dG;
-                v[7] += Gv * da_op;
-                const float dL_dG_ndc = g1.z * da_ndc;
-                const float n0 = dL_dG_ndc * dGx, n1 = dL_dG_ndc * dGy;
-                e0 += n0; e1 += n1;
-                v[2] += fabsf(n0); v[3] += fabsf(n1);
-            }
-            if (!any_hit) continue;
-            halving_reduce<NV, 0, NV>(v, lane);
-            float *row = packed + (size_t)__float_as_int(g1.w) * kRowG;
-            if constexpr (MID) {
-                u[6] = e0; u[7] = e1;
-                halving_reduce<8, 0, 8>(u, lane);
-                const int t = lane - 16;
-                const float val = lane < 16 ? v[0] : u[0];
-                const int col = lane < 16 ? lane : (t < 6 ? 16 + t : 31 + (t - 6));
-                const bool live = lane < 16 || (lane < 24 && (t >= 6 || t < CG - 8));
-                if (live && val != 0.f) atomicAdd(row + col, val);
-            } else {
-                const bool up = (lane & 1) != 0;
-                float e = (up ? e1 : e0) + __shfl_xor_sync(kFull, up ? e0 : e1, 1);
-#pragma unroll
-                for (int o = 2; o <= 16; o <<= 1) e += __shfl_xor_sync(kFull, e, o);
-                if constexpr (NV == 16) {
-                    const float val = lane < 16 ? v[0] : e;
-                    const int col = lane < 16 ? lane : 31 + (lane & 1);
-                    if (lane < 18 && val != 0.f) atomicAdd(row + col, val);
-                } else {
-                    if (lane < 8 + CG && v[0] != 0.f) atomicAdd(row + lane, v[0]);
-                    if (lane < 2 && e != 0.f) atomicAdd(row + 31 + lane, e);
-                }
-            }
-        }
-        __syncthreads();   // every warp is done with buffer c&1
-    }
-}
-
 struct RecFwdArgs {
     int C, W, H, gx, K;
     const float *rec; const int *idx_sorted; const int2 *tile_range; float bgA, bgB, bgC;
@@ -846,63 +468,31 @@ struct RecBwdArgs {
     const float *final_T; const int *ncontrib; spv::ChanPlanes planes; float *packed;
 };
 
-template <int CH, int CG>
+template <int CH, int CG, bool ABS>
 void launch_rec_bwd(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
-    constexpr int DS = (CH <= 4) ? 4 : ((CH <= 12) ? 12 : ((CH <= 20) ? 20 : 28));
-    constexpr size_t dyn = sizeof(float) * (2 * kChunk * kRec + kBlock * DS);
-    static std::atomic<unsigned long long> configured{0};   // up to 64.5 KB of dynamic shared memory: above the 48 KB default
-    spv::opt_in_dynamic_smem(blend_rec_bwd_kernel<CH, CG>, dyn, configured);
-    spv::timer_mark(1, 0, s);
-    blend_rec_bwd_kernel<CH, CG><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA, a.bgB,
-                                                            a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
-    spv::timer_mark(1, 1, s);
-}
-
-template <int CH, int CG>
-void launch_rec_bwd_ring(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
     constexpr size_t dyn = sizeof(float) * (kRing * kRingChunk * kRec + kBlock * rec_pitch(CH));
     static std::atomic<unsigned long long> configured{0};   // up to 64.5 KB of dynamic shared memory: above the 48 KB default
-    spv::opt_in_dynamic_smem(blend_rec_bwd_ring_kernel<CH, CG>, dyn, configured);
+    spv::opt_in_dynamic_smem(blend_rec_bwd_kernel<CH, CG, ABS>, dyn, configured);
     spv::timer_mark(1, 0, s);
-    blend_rec_bwd_ring_kernel<CH, CG><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA,
-                                                                 a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
+    blend_rec_bwd_kernel<CH, CG, ABS><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA, a.bgB,
+                                                                 a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
     spv::timer_mark(1, 1, s);
 }
 
-template <int CH, int CG, int R>
-void launch_rec_bwd_wide(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
-    constexpr int DS = ((CH + 4) / 4) % 2 ? CH + 4 : CH + 8;
-    constexpr size_t dyn = sizeof(float) * (2 * kChunkW * kRec + kBlock * DS);
-    static std::atomic<unsigned long long> configured{0};
-    spv::opt_in_dynamic_smem(blend_rec_bwd_wide_kernel<CH, CG, R>, dyn, configured);
-    spv::timer_mark(1, 0, s);
-    blend_rec_bwd_wide_kernel<CH, CG, R><<<ntiles, kBlock / R, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA,
-                                                                         a.bgB, a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
-    spv::timer_mark(1, 1, s);
+template <int CH, bool ABS>
+void dispatch_rec_bwd_cg(const RecBwdArgs &a, int n_grad, int ntiles, cudaStream_t s) {
+    // feature-gradient channels reduced: 4 (rgb + depth only), 8, 12, 14, or all CH
+    if (n_grad <= 4) launch_rec_bwd<CH, 4, ABS>(a, ntiles, s);
+    else if (n_grad <= 8 && CH >= 8) launch_rec_bwd<CH, (CH >= 8 ? 8 : CH), ABS>(a, ntiles, s);
+    else if (n_grad <= 12 && CH >= 16) launch_rec_bwd<CH, (CH >= 16 ? 12 : CH), ABS>(a, ntiles, s);
+    else if (n_grad <= 14 && CH >= 16) launch_rec_bwd<CH, (CH >= 16 ? 14 : CH), ABS>(a, ntiles, s);
+    else launch_rec_bwd<CH, (CH > 23 ? 23 : CH), ABS>(a, ntiles, s);
 }
 
 template <int CH>
-void dispatch_rec_bwd(const RecBwdArgs &a, int n_grad, int ntiles, cudaStream_t s) {
-    // experimental wide footprints: only the two configurations of the video trainer's frame (CH = 24, 8 or 14 gradient channels)
-    if constexpr (CH == 24) {
-        const int wide = spv::get_option("bwd_wide");
-        if (wide == 2 || wide == 4) {
-            if (n_grad > 4 && n_grad <= 8) { if (wide == 2) launch_rec_bwd_wide<24, 8, 2>(a, ntiles, s); else launch_rec_bwd_wide<24, 8, 4>(a, ntiles, s); return; }
-            if (n_grad > 8 && n_grad <= 14) { if (wide == 2) launch_rec_bwd_wide<24, 14, 2>(a, ntiles, s); else launch_rec_bwd_wide<24, 14, 4>(a, ntiles, s); return; }
-        }
-    }
-    // feature-gradient channels reduced: 4 (rgb + depth only), 8, 14, or all CH
-    if (spv::get_option("bwd_variant") != 1) {   // default: ring-staged, warps decoupled
-        if (n_grad <= 4) launch_rec_bwd_ring<CH, 4>(a, ntiles, s);
-        else if (n_grad <= 8 && CH >= 8) launch_rec_bwd_ring<CH, (CH >= 8 ? 8 : CH)>(a, ntiles, s);
-        else if (n_grad <= 14 && CH >= 16) launch_rec_bwd_ring<CH, (CH >= 16 ? 14 : CH)>(a, ntiles, s);
-        else launch_rec_bwd_ring<CH, (CH > 23 ? 23 : CH)>(a, ntiles, s);
-        return;
-    }
-    if (n_grad <= 4) launch_rec_bwd<CH, 4>(a, ntiles, s);
-    else if (n_grad <= 8 && CH >= 8) launch_rec_bwd<CH, (CH >= 8 ? 8 : CH)>(a, ntiles, s);
-    else if (n_grad <= 14 && CH >= 16) launch_rec_bwd<CH, (CH >= 16 ? 14 : CH)>(a, ntiles, s);
-    else launch_rec_bwd<CH, (CH > 23 ? 23 : CH)>(a, ntiles, s);
+void dispatch_rec_bwd(const RecBwdArgs &a, int n_grad, bool want_abs, int ntiles, cudaStream_t s) {
+    if (want_abs) dispatch_rec_bwd_cg<CH, true>(a, n_grad, ntiles, s);
+    else dispatch_rec_bwd_cg<CH, false>(a, n_grad, ntiles, s);
 }
 
 }  // namespace
@@ -949,7 +539,8 @@ int blend_records_forward(int C, int W, int H, int K, const float *rec, const in
 
 int blend_records_backward(int P, int C, int W, int H, const float *rec, const int *idx_sorted, const int *tile_range,
                            float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
-                           const float *const *planes_host, int n_grad_channels, float *packed, bool packed_is_zero, void *stream) {
+                           const float *const *planes_host, int n_grad_channels, bool want_abs, float *packed, bool packed_is_zero,
+                           void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0) return 0;
     if (C < 4 || C > 23) { spv::set_error(cudaErrorInvalidValue, "blend_records_backward: need 4 <= C <= 23"); return (int)cudaErrorInvalidValue; }
@@ -967,12 +558,12 @@ int blend_records_backward(int P, int C, int W, int H, const float *rec, const i
     a.bgA = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.final_T = final_T; a.ncontrib = ncontrib; a.packed = packed;
     for (int c = 0; c < 32; ++c) a.planes.p[c] = c < C ? planes_host[c] : nullptr;
     const int ng = n_grad_channels < 4 ? 4 : (n_grad_channels > C ? C : n_grad_channels);
-    if (C <= 4) dispatch_rec_bwd<4>(a, ng, ntiles, s);
-    else if (C <= 8) dispatch_rec_bwd<8>(a, ng, ntiles, s);
-    else if (C <= 12) dispatch_rec_bwd<12>(a, ng, ntiles, s);
-    else if (C <= 16) dispatch_rec_bwd<16>(a, ng, ntiles, s);
-    else if (C <= 20) dispatch_rec_bwd<20>(a, ng, ntiles, s);
-    else dispatch_rec_bwd<24>(a, ng, ntiles, s);
+    if (C <= 4) dispatch_rec_bwd<4>(a, ng, want_abs, ntiles, s);
+    else if (C <= 8) dispatch_rec_bwd<8>(a, ng, want_abs, ntiles, s);
+    else if (C <= 12) dispatch_rec_bwd<12>(a, ng, want_abs, ntiles, s);
+    else if (C <= 16) dispatch_rec_bwd<16>(a, ng, want_abs, ntiles, s);
+    else if (C <= 20) dispatch_rec_bwd<20>(a, ng, want_abs, ntiles, s);
+    else dispatch_rec_bwd<24>(a, ng, want_abs, ntiles, s);
     return spv::check_launch("spv_frame/blend_records_backward");
 }
 

@@ -125,6 +125,7 @@ int blend_records_forward(int C, int W, int H, int K, const float *rec, const in
                           int *gs_idx, void *stream);
 int blend_records_backward(int P, int C, int W, int H, const float *rec, const int *idx_sorted, const int *tile_range,
                            float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
-                           const float *const *planes_host, int n_grad_channels, float *packed, bool packed_is_zero, void *stream);
+                           const float *const *planes_host, int n_grad_channels, bool want_abs, float *packed, bool packed_is_zero,
+                           void *stream);
 
 }  // namespace spv

@@ -209,7 +209,8 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     const unsigned g = spv::cdiv(P, kThreads);
     float *packed = (float *)f.blend_ws;
     SPV_TRY_RC(spv::blend_records_backward(P, C, W, H, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, f.final_T,
-                                           f.ncontrib, dL_dimage_planes, n_grad_channels, packed, /*packed_is_zero=*/first_backward != 0, stream));
+                                           f.ncontrib, dL_dimage_planes, n_grad_channels, /*want_abs=*/dL_dabs_ndc != nullptr, packed,
+                                           /*packed_is_zero=*/first_backward != 0, stream));
     // deferred SH backward (frame-parallel training): the colour gradient and the clamp mask leave through the caller's
     // buffers, the SH coefficients' gradient is produced after the gradient exchange from the REDUCED colour gradient
     const bool defer_sh = dL_drgb_out != nullptr;

@@ -54,7 +54,8 @@ __device__ __forceinline__ void total_of_partials(const double *__restrict__ par
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         double v = 0.0;
-        for (int i = threadIdx.x; i < n; i += NT) v += part[(size_t)i * K + j];
+        for (int i = threadIdx.x; i < n; i += NT) v += __ldcg(part + (size_t)i * K + j);   // L2: also valid for partials written by
+                                                                                           // other CTAs of the SAME launch (ticket pattern)
         v = block_sum<NT>(v, scratch);
         if (threadIdx.x == 0) bcast[j] = v;
     }
@@ -65,32 +66,52 @@ __device__ __forceinline__ void total_of_partials(const double *__restrict__ par
 }
 
 // ------------------------------------------------------------------------------------------------ RGB: L1 + SSIM
-// forward: per (row, x, colour) SSIM value and its derivatives w.r.t. the three window sums that depend on the prediction
-// (E[p], E[p^2], E[p g]), pre-multiplied by dLoss/dSSIM; per-CTA partial sums of SSIM and |p - g|.
-__global__ void __launch_bounds__(kRow)
-ssim_fwd_kernel(int W, int H, const float *__restrict__ pred, const float *__restrict__ gt, float dscale,
-                float *__restrict__ fmaps, double *__restrict__ partials) {
-    __shared__ float sp[3][kSpan], sg[3][kSpan];
-    __shared__ double scratch[kRow / 32];
-    const int y = blockIdx.y, x0 = blockIdx.x * kRow;
+// ONE kernel, one CTA per image row (rows never mix, see the quirk above): the row of prediction and ground truth is staged
+// in shared memory, every pixel's SSIM value and its derivatives w.r.t. the three window sums that depend on the prediction
+// (E[p], E[p^2], E[p g]; pre-multiplied by dLoss/dSSIM) stay in shared memory, and after one barrier the transposed depthwise
+// convolution (the window is symmetric: the same zero-padded convolution) + the L1 sign term give
+//     dL/dp = G*fA + 2 p (G*fB) + g (G*fC) + l1scale sign(p - g).
+// 2 x 4.9 MB read and 4.9 MB written per 854x480 frame instead of the 9 derivative maps (14.7 MB) going through HBM twice.
+// The last CTA to finish (ticket) sums the per-row partials in a fixed order and writes the three scalars.
+constexpr int kRgbThreads = 256;
+
+__global__ void __launch_bounds__(kRgbThreads)
+rgb_row_kernel(int W, int H, const float *__restrict__ pred, const float *__restrict__ gt, float dscale, float l1scale,
+               float weight, float lambda, float *__restrict__ dL_dpred, double *__restrict__ partials, unsigned *__restrict__ ticket,
+               float *__restrict__ loss) {
+    extern __shared__ __align__(16) float s_row[];
+    const int span = W + 2 * kHalo;
+    float *sp = s_row, *sg = s_row + 3 * span, *sf = s_row + 6 * span;   // [3][span], [3][span], [9][span]
+    __shared__ double scratch[kRgbThreads / 32], bcast[2];
+    __shared__ bool s_last;
+    const int y = blockIdx.x;
     const size_t HW = (size_t)H * W, row = (size_t)y * W;
-    for (int i = threadIdx.x; i < 3 * kSpan; i += kRow) {
-        const int c = i / kSpan, k = i - c * kSpan, x = x0 + k - kHalo;
-        const bool in = x >= 0 && x < W;
-        sp[c][k] = in ? pred[c * HW + row + x] : 0.f;
-        sg[c][k] = in ? gt[(row + x) * 3 + c] : 0.f;
+    for (int i = threadIdx.x; i < 3 * span; i += kRgbThreads) {
+        const int c = i / span, k = i - c * span, x = k - kHalo;
+        sp[i] = (x >= 0 && x < W) ? pred[c * HW + row + x] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 3 * W; i += kRgbThreads) {     // ground truth is [H,W,3]: one contiguous row
+        const int x = i / 3, c = i - 3 * x;
+        sg[c * span + x + kHalo] = gt[row * 3 + i];
+    }
+    for (int i = threadIdx.x; i < 3 * 2 * kHalo; i += kRgbThreads) {
+        const int c = i / (2 * kHalo), k = i - c * 2 * kHalo;
+        sg[c * span + (k < kHalo ? k : W + k)] = 0.f;
+    }
+    for (int i = threadIdx.x; i < 9 * 2 * kHalo; i += kRgbThreads) {
+        const int m = i / (2 * kHalo), k = i - m * 2 * kHalo;
+        sf[m * span + (k < kHalo ? k : W + k)] = 0.f;
     }
     __syncthreads();
-    const int tx = threadIdx.x, x = x0 + tx;
     float ssim_sum = 0.f, l1_sum = 0.f;
-    if (x < W) {
+    for (int x = threadIdx.x; x < W; x += kRgbThreads) {
         float h[3][5];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
 #pragma unroll
             for (int k = 0; k < 11; ++k) {
-                const float w = kG[k], p = sp[c][tx + k], g = sg[c][tx + k];
+                const float w = kG[k], p = sp[c * span + x + k], g = sg[c * span + x + k];
                 a0 += w * p; a1 += w * g; a2 += w * (p * p); a3 += w * (g * g); a4 += w * (p * g);
             }
             h[c][0] = a0; h[c][1] = a1; h[c][2] = a2; h[c][3] = a3; h[c][4] = a4;
@@ -114,78 +135,146 @@ ssim_fwd_kernel(int W, int H, const float *__restrict__ pred, const float *__res
             const float d_s12 = 2.f * a1 * inv;
             const float d_s1 = -(a1 * a2) * inv / b2;
             const float d_mu1 = 2.f * mu2 * a2 * inv - 2.f * mu1 * (a1 * a2) * inv / b1;
-            const size_t o = row + x;
-            fmaps[(0 * 3 + c) * HW + o] = dscale * (d_mu1 - 2.f * mu1 * d_s1 - mu2 * d_s12);
-            fmaps[(1 * 3 + c) * HW + o] = dscale * d_s1;
-            fmaps[(2 * 3 + c) * HW + o] = dscale * d_s12;
-            l1_sum += fabsf(sp[c][tx + kHalo] - sg[c][tx + kHalo]);
+            sf[(0 * 3 + c) * span + x + kHalo] = dscale * (d_mu1 - 2.f * mu1 * d_s1 - mu2 * d_s12);
+            sf[(1 * 3 + c) * span + x + kHalo] = dscale * d_s1;
+            sf[(2 * 3 + c) * span + x + kHalo] = dscale * d_s12;
+            l1_sum += fabsf(sp[c * span + x + kHalo] - sg[c * span + x + kHalo]);
         }
-    }
-    const double t0 = block_sum<kRow>((double)ssim_sum, scratch);
-    const double t1 = block_sum<kRow>((double)l1_sum, scratch);
-    if (tx == 0) {
-        const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-        partials[2 * b] = t0; partials[2 * b + 1] = t1;
-    }
-}
-
-// backward: the transposed depthwise convolution of the three derivative maps (the window is symmetric, so it is the same
-// zero-padded convolution) + the L1 sign term.  dL/dp = G*fA + 2 p (G*fB) + g (G*fC) + l1scale sign(p - g).
-__global__ void __launch_bounds__(kRow)
-ssim_bwd_kernel(int W, int H, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ fmaps,
-                float l1scale, float *__restrict__ dL_dpred) {
-    __shared__ float sf[9][kSpan];
-    const int y = blockIdx.y, x0 = blockIdx.x * kRow;
-    const size_t HW = (size_t)H * W, row = (size_t)y * W;
-    for (int i = threadIdx.x; i < 9 * kSpan; i += kRow) {
-        const int m = i / kSpan, k = i - m * kSpan, x = x0 + k - kHalo;
-        sf[m][k] = (x >= 0 && x < W) ? fmaps[m * HW + row + x] : 0.f;
     }
     __syncthreads();
-    const int tx = threadIdx.x, x = x0 + tx;
-    if (x >= W) return;
-    float h[3][3];   // [kind][colour]: horizontal pass
+    if (dL_dpred) {
+        for (int x = threadIdx.x; x < W; x += kRgbThreads) {
+            float h[3][3];   // [kind][colour]: horizontal pass
 #pragma unroll
-    for (int m = 0; m < 9; ++m) {
-        float a = 0.f;
+            for (int m = 0; m < 9; ++m) {
+                float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) a += kG[k] * sf[m][tx + k];
-        h[m / 3][m % 3] = a;
-    }
+                for (int k = 0; k < 11; ++k) a += kG[k] * sf[m * span + x + k];
+                h[m / 3][m % 3] = a;
+            }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float GA = 0.f, GB = 0.f, GC = 0.f;
+            for (int c = 0; c < 3; ++c) {
+                float GA = 0.f, GB = 0.f, GC = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-            const float w = kG[5 + cc - c];
-            GA += w * h[0][cc]; GB += w * h[1][cc]; GC += w * h[2][cc];
+                for (int cc = 0; cc < 3; ++cc) {
+                    const float w = kG[5 + cc - c];
+                    GA += w * h[0][cc]; GB += w * h[1][cc]; GC += w * h[2][cc];
+                }
+                const float p = sp[c * span + x + kHalo], g = sg[c * span + x + kHalo];
+                dL_dpred[c * HW + row + x] = GA + 2.f * p * GB + g * GC + l1scale * sgnf(p - g);
+            }
         }
-        const float p = pred[c * HW + row + x], g = gt[(row + x) * 3 + c];
-        dL_dpred[c * HW + row + x] = GA + 2.f * p * GB + g * GC + l1scale * sgnf(p - g);
     }
-}
-
-__global__ void __launch_bounds__(kRed)
-rgb_finalize_kernel(const double *__restrict__ partials, int nblk, double n_elems, float weight, float lambda,
-                    float *__restrict__ loss) {
-    __shared__ double scratch[kRed / 32], bcast[2];
-    double t[2];
-    total_of_partials<kRed, 2>(partials, nblk, t, scratch, bcast);
+    const double t0 = block_sum<kRgbThreads>((double)ssim_sum, scratch);
+    const double t1 = block_sum<kRgbThreads>((double)l1_sum, scratch);
     if (threadIdx.x == 0) {
+        partials[2 * y] = t0; partials[2 * y + 1] = t1;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == (unsigned)(H - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double t[2];
+    total_of_partials<kRgbThreads, 2>(partials, H, t, scratch, bcast);
+    if (threadIdx.x == 0) {
+        const double n_elems = 3.0 * (double)H * (double)W;
         const float ssim = (float)(t[0] / n_elems), l1 = (float)(t[1] / n_elems);
         loss[0] = weight * ((1.f - lambda) * l1 + lambda * (1.f - ssim));
         loss[1] = l1;
         loss[2] = ssim;
+        *ticket = 0u;   // ready for the next call (also inside a replayed CUDA graph)
     }
 }
 
 // ------------------------------------------------------------------------------------------------ depth: depth_loss_dpt
+// torch.median of the two maps = the element of rank (n-1)/2: a three-pass radix SELECT (11 + 11 + 10 bits of the order-preserving
+// key) over both maps at once instead of two full 32-bit sorts.  Per pass: shared-memory histogram of the digit of every element
+// that still matches the prefix found so far (warp-aggregated: background pixels share one value), merged into a global
+// histogram; the last CTA of each map (ticket) walks the 2048 bins in order, fixes the digit and the remaining rank, and
+// clears the histogram for the next pass.
+constexpr int kSelBins = 2048;
+struct SelState { unsigned prefix, rank, ticket, pad; };
+
+__device__ __forceinline__ unsigned order_key(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+template <int SHIFT, int BITS>
+__global__ void __launch_bounds__(kRed)
+select_pass_kernel(int n, const float *__restrict__ a0, const float *__restrict__ a1, unsigned *__restrict__ hist /*[2][kSelBins]*/,
+                   SelState *__restrict__ state /*[2]*/, float *__restrict__ med /*[2]*/) {
+    __shared__ unsigned s_hist[kSelBins];
+    __shared__ unsigned s_scan[kRed];
+    __shared__ bool s_last;
+    const int which = blockIdx.y;
+    const float *__restrict__ src = which ? a1 : a0;
+    unsigned *gh = hist + which * kSelBins;
+    SelState *st = state + which;
+    constexpr unsigned kDigits = 1u << BITS;
+    const unsigned prefix = SHIFT + BITS < 32 ? __ldcg(&st->prefix) : 0u;
+    constexpr unsigned hi_mask = SHIFT + BITS < 32 ? (0xffffffffu << (SHIFT + BITS)) : 0u;
+    for (int i = threadIdx.x; i < kSelBins; i += kRed) s_hist[i] = 0u;
+    __syncthreads();
+    for (int i0 = blockIdx.x * kRed; i0 < n; i0 += gridDim.x * kRed) {   // whole warps iterate together (match_any below)
+        const int i = i0 + threadIdx.x;
+        unsigned digit = 0xffffffffu;
+        if (i < n) {
+            const unsigned k = order_key(src[i]);
+            if ((k & hi_mask) == prefix) digit = (k >> SHIFT) & (kDigits - 1u);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (digit != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)kDigits; i += kRed) {
+        const unsigned c = s_hist[i];
+        if (c) atomicAdd(&gh[i], c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the last CTA of this map: find the digit whose cumulative count crosses the rank
+    constexpr int per = kDigits / kRed;
+    static_assert(kDigits % kRed == 0, "bins per thread");
+    unsigned loc[per], sum = 0;
+#pragma unroll
+    for (int q = 0; q < per; ++q) { loc[q] = __ldcg(&gh[threadIdx.x * per + q]); sum += loc[q]; }
+    s_scan[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {   // 256 partial sums: a serial walk is a few hundred cycles, once per pass
+        unsigned run = 0;
+        for (int t = 0; t < kRed; ++t) { const unsigned v = s_scan[t]; s_scan[t] = run; run += v; }
+    }
+    __syncthreads();
+    const unsigned rank = SHIFT + BITS < 32 ? __ldcg(&st->rank) : (unsigned)((n - 1) / 2);
+    unsigned run = s_scan[threadIdx.x];
+#pragma unroll
+    for (int q = 0; q < per; ++q) {
+        if (rank >= run && rank < run + loc[q]) {     // exactly one (thread, q) over the CTA
+            const unsigned np = prefix | ((unsigned)(threadIdx.x * per + q) << SHIFT);
+            st->prefix = np;
+            st->rank = rank - run;
+            if (SHIFT == 0) med[which] = key_value(np);
+        }
+        run += loc[q];
+    }
+#pragma unroll
+    for (int q = 0; q < per; ++q) gh[threadIdx.x * per + q] = 0u;
+    if (threadIdx.x == 0) st->ticket = 0u;
+}
+
 // A: sum |p - t_p|, sum sign(p - t_p), sum |g - t_g|; index of the (first) element that equals the median of p
 __global__ void __launch_bounds__(kRed)
-depth_stats_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ sorted_p,
-                   const float *__restrict__ sorted_g, double *__restrict__ partA, int *__restrict__ med_idx) {
+depth_stats_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ med,
+                   double *__restrict__ partA, int *__restrict__ med_idx) {
     __shared__ double scratch[kRed / 32];
-    const float tp = sorted_p[(n - 1) / 2], tg = sorted_g[(n - 1) / 2];   // torch.median: the lower of the two middles
+    const float tp = med[0], tg = med[1];   // torch.median: the lower of the two middles (rank (n-1)/2)
     float a = 0.f, sg = 0.f, b = 0.f;
     int first = 0x7fffffff;
     for (int i = blockIdx.x * kRed + threadIdx.x; i < n; i += gridDim.x * kRed) {
@@ -202,12 +291,12 @@ depth_stats_kernel(int n, const float *__restrict__ pred, const float *__restric
 
 // B: residuals r = (p - t_p)/s_p - (g - t_g)/s_g: sum r^2, sum r, sum r * (p - t_p)/s_p
 __global__ void __launch_bounds__(kRed)
-depth_resid_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ sorted_p,
-                   const float *__restrict__ sorted_g, const double *__restrict__ partA, double *__restrict__ partB) {
+depth_resid_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ med,
+                   const double *__restrict__ partA, double *__restrict__ partB) {
     __shared__ double scratch[kRed / 32], bcast[3];
     double A[3];
     total_of_partials<kRed, 3>(partA, gridDim.x, A, scratch, bcast);
-    const float tp = sorted_p[(n - 1) / 2], tg = sorted_g[(n - 1) / 2];
+    const float tp = med[0], tg = med[1];
     const float sp = (float)(A[0] / n), sg = (float)(A[2] / n);
     float r2 = 0.f, r1 = 0.f, rd = 0.f;
     for (int i = blockIdx.x * kRed + threadIdx.x; i < n; i += gridDim.x * kRed) {
@@ -222,14 +311,14 @@ depth_resid_kernel(int n, const float *__restrict__ pred, const float *__restric
 // C: loss and gradient.  With a_j = 2 r_j / N, S_a = sum a_j, S_ad = sum a_j dn_j, m = median index:
 //   dL/dp_i = a_i/s - [i==m] S_a/s - (S_ad/s) * (1/N) (sign(p_i - t) - [i==m] sum_k sign(p_k - t))
 __global__ void __launch_bounds__(kRed)
-depth_grad_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ sorted_p,
-                  const float *__restrict__ sorted_g, const double *__restrict__ partA, const double *__restrict__ partB,
+depth_grad_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, const float *__restrict__ med,
+                  const double *__restrict__ partA, const double *__restrict__ partB,
                   const int *__restrict__ med_idx, float weight, float *__restrict__ loss, float *__restrict__ dL_dpred) {
     __shared__ double scratch[kRed / 32], bcast[3];
     double A[3], B[3];
     total_of_partials<kRed, 3>(partA, gridDim.x, A, scratch, bcast);
     total_of_partials<kRed, 3>(partB, gridDim.x, B, scratch, bcast);
-    const float tp = sorted_p[(n - 1) / 2], tg = sorted_g[(n - 1) / 2];
+    const float tp = med[0], tg = med[1];
     const float sp = (float)(A[0] / n), sg = (float)(A[2] / n);
     const float invn = 1.f / (float)n;
     const float Sa = (float)(2.0 * B[1] / n), Sad = (float)(2.0 * B[2] / n), Ssgn = (float)A[1];
@@ -309,23 +398,104 @@ track_reduce_kernel(int n, int W, int H, const float *__restrict__ track, const 
     }
 }
 
+// Up to kTrackFused query points (the TAPIR grid of one frame): everything above in ONE CTA -- per-point values, a bitonic sort
+// of a copy in shared memory for the quantile, the two masked sums, the loss and the gradient scatter.  No CUB sort, 1 launch.
+constexpr int kTrackFused = 16384;
+
+__global__ void __launch_bounds__(1024)
+track_fused_kernel(int n, int n_pad, int W, int H, const float *__restrict__ track, const int *__restrict__ query_xy,
+                   const float *__restrict__ gt_xy, const uint8_t *__restrict__ visible, const float *__restrict__ weights,
+                   float quantile, float weight, float *__restrict__ loss, float *__restrict__ dL_dtrack) {
+    extern __shared__ __align__(16) float s_track[];
+    float *s_vals = s_track, *s_sorted = s_track + n_pad;
+    __shared__ double scratch[32], bcast[2];
+    __shared__ int s_M;
+    const float inf = __int_as_float(0x7f800000);
+    const size_t HW = (size_t)H * W;
+    if (threadIdx.x == 0) s_M = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n_pad; i += 1024) {
+        float v = inf;
+        if (i < n) {
+            const int qx = query_xy[2 * i], qy = query_xy[2 * i + 1];
+            if (visible[i] && qx >= 0 && qx < W && qy >= 0 && qy < H) {
+                const size_t o = (size_t)qy * W + qx;
+                const float px = (track[o] + 1.f) * (float)W / 2.f, py = (track[HW + o] + 1.f) * (float)H / 2.f;   // util.py:82
+                v = (fabsf(px - gt_xy[2 * i]) + fabsf(py - gt_xy[2 * i + 1])) / 2.f;
+                ++mine;
+            }
+        }
+        s_vals[i] = v; s_sorted[i] = v;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_M, mine);
+    __syncthreads();
+    const int M = s_M;
+    if (M <= 0) {   // trainer_fragGS.py:569-570: no visible track -> zero loss, no gradient
+        if (threadIdx.x == 0) loss[0] = 0.f;
+        return;
+    }
+    for (int k = 2; k <= n_pad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pad; i += 1024) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const float a = s_sorted[i], b = s_sorted[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_sorted[i] = b; s_sorted[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const float pos = quantile * (float)(M - 1);
+    const int lo = (int)floorf(pos), hi = (int)ceilf(pos);
+    const float fr = pos - (float)lo, a = s_sorted[lo], b = s_sorted[hi];
+    const float thr = fr < 0.5f ? a + fr * (b - a) : b - (b - a) * (1.f - fr);   // at::lerp
+    double num = 0.0, den = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float v = s_vals[i];
+        if (v <= thr) { num += (double)(v * weights[i]); den += (double)weights[i]; }
+    }
+    num = block_sum<1024>(num, scratch);
+    if (threadIdx.x == 0) bcast[0] = num;
+    den = block_sum<1024>(den, scratch);
+    if (threadIdx.x == 0) bcast[1] = den;
+    __syncthreads();
+    const float numf = (float)bcast[0], denf = (float)bcast[1] + 1e-8f;     // ndim = 1 (criterion.py:49-51)
+    const float hw = (float)max(H, W);
+    if (threadIdx.x == 0) loss[0] = weight * (numf / denf) / hw;
+    if (dL_dtrack == nullptr) return;
+    const float kk = weight / (denf * hw);
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float v = s_vals[i];
+        if (!(v <= thr)) continue;
+        const int qx = query_xy[2 * i], qy = query_xy[2 * i + 1];
+        const size_t o = (size_t)qy * W + qx;
+        const float px = (track[o] + 1.f) * (float)W / 2.f, py = (track[HW + o] + 1.f) * (float)H / 2.f;
+        const float w = kk * weights[i] * 0.5f;
+        atomicAdd(&dL_dtrack[o], w * sgnf(px - gt_xy[2 * i]) * ((float)W / 2.f));
+        atomicAdd(&dL_dtrack[HW + o], w * sgnf(py - gt_xy[2 * i + 1]) * ((float)H / 2.f));
+    }
+}
+
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 inline unsigned row_blocks(int W) { return spv::cdiv(W, kRow); }
 
-struct DepthWs { float *sorted_p, *sorted_g; double *partA, *partB; int *med_idx; void *cub; size_t cub_bytes, total; };
+struct DepthWs { unsigned *hist; SelState *state; float *med; double *partA, *partB; int *med_idx; size_t head_bytes, total; };
 DepthWs carve_depth(void *base, int n) {
+    (void)n;
     DepthWs w{};
     size_t off = 0;
     auto take = [&](size_t bytes) { void *p = base ? (char *)base + off : nullptr; off += align256(bytes); return p; };
-    w.sorted_p = (float *)take(sizeof(float) * (size_t)n);
-    w.sorted_g = (float *)take(sizeof(float) * (size_t)n);
+    // [hist | state | med | med_idx] are cleared / preset by ONE memset + one tiny copy per call
+    w.hist = (unsigned *)take(sizeof(unsigned) * 2 * kSelBins);
+    w.state = (SelState *)take(sizeof(SelState) * 2);
+    w.med = (float *)take(sizeof(float) * 2);
+    w.head_bytes = off;
+    w.med_idx = (int *)take(sizeof(int));
     w.partA = (double *)take(sizeof(double) * 3 * kRedBlocks);
     w.partB = (double *)take(sizeof(double) * 3 * kRedBlocks);
-    w.med_idx = (int *)take(sizeof(int));
-    size_t cb = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, cb, (const float *)nullptr, (float *)nullptr, n);
-    w.cub_bytes = cb > 0 ? cb : ((size_t)n * 16 + (1 << 20));   // no device at query time (CPU-side probe): generous bound
-    w.cub = take(w.cub_bytes);
     w.total = off;
     return w;
 }
@@ -352,7 +522,7 @@ extern "C" {
 
 size_t spv_loss_rgb_workspace_bytes(int W, int H) {
     if (W <= 0 || H <= 0) return 0;
-    return align256(sizeof(float) * 9 * (size_t)H * W) + align256(sizeof(double) * 2 * (size_t)row_blocks(W) * H);
+    return align256(sizeof(double) * 2 * (size_t)H) + 256;
 }
 
 int spv_loss_rgb(int W, int H, const float *pred_chw, const float *gt_hwc, float weight, float lambda_dssim, float *loss,
@@ -360,19 +530,19 @@ int spv_loss_rgb(int W, int H, const float *pred_chw, const float *gt_hwc, float
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_loss_rgb: empty image"); return (int)cudaErrorInvalidValue; }
     if (ws_bytes < spv_loss_rgb_workspace_bytes(W, H)) { spv::set_error(cudaErrorInvalidValue, "spv_loss_rgb: workspace too small"); return (int)cudaErrorInvalidValue; }
-    float *fmaps = (float *)workspace;
-    double *partials = (double *)((char *)workspace + align256(sizeof(float) * 9 * (size_t)H * W));
-    const dim3 grid(row_blocks(W), H);
+    const size_t dyn = sizeof(float) * 15 * (size_t)(W + 2 * kHalo);
+    if (dyn > 200 * 1024) { spv::set_error(cudaErrorInvalidValue, "spv_loss_rgb: image rows wider than 3400 pixels are not supported"); return (int)cudaErrorInvalidValue; }
+    double *partials = (double *)workspace;
+    unsigned *ticket = (unsigned *)((char *)workspace + align256(sizeof(double) * 2 * (size_t)H));
+    SPV_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), s), "spv_loss_rgb");
+    static std::atomic<unsigned long long> configured{0};
+    spv::opt_in_dynamic_smem(rgb_row_kernel, 200 * 1024, configured);
     const double n_elems = 3.0 * (double)H * (double)W;
     // d(loss)/d(ssim_map element) = -weight * lambda / N ; d(loss)/d|p-g| = weight * (1 - lambda) / N
-    ssim_fwd_kernel<<<grid, kRow, 0, s>>>(W, H, pred_chw, gt_hwc, (float)(-(double)weight * lambda_dssim / n_elems), fmaps, partials);
-    int launches = 2;
-    if (dL_dpred_chw) {
-        ssim_bwd_kernel<<<grid, kRow, 0, s>>>(W, H, pred_chw, gt_hwc, fmaps, (float)((double)weight * (1.0 - lambda_dssim) / n_elems), dL_dpred_chw);
-        ++launches;
-    }
-    rgb_finalize_kernel<<<1, kRed, 0, s>>>(partials, (int)(grid.x * grid.y), n_elems, weight, lambda_dssim, loss);
-    return spv::check_launch("spv_loss_rgb", launches);
+    rgb_row_kernel<<<H, kRgbThreads, dyn, s>>>(W, H, pred_chw, gt_hwc, (float)(-(double)weight * lambda_dssim / n_elems),
+                                               (float)((double)weight * (1.0 - lambda_dssim) / n_elems), weight, lambda_dssim,
+                                               dL_dpred_chw, partials, ticket, loss);
+    return spv::check_launch("spv_loss_rgb", 1);
 }
 
 size_t spv_loss_depth_workspace_bytes(int n) { return n > 0 ? carve_depth(nullptr, n).total : 0; }
@@ -383,13 +553,16 @@ int spv_loss_depth_dpt(int n, const float *pred, const float *gt, float weight, 
     if (n <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_loss_depth_dpt: empty image"); return (int)cudaErrorInvalidValue; }
     DepthWs w = carve_depth(workspace, n);
     if (ws_bytes < w.total) { spv::set_error(cudaErrorInvalidValue, "spv_loss_depth_dpt: workspace too small"); return (int)cudaErrorInvalidValue; }
-    SPV_CUDA_TRY(cub::DeviceRadixSort::SortKeys(w.cub, w.cub_bytes, pred, w.sorted_p, n, 0, 32, s), "spv_loss_depth_dpt/sort");
-    SPV_CUDA_TRY(cub::DeviceRadixSort::SortKeys(w.cub, w.cub_bytes, gt, w.sorted_g, n, 0, 32, s), "spv_loss_depth_dpt/sort");
+    SPV_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.head_bytes, s), "spv_loss_depth_dpt");      // histograms, select state, tickets
     SPV_CUDA_TRY(cudaMemsetAsync(w.med_idx, 0x7f, sizeof(int), s), "spv_loss_depth_dpt");
-    depth_stats_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.sorted_p, w.sorted_g, w.partA, w.med_idx);
-    depth_resid_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.sorted_p, w.sorted_g, w.partA, w.partB);
-    depth_grad_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.sorted_p, w.sorted_g, w.partA, w.partB, w.med_idx, weight, loss, dL_dpred);
-    return spv::check_launch("spv_loss_depth_dpt", 3 + 2 * 4);   // + the radix-sort passes of the two CUB calls
+    const dim3 sel_grid(spv::cdiv(n, kRed * 8) < (unsigned)kRedBlocks ? spv::cdiv(n, kRed * 8) : (unsigned)kRedBlocks, 2);
+    select_pass_kernel<21, 11><<<sel_grid, kRed, 0, s>>>(n, pred, gt, w.hist, w.state, w.med);
+    select_pass_kernel<10, 11><<<sel_grid, kRed, 0, s>>>(n, pred, gt, w.hist, w.state, w.med);
+    select_pass_kernel<0, 10><<<sel_grid, kRed, 0, s>>>(n, pred, gt, w.hist, w.state, w.med);
+    depth_stats_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.med, w.partA, w.med_idx);
+    depth_resid_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.med, w.partA, w.partB);
+    depth_grad_kernel<<<kRedBlocks, kRed, 0, s>>>(n, pred, gt, w.med, w.partA, w.partB, w.med_idx, weight, loss, dL_dpred);
+    return spv::check_launch("spv_loss_depth_dpt", 6);
 }
 
 size_t spv_loss_track_workspace_bytes(int n_points) { return n_points > 0 ? carve_track(nullptr, n_points).total : 0; }
@@ -403,6 +576,16 @@ int spv_loss_track(int n_points, int W, int H, const float *track_chw, const int
     if (n_points <= 0) {
         SPV_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), s), "spv_loss_track");
         return 0;
+    }
+    if (n_points <= kTrackFused) {
+        int n_pad = 32;
+        while (n_pad < n_points) n_pad <<= 1;
+        const size_t dyn = sizeof(float) * 2 * (size_t)n_pad;
+        static std::atomic<unsigned long long> configured{0};
+        spv::opt_in_dynamic_smem(track_fused_kernel, sizeof(float) * 2 * kTrackFused, configured);
+        track_fused_kernel<<<1, 1024, dyn, s>>>(n_points, n_pad, W, H, track_chw, query_xy, target_xy, visible, weights, quantile, weight,
+                                                loss, dL_dtrack_chw);
+        return spv::check_launch("spv_loss_track", 1);
     }
     TrackWs w = carve_track(workspace, n_points);
     if (ws_bytes < w.total) { spv::set_error(cudaErrorInvalidValue, "spv_loss_track: workspace too small"); return (int)cudaErrorInvalidValue; }

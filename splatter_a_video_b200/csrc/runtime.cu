@@ -29,10 +29,9 @@ void timer_mark(int slot, int edge, cudaStream_t s) {
 
 // Small runtime switches for kernel variants (default 0).  First read falls back to the environment variable SPV_<NAME>
 // (upper case) so a run can be switched without code changes.
-//   bwd_wide    2 | 4: pixels per lane of the experimental wide-footprint backward blend kernel
-//   bwd_variant 1: the round-1 backward blend kernel (CTA barrier per chunk) instead of the ring-staged default
+//   bwd_variant reserved for A/B runs of backward blend kernel variants (none selectable at the moment)
 struct Option { const char *name; const char *env; std::atomic<int> value; };
-static Option g_options[] = {{"bwd_wide", "SPV_BWD_WIDE", {-1}}, {"bwd_variant", "SPV_BWD_VARIANT", {-1}}};
+static Option g_options[] = {{"bwd_variant", "SPV_BWD_VARIANT", {-1}}};
 int get_option(const char *name) {
     for (Option &o : g_options) {
         if (strcmp(name, o.name) != 0) continue;

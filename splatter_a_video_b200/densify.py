@@ -141,8 +141,10 @@ class FlatDensifier:
         new_adam = None
         if adam is not None:
             lrs = {k: float(adam._lrs[q]) for q, k in enumerate(old.names)}
-            new_adam = FlatAdam(new_flat, lrs, betas=adam.betas, eps=adam.eps)
+            new_adam = FlatAdam(new_flat, lrs, betas=adam.betas, eps=adam.eps, device_clock=adam.device_clock)
             new_adam.t = adam.t
+            if adam.device_clock:
+                new_adam.state_dev.copy_(adam.state_dev)       # the optimizer clock survives the restructure
             if P_new:
                 fresh = torch.where(is_new, torch.full_like(src, -1), src).contiguous()      # new points start with zero moments
                 move(fresh, adam.exp_avg, new_adam.exp_avg)

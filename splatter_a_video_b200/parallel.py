@@ -445,7 +445,9 @@ class FlatAdam:
     """torch.optim.Adam semantics (betas, eps, per-parameter learning rates) as ONE fused kernel over FlatParams
     (`spv_adam_step`).  Role of the per-attribute param groups of src/pointrix/optimizer/__init__.py:27-62."""
 
-    def __init__(self, flat: FlatParams, lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-15):
+    def __init__(self, flat: FlatParams, lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-15, device_clock: bool = False):
+        """device_clock: keep the step counter / bias corrections and the learning rates in device memory so `step()` can be
+        captured in a CUDA graph and replayed (every replay advances the clock; `set_lrs` updates the rates outside the graph)."""
         import ctypes
         self.flat, self.betas, self.eps = flat, betas, eps
         self.exp_avg = torch.zeros_like(flat.flat)
@@ -459,12 +461,30 @@ class FlatAdam:
         self._lrs = (ctypes.c_float * len(ends))(*[float(lrs[k]) for k in flat.names])
         self.nseg = len(ends)
         self.t = 0
+        self.device_clock = bool(device_clock)
+        if self.device_clock:
+            dev = flat.flat.device
+            self.state_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+            self.lr_dev = torch.tensor([float(lrs[k]) for k in flat.names], dtype=torch.float32, device=dev)
+
+    def set_lrs(self, lrs: Dict[str, float]):
+        """Learning-rate schedule hook (role of ExponLRScheduler, src/pointrix/optimizer/scheduler.py:9-100)."""
+        vals = [float(lrs[k]) for k in self.flat.names]
+        for i, v in enumerate(vals):
+            self._lrs[i] = v
+        if self.device_clock:
+            self.lr_dev.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=True)
 
     def step(self):
         from . import _lib as L
         import ctypes
         self.t += 1
         f = self.flat
+        if self.device_clock:
+            L.call("spv_adam_step_device", f.flat.numel(), L.ptr(f.flat), L.ptr(f.flat_grad), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                   self.nseg, ctypes.cast(self._ends, ctypes.c_void_p), L.ptr(self.lr_dev), float(self.betas[0]), float(self.betas[1]),
+                   float(self.eps), L.ptr(self.state_dev), L.stream())
+            return
         L.call("spv_adam_step", f.flat.numel(), L.ptr(f.flat), L.ptr(f.flat_grad), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
                self.nseg, ctypes.cast(self._ends, ctypes.c_void_p), ctypes.cast(self._lrs, ctypes.c_void_p), float(self.betas[0]),
                float(self.betas[1]), float(self.eps), int(self.t), L.stream())

@@ -216,7 +216,10 @@ class DPTROrthoEnhancedRender(_BaseRender):
             self._ndc_zero = torch.zeros(P, 2, device=position.device)
         # fresh leaves over one persistent zero buffer: the dummies' values are never read, only their .grad
         ndc = self._ndc_zero.detach().requires_grad_(True)
-        abs_ndc = self._ndc_zero.detach().requires_grad_(True)
+        # the reference returns ONE of (ndc, abs_ndc) as viewspace_points (dptr_ortho_enhanced.py:378-383): the |.| statistic is only
+        # reduced when it is the one that will be read
+        use_abs = bool(self.cfg["densify_abs_grad_enable"])
+        abs_ndc = self._ndc_zero.detach().requires_grad_(True) if use_abs else None
         bg_color = kwargs.get("bg_color", self.bg_color)
         while True:
             imgs, gs_idx, radii, status = _frame.render_ortho_frame(
@@ -235,7 +238,7 @@ class DPTROrthoEnhancedRender(_BaseRender):
         for name, img in zip(attr_names, imgs[2:]):
             split[name] = img
         return {"rendered_features_split": split,
-                "viewspace_points": abs_ndc if self.cfg["densify_abs_grad_enable"] else ndc,
+                "viewspace_points": abs_ndc if use_abs else ndc,
                 "visibility_filter": radii > 0, "radii": radii, "gs_idx": gs_idx}
 
 

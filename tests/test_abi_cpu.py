@@ -92,7 +92,7 @@ def test_runtime_options_default_to_the_validated_kernels(lib_path):
     """spv_set_option is host-only state: known names are accepted, unknown ones rejected with an error message."""
     from splatter_a_video_b200 import _lib
     lib = _lib.load()
-    assert lib.spv_set_option(b"bwd_wide", 0) == 0
+    assert lib.spv_set_option(b"bwd_variant", 0) == 0
     assert lib.spv_set_option(b"no_such_option", 1) != 0 and b"unknown option" in lib.spv_last_error()
 
 

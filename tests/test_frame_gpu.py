@@ -152,13 +152,15 @@ def test_cuda_graph_replay_of_a_full_step(cuda):
             Hh.assert_grad_close(n(got[k]), n(want[k]), f"graph replay d/d{k}", norm_tol=2e-5)
 
 
-def test_flat_adam_matches_torch_adam(cuda):
+@pytest.mark.parametrize("device_clock", [False, True])
+def test_flat_adam_matches_torch_adam(cuda, device_clock):
+    """device_clock: step counter, bias corrections and learning rates in device memory (the CUDA-graph capturable entry)."""
     from splatter_a_video_b200.parallel import FlatAdam, FlatParams
     g = torch.Generator().manual_seed(0)
     tensors = {"a": torch.randn(1000, 3, generator=g), "b": torch.randn(1000, 16, 3, generator=g), "c": torch.randn(1001, 1, generator=g)}
     lrs = {"a": 1e-3, "b": 2.5e-3, "c": 5e-2}
     flat = FlatParams({k: v.to(cuda) for k, v in tensors.items()})
-    opt = FlatAdam(flat, lrs, eps=1e-15)
+    opt = FlatAdam(flat, lrs, eps=1e-15, device_clock=device_clock)
     ref = {k: v.clone().to(cuda).requires_grad_(True) for k, v in tensors.items()}
     topt = torch.optim.Adam([{"params": [ref[k]], "lr": lrs[k]} for k in ref], eps=1e-15)
     for it in range(5):
@@ -384,41 +386,66 @@ def test_frame_backward_twice_and_gradient_free_images(cuda):
             Hh.assert_grad_close(n(b), n(a), f"pruned d/d{name}", norm_tol=2e-6)
 
 
-@pytest.mark.parametrize("option,value", [("bwd_variant", 1), ("bwd_wide", 2), ("bwd_wide", 4)])
-@pytest.mark.parametrize("track_grad", [False, True])          # 8 / 11 feature-gradient channels: the 16 and 16+8 networks
-def test_backward_kernel_variants_equal_default(cuda, option, value, track_grad):
-    """The selectable variants of the frame path's backward blend kernel -- spv_set_option("bwd_variant", 1): the chunk-barrier
-    kernel of round 1; ("bwd_wide", 2|4): R pixels per lane -- against the ring-staged default.  Same gradients up to the
-    association of the per-Gaussian sums."""
-    from splatter_a_video_b200 import _lib as L
+@pytest.mark.parametrize("grad_groups", ["mask+dino", "track+mask+dino", "track+mask+dino+extra"])   # 8 / 11 / 13 feature-gradient channels
+def test_backward_with_and_without_the_abs_pair(cuda, grad_groups):
+    """The |RGB-pass dL_duv| pair is only reduced when the caller asks for it (abs_ndc given): without it the RGB-pass pair
+    rides in its network slots and the second reduction network shrinks (blend_rec_bwd_kernel<CH,CG,ABS>: CG = 8 / 12 / 14).
+    Every other gradient must be the same either way, and equal to the staged ops' (round 1's kernels)."""
     from splatter_a_video_b200.gs.frame import render_ortho_frame
+    from splatter_a_video_b200 import gs
+    from splatter_a_video_b200.gs import fused as F_
     sc = synth.make_scene(40_000, 4, 333, 250, seed=12)
     W, H, P = sc.W, sc.H, sc.P
     g = torch.Generator().manual_seed(6)
-    gimg = [torch.randn(c, H, W, generator=g).to(cuda) for c in (3, 1, 3, 1, 12, 3)]
-    names = ("position", "scaling", "rotation", "opacity", "shs", "track", "mask", "dino")
+    extra = torch.rand(P, 2, generator=g)
+    chans = (3, 1, 3, 1, 10, 3, 2)
+    gimg = [torch.randn(c, H, W, generator=g).to(cuda) for c in chans]
+    need = {"track": "track" in grad_groups, "mask": True, "poly": False, "dino": True, "extra": "extra" in grad_groups}
+    names = ("position", "scaling", "rotation", "opacity", "shs", "track", "mask", "dino", "extra")
 
-    def run():
+    def leaves():
         d = {"position": sc.frame_position(0), "scaling": sc.scaling, "rotation": sc.rotation, "opacity": sc.opacity, "shs": sc.shs,
-             "track": sc.frame_position(1), "mask": sc.attrs["mask_attribute"], "poly": sc.attrs["pos_poly_feat"],
-             "dino": sc.attrs["dino_attribute"]}
-        L_ = {k: v.to(cuda).clone().requires_grad_(k != "poly" and (k != "track" or track_grad)) for k, v in d.items()}
+             "track": sc.frame_position(1), "mask": sc.attrs["mask_attribute"], "poly": sc.attrs["pos_poly_feat"][:, :10].contiguous(),
+             "dino": sc.attrs["dino_attribute"], "extra": extra}
+        return {k: v.to(cuda).clone().requires_grad_(need.get(k, True)) for k, v in d.items()}
+
+    def run(with_abs):
+        L_ = leaves()
+        ndc = torch.zeros(P, 2, device=cuda, requires_grad=True)
+        abs_ndc = torch.zeros(P, 2, device=cuda, requires_grad=True) if with_abs else None
         imgs, _, _, status = render_ortho_frame(L_["position"], L_["scaling"], L_["rotation"], L_["opacity"], L_["shs"],
-                                                [L_["track"], L_["mask"], L_["poly"], L_["dino"]], sc.extr.to(cuda), W, H, 20, 0.0, 8 * P,
-                                                ndc=torch.zeros(P, 2, device=cuda, requires_grad=True),
-                                                abs_ndc=torch.zeros(P, 2, device=cuda, requires_grad=True))
+                                                [L_["track"], L_["mask"], L_["poly"], L_["dino"], L_["extra"]], sc.extr.to(cuda), W, H, 20, 0.0,
+                                                8 * P, ndc=ndc, abs_ndc=abs_ndc)
         assert int(status.cpu()[1]) == 0
         torch.autograd.backward(imgs, gimg)
-        return {k: L_[k].grad for k in names if L_[k].requires_grad}
+        out = {k: L_[k].grad for k in names if L_[k].requires_grad}
+        out["ndc"] = ndc.grad
+        if with_abs:
+            out["abs_ndc"] = abs_ndc.grad
+        return out
 
-    ref = run()
-    try:
-        L.set_option(option, value)
-        got = run()
-    finally:
-        L.set_option(option, 0)
-    for k in ref:
-        Hh.assert_grad_close(n(got[k]), n(ref[k]), f"{option}={value} d/d{k}", norm_tol=2e-5)
+    with_abs, without = run(True), run(False)
+    assert float(with_abs["abs_ndc"].abs().sum()) > 0
+    for k in without:
+        Hh.assert_grad_close(n(without[k]), n(with_abs[k]), f"{grad_groups}: no-abs d/d{k}", norm_tol=2e-5)
+    # the staged single-traversal ops (blend.cu) on the same frame
+    L_ = leaves()
+    dirs = torch.zeros(P, 3, device=cuda); dirs[:, 2] = 1
+    rgb = gs.compute_sh(L_["shs"], 3, dirs)
+    uv, depth = gs.project_point_ortho(L_["position"], sc.extr.to(cuda), W, H, 0.01)
+    vis = depth != 0
+    cov3d = gs.compute_cov3d(L_["scaling"], L_["rotation"], vis)
+    conic, radius, tiles = gs.ewa_project_ortho(cov3d, sc.extr.to(cuda), uv, W, H, vis.squeeze(-1))
+    idx, tr = gs.sort_gaussian(uv, depth, W, H, radius, tiles)
+    ndc = torch.zeros(P, 2, device=cuda, requires_grad=True); abs_ndc = torch.zeros(P, 2, device=cuda, requires_grad=True)
+    attrs = torch.cat([L_["track"], L_["mask"], L_["poly"], L_["dino"], L_["extra"]], 1)
+    img, dimg, aimg, _ = F_.blend_rgb_depth_attrs(uv, conic, L_["opacity"], rgb, depth, attrs, idx, tr, 0.0, W, H, ndc, abs_ndc, K=20)
+    torch.autograd.backward([img, dimg, aimg], [gimg[0], gimg[1], torch.cat(gimg[2:], 0)])
+    for k in names:
+        if L_[k].requires_grad:
+            Hh.assert_grad_close(n(with_abs[k]), n(L_[k].grad), f"{grad_groups}: frame vs staged d/d{k}", norm_tol=2e-5)
+    Hh.assert_grad_close(n(with_abs["ndc"]), n(ndc.grad), "ndc", norm_tol=2e-5)
+    Hh.assert_grad_close(n(with_abs["abs_ndc"]), n(abs_ndc.grad), "abs_ndc", norm_tol=2e-5)
 
 
 def test_capacity_overflow_after_the_first_frame_is_reported(cuda):
@@ -462,3 +489,42 @@ def test_capacity_follows_the_population(cuda):
     assert rnd.capacity.I_cap >= 3 * (cap0 - 4096)
     rnd.capacity.drain()
     assert int(rnd.last_status.cpu()[1]) == 0 and torch.isfinite(out["rgb"]).all()
+
+
+def test_flat_adam_replays_inside_a_cuda_graph(cuda):
+    """A captured optimizer step must advance its bias corrections on every replay (the host-clock entry would freeze them at
+    capture time) and pick up learning rates changed between replays."""
+    from splatter_a_video_b200.parallel import FlatAdam, FlatParams
+    g = torch.Generator().manual_seed(1)
+    tensors = {"a": torch.randn(512, 3, generator=g), "b": torch.randn(512, 4, generator=g)}
+    lrs = {"a": 1e-2, "b": 3e-3}
+    flat = FlatParams({k: v.to(cuda) for k, v in tensors.items()})
+    opt = FlatAdam(flat, lrs, eps=1e-15, device_clock=True)
+    ref = {k: v.clone().to(cuda).requires_grad_(True) for k, v in tensors.items()}
+    topt = torch.optim.Adam([{"params": [ref[k]], "lr": lrs[k]} for k in ref], eps=1e-15)
+    grads = [{k: torch.randn(tensors[k].shape, generator=g).to(cuda) for k in tensors} for _ in range(6)]
+    static = {k: torch.zeros_like(grads[0][k]) for k in tensors}
+
+    def step():
+        for k in tensors:
+            flat[k].grad.copy_(static[k])
+        opt.step()
+
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(gr, stream=s):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    for it in range(6):
+        if it == 3:
+            lrs = {"a": 5e-3, "b": 1e-3}
+            opt.set_lrs(lrs)
+            for grp, k in zip(topt.param_groups, ref):
+                grp["lr"] = lrs[k]
+        for k in tensors:
+            static[k].copy_(grads[it][k]); ref[k].grad = grads[it][k].clone()
+        gr.replay(); topt.step()
+        torch.cuda.synchronize()
+        for k in tensors:
+            np.testing.assert_allclose(n(flat[k]), n(ref[k]), rtol=3e-6, atol=1e-7)
