@@ -159,6 +159,12 @@ class Workload:
         dev = lambda x: x.to(device)
         g = torch.Generator().manual_seed(99)
         node = 0.02 * torch.randn(sc.P, 4 * self.NI * 3, generator=g)
+        # frame mode keeps the spline coefficients interval-major ([P,NI,4,3]: the 4 coefficients of an interval are 48 contiguous
+        # bytes); the staged modes keep the reference's [P,4,NI,3] parameter layout
+        self.node_im = mode == "frame"
+        if self.node_im:
+            from splatter_a_video_b200.gs.frame import spline_to_interval_major
+            node = spline_to_interval_major(node, self.NI)
         self.flat = FlatParams({"pos_cubic_node": dev(node), "scaling": dev(sc.scaling), "rotation": dev(sc.rotation),
                                 "opacity": dev(sc.opacity), "shs": dev(sc.shs),
                                 "mask_attribute": dev(sc.attrs["mask_attribute"]), "dino_attribute": dev(sc.attrs["dino_attribute"])})
@@ -221,7 +227,7 @@ class Workload:
                                              "mask_attribute": 1e-3, "dino_attribute": 1e-3}.items()}   # x 0.01: see config.learning_rates
         self.opt = None
         self.dens = None
-        self.ndc_leaf = None
+        self.loss_streams = None
 
     def defer_linear_tails(self, exchange):
         """Frame-parallel runs: the SH and spline backward run inside the gradient exchange on the reduced / gathered upstream
@@ -244,10 +250,10 @@ class Workload:
             # frame mode: both frame times from one pass over the coefficients; `track_gs` = position at ids2 carries gradient
             # like the reference's render_dict2["position"] (trainer_fragGS.py:487,506)
             pos, track = deform_position_pair(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.idx2, self.dist2, self.NI,
-                                              self.node_sink, self.node_dirty, self.node_defer)
+                                              self.node_sink, self.node_dirty, self.node_defer, interval_major=self.node_im)
         else:
-            pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI)
-            track = deform_position(self.base, p["pos_cubic_node"], self.idx2, self.dist2, self.NI)
+            pos = deform_position(self.base, p["pos_cubic_node"], self.idx1, self.dist1, self.NI, interval_major=self.node_im)
+            track = deform_position(self.base, p["pos_cubic_node"], self.idx2, self.dist2, self.NI, interval_major=self.node_im)
         return {"position": pos, "opacity": p["opacity"], "scaling": p["scaling"], "rotation": p["rotation"], "shs": p["shs"],
                 "track_gs": track, "mask_attribute": p["mask_attribute"], "pos_poly_feat": self.pos_poly_feat,
                 "dino_attribute": p["dino_attribute"]}
@@ -290,11 +296,24 @@ class Workload:
         b, w = self.batch_dev, self.loss_w
         self.flat.zero_grad(self.autograd_names if self.sinks else None)
         out = self.renderer.render_batch(self.render_dict(), [self._batch()])
-        self.step_out = out
-        l_rgb, g_rgb = LS.rgb_loss_grad(out["rgb"][0], b["gt_rgb"], w["lambda_dssim"], w["rgb"])
-        l_dep, g_dep = LS.depth_loss_grad(out["depth"][0], b["gt_depth"], w["depth"])
-        l_trk, g_trk = LS.track_loss_grad(out["track_gs"][0], self.trk_query, b["trk_target"], self.trk_visible, b["trk_weight"], 0.98,
-                                          w["flow"], grad=self.trk_grad)
+        # what the post-exchange part needs -- NOT the output dict: holding it would keep this iteration's autograd graph (and its
+        # AccumulateGrad nodes, bound to the stream they were created on) alive into the next capture
+        self.step_out = {"ndc": out["viewspace_points"][0], "radii": out["radii"].detach(), "visibility": out["visibility"].detach()}
+        # the three losses are independent: depth and track run on two side streams next to the rgb loss (parallel branches of the
+        # captured graph); their buffers are persistent, so nothing is allocated off the main stream
+        main = torch.cuda.current_stream()
+        if self.loss_streams is None:
+            self.loss_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            self.loss_bufs = [{}, {}, {}]
+        s_dep, s_trk = self.loss_streams
+        s_dep.wait_stream(main); s_trk.wait_stream(main)
+        with torch.cuda.stream(s_dep):
+            l_dep, g_dep = LS.depth_loss_grad(out["depth"][0], b["gt_depth"], w["depth"], buffers=self.loss_bufs[1])
+        with torch.cuda.stream(s_trk):
+            l_trk, g_trk = LS.track_loss_grad(out["track_gs"][0], self.trk_query, b["trk_target"], self.trk_visible, b["trk_weight"], 0.98,
+                                              w["flow"], grad=self.trk_grad, buffers=self.loss_bufs[2])
+        l_rgb, g_rgb = LS.rgb_loss_grad(out["rgb"][0], b["gt_rgb"], w["lambda_dssim"], w["rgb"], buffers=self.loss_bufs[0])
+        main.wait_stream(s_dep); main.wait_stream(s_trk)
         self.loss_vec[0:1].copy_(l_rgb[0:1] + l_dep + l_trk)          # total loss (the scalar the trainer logs, :769)
         keys = ["rgb", "depth", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
         grads = [g_rgb[None], g_dep.reshape(1, 1, self.H, self.W), g_trk[None]] + [self.g_dev[k][None] for k in keys[3:]]
@@ -303,7 +322,7 @@ class Workload:
     def _post_exchange(self):
         """densification statistics (update_structure, atlas_gs_optimizer.py:110-121) + one fused Adam kernel."""
         out = self.step_out
-        self.dens.update_stats(out["viewspace_points"][0].grad, out["radii"], out["visibility"])
+        self.dens.update_stats(out["ndc"].grad, out["radii"], out["visibility"])
         self.opt.step()
 
     def step_full(self, frame, exchange=None):
@@ -689,12 +708,14 @@ def make_exchange(wl, world, exchange_coefficients=False):
     if world > 1 and wl.mode == "frame" and not exchange_coefficients:
         # default: the two linear tails of the backward (colour -> SH, position -> spline coefficients) are deferred behind
         # the exchange: 12 dense + 3 colour floats/Gaussian summed, 6 position-gradient floats/Gaussian gathered
-        exchange = GradExchange(wl.flat, wl.P, dirty=wl.node_dirty, deferred={"shs": "shs", "node": "pos_cubic_node", "NI": wl.NI})
+        exchange = GradExchange(wl.flat, wl.P, dirty=wl.node_dirty,
+                                deferred={"shs": "shs", "node": "pos_cubic_node", "NI": wl.NI, "interval_major": wl.node_im})
         wl.defer_linear_tails(exchange)
         kind = "deferred SH/spline backward: ONE exchange of 21 floats/Gaussian/rank (12 dense + 3 colour + 6 position gradients), summed in rank order"
     else:
         exchange = GradExchange(wl.flat, wl.P, subset={"shs": ((wl.P, 16, 3), 1, [0, 2, 6, 12])},
-                                sparse={"pos_cubic_node": ((wl.P, 4, wl.NI, 3), 2, [wl.idx1, wl.idx2])}, dirty=wl.node_dirty)
+                                sparse={"pos_cubic_node": (((wl.P, wl.NI, 4, 3), 1, [wl.idx1, wl.idx2]) if wl.node_im else
+                                                           ((wl.P, 4, wl.NI, 3), 2, [wl.idx1, wl.idx2]))}, dirty=wl.node_dirty)
         kind = "coefficient gradients: all-reduce of 24 floats/Gaussian + all-gather of 24 floats/Gaussian/rank"
     return exchange, kind
 

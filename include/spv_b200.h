@@ -198,21 +198,24 @@ SPV_API int spv_alpha_blend_groups_backward_packed(int P, int C, int W, int H, c
                                            int n_grad_channels, float *packed, void *stream);
 
 /* ---- Per-frame deformation (next row f-1): cubic-spline position of the active model
- * (src/dynamic_gaussian_with_base_point_cloud.py:236-250).  coeff = pos_cubic_node viewed as [P,4,NI,3]; the interval
- * index and in-interval distance are DEVICE scalars (graph-replayable).  Backward: gradient to the coefficients. */
-SPV_API int spv_deform_spline_forward(int P, int NI, const float *base, const float *coeff, const int *idx_dev,
+ * (src/dynamic_gaussian_with_base_point_cloud.py:236-250).  coeff = pos_cubic_node viewed as [P,4,NI,3] (layout 0, the
+ * reference's parameter layout) or stored interval-major as [P,NI,4,3] (layout 1: the 4 coefficients of one interval are 48
+ * contiguous bytes -- 2 sectors instead of 4 scattered ones per evaluation; convert with spline layout helpers of gs.frame); the
+ * interval index and in-interval distance are DEVICE scalars (graph-replayable).  Backward: gradient to the coefficients, same
+ * layout. */
+SPV_API int spv_deform_spline_forward(int P, int NI, int layout, const float *base, const float *coeff, const int *idx_dev,
                               const float *dist_dev, float *pos /*[P,3]*/, void *stream);
-SPV_API int spv_deform_spline_backward(int P, int NI, const int *idx_dev, const float *dist_dev, const float *dL_dpos,
+SPV_API int spv_deform_spline_backward(int P, int NI, int layout, const int *idx_dev, const float *dist_dev, const float *dL_dpos,
                                float *dL_dcoeff /*[P,4,NI,3]*/, int accumulate, void *stream);
 
 /* Both frame times of a training step (ids1 rendered, ids2 as the `track_gs` attribute, trainer_fragGS.py:486-508) in one
  * pass.  backward2 writes into a gradient sink kept clean incrementally: `dirty` = int[17] on the device ([0] = count,
  * then interval indices holding non-zero gradient from earlier calls or gradient exchanges; zero-initialise it together
  * with the sink); listed intervals are zeroed unless re-written, afterwards the list is {idx1, idx2}. */
-SPV_API int spv_deform_spline_forward2(int P, int NI, const float *base, const float *coeff, const int *idx1_dev,
+SPV_API int spv_deform_spline_forward2(int P, int NI, int layout, const float *base, const float *coeff, const int *idx1_dev,
                                const float *dist1_dev, const int *idx2_dev, const float *dist2_dev, float *pos1,
                                float *pos2, void *stream);
-SPV_API int spv_deform_spline_backward2(int P, int NI, const int *idx1_dev, const float *dist1_dev, const int *idx2_dev,
+SPV_API int spv_deform_spline_backward2(int P, int NI, int layout, const int *idx1_dev, const float *dist1_dev, const int *idx2_dev,
                                 const float *dist2_dev, const float *dL_dpos1, const float *dL_dpos2 /*or NULL*/,
                                 int *dirty, float *dL_dcoeff /*[P,4,NI,3] sink*/, void *stream);
 
@@ -223,7 +226,7 @@ SPV_API int spv_deform_spline_backward2(int P, int NI, const int *idx1_dev, cons
  * gathered: `world` payloads, `stride` floats apart.  `dirty` as in spv_deform_spline_backward2. */
 SPV_API int spv_deform_defer(int P, const float *dL_dpos1, const float *dL_dpos2 /*or NULL*/, const int *idx1_dev,
                      const float *dist1_dev, const int *idx2_dev, const float *dist2_dev, float *payload, void *stream);
-SPV_API int spv_deform_spline_backward_gathered(int P, int NI, int world, const float *gathered, long long stride,
+SPV_API int spv_deform_spline_backward_gathered(int P, int NI, int layout, int world, const float *gathered, long long stride,
                                         float scale /*applied to every dL_dpos, e.g. 1/world*/, int *dirty,
                                         float *dL_dcoeff /*[P,4,NI,3] sink*/, void *stream);
 
@@ -234,6 +237,13 @@ SPV_API int spv_deform_rotation_forward(int P, const float *rotation, const floa
                                 float *out /*[P,4]*/, float *inv_norm /*[P]*/, void *stream);
 SPV_API int spv_deform_rotation_backward(int P, const float *out, const float *inv_norm, const float *dL_dout,
                                  float *dL_drotation, void *stream);
+/* Polynomial(4) + Fourier(8) POSITION of the alternative model (src/dynamic_gaussian_points.py:170-186, get_position):
+ * pos = position + pos_poly_feat[P,4,3] . t^k + pos_fourier_feat[P,8,3] . {cos,sin}(t pi (1..4)); basis_dev as above.  The backward
+ * WRITES its gradients; NULL outputs are skipped (dL_dposition under detach_pos). */
+SPV_API int spv_deform_polyfourier_forward(int P, const float *position, const float *pos_poly_feat, const float *pos_fourier_feat,
+                                   const float *basis_dev, float *pos, void *stream);
+SPV_API int spv_deform_polyfourier_backward(int P, const float *basis_dev, const float *dL_dpos, float *dL_dposition,
+                                    float *dL_dpos_poly_feat, float *dL_dpos_fourier_feat, void *stream);
 
 /* ---- Fused Adam over the flat parameter buffer (next row f-3, optimizer half; torch.optim.Adam arithmetic) ---------- */
 SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,

@@ -50,6 +50,12 @@ ncubwd)
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_rec_bwd -s 2 -c 2 -f -o gpurun_out/prof_bwd_${TAG} \
       python bench.py --steps 2 --warmup 1 --profile-mode > gpurun_out/ncu_bwd_${TAG}.log 2>&1
   tail -3 gpurun_out/ncu_bwd_${TAG}.log ;;
+bigcfg)
+  # BASELINE configs[2] / configs[3] on ONE GPU (dry run of the workloads the 4- and 8-GPU lines carry as extra_configs)
+  for c in cfg3_480p_500k cfg4_1080p_2m; do
+    timeout 400 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline --quick 2> gpurun_out/bench_${c}_${TAG}.err | tee gpurun_out/bench_${c}_${TAG}.json | cut -c1-600
+    tail -2 gpurun_out/bench_${c}_${TAG}.err
+  done ;;
 trace)
   timeout 200 python bench.py --steps 10 --warmup 3 --trace gpurun_out/trace_1gpu_${TAG}.json 2>&1 | grep "us x" | head -30 ;;
 esac

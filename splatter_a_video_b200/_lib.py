@@ -60,14 +60,16 @@ _SIGS = {
                                          P_, P_, P_, P_, P_, P_, P_, c_int, P_, c_size_t, P_]),
     "spv_alpha_blend_groups_backward_packed": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float, c_float,
                                                        P_, P_, P_, c_int, P_, P_]),
-    "spv_deform_spline_forward": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_]),
-    "spv_deform_spline_backward": (c_int, [c_int, c_int, P_, P_, P_, P_, c_int, P_]),
-    "spv_deform_spline_forward2": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
-    "spv_deform_spline_backward2": (c_int, [c_int, c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_spline_forward": (c_int, [c_int, c_int, c_int, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_spline_backward": (c_int, [c_int, c_int, c_int, P_, P_, P_, P_, c_int, P_]),
+    "spv_deform_spline_forward2": (c_int, [c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_spline_backward2": (c_int, [c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_]),
     "spv_deform_defer": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_, P_]),
-    "spv_deform_spline_backward_gathered": (c_int, [c_int, c_int, c_int, P_, ctypes.c_longlong, c_float, P_, P_, P_]),
+    "spv_deform_spline_backward_gathered": (c_int, [c_int, c_int, c_int, c_int, P_, ctypes.c_longlong, c_float, P_, P_, P_]),
     "spv_deform_rotation_forward": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
     "spv_deform_rotation_backward": (c_int, [c_int, P_, P_, P_, P_, P_]),
+    "spv_deform_polyfourier_forward": (c_int, [c_int, P_, P_, P_, P_, P_, P_]),
+    "spv_deform_polyfourier_backward": (c_int, [c_int, P_, P_, P_, P_, P_, P_]),
     "spv_adam_step": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, c_int, P_]),
     "spv_adam_step_device": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, P_, P_]),
     "spv_densify_stats": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),

@@ -19,6 +19,17 @@ __global__ void adam_tick_kernel(float *__restrict__ state, float b1, float b2) 
     state[2] = (float)sqrt(1.0 - pow((double)b2, t));
 }
 
+__device__ __forceinline__ void adam_update(float &p, float g, float &m, float &v, float lr_over_bc1, float b1, float b2, float eps,
+                                            float bc2_sqrt) {
+    m = m + (g - m) * (1.f - b1);                 // lerp_
+    v = v * b2 + (1.f - b2) * g * g;              // mul_().addcmul_()
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p = p - lr_over_bc1 * (m / denom);            // addcdiv_(value=-step_size)
+}
+
+// One float4 of (param, grad, exp_avg, exp_avg_sq) per thread: 16 B read + 12 B written per element, nothing else.  The
+// per-segment learning rate is looked up ONCE per float4 (segment boundaries almost never fall inside one); streaming loads /
+// stores keep the 1 GB pass out of the way of the L2-resident Gaussian records.
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(long long n4, long long n, float4 *__restrict__ p, const float4 *__restrict__ g, float4 *__restrict__ m,
             float4 *__restrict__ v, Segs segs, float b1, float b2, float eps, float bc1, float bc2_sqrt,
@@ -26,24 +37,34 @@ adam_kernel(long long n4, long long n, float4 *__restrict__ p, const float4 *__r
     const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
     if (k >= n4) return;
     if (state) { bc1 = state[1]; bc2_sqrt = state[2]; }   // device clock (graph replay): advanced by adam_tick_kernel
-    float4 P = p[k], M = m[k], V = v[k];
-    const float4 G = g[k];
-    float *pp = &P.x, *mm = &M.x, *vv = &V.x;
-    const float *gg = &G.x;
+    float4 P = __ldcs(p + k), M = __ldcs(m + k), V = __ldcs(v + k);
+    const float4 G = __ldcs(g + k);
+    const long long e0 = 4 * k;
+    int s0 = segs.n - 1;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const long long e = 4 * k + c;
-        if (e >= n) break;
-        float lr = lr_dev ? lr_dev[segs.n - 1] : segs.lr[segs.n - 1];
+    for (int s = kMaxSeg - 2; s >= 0; --s)
+        if (s < segs.n && e0 < segs.end[s]) s0 = s;
+    const bool one = e0 + 3 < segs.end[s0] && e0 + 3 < n;   // the whole float4 lies in segment s0
+    if (one) {
+        const float lr = (lr_dev ? lr_dev[s0] : segs.lr[s0]) / bc1;
+        adam_update(P.x, G.x, M.x, V.x, lr, b1, b2, eps, bc2_sqrt);
+        adam_update(P.y, G.y, M.y, V.y, lr, b1, b2, eps, bc2_sqrt);
+        adam_update(P.z, G.z, M.z, V.z, lr, b1, b2, eps, bc2_sqrt);
+        adam_update(P.w, G.w, M.w, V.w, lr, b1, b2, eps, bc2_sqrt);
+    } else {
+        float *pp = &P.x, *mm = &M.x, *vv = &V.x;
+        const float *gg = &G.x;
 #pragma unroll
-        for (int s = kMaxSeg - 1; s >= 0; --s)
-            if (s < segs.n && e < segs.end[s]) lr = lr_dev ? lr_dev[s] : segs.lr[s];
-        mm[c] = mm[c] + (gg[c] - mm[c]) * (1.f - b1);                 // lerp_
-        vv[c] = vv[c] * b2 + (1.f - b2) * gg[c] * gg[c];              // mul_().addcmul_()
-        const float denom = sqrtf(vv[c]) / bc2_sqrt + eps;
-        pp[c] = pp[c] - (lr / bc1) * (mm[c] / denom);                 // addcdiv_(value=-step_size)
+        for (int c = 0; c < 4; ++c) {
+            const long long e = e0 + c;
+            if (e >= n) break;
+            int sc = s0;
+            while (sc + 1 < segs.n && e >= segs.end[sc]) ++sc;
+            const float lr = (lr_dev ? lr_dev[sc] : segs.lr[sc]) / bc1;
+            adam_update(pp[c], gg[c], mm[c], vv[c], lr, b1, b2, eps, bc2_sqrt);
+        }
     }
-    p[k] = P; m[k] = M; v[k] = V;
+    __stcs(p + k, P); __stcs(m + k, M); __stcs(v + k, V);
 }
 }  // namespace
 

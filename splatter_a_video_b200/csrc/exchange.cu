@@ -30,6 +30,7 @@ struct Seg {
     int nsel;
     int w;                // floats per Gaussian in the comm buffer = A * nsel * Cn
     int cta0, ncta;       // this segment's CTAs inside the 1-D grid
+    int vec4;             // dense segment whose offsets and length are multiples of 4 floats: moved as float4
     short off[kMaxWidth];         // gather modes: comm column k -> offset inside the Gaussian's [A,B,Cn] row (sparse: slice 0)
     unsigned char slot[kMaxWidth];   // sparse: which of the rank's slices column k belongs to
 };
@@ -52,7 +53,12 @@ exchange_pack_kernel(int P, Plan plan, const float *__restrict__ flat_grad, floa
     const int cta = blockIdx.x - s.cta0;
     if (s.mode == 0) {
         const long long r = (long long)cta * kThreads + threadIdx.x;
-        if (r < (long long)P * s.w) comm_ar[s.comm_off + r] = flat_grad[s.flat_off + r] * scale;
+        if (s.vec4) {
+            if (r < (long long)P * s.w / 4) {
+                const float4 v = reinterpret_cast<const float4 *>(flat_grad + s.flat_off)[r];
+                reinterpret_cast<float4 *>(comm_ar + s.comm_off)[r] = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+            }
+        } else if (r < (long long)P * s.w) comm_ar[s.comm_off + r] = flat_grad[s.flat_off + r] * scale;
         return;
     }
     const int lane = threadIdx.x & 31, i = cta * 8 + (threadIdx.x >> 5);
@@ -82,7 +88,9 @@ exchange_unpack_kernel(int P, Plan plan, int world, const float *__restrict__ co
     const int cta = blockIdx.x - s.cta0;
     if (s.mode == 0) {
         const long long r = (long long)cta * kThreads + threadIdx.x;
-        if (r < (long long)P * s.w) flat_grad[s.flat_off + r] = comm_ar[s.comm_off + r];
+        if (s.vec4) {
+            if (r < (long long)P * s.w / 4) reinterpret_cast<float4 *>(flat_grad + s.flat_off)[r] = reinterpret_cast<const float4 *>(comm_ar + s.comm_off)[r];
+        } else if (r < (long long)P * s.w) flat_grad[s.flat_off + r] = comm_ar[s.comm_off + r];
         return;
     }
     const int lane = threadIdx.x & 31, i = cta * 8 + (threadIdx.x >> 5);
@@ -270,7 +278,9 @@ int build_plan(Plan &plan, int P, int nseg, const spv_exchange_segment *segs, co
                 s.slot[k] = (unsigned char)si;
             }
         const long long n = (long long)P * s.w;
-        const long long nc = in.mode == 0 ? (n + kThreads - 1) / kThreads : ((long long)P + 7) / 8;
+        const long long comm_next = in.mode == 2 ? ag : ar;
+        s.vec4 = (in.mode == 0 && (n & 3) == 0 && (s.flat_off & 3) == 0 && (comm_next & 3) == 0) ? 1 : 0;
+        const long long nc = in.mode == 0 ? ((s.vec4 ? n / 4 : n) + kThreads - 1) / kThreads : ((long long)P + 7) / 8;
         if (cta + nc >= (1ll << 31)) { spv::set_error(cudaErrorInvalidValue, where); return (int)cudaErrorInvalidValue; }
         s.cta0 = cta; s.ncta = (int)nc; cta += (int)nc;
         if (in.mode == 2) { s.comm_off = ag; ag += n; for (int t = 0; t < s.nsel; ++t) plan.sparse_idx[t] = sparse_idx_dev[t]; }

@@ -245,15 +245,17 @@ select_pass_kernel(int n, const float *__restrict__ a0, const float *__restrict_
     unsigned loc[per], sum = 0;
 #pragma unroll
     for (int q = 0; q < per; ++q) { loc[q] = __ldcg(&gh[threadIdx.x * per + q]); sum += loc[q]; }
-    s_scan[threadIdx.x] = sum;
+    // exclusive scan of the per-thread sums: warp shuffles, then the kRed / 32 warp totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_scan[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {   // 256 partial sums: a serial walk is a few hundred cycles, once per pass
-        unsigned run = 0;
-        for (int t = 0; t < kRed; ++t) { const unsigned v = s_scan[t]; s_scan[t] = run; run += v; }
-    }
-    __syncthreads();
+    unsigned run = incl - sum;
+#pragma unroll
+    for (int w = 0; w < kRed / 32; ++w) if (w < warp) run += s_scan[w];
     const unsigned rank = SHIFT + BITS < 32 ? __ldcg(&st->rank) : (unsigned)((n - 1) / 2);
-    unsigned run = s_scan[threadIdx.x];
 #pragma unroll
     for (int q = 0; q < per; ++q) {
         if (rank >= run && rank < run + loc[q]) {     // exactly one (thread, q) over the CTA
@@ -398,35 +400,74 @@ track_reduce_kernel(int n, int W, int H, const float *__restrict__ track, const 
     }
 }
 
-// Up to kTrackFused query points (the TAPIR grid of one frame): everything above in ONE CTA -- per-point values, a bitonic sort
-// of a copy in shared memory for the quantile, the two masked sums, the loss and the gradient scatter.  No CUB sort, 1 launch.
+// Block-wide radix SELECT over `n` floats in shared memory: the value of rank `rank` (0-based, ascending) -- three passes over the
+// order-preserving keys (11 + 11 + 10 bits), shared-memory histogram + block scan per pass.  All threads of a 1024-thread CTA
+// call it; every thread gets the result.  s_hist: 2048 counters, s_aux: 36 words.
+__device__ float block_select_1024(const float *vals, int n, unsigned rank, unsigned *s_hist, unsigned *s_aux) {
+    unsigned prefix = 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0), bits = pass == 2 ? 10 : 11;
+        const unsigned hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + bits)), dmask = (1u << bits) - 1u;
+        s_hist[threadIdx.x] = 0u; s_hist[threadIdx.x + 1024] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += 1024) {
+            const unsigned k = order_key(vals[i]);
+            if ((k & hi_mask) == prefix) atomicAdd(&s_hist[(k >> shift) & dmask], 1u);
+        }
+        __syncthreads();
+        // exclusive scan of the 2048 bins: two per thread, warp shuffles, then the 32 warp totals
+        const unsigned c0 = s_hist[2 * threadIdx.x], c1 = s_hist[2 * threadIdx.x + 1];
+        unsigned incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_aux[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = s_aux[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            s_aux[lane] = w;
+        }
+        __syncthreads();
+        const unsigned before = (incl - (c0 + c1)) + (warp ? s_aux[warp - 1] : 0u);
+        if (rank >= before && rank < before + c0) { s_aux[32] = prefix | ((unsigned)(2 * threadIdx.x) << shift); s_aux[33] = rank - before; }
+        else if (rank >= before + c0 && rank < before + c0 + c1) { s_aux[32] = prefix | ((unsigned)(2 * threadIdx.x + 1) << shift); s_aux[33] = rank - before - c0; }
+        __syncthreads();
+        prefix = s_aux[32]; rank = s_aux[33];
+        __syncthreads();
+    }
+    return key_value(prefix);
+}
+
+// Up to kTrackFused query points (the TAPIR grid of one frame): everything above in ONE CTA -- per-point values in shared memory,
+// the two order statistics of the quantile by radix select (no sort), the two masked sums, the loss and the gradient scatter.
 constexpr int kTrackFused = 16384;
 
 __global__ void __launch_bounds__(1024)
-track_fused_kernel(int n, int n_pad, int W, int H, const float *__restrict__ track, const int *__restrict__ query_xy,
+track_fused_kernel(int n, int W, int H, const float *__restrict__ track, const int *__restrict__ query_xy,
                    const float *__restrict__ gt_xy, const uint8_t *__restrict__ visible, const float *__restrict__ weights,
                    float quantile, float weight, float *__restrict__ loss, float *__restrict__ dL_dtrack) {
-    extern __shared__ __align__(16) float s_track[];
-    float *s_vals = s_track, *s_sorted = s_track + n_pad;
+    extern __shared__ __align__(16) float s_vals[];
     __shared__ double scratch[32], bcast[2];
+    __shared__ unsigned s_hist[2048], s_aux[36];
     __shared__ int s_M;
     const float inf = __int_as_float(0x7f800000);
     const size_t HW = (size_t)H * W;
     if (threadIdx.x == 0) s_M = 0;
     __syncthreads();
     int mine = 0;
-    for (int i = threadIdx.x; i < n_pad; i += 1024) {
+    for (int i = threadIdx.x; i < n; i += 1024) {
         float v = inf;
-        if (i < n) {
-            const int qx = query_xy[2 * i], qy = query_xy[2 * i + 1];
-            if (visible[i] && qx >= 0 && qx < W && qy >= 0 && qy < H) {
-                const size_t o = (size_t)qy * W + qx;
-                const float px = (track[o] + 1.f) * (float)W / 2.f, py = (track[HW + o] + 1.f) * (float)H / 2.f;   // util.py:82
-                v = (fabsf(px - gt_xy[2 * i]) + fabsf(py - gt_xy[2 * i + 1])) / 2.f;
-                ++mine;
-            }
+        const int qx = query_xy[2 * i], qy = query_xy[2 * i + 1];
+        if (visible[i] && qx >= 0 && qx < W && qy >= 0 && qy < H) {
+            const size_t o = (size_t)qy * W + qx;
+            const float px = (track[o] + 1.f) * (float)W / 2.f, py = (track[HW + o] + 1.f) * (float)H / 2.f;   // util.py:82
+            v = (fabsf(px - gt_xy[2 * i]) + fabsf(py - gt_xy[2 * i + 1])) / 2.f;
+            ++mine;
         }
-        s_vals[i] = v; s_sorted[i] = v;
+        s_vals[i] = v;
     }
     mine = __reduce_add_sync(0xffffffffu, mine);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_M, mine);
@@ -436,21 +477,11 @@ track_fused_kernel(int n, int n_pad, int W, int H, const float *__restrict__ tra
         if (threadIdx.x == 0) loss[0] = 0.f;
         return;
     }
-    for (int k = 2; k <= n_pad; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n_pad; i += 1024) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const float a = s_sorted[i], b = s_sorted[p];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { s_sorted[i] = b; s_sorted[p] = a; }
-                }
-            }
-            __syncthreads();
-        }
     const float pos = quantile * (float)(M - 1);
     const int lo = (int)floorf(pos), hi = (int)ceilf(pos);
-    const float fr = pos - (float)lo, a = s_sorted[lo], b = s_sorted[hi];
+    const float fr = pos - (float)lo;
+    const float a = block_select_1024(s_vals, n, (unsigned)lo, s_hist, s_aux);
+    const float b = hi == lo ? a : block_select_1024(s_vals, n, (unsigned)hi, s_hist, s_aux);
     const float thr = fr < 0.5f ? a + fr * (b - a) : b - (b - a) * (1.f - fr);   // at::lerp
     double num = 0.0, den = 0.0;
     for (int i = threadIdx.x; i < n; i += 1024) {
@@ -555,7 +586,8 @@ int spv_loss_depth_dpt(int n, const float *pred, const float *gt, float weight, 
     if (ws_bytes < w.total) { spv::set_error(cudaErrorInvalidValue, "spv_loss_depth_dpt: workspace too small"); return (int)cudaErrorInvalidValue; }
     SPV_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.head_bytes, s), "spv_loss_depth_dpt");      // histograms, select state, tickets
     SPV_CUDA_TRY(cudaMemsetAsync(w.med_idx, 0x7f, sizeof(int), s), "spv_loss_depth_dpt");
-    const dim3 sel_grid(spv::cdiv(n, kRed * 8) < (unsigned)kRedBlocks ? spv::cdiv(n, kRed * 8) : (unsigned)kRedBlocks, 2);
+    const unsigned sel_blocks = spv::cdiv(n, kRed * 16);      // 16 elements per thread, at most one CTA per SM and map
+    const dim3 sel_grid(sel_blocks < 74u ? sel_blocks : 74u, 2);
     select_pass_kernel<21, 11><<<sel_grid, kRed, 0, s>>>(n, pred, gt, w.hist, w.state, w.med);
     select_pass_kernel<10, 11><<<sel_grid, kRed, 0, s>>>(n, pred, gt, w.hist, w.state, w.med);
     select_pass_kernel<0, 10><<<sel_grid, kRed, 0, s>>>(n, pred, gt, w.hist, w.state, w.med);
@@ -578,13 +610,11 @@ int spv_loss_track(int n_points, int W, int H, const float *track_chw, const int
         return 0;
     }
     if (n_points <= kTrackFused) {
-        int n_pad = 32;
-        while (n_pad < n_points) n_pad <<= 1;
-        const size_t dyn = sizeof(float) * 2 * (size_t)n_pad;
+        const size_t dyn = sizeof(float) * (size_t)((n_points + 3) / 4 * 4);
         static std::atomic<unsigned long long> configured{0};
-        spv::opt_in_dynamic_smem(track_fused_kernel, sizeof(float) * 2 * kTrackFused, configured);
-        track_fused_kernel<<<1, 1024, dyn, s>>>(n_points, n_pad, W, H, track_chw, query_xy, target_xy, visible, weights, quantile, weight,
-                                                loss, dL_dtrack_chw);
+        spv::opt_in_dynamic_smem(track_fused_kernel, sizeof(float) * kTrackFused, configured);
+        track_fused_kernel<<<1, 1024, dyn, s>>>(n_points, W, H, track_chw, query_xy, target_xy, visible, weights, quantile, weight, loss,
+                                                dL_dtrack_chw);
         return spv::check_launch("spv_loss_track", 1);
     }
     TrackWs w = carve_track(workspace, n_points);

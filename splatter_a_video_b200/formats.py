@@ -2,7 +2,8 @@
 point clouds, read and written without the reference's Python stack so that a reference-trained scene can be rendered by
 these kernels (and a scene trained here opened by the reference).
 
-Checkpoint `model_{step:06d}.pth` (trainer_fragGS.py:923-938, frag_model.py:345-347, pointrix/model/base_model.py:186-188):
+Checkpoint `model_{step:06d}.pth` (trainer_fragGS.py:923-938, frag_model.py:345-347, pointrix/model/base_model.py:186-188; layout
+pinned to a file written by those functions themselves: tests/golden/make_checkpoint_golden.py -> golden_checkpoint.pth):
 
     {"gs_atlases_model": {<atlas name>: {"point_cloud.position": [N,3] (frozen base cloud), "point_cloud.features": [N,1,3],
                                          "point_cloud.features_rest": [N,15,3], "point_cloud.scaling": [N,3] (log),
@@ -123,9 +124,12 @@ def save_checkpoint(path: str, atlases: Dict[str, AtlasState], active_sh_degree:
     """Writes the layout `load_model` of the reference trainer consumes (trainer_fragGS.py:941-950)."""
     model = {}
     for name, st in atlases.items():
-        sd = {PREFIX + "position": st.tensors["position"].detach().cpu()}
+        # nn.Module.state_dict order of the reference's point cloud: the Parameters in registration order, then its one remaining
+        # buffer (the frozen base `position`), then `num_pts` (pinned by tests/golden/golden_checkpoint.pth)
+        sd = {}
         for k in st.order:
             sd[PREFIX + k] = st.tensors[k].detach().cpu()
+        sd[PREFIX + "position"] = st.tensors["position"].detach().cpu()
         sd["num_pts"] = st.num_points
         model[name] = sd
     data = {"gs_atlases_model": model, "renderer": {"active_sh_degree": int(active_sh_degree)}}

@@ -248,15 +248,29 @@ def spline_interval(time: float, num_frames: int, interval_num: int) -> Tuple[in
     return idx, float(normed_time - float(intervals[idx]))
 
 
+def spline_to_interval_major(pos_cubic_node: Tensor, interval_num: int) -> Tensor:
+    """[P, 4*NI*3] in the reference's (coefficient, interval, xyz) order -> the same numbers interval-major (interval, coefficient,
+    xyz): the storage the deformation kernels read with `interval_major=True`.  Values are moved, nothing is recomputed."""
+    P = pos_cubic_node.shape[0]
+    return pos_cubic_node.reshape(P, 4, interval_num, 3).permute(0, 2, 1, 3).reshape(P, -1).contiguous()
+
+
+def spline_from_interval_major(node_im: Tensor, interval_num: int) -> Tensor:
+    """Inverse of spline_to_interval_major (e.g. before writing a reference-layout checkpoint)."""
+    P = node_im.shape[0]
+    return node_im.reshape(P, interval_num, 4, 3).permute(0, 2, 1, 3).reshape(P, -1).contiguous()
+
+
 class _DeformSpline(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, base, coeff, idx_dev, dist_dev, NI, sink):
+    def forward(ctx, base, coeff, idx_dev, dist_dev, NI, sink, layout=0):
         L.need_cuda(base, coeff, idx_dev, dist_dev)
         b, c = L.f32c(base), L.f32c(coeff)
         P = b.shape[0]
         pos = torch.empty(P, 3, dtype=torch.float32, device=b.device)
-        L.call("spv_deform_spline_forward", P, int(NI), L.ptr(b), L.ptr(c), L.ptr(idx_dev), L.ptr(dist_dev), L.ptr(pos), L.stream())
+        L.call("spv_deform_spline_forward", P, int(NI), int(layout), L.ptr(b), L.ptr(c), L.ptr(idx_dev), L.ptr(dist_dev), L.ptr(pos), L.stream())
         ctx.meta = (P, int(NI), tuple(coeff.shape), base.requires_grad)
+        ctx.layout = int(layout)
         ctx.sink = sink
         ctx.save_for_backward(idx_dev, dist_dev)
         return pos
@@ -267,16 +281,16 @@ class _DeformSpline(torch.autograd.Function):
         idx_dev, dist_dev = ctx.saved_tensors
         g_coeff = ctx.sink if ctx.sink is not None else torch.empty(shape, dtype=torch.float32, device=g_pos.device)
         gp = L.f32c(g_pos)
-        L.call("spv_deform_spline_backward", P, NI, L.ptr(idx_dev), L.ptr(dist_dev), L.ptr(gp), L.ptr(g_coeff), 0, L.stream())
-        return (gp if base_grad else None), (None if ctx.sink is not None else g_coeff), None, None, None, None
+        L.call("spv_deform_spline_backward", P, NI, ctx.layout, L.ptr(idx_dev), L.ptr(dist_dev), L.ptr(gp), L.ptr(g_coeff), 0, L.stream())
+        return (gp if base_grad else None), (None if ctx.sink is not None else g_coeff), None, None, None, None, None
 
 
 def deform_position(base: Tensor, pos_cubic_node: Tensor, idx_dev: Tensor, dist_dev: Tensor, interval_num: int,
-                    grad_sink: Optional[Tensor] = None) -> Tensor:
+                    grad_sink: Optional[Tensor] = None, interval_major: bool = False) -> Tensor:
     """position(t) = base + cubic spline; `pos_cubic_node` is [P, 4*interval_num*3]; idx_dev (int32[1]) / dist_dev
     (float32[1]) are device scalars produced from `spline_interval` (update them in place to replay a CUDA graph).
     grad_sink: optional buffer the coefficient gradient is written into (see render_ortho_frame)."""
-    return _DeformSpline.apply(base, pos_cubic_node, idx_dev, dist_dev, interval_num, grad_sink)
+    return _DeformSpline.apply(base, pos_cubic_node, idx_dev, dist_dev, interval_num, grad_sink, int(bool(interval_major)))
 
 
 class _DeformSplinePair(torch.autograd.Function):
@@ -284,14 +298,15 @@ class _DeformSplinePair(torch.autograd.Function):
     device-side dirty list (no per-step clear of the whole [P, 4*NI*3] gradient), or into a fresh zero tensor."""
 
     @staticmethod
-    def forward(ctx, base, coeff, idx1, dist1, idx2, dist2, NI, sink, dirty, defer):
+    def forward(ctx, base, coeff, idx1, dist1, idx2, dist2, NI, sink, dirty, defer, layout=0):
         L.need_cuda(base, coeff, idx1, dist1, idx2, dist2)
         ctx.defer = defer
+        ctx.layout = int(layout)
         b, c = L.f32c(base), L.f32c(coeff)
         P = b.shape[0]
         pos1 = torch.empty(P, 3, dtype=torch.float32, device=b.device)
         pos2 = torch.empty(P, 3, dtype=torch.float32, device=b.device)
-        L.call("spv_deform_spline_forward2", P, int(NI), L.ptr(b), L.ptr(c), L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2),
+        L.call("spv_deform_spline_forward2", P, int(NI), int(layout), L.ptr(b), L.ptr(c), L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2),
                L.ptr(pos1), L.ptr(pos2), L.stream())
         ctx.meta = (P, int(NI), tuple(coeff.shape), base.requires_grad)
         ctx.sink, ctx.dirty = sink, dirty
@@ -310,23 +325,23 @@ class _DeformSplinePair(torch.autograd.Function):
         if ctx.defer is not None:      # frame-parallel: only stage the position gradients; GradExchange finishes the backward
             L.call("spv_deform_defer", P, L.ptr(g1), L.ptr(g2), L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2), L.ptr(ctx.defer),
                    L.stream())
-            return (g1 if g2 is None else g1 + g2) if base_grad else None, None, None, None, None, None, None, None, None, None
+            return (g1 if g2 is None else g1 + g2) if base_grad else None, None, None, None, None, None, None, None, None, None, None
         if ctx.sink is not None:
             g_coeff, dirty, ret = ctx.sink, ctx.dirty, None
         else:
             g_coeff = torch.zeros(shape, dtype=torch.float32, device=dev)
             dirty, ret = torch.zeros(17, dtype=torch.int32, device=dev), g_coeff
-        L.call("spv_deform_spline_backward2", P, NI, L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2), L.ptr(g1), L.ptr(g2),
+        L.call("spv_deform_spline_backward2", P, NI, ctx.layout, L.ptr(idx1), L.ptr(dist1), L.ptr(idx2), L.ptr(dist2), L.ptr(g1), L.ptr(g2),
                L.ptr(dirty), L.ptr(g_coeff), L.stream())
         g_base = None
         if base_grad:
             g_base = g1 if g2 is None else g1 + g2
-        return g_base, ret, None, None, None, None, None, None, None, None
+        return g_base, ret, None, None, None, None, None, None, None, None, None
 
 
 def deform_position_pair(base: Tensor, pos_cubic_node: Tensor, idx1: Tensor, dist1: Tensor, idx2: Tensor, dist2: Tensor,
                          interval_num: int, grad_sink: Optional[Tensor] = None, dirty: Optional[Tensor] = None,
-                         defer: Optional[Tensor] = None):
+                         defer: Optional[Tensor] = None, interval_major: bool = False):
     """Positions at the two frame times of a training step (ids1 rendered; ids2 = the `track_gs` attribute,
     src/trainer_fragGS.py:486-508) from ONE pass over the spline coefficients.  Both outputs are differentiable.
     grad_sink + dirty: the coefficient gradient is WRITTEN into `grad_sink` ([P, 4*NI*3], zero-initialised once) and
@@ -334,10 +349,12 @@ def deform_position_pair(base: Tensor, pos_cubic_node: Tensor, idx1: Tensor, dis
     the next call.
     defer (frame-parallel training): float32[6P + 4] staging buffer of parallel.GradExchange -- the backward only stores the two
     position gradients there; the coefficient gradient of EVERY rank's frames is rebuilt after the all-gather
-    (`spv_deform_spline_backward_gathered`), which is 4x less traffic than exchanging coefficient gradients."""
+    (`spv_deform_spline_backward_gathered`), which is 4x less traffic than exchanging coefficient gradients.
+    interval_major: `pos_cubic_node` (and its gradient) are stored interval-major, see spline_to_interval_major."""
     if (grad_sink is None) != (dirty is None):
         raise ValueError("deform_position_pair: grad_sink and dirty go together")
-    return _DeformSplinePair.apply(base, pos_cubic_node, idx1, dist1, idx2, dist2, interval_num, grad_sink, dirty, defer)
+    return _DeformSplinePair.apply(base, pos_cubic_node, idx1, dist1, idx2, dist2, interval_num, grad_sink, dirty, defer,
+                                   int(bool(interval_major)))
 
 
 def rotation_basis(time: float, start_frame_id: int, time_len: int) -> Tensor:
@@ -373,3 +390,39 @@ def deform_rotation(rotation: Tensor, rot_poly_feat: Tensor, rot_fourier_feat: T
     """Unit quaternion of every Gaussian at frame time t (src/dynamic_gaussian_with_base_point_cloud.py:184-198); the
     poly / Fourier features enter detached, as in the reference.  `basis_dev` = rotation_basis(...).cuda()."""
     return _DeformRotation.apply(rotation, rot_poly_feat, rot_fourier_feat, basis_dev)
+
+
+class _DeformPolyFourier(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, position, pos_poly_feat, pos_fourier_feat, basis_dev):
+        L.need_cuda(position, pos_poly_feat, pos_fourier_feat, basis_dev)
+        p, pf, ff = L.f32c(position), L.f32c(pos_poly_feat), L.f32c(pos_fourier_feat)
+        P = p.shape[0]
+        if pf.numel() != P * 12 or ff.numel() != P * 24:
+            raise ValueError("deform_position_polyfourier expects pos_poly_feat [P,4,3] and pos_fourier_feat [P,8,3]")
+        out = torch.empty(P, 3, dtype=torch.float32, device=p.device)
+        L.call("spv_deform_polyfourier_forward", P, L.ptr(p), L.ptr(pf), L.ptr(ff), L.ptr(basis_dev), L.ptr(out), L.stream())
+        ctx.save_for_backward(basis_dev)
+        ctx.shapes = (tuple(pos_poly_feat.shape), tuple(pos_fourier_feat.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (basis_dev,) = ctx.saved_tensors
+        g = L.f32c(g)
+        P, dev = g.shape[0], g.device
+        need_p, need_pf, need_ff = ctx.needs_input_grad[:3]
+        gp = torch.empty(P, 3, dtype=torch.float32, device=dev) if need_p else None
+        gpf = torch.empty(ctx.shapes[0], dtype=torch.float32, device=dev) if need_pf else None
+        gff = torch.empty(ctx.shapes[1], dtype=torch.float32, device=dev) if need_ff else None
+        L.call("spv_deform_polyfourier_backward", P, L.ptr(basis_dev), L.ptr(g), L.ptr(gp), L.ptr(gpf), L.ptr(gff), L.stream())
+        return gp, gpf, gff, None
+
+
+def deform_position_polyfourier(position: Tensor, pos_poly_feat: Tensor, pos_fourier_feat: Tensor, basis_dev: Tensor,
+                                detach_pos: bool = False) -> Tensor:
+    """Position of every Gaussian at frame time t in the ALTERNATIVE model (src/dynamic_gaussian_points.py:170-186, get_position):
+    position + polynomial(4) + Fourier(8) terms, `basis_dev` = rotation_basis(time, start_frame_id, time_len).cuda() (the same 12
+    numbers the rotation uses).  All three tensors are differentiable; `detach_pos` stops the gradient to `position` like the
+    reference's flag."""
+    return _DeformPolyFourier.apply(position.detach() if detach_pos else position, pos_poly_feat, pos_fourier_feat, basis_dev)

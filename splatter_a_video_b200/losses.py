@@ -127,34 +127,38 @@ def track_loss(track_chw: Tensor, query_xy: Tensor, target_xy: Tensor, visible: 
 # A training step that hands `dL/dimage` straight to the rasterizer's backward (torch.autograd.backward(images, grads)) does not
 # need the losses on the autograd tape: one C call per loss gives the scalar(s) and the gradient image, with nothing multiplied
 # by an upstream 1.0 afterwards.
-def rgb_loss_grad(pred_chw: Tensor, gt_hwc: Tensor, lambda_dssim: float = 0.2, weight: float = 1.0) -> Tuple[Tensor, Tensor]:
-    """-> (float32[3] = (loss, l1, ssim) on the device, dL/dpred [3,H,W])."""
+def rgb_loss_grad(pred_chw: Tensor, gt_hwc: Tensor, lambda_dssim: float = 0.2, weight: float = 1.0, buffers: dict = None) -> Tuple[Tensor, Tensor]:
+    """-> (float32[3] = (loss, l1, ssim) on the device, dL/dpred [3,H,W]).  `buffers`: optional dict the call fills with its output /
+    gradient / workspace tensors on first use and re-uses afterwards (lets a caller run the losses on side streams without
+    allocating there)."""
     L.need_cuda(pred_chw, gt_hwc)
     p, g = L.f32c(pred_chw.detach()), L.f32c(gt_hwc)
     H, W = int(p.shape[1]), int(p.shape[2])
-    out = torch.empty(3, dtype=torch.float32, device=p.device)
-    grad = torch.empty_like(p)
     nbytes = L.query("spv_loss_rgb_workspace_bytes", W, H)
-    ws = _ws(nbytes, p.device)
+    buffers = buffers if buffers is not None else {}
+    if "out" not in buffers:
+        buffers.update(out=torch.empty(3, dtype=torch.float32, device=p.device), grad=torch.empty_like(p), ws=_ws(nbytes, p.device))
+    out, grad, ws = buffers["out"], buffers["grad"], buffers["ws"]
     L.call("spv_loss_rgb", W, H, L.ptr(p), L.ptr(g), float(weight), float(lambda_dssim), L.ptr(out), L.ptr(grad), L.ptr(ws), nbytes, L.stream())
     return out, grad
 
 
-def depth_loss_grad(pred_depth: Tensor, gt_depth: Tensor, weight: float = 1.0) -> Tuple[Tensor, Tensor]:
-    """-> (float32[1] loss on the device, dL/dpred with pred's shape)."""
+def depth_loss_grad(pred_depth: Tensor, gt_depth: Tensor, weight: float = 1.0, buffers: dict = None) -> Tuple[Tensor, Tensor]:
+    """-> (float32[1] loss on the device, dL/dpred with pred's shape).  `buffers`: see rgb_loss_grad."""
     L.need_cuda(pred_depth, gt_depth)
     p, g = L.f32c(pred_depth.detach()), L.f32c(gt_depth)
     n = p.numel()
-    out = torch.empty(1, dtype=torch.float32, device=p.device)
-    grad = torch.empty_like(p)
     nbytes = L.query("spv_loss_depth_workspace_bytes", n)
-    ws = _ws(nbytes, p.device)
+    buffers = buffers if buffers is not None else {}
+    if "out" not in buffers:
+        buffers.update(out=torch.empty(1, dtype=torch.float32, device=p.device), grad=torch.empty_like(p), ws=_ws(nbytes, p.device))
+    out, grad, ws = buffers["out"], buffers["grad"], buffers["ws"]
     L.call("spv_loss_depth_dpt", n, L.ptr(p), L.ptr(g), float(weight), L.ptr(out), L.ptr(grad), L.ptr(ws), nbytes, L.stream())
     return out, grad
 
 
 def track_loss_grad(track_chw: Tensor, query_xy: Tensor, target_xy: Tensor, visible: Tensor, weights: Tensor, quantile: float = 0.98,
-                    weight: float = 1.0, grad: Tensor = None) -> Tuple[Tensor, Tensor]:
+                    weight: float = 1.0, grad: Tensor = None, buffers: dict = None) -> Tuple[Tensor, Tensor]:
     """-> (float32[1] loss on the device, dL/dtrack [C,H,W] with channels >= 2 zero).  query_xy int32 [n,2], visible uint8 [n]
     (already in the kernel's dtypes: no conversion kernels on the hot path).  `grad`: optional caller-owned [C,H,W] buffer whose
     channels >= 2 are already zero (only the two coordinate planes are cleared and rewritten)."""
@@ -164,11 +168,13 @@ def track_loss_grad(track_chw: Tensor, query_xy: Tensor, target_xy: Tensor, visi
     n = int(query_xy.shape[0])
     if query_xy.dtype != torch.int32 or visible.dtype != torch.uint8:
         raise ValueError("track_loss_grad expects int32 query pixels and a uint8 visibility mask")
-    out = torch.empty(1, dtype=torch.float32, device=t.device)
+    nbytes = L.query("spv_loss_track_workspace_bytes", n)
+    buffers = buffers if buffers is not None else {}
+    if "out" not in buffers:
+        buffers.update(out=torch.empty(1, dtype=torch.float32, device=t.device), ws=_ws(nbytes, t.device))
+    out, ws = buffers["out"], buffers["ws"]
     if grad is None:
         grad = torch.zeros_like(t)
-    nbytes = L.query("spv_loss_track_workspace_bytes", n)
-    ws = _ws(nbytes, t.device)
     L.call("spv_loss_track", n, W, H, L.ptr(t), L.ptr(query_xy), L.ptr(L.f32c(target_xy)), L.ptr(visible), L.ptr(L.f32c(weights.reshape(-1))),
            float(quantile), float(weight), L.ptr(out), L.ptr(grad), L.ptr(ws), nbytes, L.stream())
     return out, grad

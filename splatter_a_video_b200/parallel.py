@@ -329,7 +329,8 @@ class GradExchange:
         from . import _lib as L
         c, d = self._cuda, self.deferred
         node = self.flat.params[d["node"]]
-        L.call("spv_deform_spline_backward_gathered", self.P, int(d["NI"]), world, c["gathered"].data_ptr(), c["gathered"].stride(0),
+        L.call("spv_deform_spline_backward_gathered", self.P, int(d["NI"]), int(bool(d.get("interval_major", False))), world,
+               c["gathered"].data_ptr(), c["gathered"].stride(0),
                float(scale), L.ptr(self.dirty), L.ptr(node.grad), L.stream())
 
     def _finish_deferred(self, world: int, scale: float, reduced: torch.Tensor):

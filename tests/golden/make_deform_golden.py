@@ -19,8 +19,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/src/dynamic_gaussian_with_base_point_cloud.py"
 
 
-def lift(names):
-    tree = ast.parse(open(SRC).read())
+SRC_ALT = "/root/reference/src/dynamic_gaussian_points.py"
+
+
+def lift(names, src=None):
+    SRC_ = src or SRC
+    tree = ast.parse(open(SRC_).read())
     ns = {"torch": torch, "np": np}
     for cls in (n for n in tree.body if isinstance(n, ast.ClassDef)):
         for fn in cls.body:
@@ -28,7 +32,7 @@ def lift(names):
                 fn.decorator_list, fn.returns = [], None
                 for a in fn.args.args:
                     a.annotation = None
-                exec(compile(ast.fix_missing_locations(ast.Module(body=[fn], type_ignores=[])), SRC, "exec"), ns)
+                exec(compile(ast.fix_missing_locations(ast.Module(body=[fn], type_ignores=[])), SRC_, "exec"), ns)
     assert all(n in ns for n in names)
     return [ns[n] for n in names]
 
@@ -61,6 +65,28 @@ def main():
                     pre + "rot_poly": o.rot_poly_feat.numpy(), pre + "rot_fourier": o.rot_fourier_feat.numpy(),
                     pre + "pos_t": pos.numpy(), pre + "rot_t": rot.numpy()})
         print(f"F={F} NI={NI}: positions {tuple(pos.shape)}, rotations {tuple(rot.shape)}")
+    # the ALTERNATIVE model (dynamic_gaussian_points.py:170-186): polynomial + Fourier position, with and without detach_pos
+    (alt_position,) = lift(["get_position"], SRC_ALT)
+    for F in (50, 7):
+        o = types.SimpleNamespace()
+        o.position = torch.randn(P, 3, generator=g)
+        o.pos_poly_feat = 0.1 * torch.randn(P, 4, 3, generator=g)
+        o.pos_fourier_feat = 0.1 * torch.randn(P, 8, 3, generator=g)
+        o.poly_feature_dim, o.fourier_feature_dim = 4, 8
+        o.start_frame_id, o.time_len = 0, F - 1
+        with torch.no_grad():
+            pos = torch.stack([alt_position(o, t) for t in range(F)])
+        # gradients of sum(pos * w) at one frame, through the reference's own expression
+        leaves = [x.clone().requires_grad_(True) for x in (o.position, o.pos_poly_feat, o.pos_fourier_feat)]
+        o2 = types.SimpleNamespace(**{**o.__dict__, "position": leaves[0], "pos_poly_feat": leaves[1], "pos_fourier_feat": leaves[2]})
+        wgt = torch.randn(P, 3, generator=g)
+        t_g = F // 3
+        (alt_position(o2, t_g) * wgt).sum().backward()
+        pre = f"ALT{F}_"
+        out.update({pre + "position": o.position.numpy(), pre + "poly": o.pos_poly_feat.numpy(), pre + "fourier": o.pos_fourier_feat.numpy(),
+                    pre + "pos_t": pos.numpy(), pre + "w": wgt.numpy(), pre + "t_grad": np.array(t_g),
+                    pre + "g_position": leaves[0].grad.numpy(), pre + "g_poly": leaves[1].grad.numpy(), pre + "g_fourier": leaves[2].grad.numpy()})
+        print(f"alternative model F={F}: positions {tuple(pos.shape)}")
     np.savez_compressed(os.path.join(HERE, "golden_deform.npz"), **out)
     print("wrote golden_deform.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB")
 

@@ -142,7 +142,7 @@ def test_spline_backward_gathered_sums_ranks_in_order(cuda):
     sink = torch.full((P, 4 * NI * 3), 7.0, device=cuda)            # stale content in the listed dirty intervals only
     sink.view(P, 4, NI, 3)[:, :, [0, 1, 4, 6, 7, 8]] = 0            # 5 is dirty but not re-written: must be cleared
     dirty = torch.tensor([4, 2, 3, 9, 5] + [0] * 12, dtype=torch.int32, device=cuda)
-    L.call("spv_deform_spline_backward_gathered", P, NI, W, L.ptr(gathered), gathered.stride(0), 0.5, L.ptr(dirty), L.ptr(sink), L.stream())
+    L.call("spv_deform_spline_backward_gathered", P, NI, 0, W, L.ptr(gathered), gathered.stride(0), 0.5, L.ptr(dirty), L.ptr(sink), L.stream())
     torch.cuda.synchronize()
     got = sink.view(P, 4, NI, 3).cpu().double()
     assert float((got - want).abs().max()) <= 1e-5

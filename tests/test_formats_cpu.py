@@ -16,11 +16,13 @@ from splatter_a_video_b200 import formats as F
 def _raw_state(n=37, NI=3, seed=0):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
-    return {"point_cloud.position": r(n, 3), "point_cloud.features": r(n, 1, 3), "point_cloud.features_rest": r(n, 15, 3),
+    # key order of the reference's state_dict (golden_checkpoint.pth): Parameters in registration order, the `position` buffer, num_pts
+    pos = r(n, 3)
+    return {"point_cloud.features": r(n, 1, 3), "point_cloud.features_rest": r(n, 15, 3),
             "point_cloud.scaling": r(n, 3) - 4, "point_cloud.rotation": r(n, 4), "point_cloud.opacity": r(n, 1),
             "point_cloud.pos_poly_feat": r(n, 4, 3), "point_cloud.pos_fourier_feat": r(n, 8, 3), "point_cloud.rot_poly_feat": 0.1 * r(n, 4, 4),
             "point_cloud.rot_fourier_feat": 0.1 * r(n, 8, 4), "point_cloud.pos_cubic_node": 0.02 * r(n, 4 * NI * 3),
-            "point_cloud.mask_attribute": r(n, 1), "point_cloud.dino_attribute": r(n, 3), "num_pts": n}
+            "point_cloud.mask_attribute": r(n, 1), "point_cloud.dino_attribute": r(n, 3), "point_cloud.position": pos, "num_pts": n}
 
 
 def test_reads_a_reference_layout_checkpoint(tmp_path):
@@ -156,3 +158,38 @@ def test_ply_matches_what_the_reference_code_writes_and_reads(tmp_path):
     assert got.dtype == np.float32 and np.array_equal(got, G["table"])
     for k in ["position"] + attr:
         assert np.array_equal(G["loaded_" + k], G["in_" + k]), k
+
+
+def test_checkpoint_layout_matches_a_file_written_by_the_reference(tmp_path):
+    """golden_checkpoint.pth was written by the reference's OWN save_model / get_state_dict / register_atribute bodies executed on
+    stub modules (tests/golden/make_checkpoint_golden.py).  load_checkpoint must read it, and save_checkpoint must write the same
+    layout back: top-level keys, per-atlas key ORDER, tensor values / dtypes, num_pts, renderer state, optimizer entries."""
+    import torch
+    from splatter_a_video_b200 import formats as F
+    path = os.path.join(os.path.dirname(__file__), "golden", "golden_checkpoint.pth")
+    ref = torch.load(path, map_location="cpu", weights_only=False)
+    atlases, renderer, optim = F.load_checkpoint(path)
+    assert list(atlases) == ["fg", "bg"] and renderer == {"active_sh_degree": 3} and sorted(optim) == ["bg_optimizer", "fg_optimizer"]
+    for name, st in atlases.items():
+        sd = ref["gs_atlases_model"][name]
+        assert st.num_points == sd["num_pts"] == 16 and st.interval_num == 3
+        assert set(st.tensors) == {k[len("point_cloud."):] for k in sd if k != "num_pts"}
+        assert st.image_attributes() == ["mask_attribute", "dino_attribute"]
+        for k, v in st.tensors.items():
+            assert torch.equal(v, sd["point_cloud." + k])
+    out = str(tmp_path / "model_000123.pth")
+    F.save_checkpoint(out, atlases, active_sh_degree=renderer["active_sh_degree"], optimizers=optim)
+    mine = torch.load(out, map_location="cpu", weights_only=False)
+    assert list(mine) == list(ref)                                           # gs_atlases_model, renderer, fg_optimizer, bg_optimizer
+    assert mine["renderer"] == ref["renderer"]
+    for name in ref["gs_atlases_model"]:
+        a, b = mine["gs_atlases_model"][name], ref["gs_atlases_model"][name]
+        assert list(a) == list(b)                                            # parameters in registration order, position, num_pts
+        for k in b:
+            if k == "num_pts":
+                assert a[k] == b[k]
+            else:
+                assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k])
+    for k in optim:
+        assert mine[k]["param_groups"] == ref[k]["param_groups"] and set(mine[k]["state"]) == set(ref[k]["state"])
+    assert F.checkpoint_step(out) == 123

@@ -528,3 +528,83 @@ def test_flat_adam_replays_inside_a_cuda_graph(cuda):
         torch.cuda.synchronize()
         for k in tensors:
             np.testing.assert_allclose(n(flat[k]), n(ref[k]), rtol=3e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("F", [50, 7])
+def test_deform_position_polyfourier_matches_reference_golden(cuda, F):
+    """gs.frame.deform_position_polyfourier (spv_deform_polyfourier_*) against get_position of the ALTERNATIVE model executed on the
+    CPU (golden_deform.npz, tests/golden/make_deform_golden.py): every frame forward, all three gradients at one frame, and the
+    detach_pos flag."""
+    import os
+    from splatter_a_video_b200.gs.frame import deform_position_polyfourier, rotation_basis
+    G = np.load(os.path.join(Hh.GOLDEN, "golden_deform.npz"))
+    pre = f"ALT{F}_"
+    leaves = [torch.from_numpy(G[pre + k]).to(cuda).requires_grad_(True) for k in ("position", "poly", "fourier")]
+    for t in range(F):
+        with torch.no_grad():
+            got = deform_position_polyfourier(*leaves, rotation_basis(t, 0, F - 1).to(cuda))
+        np.testing.assert_allclose(n(got), G[pre + "pos_t"][t], rtol=0, atol=2e-6, err_msg=f"frame {t}")
+    t_g = int(G[pre + "t_grad"])
+    w = torch.from_numpy(G[pre + "w"]).to(cuda)
+    (deform_position_polyfourier(*leaves, rotation_basis(t_g, 0, F - 1).to(cuda)) * w).sum().backward()
+    for leaf, k in zip(leaves, ("g_position", "g_poly", "g_fourier")):
+        np.testing.assert_allclose(n(leaf.grad), G[pre + k], rtol=1e-6, atol=1e-7)
+    for leaf in leaves:
+        leaf.grad = None
+    (deform_position_polyfourier(*leaves, rotation_basis(t_g, 0, F - 1).to(cuda), detach_pos=True) * w).sum().backward()
+    assert leaves[0].grad is None
+    np.testing.assert_allclose(n(leaves[1].grad), G[pre + "g_poly"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("defer", [False, True])
+def test_interval_major_spline_storage_equals_reference_layout(cuda, defer):
+    """The deformation ops on interval-major coefficients ([P,NI,4,3], gs.frame.spline_to_interval_major) give the same positions
+    and -- after converting back -- the same coefficient gradients as on the reference's [P,4,NI,3] layout: single evaluation, the
+    two-frame op with its incrementally cleaned sink, and the gathered (frame-parallel) backward."""
+    from splatter_a_video_b200 import _lib as L
+    from splatter_a_video_b200.gs.frame import (deform_position, deform_position_pair, spline_from_interval_major, spline_interval,
+                                                spline_to_interval_major)
+    P, T = 4001, 50
+    NI = -(-T // 5)
+    g = torch.Generator().manual_seed(14)
+    base = torch.randn(P, 3, generator=g).to(cuda)
+    node = (0.1 * torch.randn(P, 4 * NI * 3, generator=g)).to(cuda)
+    node_im = spline_to_interval_major(node, NI)
+    assert torch.equal(spline_from_interval_major(node_im, NI), node)
+    dev_i = lambda v: torch.tensor([v], dtype=torch.int32, device=cuda)
+    dev_f = lambda v: torch.tensor([v], dtype=torch.float32, device=cuda)
+    # single evaluation
+    for time in (0, 24, 49):
+        i, d = spline_interval(time, T, NI)
+        a = node.clone().requires_grad_(True); b = node_im.clone().requires_grad_(True)
+        pa = deform_position(base, a, dev_i(i), dev_f(d), NI)
+        pb = deform_position(base, b, dev_i(i), dev_f(d), NI, interval_major=True)
+        assert torch.equal(pa, pb)
+        gp = torch.randn(P, 3, generator=g).to(cuda)
+        pa.backward(gp); pb.backward(gp)
+        assert torch.equal(spline_from_interval_major(b.grad, NI), a.grad)
+    # two frame times into sinks kept clean through the dirty lists, several steps in a row (intervals change between steps)
+    sinks = [torch.zeros(P, 4 * NI * 3, device=cuda) for _ in range(2)]
+    dirty = [torch.zeros(17, dtype=torch.int32, device=cuda) for _ in range(2)]
+    for (t1, t2) in [(3, 4), (4, 5), (30, 31), (49, 49)]:
+        (i1, d1), (i2, d2) = spline_interval(t1, T, NI), spline_interval(t2, T, NI)
+        g1, g2 = torch.randn(P, 3, generator=g).to(cuda), torch.randn(P, 3, generator=g).to(cuda)
+        outs = []
+        for which, (coef, im) in enumerate(((node, False), (node_im, True))):
+            c = coef.clone().requires_grad_(True)
+            if defer:
+                payload = torch.zeros(6 * P + 4, device=cuda)
+                p1, p2 = deform_position_pair(base, c, dev_i(i1), dev_f(d1), dev_i(i2), dev_f(d2), NI, sinks[which], dirty[which], payload,
+                                              interval_major=im)
+                torch.autograd.backward([p1, p2], [g1, g2])
+                rows = payload.reshape(1, -1).contiguous()
+                L.call("spv_deform_spline_backward_gathered", P, NI, int(im), 1, L.ptr(rows), rows.stride(0), 1.0, L.ptr(dirty[which]),
+                       L.ptr(sinks[which]), L.stream())
+            else:
+                p1, p2 = deform_position_pair(base, c, dev_i(i1), dev_f(d1), dev_i(i2), dev_f(d2), NI, sinks[which], dirty[which],
+                                              interval_major=im)
+                torch.autograd.backward([p1, p2], [g1, g2])
+            outs.append((p1.detach(), p2.detach()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert torch.equal(spline_from_interval_major(sinks[1], NI), sinks[0])
+        assert torch.equal(dirty[0], dirty[1])

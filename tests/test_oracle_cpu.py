@@ -335,6 +335,20 @@ def test_deformation_host_logic_matches_reference_golden(F):
         np.testing.assert_allclose(q.numpy(), G[pre + "rot_t"][t], rtol=0, atol=2e-6, err_msg=f"frame {t}")
 
 
+@pytest.mark.parametrize("F", [50, 7])
+def test_polyfourier_position_basis_matches_reference_golden(F):
+    """The alternative model's position (dynamic_gaussian_points.py:170-186): gs.frame.rotation_basis -- the 12 numbers the CUDA op
+    reads from device memory -- combined with the kernel's sum order reproduces get_position(t) for every frame of the clip."""
+    from splatter_a_video_b200.gs.frame import rotation_basis
+    G = np.load(os.path.join(Hh.GOLDEN, "golden_deform.npz"))
+    pre = f"ALT{F}_"
+    pos0, poly, four = (torch.from_numpy(G[pre + k]) for k in ("position", "poly", "fourier"))
+    for t in range(F):
+        b = rotation_basis(t, 0, F - 1)
+        pos = (pos0 + (poly * b[None, :4, None]).sum(1)) + (four * b[None, 4:, None]).sum(1)
+        np.testing.assert_allclose(pos.numpy(), G[pre + "pos_t"][t], rtol=0, atol=2e-6, err_msg=f"frame {t}")
+
+
 # ---- renderer orchestration pinned to the reference's own render_batch (tests/golden/make_render_golden.py) -----------------
 def test_renderer_orchestration_matches_reference_golden():
     """oracle/torch_ref.render_ortho_frame -- the restatement tests/test_renderer_gpu.py holds the renderer plugin to -- against
