@@ -45,6 +45,8 @@ K_IDX = 20
 
 
 def log(msg):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
@@ -285,7 +287,11 @@ class Workload:
         """Optimizer (device clock: graph-capturable) + densification statistics on the flat buffer."""
         from splatter_a_video_b200.densify import FlatDensifier
         from splatter_a_video_b200.parallel import FlatAdam
-        self.opt = FlatAdam(self.flat, self.lrs, device_clock=True)
+        # frame mode: interval-lazy update of the spline coefficients (only the intervals holding gradient are streamed; identical
+        # parameters to the dense update wherever they are read -- parallel.FlatAdam, tests/test_frame_gpu.py)
+        lazy = ({"name": "pos_cubic_node", "P": self.P, "NI": self.NI, "interval_major": self.node_im, "dirty": self.node_dirty}
+                if self.mode == "frame" else None)
+        self.opt = FlatAdam(self.flat, self.lrs, device_clock=True, lazy=lazy)
         self.dens = FlatDensifier(self.flat, self.P, {"position": "base", "scaling": "scaling", "rotation": "rotation", "opacity": "opacity"},
                                   extras={"base": self.base}, scaling_is_log=False, opacity_is_logit=False)
 
@@ -295,6 +301,7 @@ class Workload:
         from splatter_a_video_b200 import losses as LS
         b, w = self.batch_dev, self.loss_w
         self.flat.zero_grad(self.autograd_names if self.sinks else None)
+        self.opt.prepare(self.idx1, self.idx2)        # lazy optimizer: the two intervals this step reads, brought up to date
         out = self.renderer.render_batch(self.render_dict(), [self._batch()])
         # what the post-exchange part needs -- NOT the output dict: holding it would keep this iteration's autograd graph (and its
         # AccumulateGrad nodes, bound to the stream they were created on) alive into the next capture
@@ -318,6 +325,13 @@ class Workload:
         keys = ["rgb", "depth", "track_gs", "mask_attribute", "pos_poly_feat", "dino_attribute"]
         grads = [g_rgb[None], g_dep.reshape(1, 1, self.H, self.W), g_trk[None]] + [self.g_dev[k][None] for k in keys[3:]]
         torch.autograd.backward([out[k] for k in keys], grads)
+
+    def reset_training(self, snapshot):
+        """Back to the initial scene and a fresh optimizer (in place: captured graphs stay valid)."""
+        self.flat.flat.copy_(snapshot)
+        self.opt.exp_avg.zero_(); self.opt.exp_avg_sq.zero_(); self.opt.state_dev.zero_()
+        if self.opt.lazy:
+            self.opt.last_dev.zero_(); self.opt.ring_dev.zero_()
 
     def _post_exchange(self):
         """densification statistics (update_structure, atlas_gs_optimizer.py:110-121) + one fused Adam kernel."""
@@ -378,6 +392,48 @@ class Workload:
             b["render_attributes_list"] = ["dino_attribute", "mask_attribute"]   # trainer_fragGS.py:1264-1306
             b["num_idx"] = 10
             self.last_render = self.renderer.render_batch(self.render_dict(), [b])["rgb"]
+
+    # ---- frame-batched rendering: several frames of the render_video loop (trainer_fragGS.py:1264-1306) in flight at once --------
+    RENDER_BATCH = 4
+
+    def set_frames_batch(self, frame):
+        B = self.RENDER_BATCH
+        if getattr(self, "rb_idx", None) is None:
+            dev = self.device
+            self.rb_idx = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(B)]
+            self.rb_dist = [torch.zeros(1, device=dev) for _ in range(B)]
+            self.rb_streams = [torch.cuda.Stream() for _ in range(B - 1)]
+        for q in range(B):
+            f = (frame + q) % self.frames
+            self.rb_idx[q].copy_(self.tab_idx[f:f + 1], non_blocking=True); self.rb_dist[q].copy_(self.tab_dist[f:f + 1], non_blocking=True)
+
+    def _render_batched(self):
+        """RENDER_BATCH consecutive frames, each on its own stream (parallel branches of ONE captured graph): the launch-bound
+        per-Gaussian / binning chain of one frame runs under the blend kernel of another."""
+        from splatter_a_video_b200.gs.frame import deform_position
+        p = self.flat.params
+        main = torch.cuda.current_stream()
+        outs = []
+        with torch.no_grad():
+            for q in range(self.RENDER_BATCH):
+                st = main if q == 0 else self.rb_streams[q - 1]
+                if q:
+                    st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    pos = deform_position(self.base, p["pos_cubic_node"], self.rb_idx[q], self.rb_dist[q], self.NI, interval_major=self.node_im)
+                    rd = {"position": pos, "opacity": p["opacity"], "scaling": p["scaling"], "rotation": p["rotation"], "shs": p["shs"],
+                          "mask_attribute": p["mask_attribute"], "dino_attribute": p["dino_attribute"]}
+                    b = dict(self.batch)
+                    b["render_attributes_list"] = ["dino_attribute", "mask_attribute"]   # trainer_fragGS.py:1264-1306
+                    b["num_idx"] = 10
+                    outs.append(self.renderer.render_batch(rd, [b])["rgb"])
+            for st in self.rb_streams:
+                main.wait_stream(st)
+        self.last_render_batch = outs
+
+    def render_batched(self, frame):
+        self.set_frames_batch(frame)
+        self._run("render_batched", self._render_batched)
 
     def _run(self, name, fn):
         """Eager, or a CUDA graph captured once per step kind (frame mode: nothing on the path syncs the host)."""
@@ -837,7 +893,7 @@ def run_ours(args):
     snapshot = wl.flat.flat.clone()          # the optimizer moves the scene: every phase starts from the initial one
 
     def restore():
-        wl.flat.flat.copy_(snapshot)
+        wl.reset_training(snapshot)
 
     # kernels of this library per step, counted on one eager step (graph replays do not pass through the host counter)
     wl.set_frame(0)
@@ -871,6 +927,10 @@ def run_ours(args):
     fps_ms, _ = time_steps(lambda f: wl.render_only(f), args.steps, args.warmup, flush, world, rank, frames_of)
     fps_e2e_ms, _ = time_steps(lambda f: wl.render_only(f, to_host=True), args.steps, args.warmup, flush, world, rank, frames_of)
     log(f"render: {fps_ms / args.steps:.3f} ms/frame, e2e {fps_e2e_ms / args.steps:.3f}")
+    fpsb_ms = None
+    if wl.mode == "frame":
+        fpsb_ms, _ = time_steps(lambda f: wl.render_batched((f * wl.RENDER_BATCH) % wl.frames), args.steps, args.warmup, flush, world, rank, frames_of)
+        log(f"render, {wl.RENDER_BATCH} frames in flight: {fpsb_ms / args.steps / wl.RENDER_BATCH:.3f} ms/frame")
     clocks = sampler.stop() if sampler else None
     # sustained: back-to-back full steps for a few seconds (no L2 flush, no per-step events), clocks sampled meanwhile
     restore()
@@ -940,6 +1000,11 @@ def run_ours(args):
                    "renderer": type(wl.renderer).__name__, "mode": wl.mode, "cuda_graph": wl.use_graph,
                    "capacity_overflow": overflow, "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
                    "grad_floats_per_gaussian": wl.flat.floats_per_gaussian(wl.P),
+                   "optimizer": ("FlatAdam (torch.optim.Adam arithmetic, device-resident step clock)" +
+                                 (", interval-lazy on the spline coefficients: only the intervals that hold gradient are streamed, the "
+                                  "zero-gradient updates of the others are replayed before they are read -- same parameters as the dense "
+                                  "update wherever they are observed (tests/test_frame_gpu.py::test_interval_lazy_adam_equals_dense_adam)"
+                                  if wl.opt.lazy else "")),
                    "learning_rates": "src/configs/frag_gs_v10.yaml:41-66 x 0.01 (same optimizer work; keeps the synthetic scene stationary "
                                      "over the thousands of timed steps); parameters restored to the initial scene before every phase"},
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "it/s", "h2d_bytes_per_step": wl.h2d_bytes_full(),
@@ -954,6 +1019,9 @@ def run_ours(args):
         "render_fps": world * args.steps / (fps_ms * 1e-3),
         "render_fps_e2e": {"value": world * args.steps / (fps_e2e_ms * 1e-3), "d2h_bytes_per_frame": 3 * wl.H * wl.W * 4,
                            "pipeline": "double-buffered D2H: frame i-1 downloads on a second stream while frame i renders"},
+        "render_fps_batched": ({"value": world * args.steps * wl.RENDER_BATCH / (fpsb_ms * 1e-3), "frames_in_flight": wl.RENDER_BATCH,
+                                "what": "the render_video loop with several consecutive frames per launch group: each frame's kernels on "
+                                        "its own stream inside one captured graph"} if fpsb_ms else None),
         "roofline": {"bound": "hbm", "kernel": dom_label,
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": ncu_traffic(traffic_key),

@@ -250,10 +250,28 @@ SPV_API int spv_adam_step(long long n, float *param, const float *grad, float *e
                   const long long *seg_end_host, const float *seg_lr_host, float beta1, float beta2, float eps, int step,
                   void *stream);
 /* Same update with the optimizer clock and the learning rates in device memory (CUDA-graph capturable: every replay advances
- * the bias corrections).  state_dev = float[4] {step, 1-b1^step, sqrt(1-b2^step), -}, zero-initialised once; lr_dev = float[nseg]. */
+ * the bias corrections).  state_dev = float[8] {step, 1-b1^step, sqrt(1-b2^step), -, b1^step and b2^step as two doubles},
+ * zero-initialised once; lr_dev = float[nseg]. */
 SPV_API int spv_adam_step_device(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,
                          const long long *seg_end_host, const float *lr_dev, float beta1, float beta2, float eps,
                          float *state_dev, void *stream);
+/* Interval-lazy variant for ONE segment of spline coefficients (segment `lazy_seg` = [P, 4*NI*3], layout as in
+ * spv_deform_spline_*): a step streams only the intervals that hold gradient (dirty_dev = the int[17] list of
+ * spv_deform_spline_backward2 / _gathered) and every other interval's zero-gradient Adam updates are replayed -- same arithmetic,
+ * same per-step constants (ring_dev = float[2*4096], zero-initialised) -- when the interval is next needed: spv_adam_lazy_prepare
+ * (the two intervals a forward pass is about to read) or spv_adam_lazy_flush (all; before densification, checkpoints, rendering
+ * other frames).  last_dev = int[NI], zero-initialised: the step each interval is current through.  Parameters are identical to
+ * spv_adam_step_device's whenever they are observed through prepare / flush. */
+SPV_API int spv_adam_step_lazy(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int nseg,
+                       const long long *seg_end_host, const float *lr_dev, float beta1, float beta2, float eps, float *state_dev,
+                       int lazy_seg, int P, int NI, int layout, const int *dirty_dev, int *last_dev, float *ring_dev, void *stream);
+SPV_API int spv_adam_lazy_prepare(long long n, int nseg, const long long *seg_end_host, int lazy_seg, int P, int NI, int layout,
+                          float *param, float *exp_avg, float *exp_avg_sq, const int *idx1_dev, const int *idx2_dev, int *last_dev,
+                          const float *ring_dev, const float *state_dev, const float *lr_dev, float beta1, float beta2, float eps,
+                          void *stream);
+SPV_API int spv_adam_lazy_flush(long long n, int nseg, const long long *seg_end_host, int lazy_seg, int P, int NI, int layout, float *param,
+                        float *exp_avg, float *exp_avg_sq, int *last_dev, const float *ring_dev, const float *state_dev,
+                        const float *lr_dev, float beta1, float beta2, float eps, void *stream);
 
 /* ---- Densification on the flat SoA (next row f-3, structure half) -------------------------------------------------
  * Role of AtlasGaussianSplattingOptimizer.update_structure / densification / prune / reset_opacity

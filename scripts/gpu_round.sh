@@ -46,6 +46,14 @@ experimental)
   for v in ${VARIANTS:-"SPV_BWD_VARIANT=0" "SPV_BWD_VARIANT=1"}; do
     env $v timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --quick 2> gpurun_out/bench_variant_${TAG}.err | python -c "import sys, json; d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v', round(d['value'], 1), 'it/s', d['kernels_in_step_ms'])"
   done ;;
+ncusmall)
+  timeout 500 ncu --set full --clock-control none --import-source on -k "regex:${NCU_SMALL:-cull_count_emit|tile_sort_small|tile_scan|pack_records|deform_fwd2|frame_geometry|sh_fwd|sh_bwd|unpack_frame|select_pass|rgb_row|track_fused|adam_lazy}" -s ${NCU_SKIP:-30} -c ${NCU_COUNT:-24} -f -o gpurun_out/prof_small_${TAG} \
+      python bench.py --steps 2 --warmup 1 --profile-mode --no-graph > gpurun_out/ncu_small_${TAG}.log 2>&1
+  tail -3 gpurun_out/ncu_small_${TAG}.log ;;
+ncufwd)
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_rec_fwd -s 2 -c 2 -f -o gpurun_out/prof_fwd_${TAG} \
+      python bench.py --steps 2 --warmup 1 --profile-mode > gpurun_out/ncu_fwd_${TAG}.log 2>&1
+  tail -3 gpurun_out/ncu_fwd_${TAG}.log ;;
 ncubwd)
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:blend_rec_bwd -s 2 -c 2 -f -o gpurun_out/prof_bwd_${TAG} \
       python bench.py --steps 2 --warmup 1 --profile-mode > gpurun_out/ncu_bwd_${TAG}.log 2>&1

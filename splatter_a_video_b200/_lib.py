@@ -72,6 +72,12 @@ _SIGS = {
     "spv_deform_polyfourier_backward": (c_int, [c_int, P_, P_, P_, P_, P_, P_]),
     "spv_adam_step": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, c_int, P_]),
     "spv_adam_step_device": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, P_, P_]),
+    "spv_adam_step_lazy": (c_int, [ctypes.c_longlong, P_, P_, P_, P_, c_int, P_, P_, c_float, c_float, c_float, P_, c_int, c_int, c_int, c_int,
+                                   P_, P_, P_, P_]),
+    "spv_adam_lazy_prepare": (c_int, [ctypes.c_longlong, c_int, P_, c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, P_, P_, P_, c_float,
+                                      c_float, c_float, P_]),
+    "spv_adam_lazy_flush": (c_int, [ctypes.c_longlong, c_int, P_, c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, P_, c_float, c_float,
+                                    c_float, P_]),
     "spv_densify_stats": (c_int, [c_int, P_, P_, P_, P_, P_, P_, P_]),
     "spv_densify_flags": (c_int, [c_int, P_, P_, P_, P_, P_, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P_, P_]),
     "spv_flat_regather": (c_int, [c_int, P_, P_, P_, c_int, P_, P_, P_, P_]),

@@ -53,6 +53,14 @@ inline int sm_count() {   // of the current device (the runtime caches device at
     return n > 0 ? n : 148;
 }
 
+// A second stream for the branches of a call that do not depend on each other (frame forward: SH colours + record packing + the
+// id-image fill next to the projection / binning / sort chain; frame backward: the SH gradient next to the covariance chain; lazy
+// Adam: the dense parameters next to the spline intervals).  Forked from and joined back into the caller's stream with events, so
+// the caller still sees one in-order stream -- and a stream capture records the branches as parallel graph nodes.  One lane per
+// (host thread, device): streams and events belong to the device that was current when they were created.  runtime.cu.
+struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, mid = nullptr, join = nullptr; bool ok = false; };
+SideLane *side_lane();
+
 inline int tiles_x(int W) { return (W + SPV_TILE - 1) / SPV_TILE; }
 inline int tiles_y(int H) { return (H + SPV_TILE - 1) / SPV_TILE; }
 inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }

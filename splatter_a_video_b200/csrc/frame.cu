@@ -116,27 +116,8 @@ inline int make_groups(AttrGroups &g, int n, const float *const *in, float *cons
 
 #define SPV_TRY_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
-// A second stream for the branches of a frame that do not depend on each other (forward: SH colours + feature packing +
-// the id-image fill next to the projection / binning / sort chain, whose radix passes leave most SMs idle; backward: the SH
-// gradient next to the covariance chain).  Forked from and joined back into the caller's stream with events, so the caller
-// still sees one in-order stream -- and a stream capture records the branches as parallel graph nodes.
-struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, mid = nullptr, join = nullptr; bool ok = false; };
-// one lane per (host thread, device): streams and events belong to the device that was current when they were created
-constexpr int kMaxDevices = 64;
-static thread_local SideLane g_side[kMaxDevices];
-SideLane *side_lane() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
-    SideLane &l = g_side[dev];
-    if (!l.ok) {
-        if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&l.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        l.ok = true;
-    }
-    return &l;
-}
+using spv::SideLane;
+using spv::side_lane;   // the per-(thread, device) second stream for independent branches of a frame (runtime.cu)
 
 }  // namespace
 

@@ -27,6 +27,22 @@ void timer_mark(int slot, int edge, cudaStream_t s) {
                              st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
+constexpr int kMaxDevices = 64;
+static thread_local SideLane g_side[kMaxDevices];
+SideLane *side_lane() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    SideLane &l = g_side[dev];
+    if (!l.ok) {
+        if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        l.ok = true;
+    }
+    return &l;
+}
+
 // Small runtime switches for kernel variants (default 0).  First read falls back to the environment variable SPV_<NAME>
 // (upper case) so a run can be switched without code changes.
 //   bwd_variant reserved for A/B runs of backward blend kernel variants (none selectable at the moment)

@@ -67,6 +67,8 @@ class FlatDensifier:
         """One call of `densification(step)`: clone + split when `duplicate`, the prune filter when `prune`.
         Returns (new FlatParams, new FlatAdam or None, new extras); `self` now tracks the new population."""
         dev, P = self.flat.flat.device, self.P
+        if adam is not None:
+            adam.flush()            # an interval-lazy optimizer brings every spline interval up to date before rows are copied
         flags = torch.zeros(P, dtype=torch.uint8, device=dev)
         scaling, opacity = L.f32c(self._tensor("scaling")), L.f32c(self._tensor("opacity").reshape(-1))
         L.call("spv_densify_flags", P, L.ptr(self.grad_accum), L.ptr(self.denom), L.ptr(scaling), L.ptr(opacity), L.ptr(self.max_radii),
@@ -141,10 +143,13 @@ class FlatDensifier:
         new_adam = None
         if adam is not None:
             lrs = {k: float(adam._lrs[q]) for q, k in enumerate(old.names)}
-            new_adam = FlatAdam(new_flat, lrs, betas=adam.betas, eps=adam.eps, device_clock=adam.device_clock)
+            lazy = dict(adam.lazy, P=P_new) if adam.lazy else None
+            new_adam = FlatAdam(new_flat, lrs, betas=adam.betas, eps=adam.eps, device_clock=adam.device_clock, lazy=lazy)
             new_adam.t = adam.t
             if adam.device_clock:
                 new_adam.state_dev.copy_(adam.state_dev)       # the optimizer clock survives the restructure
+            if adam.lazy:
+                new_adam.last_dev.copy_(adam.last_dev); new_adam.ring_dev.copy_(adam.ring_dev)
             if P_new:
                 fresh = torch.where(is_new, torch.full_like(src, -1), src).contiguous()      # new points start with zero moments
                 move(fresh, adam.exp_avg, new_adam.exp_avg)

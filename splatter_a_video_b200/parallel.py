@@ -446,9 +446,16 @@ class FlatAdam:
     """torch.optim.Adam semantics (betas, eps, per-parameter learning rates) as ONE fused kernel over FlatParams
     (`spv_adam_step`).  Role of the per-attribute param groups of src/pointrix/optimizer/__init__.py:27-62."""
 
-    def __init__(self, flat: FlatParams, lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-15, device_clock: bool = False):
+    def __init__(self, flat: FlatParams, lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-15, device_clock: bool = False,
+                 lazy: Optional[dict] = None):
         """device_clock: keep the step counter / bias corrections and the learning rates in device memory so `step()` can be
-        captured in a CUDA graph and replayed (every replay advances the clock; `set_lrs` updates the rates outside the graph)."""
+        captured in a CUDA graph and replayed (every replay advances the clock; `set_lrs` updates the rates outside the graph).
+
+        lazy = {"name": spline-coefficient parameter, "P": points, "NI": intervals, "interval_major": bool, "dirty": int32[17] device
+        list shared with gs.frame.deform_position_pair / GradExchange}: interval-lazy update of that parameter (implies
+        device_clock).  A step only streams the intervals that hold gradient; call `prepare(idx1_dev, idx2_dev)` before a forward
+        pass reads intervals and `flush()` before anything else observes the parameter (densification, checkpoints, rendering
+        other frames).  Same parameters as the dense update whenever they are observed that way (tests/test_frame_gpu.py)."""
         import ctypes
         self.flat, self.betas, self.eps = flat, betas, eps
         self.exp_avg = torch.zeros_like(flat.flat)
@@ -462,11 +469,18 @@ class FlatAdam:
         self._lrs = (ctypes.c_float * len(ends))(*[float(lrs[k]) for k in flat.names])
         self.nseg = len(ends)
         self.t = 0
-        self.device_clock = bool(device_clock)
+        self.lazy = dict(lazy) if lazy else None
+        self.device_clock = bool(device_clock) or self.lazy is not None
         if self.device_clock:
             dev = flat.flat.device
-            self.state_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+            self.state_dev = torch.zeros(8, dtype=torch.float32, device=dev)      # [step, bc1, bc2_sqrt, -, b1^t, b2^t as 2 doubles]
             self.lr_dev = torch.tensor([float(lrs[k]) for k in flat.names], dtype=torch.float32, device=dev)
+        if self.lazy:
+            dev = flat.flat.device
+            self.lazy["seg"] = flat.names.index(self.lazy["name"])
+            self.lazy["layout"] = int(bool(self.lazy.get("interval_major", False)))
+            self.last_dev = torch.zeros(int(self.lazy["NI"]), dtype=torch.int32, device=dev)
+            self.ring_dev = torch.zeros(2 * 4096, dtype=torch.float32, device=dev)
 
     def set_lrs(self, lrs: Dict[str, float]):
         """Learning-rate schedule hook (role of ExponLRScheduler, src/pointrix/optimizer/scheduler.py:9-100)."""
@@ -476,11 +490,42 @@ class FlatAdam:
         if self.device_clock:
             self.lr_dev.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=True)
 
+    def _lazy_args(self):
+        import ctypes
+        from . import _lib as L
+        z, f = self.lazy, self.flat
+        return (f.flat.numel(), self.nseg, ctypes.cast(self._ends, ctypes.c_void_p), z["seg"], int(z["P"]), int(z["NI"]), z["layout"],
+                L.ptr(f.flat), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq))
+
+    def prepare(self, idx1_dev: torch.Tensor, idx2_dev: torch.Tensor):
+        """Lazy mode: bring the intervals a forward pass is about to read (device scalars, as given to deform_position_pair) up to
+        the current optimizer step.  No-op for the dense optimizer."""
+        if not self.lazy:
+            return
+        from . import _lib as L
+        L.call("spv_adam_lazy_prepare", *self._lazy_args(), L.ptr(idx1_dev), L.ptr(idx2_dev), L.ptr(self.last_dev), L.ptr(self.ring_dev),
+               L.ptr(self.state_dev), L.ptr(self.lr_dev), float(self.betas[0]), float(self.betas[1]), float(self.eps), L.stream())
+
+    def flush(self):
+        """Lazy mode: bring EVERY interval up to the current step (before densification, checkpoints, rendering other frames)."""
+        if not self.lazy:
+            return
+        from . import _lib as L
+        L.call("spv_adam_lazy_flush", *self._lazy_args(), L.ptr(self.last_dev), L.ptr(self.ring_dev), L.ptr(self.state_dev),
+               L.ptr(self.lr_dev), float(self.betas[0]), float(self.betas[1]), float(self.eps), L.stream())
+
     def step(self):
         from . import _lib as L
         import ctypes
         self.t += 1
         f = self.flat
+        if self.lazy:
+            z = self.lazy
+            L.call("spv_adam_step_lazy", f.flat.numel(), L.ptr(f.flat), L.ptr(f.flat_grad), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                   self.nseg, ctypes.cast(self._ends, ctypes.c_void_p), L.ptr(self.lr_dev), float(self.betas[0]), float(self.betas[1]),
+                   float(self.eps), L.ptr(self.state_dev), z["seg"], int(z["P"]), int(z["NI"]), z["layout"], L.ptr(z["dirty"]),
+                   L.ptr(self.last_dev), L.ptr(self.ring_dev), L.stream())
+            return
         if self.device_clock:
             L.call("spv_adam_step_device", f.flat.numel(), L.ptr(f.flat), L.ptr(f.flat_grad), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
                    self.nseg, ctypes.cast(self._ends, ctypes.c_void_p), L.ptr(self.lr_dev), float(self.betas[0]), float(self.betas[1]),

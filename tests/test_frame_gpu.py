@@ -608,3 +608,52 @@ def test_interval_major_spline_storage_equals_reference_layout(cuda, defer):
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
         assert torch.equal(spline_from_interval_major(sinks[1], NI), sinks[0])
         assert torch.equal(dirty[0], dirty[1])
+
+
+@pytest.mark.parametrize("interval_major", [False, True])
+def test_interval_lazy_adam_equals_dense_adam(cuda, interval_major):
+    """FlatAdam(lazy=...): a step streams only the spline intervals that hold gradient and replays the zero-gradient updates of
+    the others when they are next needed.  Against the dense device-clock optimizer (itself held to torch.optim.Adam above) on the
+    same gradient schedule: the intervals a forward pass is about to read are identical after prepare(), everything is identical
+    after flush() -- parameters and both moments, including a learning-rate change on the way."""
+    from splatter_a_video_b200.parallel import FlatAdam, FlatParams
+    P, NI = 257 * 4, 7
+    g = torch.Generator().manual_seed(5)
+    tensors = {"node": 0.1 * torch.randn(P, 4 * NI * 3, generator=g), "scaling": torch.randn(P, 3, generator=g), "opacity": torch.randn(P, 1, generator=g)}
+    lrs = {"node": 2e-3, "scaling": 5e-3, "opacity": 5e-2}
+    dense_flat = FlatParams({k: v.to(cuda) for k, v in tensors.items()})
+    lazy_flat = FlatParams({k: v.to(cuda) for k, v in tensors.items()})
+    dirty = torch.zeros(17, dtype=torch.int32, device=cuda)
+    dense = FlatAdam(dense_flat, lrs, eps=1e-15, device_clock=True)
+    lazy = FlatAdam(lazy_flat, lrs, eps=1e-15, lazy={"name": "node", "P": P, "NI": NI, "interval_major": interval_major, "dirty": dirty})
+
+    def view(t):          # [P, 4*NI*3] -> [P, NI, 12] (interval, slot) whatever the storage order
+        return t.reshape(P, NI, 4, 3).reshape(P, NI, 12) if interval_major else t.reshape(P, 4, NI, 3).permute(0, 2, 1, 3).reshape(P, NI, 12)
+
+    schedule = [(0, 0), (0, 1), (1, 1), (5, 6), (6, 6), (2, 3), (0, 0), (3, 3), (6, 5), (1, 2), (4, 4), (0, 6)] * 3
+    dev_i = lambda v: torch.tensor([v], dtype=torch.int32, device=cuda)
+    for it, (i1, i2) in enumerate(schedule):
+        lazy.prepare(dev_i(i1), dev_i(i2))
+        for b in {i1, i2}:        # what the forward pass of this step would read
+            assert torch.equal(view(lazy_flat["node"].detach())[:, b], view(dense_flat["node"].detach())[:, b]), (it, b)
+        if it == 17:
+            lrs2 = {"node": 1e-3, "scaling": 2e-3, "opacity": 1e-2}
+            dense.set_lrs(lrs2); lazy.set_lrs(lrs2)
+        # this step's gradient: dense for the small parameters, the two intervals only for the coefficients
+        gn = torch.zeros(P, NI, 12)
+        for b in {i1, i2}:
+            gn[:, b] = torch.randn(P, 12, generator=g)
+        gn = (gn.reshape(P, NI, 4, 3) if interval_major else gn.reshape(P, NI, 4, 3).permute(0, 2, 1, 3)).reshape(P, -1)
+        for flat in (dense_flat, lazy_flat):
+            flat["node"].grad.copy_(gn.to(cuda))
+        for k in ("scaling", "opacity"):
+            gk = torch.randn(tensors[k].shape, generator=g).to(cuda)
+            dense_flat[k].grad.copy_(gk); lazy_flat[k].grad.copy_(gk)
+        dirty.copy_(torch.tensor([2, i1, i2] + [0] * 14, dtype=torch.int32))
+        dense.step(); lazy.step()
+    # un-flushed, idle intervals lag behind; flushed, everything is the dense optimizer's state
+    lazy.flush()
+    torch.cuda.synchronize()
+    assert torch.equal(lazy.last_dev.cpu(), torch.full((NI,), len(schedule), dtype=torch.int32))
+    for a, b, name in ((lazy_flat.flat, dense_flat.flat, "param"), (lazy.exp_avg, dense.exp_avg, "exp_avg"), (lazy.exp_avg_sq, dense.exp_avg_sq, "exp_avg_sq")):
+        np.testing.assert_allclose(n(a), n(b), rtol=2e-6, atol=1e-9, err_msg=name)
