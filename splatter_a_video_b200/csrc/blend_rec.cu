@@ -103,13 +103,13 @@ pack_records_kernel(int P, int A, const float2 *__restrict__ uv, const float *__
 template <int CH>
 __global__ void __launch_bounds__(kBlock)   // 80 registers, 3 CTAs/SM; capping at 64 registers for 4 CTAs/SM measured slower (167 vs 161 us)
 blend_rec_fwd_kernel(int C, int W, int H, int gx, int K, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
-                     const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC, float *__restrict__ rendered,
+                     const int2 *__restrict__ tile_range, const int *__restrict__ tile_order, float bgA, float bgB, float bgC, float *__restrict__ rendered,
                      float *__restrict__ final_T, int *__restrict__ ncontrib, int *__restrict__ gs_idx) {
     constexpr int RW = 8 + CH, RP = rec_pitch(RW);
     __shared__ __align__(128) float s_rec[2][kChunk * RP];
     __shared__ __align__(8) uint64_t s_bar[2];
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;   // longest tile lists first (sort.cu: tile_scan_kernel)
     const int tile_x = tile % gx, tile_y = tile / gx;
     int px, py;
     thread_pixel(tile_x, tile_y, px, py);
@@ -242,7 +242,7 @@ __device__ __forceinline__ int atom_add_acq_rel_shared(int *addr, int v) {
 template <int CH, int CG, bool ABS>
 __global__ void __launch_bounds__(kBlock, 3)
 blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
-                     const int2 *__restrict__ tile_range, float bgA, float bgB, float bgC,
+                     const int2 *__restrict__ tile_range, const int *__restrict__ tile_order, float bgA, float bgB, float bgC,
                      const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
                      float *__restrict__ packed) {
     constexpr int NV = (CG <= 14) ? 16 : 32;
@@ -258,7 +258,7 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
     __shared__ int s_done[kRing];
     __shared__ int s_max;
 
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;   // longest tile lists first (sort.cu: tile_scan_kernel)
     const int tile_x = tile % gx, tile_y = tile / gx;
     int px, py;
     thread_pixel(tile_x, tile_y, px, py);
@@ -450,21 +450,21 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
 
 struct RecFwdArgs {
     int C, W, H, gx, K;
-    const float *rec; const int *idx_sorted; const int2 *tile_range; float bgA, bgB, bgC;
+    const float *rec; const int *idx_sorted; const int2 *tile_range; const int *tile_order; float bgA, bgB, bgC;
     float *rendered, *final_T; int *ncontrib, *gs_idx;
 };
 
 template <int CH>
 void launch_rec_fwd(const RecFwdArgs &a, int ntiles, cudaStream_t s) {
     spv::timer_mark(0, 0, s);
-    blend_rec_fwd_kernel<CH><<<ntiles, kBlock, 0, s>>>(a.C, a.W, a.H, a.gx, a.K, a.rec, a.idx_sorted, a.tile_range, a.bgA, a.bgB,
+    blend_rec_fwd_kernel<CH><<<ntiles, kBlock, 0, s>>>(a.C, a.W, a.H, a.gx, a.K, a.rec, a.idx_sorted, a.tile_range, a.tile_order, a.bgA, a.bgB,
                                                       a.bgC, a.rendered, a.final_T, a.ncontrib, a.gs_idx);
     spv::timer_mark(0, 1, s);
 }
 
 struct RecBwdArgs {
     int C, W, H, gx;
-    const float *rec; const int *idx_sorted; const int2 *tile_range; float bgA, bgB, bgC;
+    const float *rec; const int *idx_sorted; const int2 *tile_range; const int *tile_order; float bgA, bgB, bgC;
     const float *final_T; const int *ncontrib; spv::ChanPlanes planes; float *packed;
 };
 
@@ -474,7 +474,7 @@ void launch_rec_bwd(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
     static std::atomic<unsigned long long> configured{0};   // up to 64.5 KB of dynamic shared memory: above the 48 KB default
     spv::opt_in_dynamic_smem(blend_rec_bwd_kernel<CH, CG, ABS>, dyn, configured);
     spv::timer_mark(1, 0, s);
-    blend_rec_bwd_kernel<CH, CG, ABS><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.bgA, a.bgB,
+    blend_rec_bwd_kernel<CH, CG, ABS><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.tile_order, a.bgA, a.bgB,
                                                                  a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
     spv::timer_mark(1, 1, s);
 }
@@ -518,14 +518,15 @@ int pack_records(int P, int A, const float *uv, const float *conic, const float 
 }
 
 int blend_records_forward(int C, int W, int H, int K, const float *rec, const int *idx_sorted, const int *tile_range,
-                          float bg_rgb, float bg_depth, float bg_attr, float *rendered, float *final_T, int *ncontrib,
-                          int *gs_idx, void *stream) {
+                          const int *tile_order, float bg_rgb, float bg_depth, float bg_attr, float *rendered, float *final_T,
+                          int *ncontrib, int *gs_idx, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) return 0;
     if (C < 4 || C > 23 || K <= 0 || !gs_idx) { spv::set_error(cudaErrorInvalidValue, "blend_records_forward: need 4 <= C <= 23 and K > 0"); return (int)cudaErrorInvalidValue; }
     const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), ntiles = gx * gy;
     RecFwdArgs a;
     a.C = C; a.W = W; a.H = H; a.gx = gx; a.K = K; a.rec = rec; a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range;
+    a.tile_order = tile_order;
     a.bgA = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.rendered = rendered; a.final_T = final_T; a.ncontrib = ncontrib;
     a.gs_idx = gs_idx;
     if (C <= 4) launch_rec_fwd<4>(a, ntiles, s);
@@ -538,7 +539,7 @@ int blend_records_forward(int C, int W, int H, int K, const float *rec, const in
 }
 
 int blend_records_backward(int P, int C, int W, int H, const float *rec, const int *idx_sorted, const int *tile_range,
-                           float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
+                           const int *tile_order, float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
                            const float *const *planes_host, int n_grad_channels, bool want_abs, float *packed, bool packed_is_zero,
                            void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -555,6 +556,7 @@ int blend_records_backward(int P, int C, int W, int H, const float *rec, const i
     C = C_live;
     RecBwdArgs a;
     a.C = C; a.W = W; a.H = H; a.gx = gx; a.rec = rec; a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range;
+    a.tile_order = tile_order;
     a.bgA = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.final_T = final_T; a.ncontrib = ncontrib; a.packed = packed;
     for (int c = 0; c < 32; ++c) a.planes.p[c] = c < C ? planes_host[c] : nullptr;
     const int ng = n_grad_channels < 4 ? 4 : (n_grad_channels > C ? C : n_grad_channels);

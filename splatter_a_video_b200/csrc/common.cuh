@@ -122,6 +122,11 @@ int frame_geometry_backward(int P, const float *packed, const float *scales, con
                             const float *depth, const uint8_t *vis, const float *cov3d, const int *radius, float *dL_dxyz,
                             float *dL_dscales, float *dL_duquats, void *stream);
 
+// sort.cu: spv_bin_tiles + the longest-list-first tile order the blend kernels launch in (tile_order = int[T] or NULL)
+int bin_tiles_ordered(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
+                      const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status, int *tile_order,
+                      void *workspace, size_t ws_bytes, void *stream);
+
 // blend_rec.cu: record-staged blending of the fused frame path.  One record of kRecordFloats floats per Gaussian:
 //   [x y a2 b2 | c2 log2(o) o id | feature[0..23] = rgb(3) depth(1) attributes, zero padded | a b c 0]
 constexpr int kRecordFloats = 36;
@@ -129,10 +134,10 @@ int pack_records(int P, int A, const float *uv, const float *conic, const float 
                  const float *depth, int n_groups, const float *const *attr_ptrs, const int *attr_channels, float *rec,
                  void *stream);
 int blend_records_forward(int C, int W, int H, int K, const float *rec, const int *idx_sorted, const int *tile_range,
-                          float bg_rgb, float bg_depth, float bg_attr, float *rendered, float *final_T, int *ncontrib,
-                          int *gs_idx, void *stream);
+                          const int *tile_order, float bg_rgb, float bg_depth, float bg_attr, float *rendered, float *final_T,
+                          int *ncontrib, int *gs_idx, void *stream);
 int blend_records_backward(int P, int C, int W, int H, const float *rec, const int *idx_sorted, const int *tile_range,
-                           float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
+                           const int *tile_order, float bg_rgb, float bg_depth, float bg_attr, const float *final_T, const int *ncontrib,
                            const float *const *planes_host, int n_grad_channels, bool want_abs, float *packed, bool packed_is_zero,
                            void *stream);
 

@@ -20,7 +20,7 @@ inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 struct FrameWs {
     float *dirs, *rgb, *uv, *depth, *cov3d, *conic, *feature, *final_T;
     uint8_t *vis, *clamped;
-    int *radius, *tiles, *idx_sorted, *tile_range, *ncontrib;
+    int *radius, *tiles, *idx_sorted, *tile_range, *tile_order, *ncontrib;
     void *bin_ws; size_t bin_bytes;
     // backward temporaries
     float *packed, *g_uv, *g_uv_rgb, *g_abs, *g_conic, *g_op, *g_feat, *g_rgb, *g_depth, *g_cov3d, *g_dirs;
@@ -39,6 +39,7 @@ FrameWs carve(void *base, int P, int64_t I_cap, int W, int H, int A) {
     f.vis = (uint8_t *)take(Pn); f.clamped = (uint8_t *)take(Pn * 3);
     f.radius = (int *)take(Pn * 4); f.tiles = (int *)take(Pn * 4);
     f.idx_sorted = (int *)take((size_t)(I_cap > 0 ? I_cap : 1) * 4); f.tile_range = (int *)take(T * 8);
+    f.tile_order = (int *)take(T * 4);
     f.ncontrib = (int *)take(HW * 4);
     f.bin_bytes = spv_bin_capacity_workspace_bytes(P, I_cap);
     { const size_t tb = spv_bin_tiles_workspace_bytes(P, I_cap, W, H); if (tb > f.bin_bytes) f.bin_bytes = tb; }
@@ -167,11 +168,11 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     static const bool radix = [] { const char *e = getenv("SPV_BIN_RADIX"); return e && e[0] == '1'; }();
     if (radix) SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
                                            status, f.bin_ws, f.bin_bytes, stream));
-    else SPV_TRY_RC(spv_bin_tiles(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
-                                  status, f.bin_ws, f.bin_bytes, stream));
+    else SPV_TRY_RC(spv::bin_tiles_ordered(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
+                                           status, f.tile_order, f.bin_ws, f.bin_bytes, stream));
     SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0), "spv_frame_ortho_forward/join");
-    return spv::blend_records_forward(C, W, H, K, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, images, f.final_T,
-                                      f.ncontrib, gs_idx, stream);
+    return spv::blend_records_forward(C, W, H, K, f.feature, f.idx_sorted, f.tile_range, radix ? nullptr : f.tile_order, bg_rgb, 1.0f,
+                                      0.0f, images, f.final_T, f.ncontrib, gs_idx, stream);
 }
 
 int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int n_grad_channels, int64_t I_cap,
@@ -189,7 +190,8 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     const int C = 4 + A;
     const unsigned g = spv::cdiv(P, kThreads);
     float *packed = (float *)f.blend_ws;
-    SPV_TRY_RC(spv::blend_records_backward(P, C, W, H, f.feature, f.idx_sorted, f.tile_range, bg_rgb, 1.0f, 0.0f, f.final_T,
+    static const bool radix = [] { const char *e = getenv("SPV_BIN_RADIX"); return e && e[0] == '1'; }();
+    SPV_TRY_RC(spv::blend_records_backward(P, C, W, H, f.feature, f.idx_sorted, f.tile_range, radix ? nullptr : f.tile_order, bg_rgb, 1.0f, 0.0f, f.final_T,
                                            f.ncontrib, dL_dimage_planes, n_grad_channels, /*want_abs=*/dL_dabs_ndc != nullptr, packed,
                                            /*packed_is_zero=*/first_backward != 0, stream));
     // deferred SH backward (frame-parallel training): the colour gradient and the clamp mask leave through the caller's

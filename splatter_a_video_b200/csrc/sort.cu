@@ -183,15 +183,18 @@ tile_range_dev_kernel(long long cap, const int *__restrict__ status, const unsig
 // shared memory (bitonic network over 64-bit keys; ids are unique, so the result is the unique (depth, id) order -- exactly
 // what the stable radix sort over emission order yields).  12 B/intersection of global traffic instead of 6 radix passes.
 constexpr int kScanThreads = 1024;
+constexpr int kOrderBuckets = 64;         // tile_order: tiles bucketed by list length (32 entries per bucket), longest first
 constexpr int kSortSmall = 1024;          // keys a 256-thread CTA sorts in static shared memory (8 KB); the heavy tail of the
                                           // tile-list distribution goes to the 1024-thread CTAs of tile_sort_big_kernel
 constexpr int kSortBig = 25600;           // keys a 1024-thread CTA sorts in 200 KB of dynamic shared memory
 
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(int T, long long cap, int *__restrict__ tile_count, int2 *__restrict__ tile_range, int *__restrict__ status,
-                 int *__restrict__ big_queue /*[0] = count, [1] = head, [2..] = tile ids*/) {
+                 int *__restrict__ big_queue /*[0] = count, [1] = head, [2..] = tile ids*/, int *__restrict__ tile_order /*or NULL*/) {
     __shared__ long long s_warp[kScanThreads / 32];
     __shared__ long long s_total;
+    __shared__ int s_bucket[kOrderBuckets], s_cursor[kOrderBuckets];
+    if (tile_order && threadIdx.x < kOrderBuckets) s_bucket[threadIdx.x] = 0;
     const int per = (T + kScanThreads - 1) / kScanThreads;
     const int lo = min(T, (int)threadIdx.x * per), hi = min(T, lo + per);
     long long sum = 0;
@@ -223,12 +226,28 @@ tile_scan_kernel(int T, long long cap, int *__restrict__ tile_count, int2 *__res
         const long long a = run < cap ? run : cap, b = (run + n) < cap ? (run + n) : cap;
         tile_range[t] = (n > 0 && b > a) ? make_int2((int)a, (int)b) : make_int2(0, 0);
         if (b - a > kSortSmall) big_queue[2 + atomicAdd(&big_queue[0], 1)] = t;
+        if (tile_order) atomicAdd(&s_bucket[min(kOrderBuckets - 1, (int)((b - a) >> 5))], 1);
         tile_count[t] = 0;   // becomes the emit pass's cursor
         run += n;
     }
     if (threadIdx.x == 0) {
         status[0] = (int)(s_total < cap ? s_total : cap);
         status[1] = s_total > cap ? 1 : 0;
+    }
+    if (!tile_order) return;
+    // Launch order of the blend kernels: CTAs are dispatched in blockIdx order as SM slots free up, so listing the tiles longest
+    // list first turns the launch into a longest-processing-time-first work queue -- the heavy tail of the list-length
+    // distribution (a few tiles under large splats) starts first instead of deciding when the kernel ends.  Counting sort over
+    // kOrderBuckets length buckets; the order inside a bucket is irrelevant (tiles are independent).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int at = 0;
+        for (int q = kOrderBuckets - 1; q >= 0; --q) { s_cursor[q] = at; at += s_bucket[q]; }
+    }
+    __syncthreads();
+    for (int t = lo; t < hi; ++t) {
+        const int2 r = tile_range[t];
+        tile_order[atomicAdd(&s_cursor[min(kOrderBuckets - 1, (r.y - r.x) >> 5)], 1)] = t;
     }
 }
 
@@ -439,6 +458,16 @@ size_t spv_bin_tiles_workspace_bytes(int P, int64_t I_cap, int W, int H) {
 int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
                   const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
                   void *workspace, size_t ws_bytes, void *stream) {
+    return spv::bin_tiles_ordered(P, I_cap, uv, depth, radius, conic, opacity, cull, W, H, idx_sorted, tile_range, status, nullptr,
+                                  workspace, ws_bytes, stream);
+}
+
+}  // extern "C"
+
+/* spv_bin_tiles + tile_order (int[T], or NULL): the tiles listed longest list first -- the blend kernels' launch order. */
+int spv::bin_tiles_ordered(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
+                           const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
+                           int *tile_order, void *workspace, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), T = gx * gy;
     SPV_CUDA_TRY(cudaMemsetAsync(tile_range, 0, sizeof(int) * 2 * (size_t)T, s), "spv_bin_tiles");
@@ -456,7 +485,7 @@ int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *depth, con
     cull_count_emit_kernel<2><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
                                                     nullptr, masks, nullptr, (long long)I_cap, nullptr, nullptr, nullptr, tile_count,
                                                     nullptr);
-    tile_scan_kernel<<<1, kScanThreads, 0, s>>>(T, (long long)I_cap, tile_count, (int2 *)tile_range, status, big_queue);
+    tile_scan_kernel<<<1, kScanThreads, 0, s>>>(T, (long long)I_cap, tile_count, (int2 *)tile_range, status, big_queue, tile_order);
     cull_count_emit_kernel<3><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
                                                     nullptr, masks, nullptr, (long long)I_cap, keys, nullptr, nullptr, tile_count,
                                                     (const int2 *)tile_range);
@@ -468,5 +497,3 @@ int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *depth, con
     tile_sort_big_kernel<<<spv::sm_count(), kScanThreads, kSortBig * 8, s>>>((const int2 *)tile_range, keys, idx_sorted, big_queue);
     return spv::check_launch("spv_bin_tiles/sort", 2);
 }
-
-}  // extern "C"

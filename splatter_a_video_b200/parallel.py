@@ -383,8 +383,16 @@ class GradExchange:
             c = self._cuda
             if self.deferred:
                 reduced = self._exchange_rows(world, scale)
-                self.unpack(reduced, c["all"])
+                # two independent consumers of the reduced block: the dense parameters' copy into the flat gradient (aux stream)
+                # next to the deferred SH backward (this stream); the spline tail already runs on the exchange's side stream
+                main = torch.cuda.current_stream()
+                if "aux" not in c:
+                    c["aux"] = torch.cuda.Stream()
+                c["aux"].wait_stream(main)
+                with torch.cuda.stream(c["aux"]):
+                    self.unpack(reduced, c["all"])
                 self._finish_deferred(world, scale, reduced)
+                main.wait_stream(c["aux"])
                 return
             if c["n_ar"]:
                 dist.all_reduce(ar, op=dist.ReduceOp.SUM)
