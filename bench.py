@@ -160,7 +160,9 @@ class Workload:
         self.device, self.mode = device, mode
         dev = lambda x: x.to(device)
         g = torch.Generator().manual_seed(99)
-        node = 0.02 * torch.randn(sc.P, 4 * self.NI * 3, generator=g)
+        # random spline coefficients (drawn on the device: 2.3 GB at 2 M Gaussians x 120 frames, times 8 ranks on one host)
+        gd = torch.Generator(device=device).manual_seed(99)
+        node = 0.02 * torch.randn(sc.P, 4 * self.NI * 3, generator=gd, device=device)
         # frame mode keeps the spline coefficients interval-major ([P,NI,4,3]: the 4 coefficients of an interval are 48 contiguous
         # bytes); the staged modes keep the reference's [P,4,NI,3] parameter layout
         self.node_im = mode == "frame"
@@ -185,8 +187,17 @@ class Workload:
         tab = [spline_interval(t, self.frames, self.NI) for t in range(self.frames)]
         self.tab_idx = torch.tensor([a for a, _ in tab], dtype=torch.int32).pin_memory()
         self.tab_dist = torch.tensor([b for _, b in tab], dtype=torch.float32).pin_memory()
-        self.idx1 = torch.zeros(1, dtype=torch.int32, device=device); self.dist1 = torch.zeros(1, device=device)
-        self.idx2 = torch.zeros(1, dtype=torch.int32, device=device); self.dist2 = torch.zeros(1, device=device)
+        # the four frame scalars of a step live in ONE 16-byte device buffer (int32 bits next to floats) filled by ONE copy from a
+        # pinned per-frame table: (idx1, dist1, idx2, dist2) of frame f = row f
+        tabs = torch.zeros(self.frames, 4, dtype=torch.float32)
+        for f in range(self.frames):
+            f2 = min(f + 1, self.frames - 1)
+            tabs[f, 0:1] = torch.tensor([tab[f][0]], dtype=torch.int32).view(torch.float32); tabs[f, 1] = tab[f][1]
+            tabs[f, 2:3] = torch.tensor([tab[f2][0]], dtype=torch.int32).view(torch.float32); tabs[f, 3] = tab[f2][1]
+        self.tab_frame = tabs.pin_memory()
+        self.frame_scalars = torch.zeros(4, dtype=torch.float32, device=device)
+        self.idx1, self.dist1 = self.frame_scalars[0:1].view(torch.int32), self.frame_scalars[1:2]
+        self.idx2, self.dist2 = self.frame_scalars[2:3].view(torch.int32), self.frame_scalars[3:4]
         # upstream image gradients resident in HBM (N(0,1)) + pinned host buffers for the e2e path
         chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
         self.g_dev = {k: torch.randn(c, self.H, self.W, generator=g).to(device) for k, c in chans.items()}
@@ -212,14 +223,32 @@ class Workload:
         # batch of the step as the reference's loader yields it (gs_data2.py:24-88) + the depth / TAPIR-track supervision the
         # trainer reads beside it (trainer_fragGS.py:537-601): pinned host copies for the e2e path, device copies for `value`
         n_trk = 4096
-        self.batch_host = {"gt_rgb": torch.rand(self.H, self.W, 3, generator=g).pin_memory(),
-                           "gt_depth": (torch.rand(self.H, self.W, generator=g) * 1.5 + 0.5).pin_memory(),
-                           "trk_target": (torch.rand(n_trk, 2, generator=g) * torch.tensor([float(self.W), float(self.H)])).pin_memory(),
-                           "trk_weight": torch.rand(n_trk, generator=g).pin_memory()}
+        # ... collated into ONE pinned buffer per step (what a collate_fn with pin_memory gives): one H2D copy per step
+        parts = {"gt_rgb": torch.rand(self.H, self.W, 3, generator=g), "gt_depth": torch.rand(self.H, self.W, generator=g) * 1.5 + 0.5,
+                 "trk_target": torch.rand(n_trk, 2, generator=g) * torch.tensor([float(self.W), float(self.H)]),
+                 "trk_weight": torch.rand(n_trk, generator=g)}
+        self.batch_layout, off = {}, 0
+        for k, v in parts.items():
+            self.batch_layout[k] = (off, tuple(v.shape)); off += (v.numel() + 3) // 4 * 4
+        self.batch_host_packed = torch.zeros(off, dtype=torch.float32).pin_memory()
+
+        def views(buf):
+            out = {}
+            for k, (o, shape) in self.batch_layout.items():
+                nel = 1
+                for d in shape:
+                    nel *= d
+                out[k] = buf[o:o + nel].view(shape)
+            return out
+        self._batch_views = views
+        self.batch_host = views(self.batch_host_packed)
+        for k, v in parts.items():
+            self.batch_host[k].copy_(v)
         qx = torch.randint(0, self.W, (n_trk,), generator=g); qy = torch.randint(0, self.H, (n_trk,), generator=g)
         self.trk_query = torch.stack([qx, qy], 1).to(torch.int32).to(device)          # query grid: fixed per clip
         self.trk_visible = (torch.rand(n_trk, generator=g) < 0.9).to(torch.uint8).to(device)
-        self.batch_dev = {k: v.to(device) for k, v in self.batch_host.items()}
+        self.batch_dev_packed = self.batch_host_packed.to(device)
+        self.batch_dev = views(self.batch_dev_packed)
         self.batch_stage = None
         self.loss_w = {"rgb": 1.0, "flow": 0.1, "depth": 0.5, "lambda_dssim": 0.2}     # trainer_fragGS.py:577-601
         self.loss_vec = torch.zeros(4, device=device)
@@ -242,8 +271,7 @@ class Workload:
     # ---- per-step pieces -------------------------------------------------------------------------------------------
     def set_frame(self, frame):
         f2 = min(frame + 1, self.frames - 1)
-        self.idx1.copy_(self.tab_idx[frame:frame + 1], non_blocking=True); self.dist1.copy_(self.tab_dist[frame:frame + 1], non_blocking=True)
-        self.idx2.copy_(self.tab_idx[f2:f2 + 1], non_blocking=True); self.dist2.copy_(self.tab_dist[f2:f2 + 1], non_blocking=True)
+        self.frame_scalars.copy_(self.tab_frame[frame], non_blocking=True)
 
     def render_dict(self):
         from splatter_a_video_b200.gs.frame import deform_position, deform_position_pair
@@ -350,8 +378,7 @@ class Workload:
         cs = self.copy_stream
         cs.wait_stream(torch.cuda.current_stream())            # not before this point of the step (stays inside its time bracket)
         with torch.cuda.stream(cs):
-            for k, v in self.batch_host.items():
-                self.batch_stage[buf][k].copy_(v, non_blocking=True)
+            self.batch_stage[buf].copy_(self.batch_host_packed, non_blocking=True)
             self.pf_event[buf].record(cs)
 
     def step_full_e2e(self, frame, exchange=None):
@@ -363,7 +390,7 @@ class Workload:
         if self.batch_stage is None:
             if self.copy_stream is None:
                 self.copy_stream = torch.cuda.Stream()
-            self.batch_stage = [{k: torch.empty_like(v) for k, v in self.batch_dev.items()} for _ in range(2)]
+            self.batch_stage = [torch.empty_like(self.batch_dev_packed) for _ in range(2)]
             self.pf_event = [torch.cuda.Event() for _ in range(2)]
             self.pf_buf = 0
             self._prefetch_full(0)
@@ -371,8 +398,7 @@ class Workload:
         main = torch.cuda.current_stream()
         self._prefetch_full(cur ^ 1)                            # overlaps this step's kernels
         main.wait_event(self.pf_event[cur])
-        for k, v in self.batch_stage[cur].items():
-            self.batch_dev[k].copy_(v, non_blocking=True)
+        self.batch_dev_packed.copy_(self.batch_stage[cur], non_blocking=True)
         self._run("full", self._fwd_loss_bwd)
         if exchange is not None:
             exchange.run()
@@ -384,7 +410,7 @@ class Workload:
         return float(self.loss_host[0])
 
     def h2d_bytes_full(self):
-        return int(sum(v.numel() * v.element_size() for v in self.batch_host.values()))
+        return int(self.batch_host_packed.numel() * 4)
 
     def _render_only(self):
         with torch.no_grad():

@@ -121,7 +121,7 @@ __device__ __forceinline__ float2 step_consts(const float2 *__restrict__ ring, i
 // One thread per (Gaussian, float4 of the interval's 12 coefficients); the CTA's interval list (deduplicated, stale entries
 // only) is built once in shared memory.  Interval-major storage: one 16-byte load / store per array and interval.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)      // <= 85 registers, no spills: latency-bound streaming, occupancy over unrolling
 adam_lazy_kernel(LazyGeom q, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  const int *__restrict__ idx1_dev, const int *__restrict__ idx2_dev, const int *__restrict__ dirty,
                  const int *__restrict__ last, const float2 *__restrict__ ring, const float *__restrict__ state,
@@ -153,18 +153,20 @@ adam_lazy_kernel(LazyGeom q, float *__restrict__ p, const float *__restrict__ g,
         const int from = MODE == 2 ? last[b] : s_from[u];
         if (MODE == 2 && from >= to) continue;
         float P_[4], M_[4], V_[4], G_[4] = {0.f, 0.f, 0.f, 0.f};
-        long long e[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) e[c] = lazy_elem(q, i, b, 4 * quad + c);
+        const long long e0 = lazy_elem(q, i, b, 4 * quad);
         if (q.layout) {      // the four slots are 16 contiguous, aligned bytes
-            const float4 a = *reinterpret_cast<const float4 *>(p + e[0]), bq = *reinterpret_cast<const float4 *>(m + e[0]),
-                         cq = *reinterpret_cast<const float4 *>(v + e[0]);
+            const float4 a = *reinterpret_cast<const float4 *>(p + e0), bq = *reinterpret_cast<const float4 *>(m + e0),
+                         cq = *reinterpret_cast<const float4 *>(v + e0);
             P_[0] = a.x; P_[1] = a.y; P_[2] = a.z; P_[3] = a.w; M_[0] = bq.x; M_[1] = bq.y; M_[2] = bq.z; M_[3] = bq.w;
             V_[0] = cq.x; V_[1] = cq.y; V_[2] = cq.z; V_[3] = cq.w;
-            if (MODE == 1) { const float4 d = *reinterpret_cast<const float4 *>(g + e[0]); G_[0] = d.x; G_[1] = d.y; G_[2] = d.z; G_[3] = d.w; }
+            if (MODE == 1) { const float4 d = *reinterpret_cast<const float4 *>(g + e0); G_[0] = d.x; G_[1] = d.y; G_[2] = d.z; G_[3] = d.w; }
         } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { P_[c] = p[e[c]]; M_[c] = m[e[c]]; V_[c] = v[e[c]]; if (MODE == 1) G_[c] = g[e[c]]; }
+            for (int c = 0; c < 4; ++c) {
+                const long long e = lazy_elem(q, i, b, 4 * quad + c);
+                P_[c] = p[e]; M_[c] = m[e]; V_[c] = v[e];
+                if (MODE == 1) G_[c] = g[e];
+            }
         }
         for (int j = from + 1; j <= to; ++j) {          // replay the zero-gradient steps (constants fetched once per step)
             const float2 cs = step_consts(ring, j, now, lr, b1, b2);
@@ -177,12 +179,12 @@ adam_lazy_kernel(LazyGeom q, float *__restrict__ p, const float *__restrict__ g,
             for (int c = 0; c < 4; ++c) adam_update(P_[c], G_[c], M_[c], V_[c], cs.x, b1, b2, eps, cs.y);
         }
         if (q.layout) {
-            *reinterpret_cast<float4 *>(p + e[0]) = make_float4(P_[0], P_[1], P_[2], P_[3]);
-            *reinterpret_cast<float4 *>(m + e[0]) = make_float4(M_[0], M_[1], M_[2], M_[3]);
-            *reinterpret_cast<float4 *>(v + e[0]) = make_float4(V_[0], V_[1], V_[2], V_[3]);
+            *reinterpret_cast<float4 *>(p + e0) = make_float4(P_[0], P_[1], P_[2], P_[3]);
+            *reinterpret_cast<float4 *>(m + e0) = make_float4(M_[0], M_[1], M_[2], M_[3]);
+            *reinterpret_cast<float4 *>(v + e0) = make_float4(V_[0], V_[1], V_[2], V_[3]);
         } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { p[e[c]] = P_[c]; m[e[c]] = M_[c]; v[e[c]] = V_[c]; }
+            for (int c = 0; c < 4; ++c) { const long long e = lazy_elem(q, i, b, 4 * quad + c); p[e] = P_[c]; m[e] = M_[c]; v[e] = V_[c]; }
         }
     }
 }

@@ -172,16 +172,28 @@ exchange_reduce_peers_kernel(long long n_red4, long long n_row4, int world, Peer
 
 // The gathered tails alone ([n_red, n_row) of every rank's row -> local `rows`): lets the caller run the gather and what
 // depends on it (the deferred spline backward) on a second stream next to the reduction.
+constexpr int kPeerUnroll = 4;   // float4 per thread and peer: world x 4 x 16 B of NVLink reads in flight per thread
 __global__ void __launch_bounds__(kThreads)
 exchange_gather_peers_kernel(long long n_red4, long long n_row4, int world, PeerPtrs peers, float4 *__restrict__ rows,
                              long long row_stride4) {
-    const long long e = n_red4 + (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (e >= n_row4) return;
-    float4 v[8];
+    const long long base = n_red4 + (long long)blockIdx.x * (kThreads * kPeerUnroll) + threadIdx.x;
+    for (int r0 = 0; r0 < world; r0 += 2) {          // two peers x kPeerUnroll loads in flight, then their stores
+        float4 v[2][kPeerUnroll];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) if (r < world) v[r] = peers.p[r][e];
+        for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = v[r];
+            for (int u = 0; u < kPeerUnroll; ++u) {
+                const long long e = base + (long long)u * kThreads;
+                if (r0 + rr < world && e < n_row4) v[rr][u] = peers.p[r0 + rr][e];
+            }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int u = 0; u < kPeerUnroll; ++u) {
+                const long long e = base + (long long)u * kThreads;
+                if (r0 + rr < world && e < n_row4) rows[(r0 + rr) * row_stride4 + e] = v[rr][u];
+            }
+    }
 }
 
 // Two-phase variant for larger groups (inbound volume 2(N-1)/N instead of N-1 times the summed block): phase 1 -- every
@@ -239,13 +251,23 @@ __global__ void __launch_bounds__(kThreads)
 exchange_nvls_kernel(long long n_red4, long long n_row4, long long chunk4, int rank, int world, const float4 *__restrict__ mc_row,
                      float4 *__restrict__ mc_red, PeerPtrs peers, float scale, float4 *__restrict__ rows, long long row_stride4) {
     const long long lo = (long long)rank * chunk4, hi = min(n_red4, lo + chunk4), mine = max(hi - lo, 0ll);
-    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (t < mine) {
-        const long long e = lo + t;
-        float4 v = multimem_ld_reduce_add(mc_row + e);
-        multimem_st(mc_red + e, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
+    const long long mine_blocks = (mine + kThreads * kPeerUnroll - 1) / (kThreads * kPeerUnroll);
+    if ((long long)blockIdx.x < mine_blocks) {
+        // kPeerUnroll in-switch reductions in flight per thread, then their multicast stores
+        const long long base = lo + (long long)blockIdx.x * (kThreads * kPeerUnroll) + threadIdx.x;
+        float4 v[kPeerUnroll];
+#pragma unroll
+        for (int u = 0; u < kPeerUnroll; ++u) {
+            const long long e = base + (long long)u * kThreads;
+            if (e < hi) v[u] = multimem_ld_reduce_add(mc_row + e);
+        }
+#pragma unroll
+        for (int u = 0; u < kPeerUnroll; ++u) {
+            const long long e = base + (long long)u * kThreads;
+            if (e < hi) multimem_st(mc_red + e, make_float4(v[u].x * scale, v[u].y * scale, v[u].z * scale, v[u].w * scale));
+        }
     } else {
-        const long long e = n_red4 + (t - mine);
+        const long long e = n_red4 + ((long long)blockIdx.x - mine_blocks) * kThreads + threadIdx.x;
         if (e >= n_row4 || !rows) return;
 #pragma unroll
         for (int r = 0; r < 8; ++r) if (r < world) rows[r * row_stride4 + e] = peers.p[r][e];
@@ -385,7 +407,7 @@ int spv_exchange_gather_peers(long long n_red, long long n_row, int world, const
     }
     PeerPtrs pp;
     for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
-    exchange_gather_peers_kernel<<<spv::cdiv((n_row - n_red) / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+    exchange_gather_peers_kernel<<<spv::cdiv((n_row - n_red) / 4, kThreads * kPeerUnroll), kThreads, 0, (cudaStream_t)stream>>>(
         n_red / 4, n_row / 4, world, pp, (float4 *)rows, row_stride / 4);
     return spv::check_launch("spv_exchange_gather_peers");
 }
@@ -403,8 +425,9 @@ int spv_exchange_nvls(long long n_red, long long n_row, int rank, int world, con
     for (int r = 0; r < 8; ++r) pp.p[r] = (const float4 *)peer_rows[r < world ? r : 0];
     const long long n_red4 = n_red / 4, n_row4 = n_row / 4, chunk4 = (n_red4 + world - 1) / world;
     const long long lo = (long long)rank * chunk4, hi = lo + chunk4 < n_red4 ? lo + chunk4 : n_red4;
-    const long long work = (hi > lo ? hi - lo : 0) + (rows ? n_row4 - n_red4 : 0);
-    exchange_nvls_kernel<<<spv::cdiv(work > 0 ? work : 1, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+    const long long mine = hi > lo ? hi - lo : 0;
+    const long long blocks = (mine + kThreads * kPeerUnroll - 1) / (kThreads * kPeerUnroll) + (rows ? (n_row4 - n_red4 + kThreads - 1) / kThreads : 0);
+    exchange_nvls_kernel<<<(unsigned)(blocks > 0 ? blocks : 1), kThreads, 0, (cudaStream_t)stream>>>(
         n_red4, n_row4, chunk4 > 0 ? chunk4 : 1, rank, world, (const float4 *)mc_row, (float4 *)mc_red, pp, scale, (float4 *)rows,
         row_stride / 4);
     return spv::check_launch("spv_exchange_nvls");

@@ -142,8 +142,6 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     FrameWs f = carve(workspace, P, I_cap, W, H, A);
     if (ws_bytes < f.total) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: workspace too small"); return (int)cudaErrorInvalidValue; }
     const unsigned g = spv::cdiv(P, kThreads);
-    frame_prep_kernel<<<g, kThreads, 0, s>>>(P, f.dirs);
-    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep"));
     const int C = 4 + A;
     // ---- side branch: SH colours (evaluated for every point: the renderer passes no visibility mask, :272), then -- once
     //      the main branch has the conics -- the per-Gaussian blend records and the -1 fill of the id image
@@ -151,6 +149,8 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     if (!lane) { spv::set_error(cudaGetLastError(), "spv_frame_ortho_forward: side stream"); return (int)cudaErrorUnknown; }
     SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_forward/fork");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_forward/fork");
+    frame_prep_kernel<<<g, kThreads, 0, lane->stream>>>(P, f.dirs);      // only the SH kernels read it: off the main branch
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep"));
     SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
     SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, lane->stream), "spv_frame_ortho_forward");
     // the backward's packed gradient rows are cleared here, off the critical path (the workspace belongs to this frame)
