@@ -908,8 +908,17 @@ def run_ours(args):
                 r[0] += 1; r[1] += float(ev.device_time if hasattr(ev, "device_time") else ev.cuda_time)
             out = [{"kernel": k, "launches_per_step": n / args.steps, "us_per_step": t / args.steps} for k, (n, t) in rows.items()]
             out.sort(key=lambda r: -r["us_per_step"])
+            # timeline of the LAST step (start relative to its first kernel, duration, stream): which kernels overlap, where the gaps are
+            evs = sorted((ev for ev in prof.events() if ev.device_type is not None and "cuda" in str(ev.device_type).lower()),
+                         key=lambda ev: ev.time_range.start)
+            per_step = max(1, len(evs) // args.steps)
+            last = evs[-per_step:]
+            t0 = last[0].time_range.start if last else 0.0
+            timeline = [{"t_us": round(ev.time_range.start - t0, 1), "dur_us": round(ev.time_range.end - ev.time_range.start, 1),
+                         "stream": int(getattr(ev, "device_resource_id", -1) or -1), "kernel": ev.name.split("(")[0][-60:]} for ev in last]
             with open(args.trace, "w") as f:
-                json.dump({"n_gpus": world, "steps": args.steps, "sum_us_per_step": sum(r["us_per_step"] for r in out), "kernels": out}, f, indent=1)
+                json.dump({"n_gpus": world, "steps": args.steps, "sum_us_per_step": sum(r["us_per_step"] for r in out), "kernels": out,
+                           "timeline_last_step": timeline}, f, indent=1)
             for r in out[:60]:
                 log(f"{r['us_per_step']:9.1f} us x{r['launches_per_step']:5.1f}  {r['kernel'][:100]}")
         if world > 1:

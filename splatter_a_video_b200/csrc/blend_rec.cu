@@ -224,17 +224,6 @@ blend_rec_fwd_kernel(int C, int W, int H, int gx, int K, const float *__restrict
 //     entry, no state selects: a lane that did not take the Gaussian has w = 0) instead of the normalised accum_rec form:
 //         dL_dalpha = T <f, d> - (R + T_final <bg, d>) / (1 - alpha)         (alpha_blending.cu:180-246, same sum)
 constexpr int kRing = 4, kRingChunk = 64;
-// Few-hits path.  A third of the (8x4 block, entry) pairs have <= 8 of their 32 pixels inside the Gaussian's footprint (tests/
-// hit_stats.py); for those the reduction network (22-36 shuffles, twice that many selects) sums mostly zeros.  With <= sparse_k
-// hit lanes the hit lanes store their values as rows of a per-warp shared-memory scratch and lane l adds up column l:
-// TV/4 STS.128 + one LDS + FADD per hit lane instead of the network.
-constexpr int kFewMax = 8, kFewDefault = 8;
-constexpr int bwd_nv(int CG) { return CG <= 14 ? 16 : 32; }
-constexpr int bwd_nu(int CG, bool ABS) { return (CG <= 8 || bwd_nv(CG) == 32) ? 0 : ((!ABS && CG <= 12) ? 4 : 8); }
-// values a (block, entry) pair sums over the warp: the first network, the second one, the RGB-pass pair of <ABS, no second>
-constexpr int bwd_tv(int CG, bool ABS) { return bwd_nv(CG) + bwd_nu(CG, ABS) + ((ABS && bwd_nu(CG, ABS) == 0) ? 2 : 0); }
-constexpr int few_pitch(int CG, bool ABS) { return ((bwd_tv(CG, ABS) + 3) / 4 * 4) | 4; }   // pitch/4 odd: the 8 slots fall on distinct banks
-constexpr int few_floats(int CG, bool ABS) { return bwd_tv(CG, ABS) <= 32 ? (kBlock / 32) * kFewMax * few_pitch(CG, ABS) : 0; }
 
 __device__ __forceinline__ int atom_add_acq_rel_shared(int *addr, int v) {
     int old;
@@ -255,20 +244,16 @@ __global__ void __launch_bounds__(kBlock, 3)
 blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec, const int *__restrict__ idx_sorted,
                      const int2 *__restrict__ tile_range, const int *__restrict__ tile_order, float bgA, float bgB, float bgC,
                      const float *__restrict__ final_T, const int *__restrict__ ncontrib, const spv::ChanPlanes planes,
-                     float *__restrict__ packed, int sparse_k) {
-    constexpr int NV = bwd_nv(CG);
-    constexpr int NU = bwd_nu(CG, ABS);   // second network: features 8.. (+ the pair if ABS)
+                     float *__restrict__ packed) {
+    constexpr int NV = (CG <= 14) ? 16 : 32;
+    constexpr int NU = (CG <= 8 || NV == 32) ? 0 : ((!ABS && CG <= 12) ? 4 : 8);   // second network: features 8.. (+ the pair if ABS)
     static_assert(CH % 4 == 0 && CH >= 4 && CH <= 24 && 8 + CG <= 32 && CG <= CH, "unsupported channel configuration");
     static_assert(kRing * kRingChunk == kBlock, "one bulk copy per thread fills the whole ring");
     constexpr int RP = kRec;                        // 36: pitch/4 = 9 is odd
     constexpr int DS = rec_pitch(CH);               // dL_dpixel row pitch, pitch/4 odd
-    constexpr int TV = bwd_tv(CG, ABS);
-    constexpr bool kHasSparse = TV <= 32;           // one lane per value in the few-hits path
-    constexpr int SP = few_pitch(CG, ABS);          // floats per slot
     extern __shared__ __align__(128) float s_dyn[];
     float *s_rec0 = s_dyn;                                            // [kRing][kRingChunk][RP]
     float *dq = s_dyn + kRing * kRingChunk * RP + threadIdx.x * DS;   // this pixel's dL_dpixel row
-    float *s_few = s_dyn + kRing * kRingChunk * RP + kBlock * DS + (threadIdx.x >> 5) * (kFewMax * SP);   // [kFewMax][SP] per warp
     __shared__ __align__(8) uint64_t s_full[kRing];
     __shared__ int s_done[kRing];
     __shared__ int s_max;
@@ -355,8 +340,7 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
                 float p2 = splat_p2(g0, g1.x, pxf, pyf, dx, dy);
                 // did this pixel apply the Gaussian in the forward pass?  (same test, and before its last contributor)
                 const bool hit = splat_hits<false>(p2, g1) && (p_hi - 1 - j) < last_contrib;
-                const unsigned hm = __ballot_sync(kFull, hit);
-                if (!hm) continue;
+                if (!__any_sync(kFull, hit)) continue;
                 float v[NV];
                 float u[NU > 0 ? NU : 1];   // second network: features 8.. (| RGB-pass pair when ABS)
                 float n0, n1;
@@ -407,44 +391,10 @@ blend_rec_bwd_kernel(int C, int W, int H, int gx, const float *__restrict__ rec,
                     if constexpr (ABS) { v[2] = fabsf(n0); v[3] = fabsf(n1); }
                     else { v[2] = n0; v[3] = n1; }        // the RGB-pass pair rides in the |.| slots
                 }
+                halving_reduce<NV, 0, NV>(v, lane);   // lane l (< NV) now holds the warp-wide sum of value l
                 float *row = packed + (size_t)__float_as_int(g1.w) * kRowG;
                 // network slot -> packed column: 2,3 hold the RGB-pass pair (columns 31,32) when !ABS
                 const int vcol = (!ABS && (lane == 2 || lane == 3)) ? 29 + lane : lane;
-                if constexpr (kHasSparse) {
-                    const int nh = __popc(hm);
-                    if (nh <= sparse_k) {
-                        if (hit) {
-                            float4 *d = reinterpret_cast<float4 *>(s_few + __popc(hm & ((1u << lane) - 1u)) * SP);
-#pragma unroll
-                            for (int q = 0; q < NV / 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            if constexpr (NU > 0) {
-                                if constexpr (ABS) { u[NU - 2] = n0; u[NU - 1] = n1; }
-#pragma unroll
-                                for (int q = 0; q < NU / 4; ++q) d[NV / 4 + q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-                            } else if constexpr (ABS) {
-                                *reinterpret_cast<float2 *>(s_few + __popc(hm & ((1u << lane) - 1u)) * SP + NV) = make_float2(n0, n1);
-                            }
-                        }
-                        __syncwarp();
-                        float sum = 0.f;
-                        if (lane < TV) {
-#pragma unroll
-                            for (int q = 0; q < kFewMax; ++q) if (q < nh) sum += s_few[q * SP + lane];
-                        }
-                        __syncwarp();
-                        // lane -> packed column, as the networks below leave them
-                        int col; bool live;
-                        if (lane < NV) { col = vcol; live = lane < 8 + (NU > 0 ? 8 : CG); }
-                        else if constexpr (NU > 0) {
-                            const int t = lane - NV, nf = ABS ? NU - 2 : NU;
-                            col = t < nf ? 16 + t : 31 + (t - nf);
-                            live = lane < NV + NU && (t >= nf || t < CG - 8);
-                        } else { col = 31 + (lane - NV); live = lane < TV; }
-                        if (live && sum != 0.f) atomicAdd(row + col, sum);
-                        continue;
-                    }
-                }
-                halving_reduce<NV, 0, NV>(v, lane);   // lane l (< NV) now holds the warp-wide sum of value l
                 if constexpr (NU > 0) {
                     if constexpr (ABS) { u[NU - 2] = n0; u[NU - 1] = n1; }
                     halving_reduce<NU, 0, NU>(u, lane);     // lane l holds the sum of u[l % NU]
@@ -515,17 +465,17 @@ void launch_rec_fwd(const RecFwdArgs &a, int ntiles, cudaStream_t s) {
 struct RecBwdArgs {
     int C, W, H, gx;
     const float *rec; const int *idx_sorted; const int2 *tile_range; const int *tile_order; float bgA, bgB, bgC;
-    const float *final_T; const int *ncontrib; spv::ChanPlanes planes; float *packed; int sparse_k;
+    const float *final_T; const int *ncontrib; spv::ChanPlanes planes; float *packed;
 };
 
 template <int CH, int CG, bool ABS>
 void launch_rec_bwd(const RecBwdArgs &a, int ntiles, cudaStream_t s) {
-    constexpr size_t dyn = sizeof(float) * (kRing * kRingChunk * kRec + kBlock * rec_pitch(CH) + few_floats(CG, ABS));
+    constexpr size_t dyn = sizeof(float) * (kRing * kRingChunk * kRec + kBlock * rec_pitch(CH));
     static std::atomic<unsigned long long> configured{0};   // up to 64.5 KB of dynamic shared memory: above the 48 KB default
     spv::opt_in_dynamic_smem(blend_rec_bwd_kernel<CH, CG, ABS>, dyn, configured);
     spv::timer_mark(1, 0, s);
     blend_rec_bwd_kernel<CH, CG, ABS><<<ntiles, kBlock, dyn, s>>>(a.C, a.W, a.H, a.gx, a.rec, a.idx_sorted, a.tile_range, a.tile_order, a.bgA, a.bgB,
-                                                                 a.bgC, a.final_T, a.ncontrib, a.planes, a.packed, a.sparse_k);
+                                                                 a.bgC, a.final_T, a.ncontrib, a.planes, a.packed);
     spv::timer_mark(1, 1, s);
 }
 
@@ -608,10 +558,6 @@ int blend_records_backward(int P, int C, int W, int H, const float *rec, const i
     a.C = C; a.W = W; a.H = H; a.gx = gx; a.rec = rec; a.idx_sorted = idx_sorted; a.tile_range = (const int2 *)tile_range;
     a.tile_order = tile_order;
     a.bgA = bg_rgb; a.bgB = bg_depth; a.bgC = bg_attr; a.final_T = final_T; a.ncontrib = ncontrib; a.packed = packed;
-    {   // bwd_variant: -1 / 0 = default threshold of the few-hits path, 100 = off, 1..8 = that threshold (A/B runs)
-        const int opt = spv::get_option("bwd_variant");
-        a.sparse_k = opt <= 0 ? kFewDefault : (opt >= 100 ? 0 : (opt > kFewMax ? kFewMax : opt));
-    }
     for (int c = 0; c < 32; ++c) a.planes.p[c] = c < C ? planes_host[c] : nullptr;
     const int ng = n_grad_channels < 4 ? 4 : (n_grad_channels > C ? C : n_grad_channels);
     if (C <= 4) dispatch_rec_bwd<4>(a, ng, want_abs, ntiles, s);
