@@ -58,7 +58,13 @@ inline int sm_count() {   // of the current device (the runtime caches device at
 // Adam: the dense parameters next to the spline intervals).  Forked from and joined back into the caller's stream with events, so
 // the caller still sees one in-order stream -- and a stream capture records the branches as parallel graph nodes.  One lane per
 // (host thread, device): streams and events belong to the device that was current when they were created.  runtime.cu.
-struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, mid = nullptr, join = nullptr; bool ok = false; };
+// `stream`: side work next to the caller's stream.  `hi`: a stream of the greatest priority for serial chains of small kernels
+// (the binning chain): the block scheduler hands free SM slots to its kernels before the backlog of a big side-lane grid.
+struct SideLane {
+    cudaStream_t stream = nullptr, hi = nullptr;
+    cudaEvent_t fork = nullptr, mid = nullptr, join = nullptr, hi_join = nullptr;
+    bool ok = false;
+};
 SideLane *side_lane();
 
 inline int tiles_x(int W) { return (W + SPV_TILE - 1) / SPV_TILE; }
@@ -125,7 +131,9 @@ int frame_geometry_backward(int P, const float *packed, const float *scales, con
 // sort.cu: spv_bin_tiles + the longest-list-first tile order the blend kernels launch in (tile_order = int[T] or NULL)
 int bin_tiles_ordered(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
                       const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status, int *tile_order,
-                      void *workspace, size_t ws_bytes, void *stream);
+                      bool cleared, void *workspace, size_t ws_bytes, void *stream);
+// clears tile_range / status / the workspace's counters in one launch (bin_tiles_ordered(cleared = true) then skips it)
+int bin_tiles_clear(int P, int64_t I_cap, int W, int H, int *tile_range, int *status, void *workspace, void *stream);
 
 // blend_rec.cu: record-staged blending of the fused frame path.  One record of kRecordFloats floats per Gaussian:
 //   [x y a2 b2 | c2 log2(o) o id | feature[0..23] = rgb(3) depth(1) attributes, zero padded | a b c 0]

@@ -147,29 +147,40 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     //      the main branch has the conics -- the per-Gaussian blend records and the -1 fill of the id image
     SideLane *lane = side_lane();
     if (!lane) { spv::set_error(cudaGetLastError(), "spv_frame_ortho_forward: side stream"); return (int)cudaErrorUnknown; }
+    // The serial chain geometry -> count -> scan -> emit -> tile sort is the critical path up to the forward blend; it runs on the
+    // lane's high-priority stream so that its (small, latency-bound) kernels are not queued behind the CTA backlog of the side
+    // branch's streaming kernels (measured: tile_scan's single CTA waited 20 us for pack_records' 7000).
+    const bool flat = spv::get_option("flat_chain") != 0;
+    cudaStream_t hs = flat ? s : lane->hi;
     SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_forward/fork");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_forward/fork");
+    if (!flat) SPV_CUDA_TRY(cudaStreamWaitEvent(hs, lane->fork, 0), "spv_frame_ortho_forward/fork");
     frame_prep_kernel<<<g, kThreads, 0, lane->stream>>>(P, f.dirs);      // only the SH kernels read it: off the main branch
     SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep"));
     SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
-    SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, lane->stream), "spv_frame_ortho_forward");
-    // the backward's packed gradient rows are cleared here, off the critical path (the workspace belongs to this frame)
-    SPV_CUDA_TRY(cudaMemsetAsync(f.blend_ws, 0, sizeof(float) * (size_t)spv::kPackedRowGroups * P, lane->stream), "spv_frame_ortho_forward");
     // ---- main branch: projection, visibility, covariance, conic / radius / tile rectangle in ONE pass (geometry.cu: the staged
     //      kernels' bodies back to back, bit-identical results), then culled binning + tile sort
+    static const bool radix = [] { const char *e = getenv("SPV_BIN_RADIX"); return e && e[0] == '1'; }();
+    if (!radix) SPV_TRY_RC(spv::bin_tiles_clear(P, I_cap, W, H, f.tile_range, status, f.bin_ws, (void *)hs));   // one launch, before the chain
     SPV_TRY_RC(spv::frame_geometry_forward(P, position, scaling, rotation, extr, W, H, nearest, extent, f.uv, f.depth, f.vis, f.cov3d,
-                                           f.conic, f.radius, f.tiles, radii, stream));
-    SPV_CUDA_TRY(cudaEventRecord(lane->mid, s), "spv_frame_ortho_forward/mid");
+                                           f.conic, f.radius, f.tiles, radii, (void *)hs));
+    SPV_CUDA_TRY(cudaEventRecord(lane->mid, hs), "spv_frame_ortho_forward/mid");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->mid, 0), "spv_frame_ortho_forward/mid");
     SPV_TRY_RC(spv::pack_records(P, A, f.uv, f.conic, opacity, f.radius, f.rgb, f.depth, n_groups, attr_ptrs, attr_channels,
                                  f.feature, (void *)lane->stream));
+    SPV_CUDA_TRY(cudaMemsetAsync(gs_idx, 0xFF, sizeof(int) * (size_t)H * W * K, lane->stream), "spv_frame_ortho_forward");
+    // the backward's packed gradient rows are cleared here, off the critical path (the workspace belongs to this frame)
+    SPV_CUDA_TRY(cudaMemsetAsync(f.blend_ws, 0, sizeof(float) * (size_t)spv::kPackedRowGroups * P, lane->stream), "spv_frame_ortho_forward");
     SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_forward/join");
     // binning: per-tile segments + shared-memory tile sort (SPV_BIN_RADIX=1 selects the global radix sort for A/B runs)
-    static const bool radix = [] { const char *e = getenv("SPV_BIN_RADIX"); return e && e[0] == '1'; }();
     if (radix) SPV_TRY_RC(spv_bin_capacity(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
-                                           status, f.bin_ws, f.bin_bytes, stream));
+                                           status, f.bin_ws, f.bin_bytes, (void *)hs));
     else SPV_TRY_RC(spv::bin_tiles_ordered(P, I_cap, f.uv, f.depth, f.radius, f.conic, opacity, cull, W, H, f.idx_sorted, f.tile_range,
-                                           status, f.tile_order, f.bin_ws, f.bin_bytes, stream));
+                                           status, f.tile_order, /*cleared=*/true, f.bin_ws, f.bin_bytes, (void *)hs));
+    if (!flat) {
+        SPV_CUDA_TRY(cudaEventRecord(lane->hi_join, hs), "spv_frame_ortho_forward/join");
+        SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->hi_join, 0), "spv_frame_ortho_forward/join");
+    }
     SPV_CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0), "spv_frame_ortho_forward/join");
     return spv::blend_records_forward(C, W, H, K, f.feature, f.idx_sorted, f.tile_range, radix ? nullptr : f.tile_order, bg_rgb, 1.0f,
                                       0.0f, images, f.final_T, f.ncontrib, gs_idx, stream);

@@ -35,6 +35,10 @@ SideLane *side_lane() {
     SideLane &l = g_side[dev];
     if (!l.ok) {
         if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&l.hi, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.hi_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&l.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -45,9 +49,10 @@ SideLane *side_lane() {
 
 // Small runtime switches for kernel variants (default 0).  First read falls back to the environment variable SPV_<NAME>
 // (upper case) so a run can be switched without code changes.
-//   bwd_variant reserved for A/B runs of backward blend kernel variants (none selectable at the moment)
+//   bwd_variant   reserved for A/B runs of backward blend kernel variants (none selectable at the moment)
+//   flat_chain    1: the frame path's geometry + binning chain runs on the caller's stream instead of the high-priority lane
 struct Option { const char *name; const char *env; std::atomic<int> value; };
-static Option g_options[] = {{"bwd_variant", "SPV_BWD_VARIANT", {-1}}};
+static Option g_options[] = {{"bwd_variant", "SPV_BWD_VARIANT", {-1}}, {"flat_chain", "SPV_FLAT_CHAIN", {-1}}};
 int get_option(const char *name) {
     for (Option &o : g_options) {
         if (strcmp(name, o.name) != 0) continue;

@@ -459,28 +459,60 @@ int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *depth, con
                   const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
                   void *workspace, size_t ws_bytes, void *stream) {
     return spv::bin_tiles_ordered(P, I_cap, uv, depth, radius, conic, opacity, cull, W, H, idx_sorted, tile_range, status, nullptr,
-                                  workspace, ws_bytes, stream);
+                                  /*cleared=*/false, workspace, ws_bytes, stream);
 }
 
 }  // extern "C"
 
-/* spv_bin_tiles + tile_order (int[T], or NULL): the tiles listed longest list first -- the blend kernels' launch order. */
+namespace {
+struct TileBinWs { unsigned long long *keys, *masks; int *tile_count, *big_queue; };
+TileBinWs carve_tile_bin(void *workspace, int P, int64_t I_cap, int T) {
+    char *w = (char *)workspace;
+    TileBinWs b;
+    b.keys = (unsigned long long *)w; w += align_up(8 * (size_t)I_cap);
+    b.masks = (unsigned long long *)w; w += align_up(8 * (size_t)(P > 0 ? P : 1));
+    b.tile_count = (int *)w; w += align_up(4 * (size_t)T);
+    b.big_queue = (int *)w;
+    return b;
+}
+// tile_range[2T] = 0, status[2] = 0, tile_count[T] = 0, queue count / head = 0: ONE launch instead of three memset nodes (in a
+// captured graph every memset node costs ~5 us of dependency latency in front of the count pass)
+__global__ void __launch_bounds__(kThreads)
+bin_clear_kernel(int T, int *__restrict__ tile_range, int *__restrict__ status, int *__restrict__ tile_count, int *__restrict__ queue) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < 2 * T) tile_range[i] = 0;
+    if (i < T) tile_count[i] = 0;
+    if (i < 2) { status[i] = 0; queue[i] = 0; }
+}
+}  // namespace
+
+int spv::bin_tiles_clear(int P, int64_t I_cap, int W, int H, int *tile_range, int *status, void *workspace, void *stream) {
+    const int T = spv::tiles_x(W) * spv::tiles_y(H);
+    if (T <= 0) return 0;
+    if (I_cap <= 0) I_cap = 1;
+    TileBinWs b = carve_tile_bin(workspace, P, I_cap, T);
+    bin_clear_kernel<<<spv::cdiv(2 * (long long)T, kThreads), kThreads, 0, (cudaStream_t)stream>>>(T, tile_range, status, b.tile_count, b.big_queue);
+    return spv::check_launch("spv_bin_tiles/clear");
+}
+
+/* spv_bin_tiles + tile_order (int[T], or NULL): the tiles listed longest list first -- the blend kernels' launch order.
+ * cleared: the caller already ran bin_tiles_clear on this workspace / tile_range / status (the frame path does, ahead of its chain). */
 int spv::bin_tiles_ordered(int P, int64_t I_cap, const float *uv, const float *depth, const int *radius, const float *conic,
                            const float *opacity, int cull, int W, int H, int *idx_sorted, int *tile_range, int *status,
-                           int *tile_order, void *workspace, size_t ws_bytes, void *stream) {
+                           int *tile_order, bool cleared, void *workspace, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int gx = spv::tiles_x(W), gy = spv::tiles_y(H), T = gx * gy;
-    SPV_CUDA_TRY(cudaMemsetAsync(tile_range, 0, sizeof(int) * 2 * (size_t)T, s), "spv_bin_tiles");
-    SPV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * 2, s), "spv_bin_tiles");
-    if (P <= 0 || I_cap <= 0 || T <= 0) return 0;
+    if (P <= 0 || I_cap <= 0 || T <= 0) {   // nothing to bin: empty ranges, no workspace needed
+        if (!cleared && T > 0) SPV_CUDA_TRY(cudaMemsetAsync(tile_range, 0, sizeof(int) * 2 * (size_t)T, s), "spv_bin_tiles");
+        if (!cleared) SPV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * 2, s), "spv_bin_tiles");
+        return 0;
+    }
     if (I_cap >= (1ll << 31)) { spv::set_error(cudaErrorInvalidValue, "spv_bin_tiles: capacity too large"); return (int)cudaErrorInvalidValue; }
     if (ws_bytes < spv_bin_tiles_workspace_bytes(P, I_cap, W, H)) { spv::set_error(cudaErrorInvalidValue, "spv_bin_tiles: workspace too small"); return (int)cudaErrorInvalidValue; }
-    char *w = (char *)workspace;
-    unsigned long long *keys = (unsigned long long *)w; w += align_up(8 * (size_t)I_cap);
-    unsigned long long *masks = (unsigned long long *)w; w += align_up(8 * (size_t)P);
-    int *tile_count = (int *)w; w += align_up(4 * (size_t)T);
-    int *big_queue = (int *)w;
-    SPV_CUDA_TRY(cudaMemsetAsync(tile_count, 0, align_up(4 * (size_t)T) + 8, s), "spv_bin_tiles");   // counts + queue count/head
+    if (!cleared) { const int rc0 = spv::bin_tiles_clear(P, I_cap, W, H, tile_range, status, workspace, stream); if (rc0) return rc0; }
+    TileBinWs b = carve_tile_bin(workspace, P, I_cap, T);
+    unsigned long long *keys = b.keys, *masks = b.masks;
+    int *tile_count = b.tile_count, *big_queue = b.big_queue;
     const unsigned g = spv::cdiv((long long)P * kLanesPerSplat, kThreads);
     cull_count_emit_kernel<2><<<g, kThreads, 0, s>>>(P, (const float2 *)uv, depth, radius, conic, opacity, cull, W, H, gx, gy,
                                                     nullptr, masks, nullptr, (long long)I_cap, nullptr, nullptr, nullptr, tile_count,

@@ -153,6 +153,9 @@ class _FrameOrtho(torch.autograd.Function):
         ctx.attr_needs = [bool(attr_groups[i].requires_grad) for i in order]
         ctx.save_for_backward(sc, rot, op, sh, ex, ws)
         ctx.mark_non_differentiable(gs_idx, radii, status)
+        # outputs without an upstream gradient arrive as None in backward (handled there) instead of as zero-filled tensors:
+        # autograd would otherwise materialise one for EVERY output, the [H,W,K] id image included (33 MB of fill per step)
+        ctx.set_materialize_grads(False)
         # the per-image views are created inside forward: autograd hands their gradients to backward one by one, so no
         # zero-filled [C,H,W] gradient image is ever assembled
         views, c = [None] * len(order), 4
@@ -197,7 +200,11 @@ class _FrameOrtho(torch.autograd.Function):
             g_sh, r_sh = None, None
         else:
             g_sh, r_sh = out("shs", P, 16, 3)
-        g_attr = [torch.empty(P, n, dtype=torch.float32, device=dev) if need else None for n, need in zip(chans, ctx.attr_needs)]
+        # attribute groups: sink key ("attr", i) = the i-th group the caller passed
+        g_attr, r_attr = [], []
+        for slot, n, need in zip(ctx.order, chans, ctx.attr_needs):
+            t, r = out(("attr", slot), P, n) if need else (None, None)
+            g_attr.append(t); r_attr.append(r)
         g_ndc = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_ndc else None
         g_abs = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_abs else None
         ch_arr = (ctypes.c_int * max(ng, 1))(*chans)
@@ -207,7 +214,7 @@ class _FrameOrtho(torch.autograd.Function):
                L.ptr(g_ndc), L.ptr(g_abs), L.ptr(defer[0]) if defer is not None else None,
                L.ptr(defer[1]) if defer is not None else None, int(first), L.ptr(ws), ws.numel(), L.stream())
         g_user = [None] * ng
-        for slot, t in zip(ctx.order, g_attr):
+        for slot, t in zip(ctx.order, r_attr):
             g_user[slot] = t
         return (g_pos, r_sc, r_rot, r_op, r_sh, None, None, None, None, None, None, None, None, None, g_ndc, g_abs, None, *g_user)
 
@@ -223,7 +230,8 @@ def render_ortho_frame(position: Tensor, scaling: Tensor, rotation: Tensor, opac
     Returns (images, gs_idx[H,W,K], radii[P], status[2] = (intersections, overflow) on device) where `images` is the
     [4+A,H,W] stack rgb|depth|attrs when `attrs` is a tensor / None, or a list [rgb, depth, attr_0, ...] when it is a list.
 
-    grad_sinks (optional): {"scaling"|"rotation"|"opacity"|"shs": tensor}.  The backward pass WRITES (not accumulates)
+    grad_sinks (optional): {"scaling"|"rotation"|"opacity"|"shs"|("attr", i): tensor}, ("attr", i) = the i-th attribute tensor
+    of `attrs`.  The backward pass WRITES (not accumulates)
     that input's gradient straight into the given buffer -- e.g. the parameter's slice of a flat gradient buffer -- and
     returns no gradient to autograd for it: no zero-fill, no accumulation pass (one backward per step)."""
     as_list = isinstance(attrs, (list, tuple))

@@ -221,10 +221,14 @@ class DPTROrthoEnhancedRender(_BaseRender):
         use_abs = bool(self.cfg["densify_abs_grad_enable"])
         abs_ndc = self._ndc_zero.detach().requires_grad_(True) if use_abs else None
         bg_color = kwargs.get("bg_color", self.bg_color)
+        # gradient sinks are named like the render_dict entries; the op addresses attribute tensors by their position
+        sinks = kwargs.get("grad_sinks")
+        if sinks:
+            sinks = {(("attr", attr_names.index(k)) if k in attr_names else k): v for k, v in sinks.items()}
         while True:
             imgs, gs_idx, radii, status = _frame.render_ortho_frame(
                 position, scaling, rotation, opacity, shs, groups, extr, width, height, kwargs.get("num_idx", 10), bg_color,
-                cap.I_cap, self.cull, 0.01, 1.3, ndc, abs_ndc, grad_sinks=kwargs.get("grad_sinks"))
+                cap.I_cap, self.cull, 0.01, 1.3, ndc, abs_ndc, grad_sinks=sinks)
             self.last_status = status
             if not self.observe_capacity:
                 break

@@ -201,6 +201,37 @@ def test_grad_sinks_write_in_place(cuda):
     Hh.assert_grad_close(n(b), n(a), "sinks vs autograd accumulation", norm_tol=2e-5)
 
 
+def test_attribute_gradient_sinks_by_name(cuda):
+    """grad_sinks keyed by render_dict names: attribute tensors' gradients are written into the caller's buffers (stale content
+    overwritten), the autograd leaves get none, values equal the autograd path."""
+    from splatter_a_video_b200.renderer import parse_renderer
+    P, W, H = 8000, 160, 96
+    sc = synth.make_scene(P, 6, W, H, seed=23)
+    g = torch.Generator().manual_seed(4)
+    chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
+    gimgs = {k: torch.randn(c, H, W, generator=g).to(cuda) for k, c in chans.items()}
+    keys = ["rgb", "depth"] + ATTRS
+
+    def run(sinks):
+        rd = _rd(sc, cuda)
+        rnd = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+        b = _batch(sc, cuda)
+        if sinks:
+            b["grad_sinks"] = sinks
+        out = rnd.render_batch(rd, [b])
+        torch.autograd.backward([out[k][0] for k in keys], [gimgs[k] for k in keys])
+        return rd
+
+    want = run(None)
+    sinks = {k: torch.full((P, chans[k]), 7.0, device=cuda) for k in ("mask_attribute", "dino_attribute")}
+    got = run(sinks)
+    for k in sinks:
+        assert got[k].grad is None
+        Hh.assert_grad_close(n(sinks[k]), n(want[k].grad), f"sink {k}", norm_tol=2e-5)
+    for k in ("position", "track_gs", "pos_poly_feat", "scaling"):
+        Hh.assert_grad_close(n(got[k].grad), n(want[k].grad), f"d/d{k}", norm_tol=2e-5)
+
+
 def test_deform_rotation_matches_reference_formula(cuda):
     from splatter_a_video_b200.gs.frame import deform_rotation, rotation_basis
     P = 2000
