@@ -338,7 +338,7 @@ class Workload:
         # captured graph); their buffers are persistent, so nothing is allocated off the main stream
         main = torch.cuda.current_stream()
         if self.loss_streams is None:
-            self.loss_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            self.loss_streams = [torch.cuda.Stream(priority=-1), torch.cuda.Stream()]   # the depth loss is the longest branch
             self.loss_bufs = [{}, {}, {}]
         s_dep, s_trk = self.loss_streams
         s_dep.wait_stream(main); s_trk.wait_stream(main)

@@ -44,6 +44,19 @@ inline void opt_in_dynamic_smem(Kernel kernel, size_t bytes, std::atomic<unsigne
     const unsigned long long bit = dev < 64 ? (1ull << dev) : 0ull;
     if (bit && (done.load(std::memory_order_acquire) & bit)) return;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // ... and the maximal carve-out: an SM keeps its shared-memory / L1 split while CTAs are resident, so kernels meant to run
+    // side by side (the three image losses; a frame's blend next to another frame's) must ask for the same split
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (bit) done.fetch_or(bit, std::memory_order_release);
+}
+// the same carve-out preference for a kernel with static shared memory only
+template <typename Kernel>
+inline void prefer_max_carveout(Kernel kernel, std::atomic<unsigned long long> &done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = dev < 64 ? (1ull << dev) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (bit) done.fetch_or(bit, std::memory_order_release);
 }
 inline int sm_count() {   // of the current device (the runtime caches device attributes: this is a table lookup)

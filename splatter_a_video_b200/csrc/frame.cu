@@ -205,19 +205,20 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     SPV_TRY_RC(spv::blend_records_backward(P, C, W, H, f.feature, f.idx_sorted, f.tile_range, radix ? nullptr : f.tile_order, bg_rgb, 1.0f, 0.0f, f.final_T,
                                            f.ncontrib, dL_dimage_planes, n_grad_channels, /*want_abs=*/dL_dabs_ndc != nullptr, packed,
                                            /*packed_is_zero=*/first_backward != 0, stream));
-    // deferred SH backward (frame-parallel training): the colour gradient and the clamp mask leave through the caller's
-    // buffers, the SH coefficients' gradient is produced after the gradient exchange from the REDUCED colour gradient
+    // Two independent readers of the packed rows: (side stream) the unpack of the opacity / colour / attribute / ndc gradients and,
+    // behind it, colours -> SH coefficients (view direction is a constant: its gradient is discarded); (caller's stream)
+    // uv, depth -> position ; conic -> cov3d -> scaling, rotation.
+    // Deferred SH backward (frame-parallel training): the colour gradient and the clamp mask leave through the caller's
+    // buffers, the SH coefficients' gradient is produced after the gradient exchange from the REDUCED colour gradient.
     const bool defer_sh = dL_drgb_out != nullptr;
     float *g_rgb = defer_sh ? dL_drgb_out : f.g_rgb;
-    unpack_frame_kernel<<<g, kThreads, 0, s>>>(P, A, packed, nullptr, nullptr, dL_dopacity, g_rgb, nullptr, gr,
-                                               (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
-    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));
-    // colours -> SH coefficients (view direction is a constant: its gradient is discarded) on the side stream, next to
-    // uv, depth -> position ; conic -> cov3d -> scaling, rotation on the caller's
     SideLane *lane = side_lane();
     if (!lane) { spv::set_error(cudaGetLastError(), "spv_frame_ortho_backward: side stream"); return (int)cudaErrorUnknown; }
     SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_backward/fork");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_backward/fork");
+    unpack_frame_kernel<<<g, kThreads, 0, lane->stream>>>(P, A, packed, nullptr, nullptr, dL_dopacity, g_rgb, nullptr, gr,
+                                                          (float2 *)dL_dndc, (float2 *)dL_dabs_ndc, 0.5f * (float)W, 0.5f * (float)H);
+    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_backward/unpack"));
     if (defer_sh) {
         if (clamped_out) SPV_CUDA_TRY(cudaMemcpyAsync(clamped_out, f.clamped, (size_t)P * 3, cudaMemcpyDeviceToDevice, lane->stream), "spv_frame_ortho_backward");
     } else {

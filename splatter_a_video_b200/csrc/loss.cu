@@ -339,6 +339,189 @@ depth_grad_kernel(int n, const float *__restrict__ pred, const float *__restrict
     }
 }
 
+// ---- the whole depth loss as ONE kernel ------------------------------------------------------------------------------------
+// The six kernels above are a chain of global reductions (3 select passes -> MAD -> residual sums -> gradient), each a few
+// microseconds of work behind a launch boundary: 66 us on the step's critical path at 854x480.  Here one grid of <= one CTA per
+// SM walks the same phases and meets at a device-side barrier between them (a monotone arrival counter in global memory; all
+// CTAs are co-resident -- the grid never exceeds the SM count and a CTA needs 17 KB of shared memory and 512 threads).  Both
+// maps (3.3 MB) stay in L2 between the phases.  Same arithmetic per element as the kernels above; every CTA derives the select
+// result and the totals from the shared histograms / per-CTA partials itself, in the same fixed order.
+constexpr int kDepthThreads = 512;
+struct DepthCtl { unsigned arrived; unsigned bail; unsigned med_pos; unsigned pad; };   // med_pos = n - (first index with p == median), 0 = none yet
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs of the grid: arrive, then wait until `target` arrivals have been counted since the launch's memset
+__device__ __forceinline__ void grid_barrier(DepthCtl *ctl, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                               // this CTA's histogram atomics / partials before its arrival
+        atomicAdd(&ctl->arrived, 1u);
+        unsigned spins = 0;
+        while (ld_acquire_gpu(&ctl->arrived) < target) {
+            if (++spins > (1u << 24)) { ctl->bail = 1u; break; }   // ~0.1 s of polling: give up (the loss comes out as NaN) instead of hanging
+        }
+    }
+    __syncthreads();
+}
+
+// one select pass over both maps: digit histograms of the elements matching the prefixes found so far, merged into the pass's
+// global histograms; after the barrier EVERY CTA walks the 2 x kDigits bins and fixes (prefix, rank) of both maps.
+// cp / cg: this thread's elements (index start + q * stride), loaded once by the caller -- the passes never touch memory again.
+constexpr int kDepthPerThread = 8;
+template <int SHIFT, int BITS>
+__device__ __forceinline__ void depth_select_pass(int n, int start, int stride, const float (&cp)[kDepthPerThread],
+                                                  const float (&cg)[kDepthPerThread],
+                                                  unsigned *__restrict__ ghist /*[2][kSelBins] of this pass*/, DepthCtl *ctl,
+                                                  unsigned barrier_target, unsigned (&prefix)[2], unsigned (&rank)[2],
+                                                  unsigned (*s_hist)[kSelBins], unsigned *s_scan, unsigned (*s_sel)[2]) {
+    constexpr unsigned kDigits = 1u << BITS;
+    constexpr unsigned hi_mask = SHIFT + BITS < 32 ? (0xffffffffu << (SHIFT + BITS)) : 0u;
+    for (int i = threadIdx.x; i < 2 * kSelBins; i += kDepthThreads) (&s_hist[0][0])[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kDepthPerThread; ++q) {          // every thread runs all rounds (match_all below is warp-wide)
+        const bool live = start + q * stride < n;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            unsigned digit = 0xffffffffu;
+            if (live) {
+                const unsigned k = order_key(m ? cg[q] : cp[q]);
+                if ((k & hi_mask) == prefix[m]) digit = (k >> SHIFT) & (kDigits - 1u);
+            }
+            int same;
+            __match_all_sync(0xffffffffu, digit, &same);     // background pixels share one value: one atomic per warp
+            if (same) { if (digit != 0xffffffffu && (threadIdx.x & 31) == 0) atomicAdd(&s_hist[m][digit], 32u); }
+            else if (digit != 0xffffffffu) atomicAdd(&s_hist[m][digit], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * (int)kSelBins; i += kDepthThreads) {
+        const unsigned c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+    grid_barrier(ctl, barrier_target);
+    constexpr int per = (kDigits + kDepthThreads - 1) / kDepthThreads;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        unsigned loc[per], sum = 0;
+#pragma unroll
+        for (int q = 0; q < per; ++q) {
+            const int bin = threadIdx.x * per + q;
+            loc[q] = bin < (int)kDigits ? __ldcg(&ghist[m * kSelBins + bin]) : 0u;
+            sum += loc[q];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        unsigned run = incl - sum;
+#pragma unroll
+        for (int w = 0; w < kDepthThreads / 32; ++w) if (w < warp) run += s_scan[w];
+#pragma unroll
+        for (int q = 0; q < per; ++q) {
+            if (rank[m] >= run && rank[m] < run + loc[q]) {     // exactly one (thread, q) over the CTA
+                s_sel[m][0] = prefix[m] | ((unsigned)(threadIdx.x * per + q) << SHIFT);
+                s_sel[m][1] = rank[m] - run;
+            }
+            run += loc[q];
+        }
+        __syncthreads();
+        prefix[m] = s_sel[m][0]; rank[m] = s_sel[m][1];
+        __syncthreads();
+    }
+}
+
+// n <= gridDim.x * kDepthThreads * kDepthPerThread (the launcher falls back to the kernel chain above for larger images)
+__global__ void __launch_bounds__(kDepthThreads)
+depth_fused_kernel(int n, const float *__restrict__ pred, const float *__restrict__ gt, float weight, DepthCtl *__restrict__ ctl,
+                   unsigned *__restrict__ hist /*[3][2][kSelBins]*/, double *__restrict__ partA, double *__restrict__ partB,
+                   float *__restrict__ loss, float *__restrict__ dL_dpred) {
+    __shared__ unsigned s_hist[2][kSelBins];
+    __shared__ unsigned s_scan[kDepthThreads / 32];
+    __shared__ unsigned s_sel[2][2];
+    __shared__ double scratch[kDepthThreads / 32], bcast[3];
+    const unsigned G = gridDim.x;
+    const int start = blockIdx.x * kDepthThreads + threadIdx.x, stride = G * kDepthThreads;
+    float cp[kDepthPerThread], cg[kDepthPerThread];
+#pragma unroll
+    for (int q = 0; q < kDepthPerThread; ++q) {      // 2 x 8 independent loads in flight; the maps are not read again
+        const int i = start + q * stride;
+        cp[q] = i < n ? pred[i] : 0.f;
+        cg[q] = i < n ? gt[i] : 0.f;
+    }
+    // torch.median = the element of rank (n-1)/2 (the lower of the two middles)
+    unsigned prefix[2] = {0u, 0u}, rank[2] = {(unsigned)((n - 1) / 2), (unsigned)((n - 1) / 2)};
+    depth_select_pass<21, 11>(n, start, stride, cp, cg, hist, ctl, G, prefix, rank, s_hist, s_scan, s_sel);
+    depth_select_pass<10, 11>(n, start, stride, cp, cg, hist + 2 * kSelBins, ctl, 2 * G, prefix, rank, s_hist, s_scan, s_sel);
+    depth_select_pass<0, 10>(n, start, stride, cp, cg, hist + 4 * kSelBins, ctl, 3 * G, prefix, rank, s_hist, s_scan, s_sel);
+    const float tp = key_value(prefix[0]), tg = key_value(prefix[1]);
+    // A: sum |p - t_p|, sum sign(p - t_p), sum |g - t_g|; the (first) element that equals the median of p
+    {
+        float a = 0.f, sg = 0.f, b = 0.f;
+        int first = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < kDepthPerThread; ++q) {
+            const int i = start + q * stride;
+            if (i < n) {
+                const float p = cp[q], d = p - tp;
+                a += fabsf(d); sg += sgnf(d); b += fabsf(cg[q] - tg);
+                if (p == tp) first = min(first, i);
+            }
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        if ((threadIdx.x & 31) == 0 && first != 0x7fffffff) atomicMax(&ctl->med_pos, (unsigned)(n - first));
+        const double t0 = block_sum<kDepthThreads>((double)a, scratch), t1 = block_sum<kDepthThreads>((double)sg, scratch),
+                     t2 = block_sum<kDepthThreads>((double)b, scratch);
+        if (threadIdx.x == 0) { partA[3 * blockIdx.x] = t0; partA[3 * blockIdx.x + 1] = t1; partA[3 * blockIdx.x + 2] = t2; }
+    }
+    grid_barrier(ctl, 4 * G);
+    double A[3], B[3];
+    total_of_partials<kDepthThreads, 3>(partA, (int)G, A, scratch, bcast);
+    const float sp = (float)(A[0] / n), sgt = (float)(A[2] / n);
+    // B: residuals r = (p - t_p)/s_p - (g - t_g)/s_g: sum r^2, sum r, sum r * (p - t_p)/s_p
+    {
+        float r2 = 0.f, r1 = 0.f, rd = 0.f;
+#pragma unroll
+        for (int q = 0; q < kDepthPerThread; ++q) {
+            if (start + q * stride < n) {
+                const float dn = (cp[q] - tp) / sp, gn = (cg[q] - tg) / sgt, r = dn - gn;
+                r2 += r * r; r1 += r; rd += r * dn;
+            }
+        }
+        const double t0 = block_sum<kDepthThreads>((double)r2, scratch), t1 = block_sum<kDepthThreads>((double)r1, scratch),
+                     t2 = block_sum<kDepthThreads>((double)rd, scratch);
+        if (threadIdx.x == 0) { partB[3 * blockIdx.x] = t0; partB[3 * blockIdx.x + 1] = t1; partB[3 * blockIdx.x + 2] = t2; }
+    }
+    grid_barrier(ctl, 5 * G);
+    total_of_partials<kDepthThreads, 3>(partB, (int)G, B, scratch, bcast);
+    // C: loss and gradient (formula at depth_grad_kernel)
+    const bool bailed = __ldcg(&ctl->bail) != 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) loss[0] = bailed ? __int_as_float(0x7fc00000) : weight * (float)(B[0] / n);
+    if (dL_dpred == nullptr) return;
+    const float invn = 1.f / (float)n;
+    const float Sa = (float)(2.0 * B[1] / n), Sad = (float)(2.0 * B[2] / n), Ssgn = (float)A[1];
+    const unsigned mp = __ldcg(&ctl->med_pos);
+    const int m = mp ? n - (int)mp : 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < kDepthPerThread; ++q) {
+        const int i = start + q * stride;
+        if (i < n) {
+            const float p = cp[q], dn = (p - tp) / sp, gn = (cg[q] - tg) / sgt;
+            const float a = 2.f * (dn - gn) * invn;
+            float g = a / sp - (Sad / sp) * (sgnf(p - tp) * invn);
+            if (i == m) g += -Sa / sp + (Sad / sp) * (Ssgn * invn);
+            dL_dpred[i] = weight * g;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ track: trimmed masked L1
 // per point: mean_c |denormalised rendered track - target| (invisible points: +inf so they sort last); count of visible
 __global__ void __launch_bounds__(kRed)
@@ -516,7 +699,8 @@ track_fused_kernel(int n, int W, int H, const float *__restrict__ track, const i
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 inline unsigned row_blocks(int W) { return spv::cdiv(W, kRow); }
 
-struct DepthWs { unsigned *hist; SelState *state; float *med; double *partA, *partB; int *med_idx; size_t head_bytes, total; };
+struct DepthWs { unsigned *hist; SelState *state; float *med; double *partA, *partB; int *med_idx; size_t head_bytes, total;
+                 DepthCtl *ctl; unsigned *fhist; size_t fused_head_bytes; };
 DepthWs carve_depth(void *base, int n) {
     (void)n;
     DepthWs w{};
@@ -530,6 +714,11 @@ DepthWs carve_depth(void *base, int n) {
     w.med_idx = (int *)take(sizeof(int));
     w.partA = (double *)take(sizeof(double) * 3 * kRedBlocks);
     w.partB = (double *)take(sizeof(double) * 3 * kRedBlocks);
+    // single-kernel path: [barrier / flags | 3 passes x 2 maps of histograms] cleared by ONE memset per call
+    const size_t f0 = off;
+    w.ctl = (DepthCtl *)take(sizeof(DepthCtl));
+    w.fhist = (unsigned *)take(sizeof(unsigned) * 6 * kSelBins);
+    w.fused_head_bytes = off - f0;
     w.total = off;
     return w;
 }
@@ -587,6 +776,19 @@ int spv_loss_depth_dpt(int n, const float *pred, const float *gt, float weight, 
     if (n <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_loss_depth_dpt: empty image"); return (int)cudaErrorInvalidValue; }
     DepthWs w = carve_depth(workspace, n);
     if (ws_bytes < w.total) { spv::set_error(cudaErrorInvalidValue, "spv_loss_depth_dpt: workspace too small"); return (int)cudaErrorInvalidValue; }
+    // one grid of one CTA per SM (co-resident: the phases meet at device-side barriers) holding the image in registers
+    const unsigned sms = (unsigned)spv::sm_count();
+    const unsigned G = spv::cdiv(n, kDepthThreads) < sms ? spv::cdiv(n, kDepthThreads) : sms;
+    if (spv::get_option("depth_staged") == 0 && (long long)n <= (long long)G * kDepthThreads * kDepthPerThread && G <= (unsigned)kRedBlocks) {
+        SPV_CUDA_TRY(cudaMemsetAsync(w.ctl, 0, w.fused_head_bytes, s), "spv_loss_depth_dpt");
+        // An SM keeps its shared-memory carve-out while CTAs are resident: with the default (small) preference this kernel's CTAs,
+        // one on every SM, kept the rgb loss (52 KB of dynamic shared memory per CTA) off the GPU until they were done
+        // (measured: rgb_row_kernel started 48 us late).  Ask for the same maximal carve-out the other loss kernels run with.
+        static std::atomic<unsigned long long> carve{0};
+        spv::prefer_max_carveout(depth_fused_kernel, carve);
+        depth_fused_kernel<<<G, kDepthThreads, 0, s>>>(n, pred, gt, weight, w.ctl, w.fhist, w.partA, w.partB, loss, dL_dpred);
+        return spv::check_launch("spv_loss_depth_dpt", 1);
+    }
     SPV_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.head_bytes, s), "spv_loss_depth_dpt");      // histograms, select state, tickets
     SPV_CUDA_TRY(cudaMemsetAsync(w.med_idx, 0x7f, sizeof(int), s), "spv_loss_depth_dpt");
     const unsigned sel_blocks = spv::cdiv(n, kRed * 4);       // measured: 296 x 2 CTAs (12 / 12 / 8 us per pass at 854x480) beat 74 x 2 (24 / 18 / 10)

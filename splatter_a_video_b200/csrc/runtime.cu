@@ -51,8 +51,10 @@ SideLane *side_lane() {
 // (upper case) so a run can be switched without code changes.
 //   bwd_variant   reserved for A/B runs of backward blend kernel variants (none selectable at the moment)
 //   flat_chain    1: the frame path's geometry + binning chain runs on the caller's stream instead of the high-priority lane
+//   depth_staged  1: spv_loss_depth_dpt as six kernels (select passes, statistics, residuals, gradient) instead of the fused one
 struct Option { const char *name; const char *env; std::atomic<int> value; };
-static Option g_options[] = {{"bwd_variant", "SPV_BWD_VARIANT", {-1}}, {"flat_chain", "SPV_FLAT_CHAIN", {-1}}};
+static Option g_options[] = {{"bwd_variant", "SPV_BWD_VARIANT", {-1}}, {"flat_chain", "SPV_FLAT_CHAIN", {-1}},
+                             {"depth_staged", "SPV_DEPTH_STAGED", {-1}}};
 int get_option(const char *name) {
     for (Option &o : g_options) {
         if (strcmp(name, o.name) != 0) continue;

@@ -282,6 +282,67 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long *keys, int n
     }
 }
 
+// Register-blocked bitonic network for one tile segment: E consecutive keys per thread (256 E >= n, padded with all-ones keys).
+// Compare-exchange distances below E stay inside a thread, distances below 32 E are lane shuffles, only the rest (6 of the 36 / 45 /
+// 55 stages for E = 1 / 2 / 4) go through shared memory with a CTA barrier -- the all-shared-memory network above pays a barrier
+// per stage (measured 34 us for the 1620 tiles of a 854x480 frame, average list 286 keys).  Keys are unique (Gaussian id in the
+// low word), so the result is the same permutation whatever the network.
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int mask) {
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, mask), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), mask);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int E>
+__device__ __forceinline__ void tile_sort_regs(const int2 r, const unsigned long long *__restrict__ keys, int *__restrict__ idx_sorted,
+                                               unsigned long long *s_keys) {
+    constexpr int N = kThreads * E;
+    const int n = r.y - r.x, t = threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = E * t + e < n ? keys[r.x + E * t + e] : ~0ull;
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            if (j < E) {                              // both keys in this thread (jj: compile-time copy of j, registers stay registers)
+#pragma unroll
+                for (int jj = E >> 1; jj >= 1; jj >>= 1) {
+                    if (j != jj) continue;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if ((e & jj) == 0) {
+                            const bool asc = ((E * t + e) & k) == 0;
+                            const unsigned long long a = v[e], b = v[e | jj];
+                            if ((a > b) == asc) { v[e] = b; v[e | jj] = a; }
+                        }
+                    }
+                }
+            } else if (j < 32 * E) {                  // partner in this warp
+                const bool lower = (t & (j / E)) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned long long o = shfl_xor_u64(v[e], j / E);
+                    const bool keep_min = lower == (((E * t + e) & k) == 0);
+                    v[e] = (keep_min == (v[e] < o)) ? v[e] : o;
+                }
+            } else {                                  // partner in another warp
+#pragma unroll
+                for (int e = 0; e < E; ++e) s_keys[E * t + e] = v[e];
+                __syncthreads();
+                const bool lower = (t & (j / E)) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned long long o = s_keys[(E * t + e) ^ j];
+                    const bool keep_min = lower == (((E * t + e) & k) == 0);
+                    v[e] = (keep_min == (v[e] < o)) ? v[e] : o;
+                }
+                __syncthreads();
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (E * t + e < n) idx_sorted[r.x + E * t + e] = (int)(unsigned)(v[e] & 0xffffffffull);
+}
+
 __global__ void __launch_bounds__(kThreads)
 tile_sort_small_kernel(const int2 *__restrict__ tile_range, const unsigned long long *__restrict__ keys,
                        int *__restrict__ idx_sorted) {
@@ -289,10 +350,9 @@ tile_sort_small_kernel(const int2 *__restrict__ tile_range, const unsigned long 
     const int2 r = tile_range[blockIdx.x];
     const int n = r.y - r.x;
     if (n <= 0 || n > kSortSmall) return;   // larger segments: tile_sort_big_kernel
-    for (int i = threadIdx.x; i < n; i += kThreads) s_keys[i] = keys[r.x + i];
-    __syncthreads();
-    bitonic_sort_u64<kThreads>(s_keys, n);
-    for (int i = threadIdx.x; i < n; i += kThreads) idx_sorted[r.x + i] = (int)(unsigned)(s_keys[i] & 0xffffffffull);
+    if (n <= kThreads) tile_sort_regs<1>(r, keys, idx_sorted, s_keys);
+    else if (n <= 2 * kThreads) tile_sort_regs<2>(r, keys, idx_sorted, s_keys);
+    else tile_sort_regs<4>(r, keys, idx_sorted, s_keys);
 }
 
 // Persistent CTAs over the queue of segments with more than kSortSmall keys (a few dozen heavy tiles on the DAVIS-shaped

@@ -102,8 +102,19 @@ def test_depth_loss_matches_reference_golden(cuda, tag):
     _close_grad(g, G[f"depth_{tag}_grad"], "dL/ddepth")
 
 
-@pytest.mark.parametrize("H,W,bg_frac", [(1, 2, 0.0), (1, 3, 0.0), (17, 23, 0.0), (64, 64, 0.6), (480, 854, 0.0), (480, 854, 0.55)])
-def test_depth_loss_matches_oracle(cuda, H, W, bg_frac):
+@pytest.fixture(params=["fused", "staged"])
+def depth_path(request):
+    """spv_loss_depth_dpt as one kernel with device-side barriers (images up to ~600 k pixels) or as the chain of six kernels
+    larger images fall back to; both must match the oracle."""
+    from splatter_a_video_b200 import _lib as L
+    L.set_option("depth_staged", 1 if request.param == "staged" else 0)
+    yield request.param
+    L.set_option("depth_staged", 0)
+
+
+@pytest.mark.parametrize("H,W,bg_frac", [(1, 2, 0.0), (1, 3, 0.0), (17, 23, 0.0), (64, 64, 0.6), (480, 854, 0.0), (480, 854, 0.55),
+                                         (1080, 1920, 0.3)])
+def test_depth_loss_matches_oracle(cuda, depth_path, H, W, bg_frac):
     """bg_frac > 0.5 puts the median inside the tie group of background pixels (rendered depth == bg == 1.0 exactly)."""
     rng = np.random.default_rng(H + W)
     pred = (0.5 + 1.5 * rng.random((H, W, 1))).astype(np.float32)
