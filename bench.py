@@ -169,8 +169,18 @@ class Workload:
         if self.node_im:
             from splatter_a_video_b200.gs.frame import spline_to_interval_major
             node = spline_to_interval_major(node, self.NI)
+        # frame mode: only the SH bases the renderer's constant view direction (0,0,1) reaches -- 0, 2, 6, 12 -- are trainable
+        # parameters ([P,4,3]); the other twelve receive gradient 0 on every step under this renderer, which torch.optim.Adam
+        # answers by never moving them (exp_avg = exp_avg_sq = 0), so they stay outside the optimizer's flat buffer (carried
+        # through densification as an extra per-Gaussian tensor; gs.frame.sh_z_merge rebuilds [P,16,3] for checkpoints)
+        self.sh_z = mode == "frame" and not os.environ.get("SPV_FULL_SH")
+        shs = dev(sc.shs)
+        self.shs_rest = None
+        if self.sh_z:
+            from splatter_a_video_b200.gs.frame import sh_z_split
+            shs, self.shs_rest = sh_z_split(shs)
         self.flat = FlatParams({"pos_cubic_node": dev(node), "scaling": dev(sc.scaling), "rotation": dev(sc.rotation),
-                                "opacity": dev(sc.opacity), "shs": dev(sc.shs),
+                                "opacity": dev(sc.opacity), "shs": shs,
                                 "mask_attribute": dev(sc.attrs["mask_attribute"]), "dino_attribute": dev(sc.attrs["dino_attribute"])})
         self.base = dev(sc.position)
         self.pos_poly_feat = dev(sc.attrs["pos_poly_feat"])
@@ -320,8 +330,11 @@ class Workload:
         lazy = ({"name": "pos_cubic_node", "P": self.P, "NI": self.NI, "interval_major": self.node_im, "dirty": self.node_dirty}
                 if self.mode == "frame" else None)
         self.opt = FlatAdam(self.flat, self.lrs, device_clock=True, lazy=lazy)
+        extras = {"base": self.base}
+        if self.shs_rest is not None:
+            extras["shs_rest"] = self.shs_rest
         self.dens = FlatDensifier(self.flat, self.P, {"position": "base", "scaling": "scaling", "rotation": "rotation", "opacity": "opacity"},
-                                  extras={"base": self.base}, scaling_is_log=False, opacity_is_logit=False)
+                                  extras=extras, scaling_is_log=False, opacity_is_logit=False)
 
     def _fwd_loss_bwd(self):
         """render -> the trainer's three image losses -> backward.  Losses hand dL/dimage straight to the rasterizer's backward
@@ -372,12 +385,23 @@ class Workload:
         self.dens.update_stats(out["ndc"].grad, out["radii"], out["visibility"])
         self.opt.step()
 
+    def _step_graphs(self, exchange):
+        """One rank: the whole step is ONE captured graph.  Frame-parallel: the gradient exchange (symmetric-memory barriers,
+        not capturable) sits between the two halves."""
+        if exchange is None or not getattr(exchange, "is_collective", True):
+            self._run("full+post", self._whole_step)
+            return
+        self._run("full", self._fwd_loss_bwd)
+        exchange.run()
+        self._run("post", self._post_exchange)
+
+    def _whole_step(self):
+        self._fwd_loss_bwd()
+        self._post_exchange()
+
     def step_full(self, frame, exchange=None):
         self.set_frame(frame)
-        self._run("full", self._fwd_loss_bwd)
-        if exchange is not None:
-            exchange.run()
-        self._run("post", self._post_exchange)
+        self._step_graphs(exchange)
 
     def _prefetch_full(self, buf):
         cs = self.copy_stream
@@ -404,10 +428,7 @@ class Workload:
         self._prefetch_full(cur ^ 1)                            # overlaps this step's kernels
         main.wait_event(self.pf_event[cur])
         self.batch_dev_packed.copy_(self.batch_stage[cur], non_blocking=True)
-        self._run("full", self._fwd_loss_bwd)
-        if exchange is not None:
-            exchange.run()
-        self._run("post", self._post_exchange)
+        self._step_graphs(exchange)
         self.loss_host.copy_(self.loss_vec[0:1], non_blocking=True)
         main.wait_event(self.pf_event[cur ^ 1])                 # the bracket ends only after the prefetch it started
         self.pf_buf = cur ^ 1
@@ -473,7 +494,7 @@ class Workload:
         if name not in self.graphs:
             self.renderer.observe_capacity = True
             fn(); torch.cuda.synchronize()                      # settles the intersection capacity (the only sync, once)
-            if name in ("train", "full") and not getattr(self, "_headroom", False):
+            if name in ("train", "full", "full+post") and not getattr(self, "_headroom", False):
                 self.renderer.capacity.I_cap = int(self.renderer.capacity.I_cap * 1.2)   # head-room across frames
                 self._headroom = True
             self.renderer.observe_capacity = False
@@ -673,6 +694,9 @@ def stage_breakdown(wl: Workload, frame):
         return out
 
     dirs = torch.zeros_like(rd["position"]); dirs[:, 2] = 1
+    if wl.sh_z:       # the staged ops take the reference's full [P,16,3] tensor
+        from splatter_a_video_b200.gs.frame import sh_z_merge
+        rd["shs"] = sh_z_merge(rd["shs"], wl.shs_rest)
     rgb = timed("compute_sh", lambda: gs.compute_sh(rd["shs"], 3, dirs))
     uv, depth = timed("project_point_ortho", lambda: gs.project_point_ortho(rd["position"], wl.extr, W, H, 0.01))
     vis = depth != 0
@@ -800,7 +824,7 @@ def make_exchange(wl, world, exchange_coefficients=False):
         wl.defer_linear_tails(exchange)
         kind = "deferred SH/spline backward: ONE exchange of 21 floats/Gaussian/rank (12 dense + 3 colour + 6 position gradients), summed in rank order"
     else:
-        exchange = GradExchange(wl.flat, wl.P, subset={"shs": ((wl.P, 16, 3), 1, [0, 2, 6, 12])},
+        exchange = GradExchange(wl.flat, wl.P, subset=None if wl.sh_z else {"shs": ((wl.P, 16, 3), 1, [0, 2, 6, 12])},
                                 sparse={"pos_cubic_node": (((wl.P, wl.NI, 4, 3), 1, [wl.idx1, wl.idx2]) if wl.node_im else
                                                            ((wl.P, 4, wl.NI, 3), 2, [wl.idx1, wl.idx2]))}, dirty=wl.node_dirty)
         kind = "coefficient gradients: all-reduce of 24 floats/Gaussian + all-gather of 24 floats/Gaussian/rank"

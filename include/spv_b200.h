@@ -100,6 +100,11 @@ SPV_API int spv_compute_sh_forward(int P, const float *shs, int deg, const float
 SPV_API int spv_compute_sh_backward(int P, const float *shs, int deg, const float *dirs, const uint8_t *visible,
                             const uint8_t *clamped /*NULL if free*/, const float *dL_dcolors, int S_alloc,
                             float *dL_dshs, float *dL_ddirs, void *stream);
+/* SH colour along the constant direction (0,0,1) from the coefficients of the bases 0, 2, 6, 12 alone (shs_z = [P,4,3]): what
+ * DPTROrthoEnhancedRender evaluates (dptr_ortho_enhanced.py:270-271), bit-identical to spv_compute_sh_forward / _backward with
+ * deg = 3 and dirs = (0,0,1) on the full tensor, at 48 instead of 192 bytes per Gaussian. */
+SPV_API int spv_compute_sh_z_forward(int P, const float *shs_z, float *colors, uint8_t *clamped /*[P,3] or NULL*/, void *stream);
+SPV_API int spv_compute_sh_z_backward(int P, const uint8_t *clamped /*or NULL*/, const float *dL_dcolors, float *dL_dshs_z, void *stream);
 
 /* ---- K11-K14: sort_gaussian (ext.cpp:21-22; gs/sort_gaussian.py:41-54; src/sort_gaussian.cu) ------ */
 /* Step 1: inclusive scan of tiles-touched (torch.cumsum in the reference).  offsets[P-1] = I.        */
@@ -168,8 +173,10 @@ SPV_API int spv_bin_tiles(int P, int64_t I_cap, const float *uv, const float *de
 SPV_API size_t spv_frame_workspace_bytes(int P, int64_t I_cap, int W, int H, int A);
 SPV_API int spv_frame_ortho_forward(int P, int W, int H, int n_groups /*<= 8*/, const float *const *attr_ptrs /*host array of device ptrs*/,
                             const int *attr_channels /*host*/, int K, int64_t I_cap, int cull, const float *position,
-                            const float *scaling, const float *rotation, const float *opacity, const float *shs /*[P,16,3]*/,
-                            const float *extr, float nearest, float extent, float bg_rgb, float *images /*[4+A,H,W]*/,
+                            const float *scaling, const float *rotation, const float *opacity,
+                            const float *shs /*[P,16,3], or [P,4,3] = the bases 0, 2, 6, 12 alone (sh_bases = 4): the renderer's
+                                               constant view direction (0,0,1) reaches no other basis*/,
+                            int sh_bases /*16 or 4*/, const float *extr, float nearest, float extent, float bg_rgb, float *images /*[4+A,H,W]*/,
                             int *gs_idx /*[H,W,K]*/, int *radii /*[P]*/, int *status /*[2]*/, void *workspace,
                             size_t ws_bytes, void *stream);
 /* dL_dimage_planes: host array of 4+A device pointers, one [H,W] gradient plane per image channel (NULL = no gradient);
@@ -179,8 +186,9 @@ SPV_API int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const in
                                                     gradient is wanted; gradient-free groups must come last */,
                              int64_t I_cap,
                              const float *scaling, const float *rotation, const float *opacity, const float *shs,
+                             int sh_bases /*as in the forward call*/,
                              const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
-                             float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs /*[P,16,3]*/,
+                             float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs /*[P,sh_bases,3]*/,
                              float *const *dL_dattr_ptrs, float *dL_dndc /*[P,2] or NULL*/, float *dL_dabs_ndc /*[P,2] or NULL*/,
                              float *dL_drgb_out /*[P,3] or NULL.  Non-NULL defers the SH backward (frame-parallel training):
                                                   the gradient of the SH-evaluated colours is written here, dL_dshs is not

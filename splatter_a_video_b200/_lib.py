@@ -35,6 +35,8 @@ _SIGS = {
     "spv_ewa_project_ortho_backward": (c_int, [c_int, P_, P_, c_int, c_int, P_, P_, P_, P_]),
     "spv_compute_sh_forward": (c_int, [c_int, P_, c_int, P_, P_, c_int, P_, P_, P_]),
     "spv_compute_sh_backward": (c_int, [c_int, P_, c_int, P_, P_, P_, P_, c_int, P_, P_, P_]),
+    "spv_compute_sh_z_forward": (c_int, [c_int, P_, P_, P_, P_]),
+    "spv_compute_sh_z_backward": (c_int, [c_int, P_, P_, P_, P_]),
     "spv_sort_scan_workspace_bytes": (c_size_t, [c_int]),
     "spv_sort_scan": (c_int, [c_int, P_, P_, P_, c_size_t, P_]),
     "spv_sort_workspace_bytes": (c_size_t, [c_int, c_int64]),
@@ -54,9 +56,9 @@ _SIGS = {
     "spv_bin_tiles_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
     "spv_bin_tiles": (c_int, [c_int, c_int64, P_, P_, P_, P_, P_, c_int, c_int, c_int, P_, P_, P_, P_, c_size_t, P_]),
     "spv_frame_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
-    "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, c_int, c_int64, c_int, P_, P_, P_, P_, P_, P_, c_float,
+    "spv_frame_ortho_forward": (c_int, [c_int, c_int, c_int, c_int, P_, P_, c_int, c_int64, c_int, P_, P_, P_, P_, P_, c_int, P_, c_float,
                                         c_float, c_float, P_, P_, P_, P_, P_, c_size_t, P_]),
-    "spv_frame_ortho_backward": (c_int, [c_int, c_int, c_int, c_int, P_, c_int, c_int64, P_, P_, P_, P_, P_, c_float, P_, P_, P_, P_,
+    "spv_frame_ortho_backward": (c_int, [c_int, c_int, c_int, c_int, P_, c_int, c_int64, P_, P_, P_, P_, c_int, P_, c_float, P_, P_, P_, P_,
                                          P_, P_, P_, P_, P_, P_, P_, c_int, P_, c_size_t, P_]),
     "spv_alpha_blend_groups_backward_packed": (c_int, [c_int, c_int, c_int, c_int, P_, P_, P_, P_, P_, P_, c_float, c_float, c_float,
                                                        P_, P_, P_, c_int, P_, P_]),

@@ -130,7 +130,7 @@ size_t spv_frame_workspace_bytes(int P, int64_t I_cap, int W, int H, int A) {
 
 int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *const *attr_ptrs, const int *attr_channels,
                             int K, int64_t I_cap, int cull, const float *position, const float *scaling,
-                            const float *rotation, const float *opacity, const float *shs, const float *extr,
+                            const float *rotation, const float *opacity, const float *shs, int sh_bases, const float *extr,
                             float nearest, float extent, float bg_rgb, float *images, int *gs_idx, int *radii,
                             int *status, void *workspace, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -139,6 +139,7 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     AttrGroups gr;
     const int A = make_groups(gr, n_groups, attr_ptrs, nullptr, attr_channels);
     if (4 + A > 23 || K <= 0) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: need at most 19 attribute channels and K > 0"); return (int)cudaErrorInvalidValue; }
+    if (sh_bases != 16 && sh_bases != 4) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: shs is [P,16,3] (degree 3) or [P,4,3] (bases 0, 2, 6, 12)"); return (int)cudaErrorInvalidValue; }
     FrameWs f = carve(workspace, P, I_cap, W, H, A);
     if (ws_bytes < f.total) { spv::set_error(cudaErrorInvalidValue, "spv_frame_ortho_forward: workspace too small"); return (int)cudaErrorInvalidValue; }
     const unsigned g = spv::cdiv(P, kThreads);
@@ -155,9 +156,13 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
     SPV_CUDA_TRY(cudaEventRecord(lane->fork, s), "spv_frame_ortho_forward/fork");
     SPV_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0), "spv_frame_ortho_forward/fork");
     if (!flat) SPV_CUDA_TRY(cudaStreamWaitEvent(hs, lane->fork, 0), "spv_frame_ortho_forward/fork");
-    frame_prep_kernel<<<g, kThreads, 0, lane->stream>>>(P, f.dirs);      // only the SH kernels read it: off the main branch
-    SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep"));
-    SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
+    if (sh_bases == 4) {     // only the coefficients the constant view direction reaches: 48 B per Gaussian, no direction array
+        SPV_TRY_RC(spv_compute_sh_z_forward(P, shs, f.rgb, f.clamped, (void *)lane->stream));
+    } else {
+        frame_prep_kernel<<<g, kThreads, 0, lane->stream>>>(P, f.dirs);      // only the SH kernels read it: off the main branch
+        SPV_TRY_RC(spv::check_launch("spv_frame_ortho_forward/prep"));
+        SPV_TRY_RC(spv_compute_sh_forward(P, shs, 3, f.dirs, nullptr, 0, f.rgb, f.clamped, (void *)lane->stream));
+    }
     // ---- main branch: projection, visibility, covariance, conic / radius / tile rectangle in ONE pass (geometry.cu: the staged
     //      kernels' bodies back to back, bit-identical results), then culled binning + tile sort
     static const bool radix = [] { const char *e = getenv("SPV_BIN_RADIX"); return e && e[0] == '1'; }();
@@ -187,7 +192,7 @@ int spv_frame_ortho_forward(int P, int W, int H, int n_groups, const float *cons
 }
 
 int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_channels, int n_grad_channels, int64_t I_cap,
-                             const float *scaling, const float *rotation, const float *opacity, const float *shs,
+                             const float *scaling, const float *rotation, const float *opacity, const float *shs, int sh_bases,
                              const float *extr, float bg_rgb, const float *const *dL_dimage_planes, float *dL_dposition,
                              float *dL_dscaling, float *dL_drotation, float *dL_dopacity, float *dL_dshs,
                              float *const *dL_dattr_ptrs, float *dL_dndc, float *dL_dabs_ndc, float *dL_drgb_out,
@@ -222,7 +227,8 @@ int spv_frame_ortho_backward(int P, int W, int H, int n_groups, const int *attr_
     if (defer_sh) {
         if (clamped_out) SPV_CUDA_TRY(cudaMemcpyAsync(clamped_out, f.clamped, (size_t)P * 3, cudaMemcpyDeviceToDevice, lane->stream), "spv_frame_ortho_backward");
     } else {
-        SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, nullptr, f.clamped, f.g_rgb, 16, dL_dshs, /*dL_ddirs=*/nullptr, (void *)lane->stream));   // constant view direction: its gradient is discarded
+        if (sh_bases == 4) SPV_TRY_RC(spv_compute_sh_z_backward(P, f.clamped, f.g_rgb, dL_dshs, (void *)lane->stream));
+        else SPV_TRY_RC(spv_compute_sh_backward(P, shs, 3, f.dirs, nullptr, f.clamped, f.g_rgb, 16, dL_dshs, /*dL_ddirs=*/nullptr, (void *)lane->stream));   // constant view direction: its gradient is discarded
     }
     SPV_CUDA_TRY(cudaEventRecord(lane->join, lane->stream), "spv_frame_ortho_backward/join");
     SPV_TRY_RC(spv::frame_geometry_backward(P, packed, scaling, rotation, extr, W, H, f.depth, f.vis, f.cov3d, f.radius, dL_dposition,

@@ -778,6 +778,48 @@ sh_bwd_kernel(int P, const float *__restrict__ shs, const float *__restrict__ di
     sh_slab_store<ROW, kShBwdThreads>(dL_dshs + (size_t)base * ROW, s_g, rows);
 }
 
+// ---- SH along the constant view direction (0,0,1) -----------------------------------------------------------------------------
+// The ortho renderers evaluate the colour along direction (0,0,1) for every Gaussian (dptr_ortho_enhanced.py:270-271).  There only
+// the bases 0, 2, 6 and 12 are non-zero; every other basis multiplies its coefficient by 0 on the way in and its gradient by 0 on
+// the way out.  These two kernels take the coefficients of those four bases alone, [P,4,3] in that order: 48 instead of 192 bytes
+// per Gaussian.  Same operations in the same order as sh_fwd_kernel<3> / sh_bwd_kernel<3,false> with x = y = 0, z = 1 (the
+// skipped terms are exact zeros), so colours and gradients are bit-identical to the 16-basis kernels'.
+__global__ void __launch_bounds__(kThreads)
+sh_z_fwd_kernel(int P, const float4 *__restrict__ shs_z, float *__restrict__ colors, uint8_t *__restrict__ clamped) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const float4 a = shs_z[3 * i], b = shs_z[3 * i + 1], c = shs_z[3 * i + 2];
+    const float s[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    const float k2 = SH_C2[2] * 2.0f, k3 = SH_C3[3] * 2.0f;    // C2[2] (2 zz - xx - yy), C3[3] z (2 zz - 3 xx - 3 yy) at z = 1
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float r = SH_C0 * s[ch];
+        r = r + SH_C1 * s[3 + ch];
+        r = r + k2 * s[6 + ch];
+        r = r + k3 * s[9 + ch];
+        r += 0.5f;
+        if (clamped) clamped[3 * i + ch] = (r < 0);
+        colors[3 * i + ch] = r < 0.0f ? 0.0f : r;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+sh_z_bwd_kernel(int P, const uint8_t *__restrict__ clamped, const float *__restrict__ dL_dcolors, float4 *__restrict__ dL_dshs_z) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const float k2 = SH_C2[2] * 2.0f, k3 = SH_C3[3] * 2.0f;
+    float d[12];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float g = dL_dcolors[3 * i + ch];
+        if (clamped) g *= clamped[3 * i + ch] ? 0.0f : 1.0f;
+        d[ch] = SH_C0 * g; d[3 + ch] = SH_C1 * g; d[6 + ch] = k2 * g; d[9 + ch] = k3 * g;
+    }
+    dL_dshs_z[3 * i] = make_float4(d[0], d[1], d[2], d[3]);
+    dL_dshs_z[3 * i + 1] = make_float4(d[4], d[5], d[6], d[7]);
+    dL_dshs_z[3 * i + 2] = make_float4(d[8], d[9], d[10], d[11]);
+}
+
 inline dim3 grid_for(int P) { return dim3(spv::cdiv(P, kThreads)); }
 
 }  // namespace
@@ -903,6 +945,20 @@ int spv_ewa_project_ortho_backward(int P, const float *cov3d, const float *extr,
     ewa_ortho_bwd_kernel<<<grid_for(P), kThreads, 0, (cudaStream_t)stream>>>(
         P, cov3d, extr, (float)((double)W / 2.0), (float)((double)H / 2.0), radius, dL_dconic, dL_dcov3d);
     return spv::check_launch("spv_ewa_project_ortho_backward");
+}
+
+/* SH colour along the constant direction (0,0,1): shs_z = [P,4,3], the coefficients of the bases 0, 2, 6, 12 (the only ones that
+ * direction reaches).  Bit-identical to spv_compute_sh_forward / _backward(deg 3, dirs = (0,0,1)) on the full [P,16,3] tensor. */
+int spv_compute_sh_z_forward(int P, const float *shs_z, float *colors, uint8_t *clamped, void *stream) {
+    if (P <= 0) return 0;
+    sh_z_fwd_kernel<<<grid_for(P), kThreads, 0, (cudaStream_t)stream>>>(P, (const float4 *)shs_z, colors, clamped);
+    return spv::check_launch("spv_compute_sh_z_forward");
+}
+
+int spv_compute_sh_z_backward(int P, const uint8_t *clamped, const float *dL_dcolors, float *dL_dshs_z, void *stream) {
+    if (P <= 0) return 0;
+    sh_z_bwd_kernel<<<grid_for(P), kThreads, 0, (cudaStream_t)stream>>>(P, clamped, dL_dcolors, (float4 *)dL_dshs_z);
+    return spv::check_launch("spv_compute_sh_z_backward");
 }
 
 int spv_compute_sh_forward(int P, const float *shs, int deg, const float *dirs, const uint8_t *visible,

@@ -52,6 +52,8 @@ class FlatDensifier:
         L.need_cuda(ndc_grad, radii)
         g = L.f32c(ndc_grad[:, :2])
         r = radii.to(torch.int32).contiguous()
+        if visibility is not None and visibility.dtype == torch.bool:
+            visibility = visibility.contiguous().view(torch.uint8)      # same bytes (0 / 1): no conversion kernel on the step
         v = None if visibility is None else visibility.to(torch.uint8).contiguous()
         L.call("spv_densify_stats", self.P, L.ptr(g), L.ptr(r), L.ptr(v), L.ptr(self.grad_accum), L.ptr(self.denom), L.ptr(self.max_radii),
                L.stream())

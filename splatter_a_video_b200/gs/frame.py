@@ -131,8 +131,9 @@ class _FrameOrtho(torch.autograd.Function):
         P = pos.shape[0]
         chans = [int(g.shape[1]) for g in groups]
         A = sum(chans)
-        if sh.shape[1] != 16:
-            raise ValueError("render_ortho_frame needs degree-3 SH coefficients [P,16,3]")
+        if sh.dim() != 3 or sh.shape[1] not in (16, 4) or sh.shape[2] != 3:
+            raise ValueError("render_ortho_frame needs degree-3 SH coefficients [P,16,3], or [P,4,3] = the bases 0, 2, 6, 12 alone")
+        nb = int(sh.shape[1])
         if len(groups) > 8 or A > 19:
             raise ValueError("render_ortho_frame handles at most 8 attribute groups / 19 attribute channels")
         dev = pos.device
@@ -145,9 +146,9 @@ class _FrameOrtho(torch.autograd.Function):
         ch_arr = (ctypes.c_int * max(len(chans), 1))(*chans)
         L.call("spv_frame_ortho_forward", P, int(W), int(H), len(groups), ctypes.cast(_ptr_array([g.data_ptr() for g in groups]), ctypes.c_void_p),
                ctypes.cast(ch_arr, ctypes.c_void_p), int(K), int(I_cap), int(bool(cull)), L.ptr(pos), L.ptr(sc), L.ptr(rot), L.ptr(op),
-               L.ptr(sh), L.ptr(ex), float(nearest), float(extent), float(bg_rgb), L.ptr(images), L.ptr(gs_idx), L.ptr(radii),
+               L.ptr(sh), nb, L.ptr(ex), float(nearest), float(extent), float(bg_rgb), L.ptr(images), L.ptr(gs_idx), L.ptr(radii),
                L.ptr(status), L.ptr(ws), nbytes, L.stream())
-        ctx.meta = (P, int(W), int(H), chans, int(I_cap), float(bg_rgb), ndc is not None, abs_ndc is not None)
+        ctx.meta = (P, int(W), int(H), chans, int(I_cap), float(bg_rgb), ndc is not None, abs_ndc is not None, nb)
         ctx.sinks = dict(sinks) if sinks else {}
         ctx.order = order
         ctx.attr_needs = [bool(attr_groups[i].requires_grad) for i in order]
@@ -166,7 +167,7 @@ class _FrameOrtho(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         import ctypes
-        P, W, H, chans, I_cap, bg_rgb, has_ndc, has_abs = ctx.meta
+        P, W, H, chans, I_cap, bg_rgb, has_ndc, has_abs, nb = ctx.meta
         sc, rot, op, sh, ex, ws = ctx.saved_tensors
         first = not getattr(ctx, "backward_ran", False)     # a second backward over the same graph must clear the packed rows itself
         ctx.backward_ran = True
@@ -199,7 +200,7 @@ class _FrameOrtho(torch.autograd.Function):
         if defer is not None:
             g_sh, r_sh = None, None
         else:
-            g_sh, r_sh = out("shs", P, 16, 3)
+            g_sh, r_sh = out("shs", P, nb, 3)
         # attribute groups: sink key ("attr", i) = the i-th group the caller passed
         g_attr, r_attr = [], []
         for slot, n, need in zip(ctx.order, chans, ctx.attr_needs):
@@ -209,7 +210,7 @@ class _FrameOrtho(torch.autograd.Function):
         g_abs = torch.empty(P, 2, dtype=torch.float32, device=dev) if has_abs else None
         ch_arr = (ctypes.c_int * max(ng, 1))(*chans)
         L.call("spv_frame_ortho_backward", P, W, H, ng, ctypes.cast(ch_arr, ctypes.c_void_p), n_grad_channels, I_cap, L.ptr(sc), L.ptr(rot), L.ptr(op),
-               L.ptr(sh), L.ptr(ex), bg_rgb, ctypes.cast(_ptr_array(planes), ctypes.c_void_p), L.ptr(g_pos), L.ptr(g_sc), L.ptr(g_rot),
+               L.ptr(sh), nb, L.ptr(ex), bg_rgb, ctypes.cast(_ptr_array(planes), ctypes.c_void_p), L.ptr(g_pos), L.ptr(g_sc), L.ptr(g_rot),
                L.ptr(g_op), L.ptr(g_sh), ctypes.cast(_ptr_array([None if t is None else t.data_ptr() for t in g_attr]), ctypes.c_void_p),
                L.ptr(g_ndc), L.ptr(g_abs), L.ptr(defer[0]) if defer is not None else None,
                L.ptr(defer[1]) if defer is not None else None, int(first), L.ptr(ws), ws.numel(), L.stream())
@@ -219,11 +220,37 @@ class _FrameOrtho(torch.autograd.Function):
         return (g_pos, r_sc, r_rot, r_op, r_sh, None, None, None, None, None, None, None, None, None, g_ndc, g_abs, None, *g_user)
 
 
+# The bases of a degree-3 SH expansion that are non-zero along the ortho renderers' constant view direction (0,0,1)
+# (dptr_ortho_enhanced.py:270-271).  A trainer that only ever renders through those renderers can keep just these coefficients
+# trainable ([P,4,3], `sh_z_split`): the other twelve get gradient 0 on every step, so torch.optim.Adam never moves them.
+SH_Z_BASES = (0, 2, 6, 12)
+
+
+def sh_z_split(shs: Tensor) -> Tuple[Tensor, Tensor]:
+    """[P,16,3] -> ([P,4,3] coefficients of SH_Z_BASES, [P,12,3] the others in ascending basis order)."""
+    act = list(SH_Z_BASES)
+    rest = [b for b in range(16) if b not in act]
+    return shs[:, act].contiguous(), shs[:, rest].contiguous()
+
+
+def sh_z_merge(shs_z: Tensor, shs_rest: Tensor) -> Tensor:
+    """Inverse of sh_z_split: the [P,16,3] tensor the reference's checkpoints / PLY files hold."""
+    act = list(SH_Z_BASES)
+    rest = [b for b in range(16) if b not in act]
+    out = torch.empty(shs_z.shape[0], 16, 3, dtype=shs_z.dtype, device=shs_z.device)
+    out[:, act] = shs_z
+    out[:, rest] = shs_rest.to(out.device)
+    return out
+
+
 def render_ortho_frame(position: Tensor, scaling: Tensor, rotation: Tensor, opacity: Tensor, shs: Tensor,
                        attrs, extr: Tensor, W: int, H: int, K: int, bg_rgb: float, I_cap: int,
                        cull: bool = True, nearest: float = 0.01, extent: float = 1.3, ndc: Optional[Tensor] = None,
                        abs_ndc: Optional[Tensor] = None, grad_sinks: Optional[dict] = None):
     """One frame of DPTROrthoEnhancedRender.render_iter as one autograd node.
+
+    shs: [P,16,3], or [P,4,3] holding the coefficients of SH_Z_BASES alone (bit-identical images and gradients; the SH kernels
+    then move 48 instead of 192 bytes per Gaussian).
 
     attrs: None, one [P,A] tensor, or a list/tuple of per-Gaussian attribute tensors (<= 8 groups, <= 19 channels in total);
     they are read in place (no concatenation) and each receives its own gradient.

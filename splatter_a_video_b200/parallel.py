@@ -338,8 +338,11 @@ class GradExchange:
         c, P, d = self._cuda, self.P, self.deferred
         g_rgb_red = reduced[c["n_dense"]:c["n_dense"] + 3 * P]
         shs = self.flat.params[d["shs"]]
-        L.call("spv_compute_sh_backward", P, L.ptr(shs), 3, L.ptr(c["dirs"]), None, L.ptr(c["clamped"]), L.ptr(g_rgb_red), 16,
-               L.ptr(shs.grad), None, L.stream())
+        if shs.shape[1] == 4:          # only the bases the constant view direction reaches are kept (gs.frame.sh_z_split)
+            L.call("spv_compute_sh_z_backward", P, L.ptr(c["clamped"]), L.ptr(g_rgb_red), L.ptr(shs.grad), L.stream())
+        else:
+            L.call("spv_compute_sh_backward", P, L.ptr(shs), 3, L.ptr(c["dirs"]), None, L.ptr(c["clamped"]), L.ptr(g_rgb_red), 16,
+                   L.ptr(shs.grad), None, L.stream())
         p = c.get("p2p")
         if p and p.get("side_pending"):          # the spline tail already runs on the side stream: join it
             torch.cuda.current_stream().wait_stream(p["side"])
@@ -365,6 +368,12 @@ class GradExchange:
                L.ptr(reduced), L.ptr(gathered), L.ptr(self.flat.flat_grad), L.ptr(self.dirty), L.stream())
 
     # ---- the exchange ----------------------------------------------------------------------------------------------
+    @property
+    def is_collective(self) -> bool:
+        """False when run() is a no-op (one process, nothing deferred): the caller may then capture the whole step in one graph."""
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        return bool(multi or self.deferred)
+
     def run(self, average: bool = True):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             if self.deferred:                      # single process: no collective, but the deferred tails still have to run

@@ -150,8 +150,11 @@ class DPTROrthoEnhancedRender(_BaseRender):
                     scaling_modifier=1.0, render_xyz=False, **kwargs) -> dict:
         dev = position.device
         extr = extrinsic_matrix.to(dev)
-        if self.frame and kwargs.get("enable_ortho_projection", True) and shs.shape[1] == 16:
+        # shs [P,4,3]: the coefficients of the bases (0, 2, 6, 12) the constant view direction reaches (gs.frame.sh_z_split)
+        if self.frame and kwargs.get("enable_ortho_projection", True) and shs.shape[1] in (16, 4):
             return self._render_iter_frame(height, width, extr, position, opacity, scaling, rotation, shs, **kwargs)
+        if shs.shape[1] == 4:
+            raise ValueError("the 4-basis SH tensor (gs.frame.sh_z_split) is only understood by the fused frame path")
         direction = torch.zeros_like(position)
         direction[:, 2] = 1.0
         rgb = _gs.compute_sh(shs, 3, direction)

@@ -688,3 +688,66 @@ def test_interval_lazy_adam_equals_dense_adam(cuda, interval_major):
     assert torch.equal(lazy.last_dev.cpu(), torch.full((NI,), len(schedule), dtype=torch.int32))
     for a, b, name in ((lazy_flat.flat, dense_flat.flat, "param"), (lazy.exp_avg, dense.exp_avg, "exp_avg"), (lazy.exp_avg_sq, dense.exp_avg_sq, "exp_avg_sq")):
         np.testing.assert_allclose(n(a), n(b), rtol=2e-6, atol=1e-9, err_msg=name)
+
+
+def test_sh_along_z_from_four_bases_is_bit_identical(cuda):
+    """spv_compute_sh_z_forward / _backward on the [P,4,3] coefficients of the bases (0, 2, 6, 12) == compute_sh(deg 3) along the
+    renderer's constant direction (0,0,1) on the full [P,16,3] tensor: colours and clamp pattern bit for bit, coefficient
+    gradients bit for bit on the four bases and exactly zero on the other twelve."""
+    from splatter_a_video_b200 import _lib as L
+    from splatter_a_video_b200 import gs
+    from splatter_a_video_b200.gs.frame import SH_Z_BASES, sh_z_merge, sh_z_split
+    P = 70_001
+    g = torch.Generator().manual_seed(31)
+    shs = torch.randn(P, 16, 3, generator=g).to(cuda)         # about half of the colours clamp at zero
+    dirs = torch.zeros(P, 3, device=cuda); dirs[:, 2] = 1
+    full = shs.clone().requires_grad_(True)
+    want = gs.compute_sh(full, 3, dirs)
+    gcol = torch.randn(P, 3, generator=g).to(cuda)
+    want.backward(gcol)
+    shs_z, rest = sh_z_split(shs)
+    assert torch.equal(sh_z_merge(shs_z, rest), shs)
+    col = torch.empty(P, 3, device=cuda); clamped = torch.empty(P, 3, dtype=torch.uint8, device=cuda)
+    L.call("spv_compute_sh_z_forward", P, L.ptr(shs_z), L.ptr(col), L.ptr(clamped), L.stream())
+    assert torch.equal(col, want.detach())
+    assert bool((want.detach()[clamped.bool()] == 0).all()) and int(clamped.sum()) > P // 10      # clamped => colour 0; the mask is exercised
+    gz = torch.empty(P, 4, 3, device=cuda)
+    L.call("spv_compute_sh_z_backward", P, L.ptr(clamped), L.ptr(gcol), L.ptr(gz), L.stream())
+    act = list(SH_Z_BASES)
+    assert torch.equal(gz, full.grad[:, act])
+    dead = [b for b in range(16) if b not in act]
+    assert float(full.grad[:, dead].abs().max()) == 0.0
+
+
+def test_frame_path_with_the_four_reachable_sh_bases(cuda):
+    """DPTROrthoEnhancedRenderB200 fed shs = [P,4,3] (gs.frame.sh_z_split): the same images and gradients as with [P,16,3], the SH
+    gradient restricted to the four bases; the staged renderers refuse the short tensor."""
+    from splatter_a_video_b200.gs.frame import SH_Z_BASES, sh_z_split
+    from splatter_a_video_b200.renderer import parse_renderer
+    P, W, H = 20_000, 256, 160
+    sc = synth.make_scene(P, 6, W, H, seed=19)
+    g = torch.Generator().manual_seed(6)
+    keys = ["rgb", "depth"] + ATTRS
+    chans = {"rgb": 3, "depth": 1, "track_gs": 3, "mask_attribute": 1, "pos_poly_feat": 12, "dino_attribute": 3}
+    gimgs = {k: torch.randn(c, H, W, generator=g).to(cuda) for k, c in chans.items()}
+
+    def run(short):
+        rd = _rd(sc, cuda)
+        if short:
+            rd["shs"] = sh_z_split(rd["shs"].detach())[0].requires_grad_(True)
+        rnd = parse_renderer({"name": "DPTROrthoEnhancedRenderB200"}, white_bg=False, device=cuda)
+        out = rnd.render_batch(rd, [_batch(sc, cuda)])
+        torch.autograd.backward([out[k][0] for k in keys], [gimgs[k] for k in keys])
+        return out, rd
+
+    o16, r16 = run(False)
+    o4, r4 = run(True)
+    for k in keys:
+        assert torch.equal(o16[k], o4[k]), k
+    Hh.assert_grad_close(n(r4["shs"].grad), n(r16["shs"].grad[:, list(SH_Z_BASES)]), "d/dshs", norm_tol=2e-5)
+    for k in ("position", "scaling", "rotation", "opacity", "mask_attribute"):
+        Hh.assert_grad_close(n(r4[k].grad), n(r16[k].grad), f"d/d{k}", norm_tol=2e-5)
+    rd = _rd(sc, cuda)
+    rd["shs"] = sh_z_split(rd["shs"].detach())[0]
+    with pytest.raises(ValueError):
+        parse_renderer({"name": "DPTROrthoEnhancedRender"}, white_bg=False, device=cuda).render_batch(rd, [_batch(sc, cuda)])
