@@ -359,6 +359,12 @@ SPV_API int spv_exchange_reduce_scatter_peers(long long n_red, long long n_row, 
  * after the caller's second barrier each rank finds the whole summed block in its own red area. */
 SPV_API int spv_exchange_nvls(long long n_red, long long n_row, int rank, int world, const float *mc_row, float *mc_red,
                       const float *const *peer_rows, float scale, float *rows, long long row_stride, void *stream);
+/* NVLS mode, publish by push: the summed block row[0, n_red) is copied into this rank's symmetric staging row (sym_row, local
+ * address; the peers' multimem.ld_reduce reads it), the gathered tail row[n_red, n_row) is multicast-stored into slot `rank` of
+ * every rank's gathered area (mc_gathered_slot = multicast address of that slot).  After the barrier that follows every rank
+ * holds all tails locally -- no peer loads. */
+SPV_API int spv_exchange_publish(long long n_red, long long n_row, const float *row, float *sym_row, float *mc_gathered_slot,
+                         void *stream);
 SPV_API int spv_exchange_fetch_reduced(long long n_red, int rank, int world, const float *const *peer_red, float *reduced,
                                void *stream);
 SPV_API int spv_exchange_unpack(int P, int nseg, const spv_exchange_segment *segs, int world, const float *comm_allreduce,

@@ -93,6 +93,7 @@ _SIGS = {
                                                   ctypes.c_longlong, P_]),
     "spv_exchange_gather_peers": (c_int, [ctypes.c_longlong, ctypes.c_longlong, c_int, P_, P_, ctypes.c_longlong, P_]),
     "spv_exchange_nvls": (c_int, [ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, P_, P_, P_, c_float, P_, ctypes.c_longlong, P_]),
+    "spv_exchange_publish": (c_int, [ctypes.c_longlong, ctypes.c_longlong, P_, P_, P_, P_]),
     "spv_exchange_fetch_reduced": (c_int, [ctypes.c_longlong, c_int, c_int, P_, P_, P_]),
     "spv_exchange_unpack": (c_int, [c_int, c_int, P_, c_int, P_, P_, P_, P_, P_]),
     "spv_loss_rgb_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),

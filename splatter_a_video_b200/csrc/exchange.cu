@@ -247,6 +247,31 @@ __device__ __forceinline__ void multimem_st(float4 *mc, float4 v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Publish by PUSH (NVLS mode): the summed block of the staging row is copied into this rank's half of the symmetric buffer (where
+// the peers' multimem.ld_reduce will read it) and the gathered tail -- position gradients + frame scalars, which every rank needs
+// from every rank -- is written with ONE multicast store per 16 bytes into slot `rank` of EVERY rank's gathered area.  Stores are
+// fire-and-forget: after the barrier that follows, every rank holds all tails locally and the spline backward can start at once,
+// next to the in-switch reduction, instead of behind a pull of (N-1) x 24 B per Gaussian through peer LOADS (measured at N = 4:
+// 74 us of gather + 33 us of spline tail behind it, the longest branch of the exchange).
+__global__ void __launch_bounds__(kThreads)
+exchange_publish_kernel(long long n_red4, long long n_row4, const float4 *__restrict__ row, float4 *__restrict__ sym_row,
+                        float4 *__restrict__ mc_gathered_slot) {
+    const long long e0 = (long long)blockIdx.x * (kThreads * kPeerUnroll) + threadIdx.x;
+    float4 v[kPeerUnroll];
+#pragma unroll
+    for (int u = 0; u < kPeerUnroll; ++u) {
+        const long long e = e0 + (long long)u * kThreads;
+        if (e < n_row4) v[u] = row[e];
+    }
+#pragma unroll
+    for (int u = 0; u < kPeerUnroll; ++u) {
+        const long long e = e0 + (long long)u * kThreads;
+        if (e >= n_row4) continue;
+        if (e < n_red4) sym_row[e] = v[u];
+        else multimem_st(mc_gathered_slot + (e - n_red4), v[u]);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 exchange_nvls_kernel(long long n_red4, long long n_row4, long long chunk4, int rank, int world, const float4 *__restrict__ mc_row,
                      float4 *__restrict__ mc_red, PeerPtrs peers, float scale, float4 *__restrict__ rows, long long row_stride4) {
@@ -431,6 +456,19 @@ int spv_exchange_nvls(long long n_red, long long n_row, int rank, int world, con
         n_red4, n_row4, chunk4 > 0 ? chunk4 : 1, rank, world, (const float4 *)mc_row, (float4 *)mc_red, pp, scale, (float4 *)rows,
         row_stride / 4);
     return spv::check_launch("spv_exchange_nvls");
+}
+
+/* NVLS publish: row[0, n_red) -> sym_row (this rank's symmetric staging row, local address); row[n_red, n_row) -> multicast store
+ * into mc_gathered_slot = the multicast address of slot `rank` of the gathered area (n_row - n_red floats per slot). */
+int spv_exchange_publish(long long n_red, long long n_row, const float *row, float *sym_row, float *mc_gathered_slot, void *stream) {
+    if (n_row <= 0) return 0;
+    if ((n_red & 3) || (n_row & 3) || n_red > n_row || !row || !sym_row || !mc_gathered_slot) {
+        spv::set_error(cudaErrorInvalidValue, "spv_exchange_publish: sizes must be multiples of 4, pointers set");
+        return (int)cudaErrorInvalidValue;
+    }
+    exchange_publish_kernel<<<spv::cdiv(n_row / 4, kThreads * kPeerUnroll), kThreads, 0, (cudaStream_t)stream>>>(
+        n_red / 4, n_row / 4, (const float4 *)row, (float4 *)sym_row, (float4 *)mc_gathered_slot);
+    return spv::check_launch("spv_exchange_publish");
 }
 
 int spv_exchange_fetch_reduced(long long n_red, int rank, int world, const float *const *peer_red, float *reduced, void *stream) {

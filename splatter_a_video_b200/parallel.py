@@ -237,7 +237,9 @@ class GradExchange:
             import ctypes
             import torch.distributed._symmetric_memory as symm
             row, n_red = c["row"].numel(), int(c["n_red"])
-            span = row + n_red                       # per half: [staging row | this rank's published slice of the reduced block]
+            world_n = dist.get_world_size()
+            # per half: [staging row | the reduced block | NVLS push mode: every rank's gathered tail, slot r written by rank r]
+            span = row + n_red + world_n * (row - n_red)
             buf = symm.empty(2 * span, dtype=torch.float32, device=c["row"].device)
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
@@ -256,9 +258,11 @@ class GradExchange:
                 want = "nvls" if (mc and dist.get_world_size() >= 4) else "oneshot"
             if want == "nvls" and not mc:
                 want = "oneshot"
-            c["p2p"] = dict(buf=buf, hdl=hdl, arrs=arrs, reds=reds, span=span, step=0, mode=want, mc=mc)
+            push = want == "nvls" and os.environ.get("SPV_EXCHANGE_PULL", "0") != "1"
+            c["p2p"] = dict(buf=buf, hdl=hdl, arrs=arrs, reds=reds, span=span, step=0, mode=want, mc=mc, push=push)
             self.exchange_path = {"oneshot": "p2p one-shot (peer loads)", "twophase": "p2p two-phase (peer loads)",
-                                  "nvls": "nvls (multimem.ld_reduce / multimem.st through the NVSwitch)"}[want]
+                                  "nvls": "nvls (multimem.ld_reduce / multimem.st through the NVSwitch; tails "
+                                          + ("pushed by multicast stores)" if push else "pulled by peer loads)")}[want]
         except Exception as e:   # noqa: BLE001 -- any failure here means: no peer mapping on this system
             self.exchange_path = f"nccl ({type(e).__name__}: {str(e)[:80]})"
             import warnings
@@ -275,18 +279,31 @@ class GradExchange:
         p = c["p2p"]
         half, row, span, n_red = p["step"] & 1, c["row"].numel(), p["span"], int(c["n_red"])
         p["step"] += 1
-        p["buf"][half * span:half * span + row].copy_(c["row"])
-        p["hdl"].barrier(channel=0)
-        rows_ptr = ctypes.cast(p["arrs"][half], ctypes.c_void_p)
-        # ---- side stream: gather every rank's position gradients + frame scalars, rebuild the spline-coefficient gradient
         main = torch.cuda.current_stream()
         if "side" not in p:
             p["side"] = torch.cuda.Stream()
         side = p["side"]
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            L.call("spv_exchange_gather_peers", n_red, row, world, rows_ptr, L.ptr(c["rows"]), c["rows"].stride(0), L.stream())
-            self._spline_tail(world, scale)
+        rows_ptr = ctypes.cast(p["arrs"][half], ctypes.c_void_p)
+        if p["push"]:
+            # publish by push: the summed block into this rank's half, the gathered tail multicast into slot `rank` of every rank's
+            # gathered area; after the barrier the spline backward reads all tails LOCALLY, next to the in-switch reduction
+            gath, rank = row - n_red, dist.get_rank()
+            g0 = half * span + row + n_red                       # float offset of the gathered area inside the symmetric buffer
+            L.call("spv_exchange_publish", n_red, row, L.ptr(c["row"]), p["buf"].data_ptr() + half * span * 4,
+                   p["mc"] + (g0 + rank * gath) * 4, L.stream())
+            p["hdl"].barrier(channel=0)
+            gathered = p["buf"][g0:g0 + world * gath].view(world, gath)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._spline_tail(world, scale, gathered)
+        else:
+            p["buf"][half * span:half * span + row].copy_(c["row"])
+            p["hdl"].barrier(channel=0)
+            # ---- side stream: gather every rank's position gradients + frame scalars, rebuild the spline-coefficient gradient
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                L.call("spv_exchange_gather_peers", n_red, row, world, rows_ptr, L.ptr(c["rows"]), c["rows"].stride(0), L.stream())
+                self._spline_tail(world, scale)
         p["side_pending"] = True
         # ---- main stream: the summed block
         if p["mode"] == "oneshot":
@@ -325,12 +342,13 @@ class GradExchange:
         L.call("spv_exchange_reduce", int(c["n_red"]), world, L.ptr(c["rows"]), c["rows"].stride(0), float(scale), L.ptr(c["reduced"]),
                L.stream())
 
-    def _spline_tail(self, world: int, scale: float):
+    def _spline_tail(self, world: int, scale: float, gathered: Optional[torch.Tensor] = None):
         from . import _lib as L
         c, d = self._cuda, self.deferred
         node = self.flat.params[d["node"]]
+        gathered = c["gathered"] if gathered is None else gathered          # [world, 6P + 4 (+pad)] rows
         L.call("spv_deform_spline_backward_gathered", self.P, int(d["NI"]), int(bool(d.get("interval_major", False))), world,
-               c["gathered"].data_ptr(), c["gathered"].stride(0),
+               gathered.data_ptr(), gathered.stride(0),
                float(scale), L.ptr(self.dirty), L.ptr(node.grad), L.stream())
 
     def _finish_deferred(self, world: int, scale: float, reduced: torch.Tensor):
