@@ -60,3 +60,34 @@ def test_capacity_grows_before_it_overflows_and_follows_population(fake_events):
     assert c.I_cap >= 3 * cap
     c.set_population(150)                                   # pruning never shrinks the buffers
     assert c.I_cap >= 3 * cap
+
+
+def test_sh_z_split_and_merge_round_trip():
+    """gs.frame.sh_z_split / sh_z_merge: the four bases the ortho renderers' constant view direction (0,0,1) reaches are exactly the
+    ones whose degree-3 SH basis function is non-zero there (oracle/torch_ref.py evaluates the reference's polynomial)."""
+    from oracle import torch_ref as TR
+    g = torch.Generator().manual_seed(2)
+    shs = torch.randn(50, 16, 3, generator=g)
+    z, rest = F.sh_z_split(shs)
+    assert z.shape == (50, 4, 3) and rest.shape == (50, 12, 3)
+    assert torch.equal(F.sh_z_merge(z, rest), shs)
+    assert torch.equal(z, shs[:, list(F.SH_Z_BASES)])
+    # which bases does direction (0,0,1) reach?  d colour / d coefficient of the reference's SH evaluation
+    dirs = torch.zeros(50, 3); dirs[:, 2] = 1
+    x = shs.clone().requires_grad_(True)
+    TR.compute_sh(x, 3, dirs).sum().backward() if hasattr(TR, "compute_sh") else pytest.skip("no torch SH in the oracle")
+    reached = (x.grad.abs().sum(dim=(0, 2)) > 0).nonzero().flatten().tolist()
+    assert set(reached) <= set(F.SH_Z_BASES)            # clamped colours may hide a basis for SOME points, never add one
+    assert len(reached) >= 1
+
+
+def test_exchange_is_not_collective_on_one_process():
+    """One process, nothing deferred: GradExchange.run() is a no-op, so a trainer may capture the whole step in one graph."""
+    from splatter_a_video_b200.parallel import FlatParams, GradExchange
+    flat = FlatParams({"a": torch.zeros(8, 3), "b": torch.zeros(8, 16, 3)})
+    ex = GradExchange(flat, 8)
+    assert ex.is_collective is False
+    before = flat.flat_grad.clone()
+    ex.run()
+    assert torch.equal(flat.flat_grad, before)
+    assert GradExchange(flat, 8, deferred={"shs": "b", "node": "a", "NI": 1}).is_collective is True
