@@ -1064,6 +1064,11 @@ def run_ours(args):
                    "renderer": type(wl.renderer).__name__, "mode": wl.mode, "cuda_graph": wl.use_graph,
                    "capacity_overflow": overflow, "l2": "512 MiB device write between timed steps (outside the per-step event bracket)",
                    "grad_floats_per_gaussian": wl.flat.floats_per_gaussian(wl.P),
+                   "sh_parameter": ("[P,4,3]: the SH bases 0, 2, 6, 12 -- the only ones the renderer's constant view direction (0,0,1) reaches "
+                                    "(dptr_ortho_enhanced.py:270-271); the other twelve receive gradient 0 on every step, torch.optim.Adam "
+                                    "never moves them, and they are carried as a frozen per-Gaussian tensor outside the optimizer's buffer "
+                                    "(bit-identical colours and gradients: tests/test_frame_gpu.py::test_sh_along_z_from_four_bases_is_bit_identical; "
+                                    "SPV_FULL_SH=1 trains all sixteen)" if wl.sh_z else "[P,16,3]"),
                    "optimizer": ("FlatAdam (torch.optim.Adam arithmetic, device-resident step clock)" +
                                  (", interval-lazy on the spline coefficients: only the intervals that hold gradient are streamed, the "
                                   "zero-gradient updates of the others are replayed before they are read -- same parameters as the dense "
